@@ -1,0 +1,226 @@
+/*
+ * materialist_b200.h — C-ABI of the B200-native differentiable envmap-shading path.
+ *
+ * This is the drop-in boundary.  Every entry point takes plain
+ * pointers and sizes; there are no torch / C++ types in any signature.  All
+ * pointers are DEVICE pointers unless the parameter name ends in `_host`.
+ * Every function returns MB200_OK (0) or a negative MB200_E* code, never
+ * throws, never allocates device memory and enqueues its work on the stream
+ * passed as `void* stream` (a cudaStream_t; NULL = legacy default stream).
+ *
+ * What each entry point replaces in the reference (lez-s/Materialist @ bdd146f):
+ *
+ *   mb200_env_prepare      Mitsuba EnvironmentMapEmitter::parameters_changed('data')
+ *                          reached from  inverse_img_w_mi.py:63-64  (params['emitter.data']=...;
+ *                          params.update())  and the envmap file load at inverse_img_w_mi.py:54,
+ *                          render_final.py:52.  [upstream mitsuba==3.5.2 src/emitters/envmap.cpp,
+ *                          include/mitsuba/core/distr_2d.h Hierarchical2D]
+ *   mb200_shade_fwd        mi.render(scene, params, spp, seed) forward —
+ *                          inverse_img_w_mi.py:65, :79; render_final.py:194, :227, :391 —
+ *                          with the BSDF virtual calls MatDiffBSDF.eval_pdf / .sample
+ *                          (myutils/mi_plugin.py:1429-1460) fused in.
+ *   mb200_film_develop     HDRFilm::develop (rgb / weight) at the end of mi.render.
+ *   mb200_film_weights     the ImageBlock::put weight channel of the seed_grad re-render
+ *                          (Integrator::render_backward re-renders).
+ *   mb200_shade_bwd        the loss.backward() leg of  render_w_brdf / render_envmap
+ *                          (inverse_img_w_mi.py:59-80, :248, :419): Mitsuba
+ *                          render_backward(seed_grad) + dr.backward, returning
+ *                          d/d{a,r,m,n} and d/d{emitter.data}.
+ *   mb200_env_grad_finish  adjoint of the column-average / appended-column map of
+ *                          parameters_changed.
+ *   mb200_bsdf_eval_pdf    MatDiffBSDF.eval_pdf  (myutils/mi_plugin.py:1449-1460) on an array of lanes.
+ *   mb200_bsdf_sample      MatDiffBSDF.sample    (myutils/mi_plugin.py:1429-1446) on an array of lanes.
+ *   mb200_debug_sample_indices
+ *                          not in the reference: exposes the integer decisions of the path
+ *                          (hierarchy offsets, texel index, lobe) so tests can assert them bit-exact.
+ *   mb200_posmlp_*         PosMLP.forward (+autograd backward) mymodels/mlps.py:211-251 as used at
+ *                          inverse_img_w_mi.py:163,:493 (brdf_net) and :117,:238 (envmap_net).
+ *   mb200_cdf_build        build_envmap   myutils/envmap_utils.py:43-66
+ *   mb200_cdf_sample       sample_envmap  myutils/envmap_utils.py:172-201
+ *   mb200_sh_project       computeSHFromImage-style order-4 projection  myutils/computeSH.py:299-347
+ *                          (deterministic sample positions supplied by the caller)
+ *   mb200_sh_reconstruct   reconstImageFromSH  myutils/computeSH.py:226-240
+ */
+#ifndef MATERIALIST_B200_H
+#define MATERIALIST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- errors */
+#define MB200_OK             0
+#define MB200_EINVAL        -1   /* bad argument (null pointer, non-positive size, ...) */
+#define MB200_ERANGE        -2   /* size out of supported range (e.g. H*W*spp >= 2^32)   */
+#define MB200_ELAUNCH       -3   /* CUDA launch / runtime error (see mb200_last_cuda_error) */
+#define MB200_EUNSUPPORTED  -4   /* valid request, not implemented by this build */
+
+/* ---------------------------------------------------------------- flags  */
+/* cfg.flags — reference-exact quirks, all ON by default in the Python host. */
+#define MB200_FLAG_WO_WORLD_QUIRK   1  /* bs.wo returned in world space is pushed through si.to_world
+                                          again by the integrator (mi_plugin.py:1444) */
+#define MB200_FLAG_ROW_STRIDE_H     2  /* texel index = x + y*shape[0] (mi_plugin.py:1310,1381);
+                                          off: x + y*W (the intended behaviour for W != H) */
+#define MB200_FLAG_ENV_HALF_TEXEL   4  /* u -= .5/(res.x-1) in envmap eval / pdf, += in sample
+                                          (mitsuba 3.5 envmap.cpp) */
+#define MB200_FLAG_AD_WEIGHTS       8  /* use the AD-pass BSDF-sample weight f2/p2
+                                          instead of the primal f/(p+1e-6); set by shade_bwd itself,
+                                          may be set on shade_fwd to render the primal of the AD pass */
+
+#define MB200_FILTER_BOX       0
+#define MB200_FILTER_GAUSSIAN  1
+
+/* envmap ingest modes for mb200_env_prepare */
+#define MB200_ENV_ASSIGNED  0  /* tensor assigned through params['emitter.data']: width kept,
+                                  first/last column averaged (Appendix A5) */
+#define MB200_ENV_FILE      1  /* bitmap loaded from file: one column appended = copy of col 0 */
+
+#define MB200_MAX_LEVELS 24
+#define MB200_FILM_TAPS  25   /* 5x5 footprint of the radius-2 gaussian */
+
+/* ---------------------------------------------------------------- types  */
+typedef struct mb200_cfg {
+    int32_t  H, W;            /* full image size (pixels)                                   */
+    int32_t  spp;             /* samples per pixel                                          */
+    int32_t  max_depth;       /* path integrator max_depth (>= 2)            */
+    uint32_t seed;            /* sampler seed (mi.render seed, or seed_grad for the adjoint) */
+    int32_t  filter;          /* MB200_FILTER_*                                             */
+    int32_t  flags;           /* MB200_FLAG_*                                               */
+    int32_t  use_mesh_normal; /* 1: shade with G-buffer normal, 0: with the n map           */
+    int32_t  row0, rows;      /* pixel shard: image rows [row0, row0+rows)                  */
+    float    view[16];        /* world -> camera, row-major (MatDiffBSDF.view_matrix)       */
+    float    proj[16];        /* camera -> clip, row-major (MatDiffBSDF.persp_proj_matx)    */
+    float    cam_to_world[16];/* sensor to_world, row-major                                 */
+    float    tan_half_fov_x;  /* tan(x_fov/2) of the perspective sensor                     */
+    float    env_u_shift;     /* .5/(res.x-1) when MB200_FLAG_ENV_HALF_TEXEL else 0 (filled by host) */
+} mb200_cfg;
+
+/* Layout of the Hierarchical2D sampling pyramid inside one float buffer.
+ * level 0 = vertex values (res_x * res_y, row-major, normalised);
+ * level l>=1 = patch sums, 2x2-swizzled, size lvl_w[l] x lvl_h[l] (even). */
+typedef struct mb200_hier_desc {
+    int32_t res_x, res_y;                 /* internal envmap resolution (vertices) */
+    int32_t n_levels;                     /* number of levels incl. level 0        */
+    int32_t lvl_off[MB200_MAX_LEVELS];    /* offset (floats) of each level         */
+    int32_t lvl_w[MB200_MAX_LEVELS];
+    int32_t lvl_h[MB200_MAX_LEVELS];
+    int32_t total_floats;
+} mb200_hier_desc;
+
+/* ---------------------------------------------------------------- host helpers (no GPU needed) */
+const char* mb200_strerror(int code);
+const char* mb200_last_cuda_error(void);            /* text of the last CUDA error seen by this thread */
+int  mb200_version(void);
+/* internal width for a user envmap of width We under `mode` */
+int  mb200_env_internal_width(int We, int mode);
+/* fills `out` for an internal resolution (res_x, res_y) */
+int  mb200_hier_describe(int res_x, int res_y, mb200_hier_desc* out_host);
+/* bytes of scratch mb200_env_prepare needs */
+size_t mb200_env_scratch_bytes(int res_x, int res_y);
+/* number of rows (incl. film halo) shade_fwd writes partials for, and the first such row */
+int  mb200_fwd_partial_rows(const mb200_cfg* cfg_host, int* first_row_host);
+/* floats per pixel in the `partials` buffer for cfg.filter */
+int  mb200_partial_stride(int filter);
+
+/* ---------------------------------------------------------------- envmap */
+/* env_in  : (He, We, 3) fp32 user envmap
+ * env4    : (He, Wi, 4) fp32 internal texels (rgb, 0), Wi = mb200_env_internal_width
+ * hier    : desc.total_floats fp32
+ * scratch : mb200_env_scratch_bytes bytes (8-byte aligned) */
+int mb200_env_prepare(const float* env_in, int He, int We, int mode,
+                      float* env4, float* hier, const mb200_hier_desc* desc_host,
+                      void* scratch, void* stream);
+
+/* g_env4 (He, Wi, 4) -> g_env (He, We, 3), adjoint of the ingest map; g_env is OVERWRITTEN */
+int mb200_env_grad_finish(const float* g_env4, int He, int We, int mode, float* g_env, void* stream);
+
+/* ---------------------------------------------------------------- render */
+/* G-buffer: gpos (H,W,4) = (x,y,z,valid?1:0), gnrm (H,W,4) = (nx,ny,nz,0)  — full image, fp32.
+ * a (H,W,3), r (H,W,1), m (H,W,1), n_opt (H,W,3) or NULL — full image.
+ * partials : (prow_count, W, stride) with stride = mb200_partial_stride(filter),
+ *            prow_count / first row from mb200_fwd_partial_rows. */
+int mb200_shade_fwd(const mb200_cfg* cfg_host,
+                    const float* gpos, const float* gnrm,
+                    const float* a, const float* r, const float* m, const float* n_opt,
+                    const float* env4, const float* hier, const mb200_hier_desc* desc_host,
+                    float* partials, void* stream);
+
+/* partials -> img (rows, W, 3) for the shard rows; */
+int mb200_film_develop(const mb200_cfg* cfg_host, const float* partials, float* img, void* stream);
+
+/* Weight channel only (uses nothing but the RNG): wpart (prow_count, W, 25) for gaussian.
+ * Then G[q] = grad_img[q] / W_q is formed by mb200_film_adjoint for rows [row0-2, row0+rows+2) ∩ image:
+ * grad_img_halo : (grow_count, W, 3) incl. the 2-row halo (rows outside the image absent),
+ * gadj          : (grow_count, W, 4) = (G.rgb, 0). For the box filter wpart may be NULL and gadj = grad/spp. */
+int mb200_film_weights(const mb200_cfg* cfg_host, float* wpart, void* stream);
+int mb200_film_adjoint(const mb200_cfg* cfg_host, const float* wpart, const float* grad_img_halo,
+                       float* gadj, void* stream);
+/* rows of wpart (needs a 4-row halo) and of gadj / grad_img_halo (2-row halo) */
+int mb200_bwd_wpart_rows(const mb200_cfg* cfg_host, int* first_row_host);
+int mb200_bwd_gadj_rows(const mb200_cfg* cfg_host, int* first_row_host);
+
+/* Adjoint render (cfg.seed = seed_grad).  Accumulates (+=) into the gradient buffers:
+ * g_a (H,W,3), g_r (H,W,1), g_m (H,W,1), g_n (H,W,3) full-image, any may be NULL;
+ * g_env4 (He, Wi, 4) or NULL.  Caller zeroes them. */
+int mb200_shade_bwd(const mb200_cfg* cfg_host,
+                    const float* gpos, const float* gnrm,
+                    const float* a, const float* r, const float* m, const float* n_opt,
+                    const float* env4, const float* hier, const mb200_hier_desc* desc_host,
+                    const float* gadj,
+                    float* g_a, float* g_r, float* g_m, float* g_n, float* g_env4,
+                    void* stream);
+
+/* (S,4) int32 per lane: (hier off.x, off.y, texel flat index, lobe 0=specular 1=diffuse); shard rows only */
+int mb200_debug_sample_indices(const mb200_cfg* cfg_host, const float* gpos, const float* r,
+                               const float* hier, const mb200_hier_desc* desc_host,
+                               int32_t* out, void* stream);
+
+/* ---------------------------------------------------------------- BSDF plugin on lanes */
+/* All lane arrays are (L,3) / (L) fp32.  cfg supplies view/proj/H/W/flags/use_mesh_normal.
+ * eval_pdf: wo_world = light direction, wi_world = view direction (mi_plugin.py:1449-1460). */
+int mb200_bsdf_eval_pdf(const mb200_cfg* cfg_host, int64_t L,
+                        const float* p, const float* n_geo, const float* wi_world, const float* wo_world,
+                        const float* a, const float* r, const float* m, const float* n_opt,
+                        float* out_f /*(L,3)*/, float* out_pdf /*(L)*/, void* stream);
+int mb200_bsdf_sample(const mb200_cfg* cfg_host, int64_t L,
+                      const float* p, const float* n_geo, const float* wi_world,
+                      const float* sample1 /*(L)*/, const float* sample2 /*(L,2)*/,
+                      const float* a, const float* r, const float* m, const float* n_opt,
+                      float* out_wo /*(L,3) world*/, float* out_pdf /*(L)*/, float* out_weight /*(L,3)*/,
+                      void* stream);
+
+/* ---------------------------------------------------------------- PosMLP */
+typedef struct mb200_posmlp_desc {
+    int32_t n_color;      /* colour / feature channels of the input image (5 for 'arm', 3 for envmap_net) */
+    int32_t n_out;        /* output channels                                                   */
+    int32_t hidden;       /* 256                                                               */
+    int32_t n_freq;       /* multires_view (2)                                                 */
+    int32_t output_type;  /* 0 = 'envmap' (softplus), 1 = 'arm' (1.3*tanh + img, STE clamp)    */
+    int32_t H, W;         /* pixel grid the N rows enumerate (row-major)                       */
+} mb200_posmlp_desc;
+/* parameter packing: [W0 (h0 x d0) | b0 | W1 | b1 | W2 | b2 | W3 | b3 | W4 | b4], nn.Linear row-major (out,in) */
+int64_t mb200_posmlp_param_count(const mb200_posmlp_desc* d_host);
+size_t  mb200_posmlp_cache_bytes(const mb200_posmlp_desc* d_host, int64_t N);
+int mb200_posmlp_fwd(const mb200_posmlp_desc* d_host, const float* params, const float* img /*(N,n_color)*/,
+                     int64_t N, float* out /*(N,n_out)*/, void* cache /* or NULL: inference */, void* stream);
+int mb200_posmlp_bwd(const mb200_posmlp_desc* d_host, const float* params, const float* img, int64_t N,
+                     const void* cache, const float* g_out /*(N,n_out)*/,
+                     float* g_params /* += */, float* g_img /*(N,n_color) or NULL*/, void* stream);
+
+/* ---------------------------------------------------------------- envmap_utils / computeSH */
+/* build_envmap: env (h,w,3) -> c_cdf (h,w), m_cdf (h) */
+int mb200_cdf_build(const float* env, int h, int w, float* c_cdf, float* m_cdf, void* stream);
+/* sample_envmap: sample2 (2,n) -> dirs (n,3), pdf (n,1), v_idx (n) int64, u_idx (n) int64 */
+int mb200_cdf_sample(const float* c_cdf, const float* m_cdf, int h, int w, const float* sample2, int64_t n,
+                     float* dirs, float* pdf, int64_t* v_idx, int64_t* u_idx, void* stream);
+/* order-4 real SH (25 coef).  angles (n,2) = (theta, phi) fp64; im (h,w,3) fp64; coef (25,3) fp64 */
+int mb200_sh_project(const double* im, int h, int w, const double* angles, int64_t n, double* coef, void* stream);
+int mb200_sh_reconstruct(const double* coef, int nrows, int ncols, int clip, double* img /*(nrows,ncols,3)*/, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MATERIALIST_B200_H */

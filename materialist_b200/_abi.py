@@ -1,0 +1,125 @@
+"""ctypes binding of libmaterialist_b200.so — the C-ABI declared in include/materialist_b200.h.
+
+The library is built in-tree by materialist_b200/csrc/Makefile (nvcc, sm_100a).  There is NO CPU
+fallback: if the shared library is missing the import of this module raises, and every compute call
+raises if the tensors are not CUDA tensors.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmaterialist_b200.so")
+
+MAX_LEVELS = 24
+FILM_TAPS = 25
+
+OK, EINVAL, ERANGE, ELAUNCH, EUNSUPPORTED = 0, -1, -2, -3, -4
+FLAG_WO_WORLD_QUIRK, FLAG_ROW_STRIDE_H, FLAG_ENV_HALF_TEXEL, FLAG_AD_WEIGHTS = 1, 2, 4, 8
+FILTER_BOX, FILTER_GAUSSIAN = 0, 1
+ENV_ASSIGNED, ENV_FILE = 0, 1
+
+
+class Cfg(C.Structure):
+    _fields_ = [("H", C.c_int32), ("W", C.c_int32), ("spp", C.c_int32), ("max_depth", C.c_int32),
+                ("seed", C.c_uint32), ("filter", C.c_int32), ("flags", C.c_int32), ("use_mesh_normal", C.c_int32),
+                ("row0", C.c_int32), ("rows", C.c_int32),
+                ("view", C.c_float * 16), ("proj", C.c_float * 16), ("cam_to_world", C.c_float * 16),
+                ("tan_half_fov_x", C.c_float), ("env_u_shift", C.c_float)]
+
+
+class HierDesc(C.Structure):
+    _fields_ = [("res_x", C.c_int32), ("res_y", C.c_int32), ("n_levels", C.c_int32),
+                ("lvl_off", C.c_int32 * MAX_LEVELS), ("lvl_w", C.c_int32 * MAX_LEVELS), ("lvl_h", C.c_int32 * MAX_LEVELS),
+                ("total_floats", C.c_int32)]
+
+
+class PosMLPDesc(C.Structure):
+    _fields_ = [("n_color", C.c_int32), ("n_out", C.c_int32), ("hidden", C.c_int32), ("n_freq", C.c_int32),
+                ("output_type", C.c_int32), ("H", C.c_int32), ("W", C.c_int32)]
+
+
+class MB200Error(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: the CUDA extension is not built. Run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C materialist_b200/csrc`. There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+    pc, ph, pm = C.POINTER(Cfg), C.POINTER(HierDesc), C.POINTER(PosMLPDesc)
+    sig = {
+        "mb200_strerror": (C.c_char_p, [i32]),
+        "mb200_last_cuda_error": (C.c_char_p, []),
+        "mb200_version": (i32, []),
+        "mb200_env_internal_width": (i32, [i32, i32]),
+        "mb200_hier_describe": (i32, [i32, i32, ph]),
+        "mb200_env_scratch_bytes": (sz, [i32, i32]),
+        "mb200_fwd_partial_rows": (i32, [pc, C.POINTER(C.c_int)]),
+        "mb200_partial_stride": (i32, [i32]),
+        "mb200_env_prepare": (i32, [vp, i32, i32, i32, vp, vp, ph, vp, vp]),
+        "mb200_env_grad_finish": (i32, [vp, i32, i32, i32, vp, vp]),
+        "mb200_shade_fwd": (i32, [pc] + [vp] * 9 + [ph, vp, vp]),
+        "mb200_film_develop": (i32, [pc, vp, vp, vp]),
+        "mb200_film_weights": (i32, [pc, vp, vp]),
+        "mb200_film_adjoint": (i32, [pc, vp, vp, vp, vp]),
+        "mb200_bwd_wpart_rows": (i32, [pc, C.POINTER(C.c_int)]),
+        "mb200_bwd_gadj_rows": (i32, [pc, C.POINTER(C.c_int)]),
+        "mb200_shade_bwd": (i32, [pc] + [vp] * 9 + [ph] + [vp] * 7),
+        "mb200_debug_sample_indices": (i32, [pc, vp, vp, vp, ph, vp, vp]),
+        "mb200_bsdf_eval_pdf": (i32, [pc, i64] + [vp] * 11),
+        "mb200_bsdf_sample": (i32, [pc, i64] + [vp] * 13),
+        "mb200_posmlp_param_count": (i64, [pm]),
+        "mb200_posmlp_cache_bytes": (sz, [pm, i64]),
+        "mb200_posmlp_fwd": (i32, [pm, vp, vp, i64, vp, vp, vp]),
+        "mb200_posmlp_bwd": (i32, [pm, vp, vp, i64, vp, vp, vp, vp, vp]),
+        "mb200_cdf_build": (i32, [vp, i32, i32, vp, vp, vp]),
+        "mb200_cdf_sample": (i32, [vp, vp, i32, i32, vp, i64, vp, vp, vp, vp, vp]),
+        "mb200_sh_project": (i32, [vp, i32, i32, vp, i64, vp, vp]),
+        "mb200_sh_reconstruct": (i32, [vp, i32, i32, i32, vp, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)           # AttributeError here = header / library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    return lib, tuple(sig)
+
+
+lib, EXPORTS = _load()
+
+
+def check(rc, what=""):
+    if rc != OK:
+        msg = lib.mb200_strerror(rc).decode()
+        if rc == ELAUNCH:
+            msg += " — " + lib.mb200_last_cuda_error().decode()
+        if rc == EINVAL:
+            raise ValueError(f"{what}: {msg}")
+        raise MB200Error(f"{what}: {msg} (rc={rc})")
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL). Raises on CPU tensors: no fallback."""
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"expected a torch.Tensor, got {type(t)}")
+    if not t.is_cuda:
+        raise ValueError("materialist_b200 runs on CUDA tensors only (no CPU fallback); got a CPU tensor")
+    if not t.is_contiguous():
+        raise ValueError("tensor must be contiguous")
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def hier_describe(res_x, res_y):
+    d = HierDesc()
+    check(lib.mb200_hier_describe(res_x, res_y, C.byref(d)), "mb200_hier_describe")
+    return d

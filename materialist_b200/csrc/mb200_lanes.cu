@@ -1,0 +1,76 @@
+// mb200_lanes.cu — the inner (plugin) boundary: MatDiffBSDF.eval_pdf / .sample on arrays of lanes
+// (myutils/mi_plugin.py:1429-1460).  One thread per lane; used for unit parity of a single BSDF
+// evaluation against the oracle and the reference's torch BRDF sub-terms, not by the render hot loop.
+#include "mb200_device.cuh"
+#include "mb200_host.h"
+
+using namespace mb;
+
+namespace {
+
+struct LaneParams {
+    CamView cam; int use_mesh_normal; long long L;
+    const float *p, *n_geo, *wi, *wo, *s1, *s2, *a, *r, *m, *n_opt;
+    float *o3, *o1, *ow;
+};
+__device__ __forceinline__ float3 ld3(const float* q, long long i) { return f3(q[3 * i], q[3 * i + 1], q[3 * i + 2]); }
+__device__ __forceinline__ void st3(float* q, long long i, float3 v) { q[3 * i] = v.x; q[3 * i + 1] = v.y; q[3 * i + 2] = v.z; }
+__device__ __forceinline__ Material lane_material(const LaneParams& P, long long i) {
+    const long long flat = texel_index(P.cam, ld3(P.p, i));
+    Material mt; mt.a = ld3(P.a, flat); mt.r = P.r[flat]; mt.m = P.m[flat];
+    mt.n = (P.use_mesh_normal || !P.n_opt) ? ld3(P.n_geo, i) : ld3(P.n_opt, flat);
+    return mt;
+}
+__global__ void bsdf_eval_pdf_kernel(const __grid_constant__ LaneParams P) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.L) return;
+    const Material mt = lane_material(P, i);
+    const BsdfVal v = eval_brdf(ld3(P.wo, i), ld3(P.wi, i), mt);   // eval_brdf(wi := light (wo), wo := view (si.wi))
+    st3(P.o3, i, v.f); P.o1[i] = v.pdf;
+}
+__global__ void bsdf_sample_kernel(const __grid_constant__ LaneParams P) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.L) return;
+    const Material mt = lane_material(P, i);
+    const Frame fs = make_frame(mt.n);
+    const BsdfSample s = sample_brdf(P.s1[i], P.s2[2 * i], P.s2[2 * i + 1], ld3(P.wi, i), mt, fs);
+    st3(P.o3, i, s.wi); P.o1[i] = s.pdf; st3(P.ow, i, s.weight);
+}
+int fill(const mb200_cfg* c, LaneParams& P) {
+    if (!c || c->H <= 0 || c->W <= 0) return MB200_EINVAL;
+    memset(&P, 0, sizeof(P));
+    for (int i = 0; i < 16; ++i) { P.cam.view[i] = c->view[i]; P.cam.proj[i] = c->proj[i]; P.cam.c2w[i] = c->cam_to_world[i]; }
+    P.cam.tan_half_fov_x = c->tan_half_fov_x; P.cam.H = c->H; P.cam.W = c->W;
+    P.cam.stride = (c->flags & MB200_FLAG_ROW_STRIDE_H) ? c->H : c->W;
+    P.use_mesh_normal = c->use_mesh_normal;
+    return MB200_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int mb200_bsdf_eval_pdf(const mb200_cfg* c, int64_t L, const float* p, const float* n_geo, const float* wi_world,
+                        const float* wo_world, const float* a, const float* r, const float* m, const float* n_opt,
+                        float* out_f, float* out_pdf, void* stream) {
+    LaneParams P; int rc = fill(c, P); if (rc) return rc;
+    if (L < 0 || !p || !n_geo || !wi_world || !wo_world || !a || !r || !m || !out_f || !out_pdf) return MB200_EINVAL;
+    if (L == 0) return MB200_OK;
+    P.L = L; P.p = p; P.n_geo = n_geo; P.wi = wi_world; P.wo = wo_world; P.a = a; P.r = r; P.m = m; P.n_opt = n_opt;
+    P.o3 = out_f; P.o1 = out_pdf;
+    bsdf_eval_pdf_kernel<<<(unsigned)((L + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P);
+    return mb200_check_launch();
+}
+
+int mb200_bsdf_sample(const mb200_cfg* c, int64_t L, const float* p, const float* n_geo, const float* wi_world,
+                      const float* sample1, const float* sample2, const float* a, const float* r, const float* m,
+                      const float* n_opt, float* out_wo, float* out_pdf, float* out_weight, void* stream) {
+    LaneParams P; int rc = fill(c, P); if (rc) return rc;
+    if (L < 0 || !p || !n_geo || !wi_world || !sample1 || !sample2 || !a || !r || !m || !out_wo || !out_pdf || !out_weight) return MB200_EINVAL;
+    if (L == 0) return MB200_OK;
+    P.L = L; P.p = p; P.n_geo = n_geo; P.wi = wi_world; P.s1 = sample1; P.s2 = sample2; P.a = a; P.r = r; P.m = m; P.n_opt = n_opt;
+    P.o3 = out_wo; P.o1 = out_pdf; P.ow = out_weight;
+    bsdf_sample_kernel<<<(unsigned)((L + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P);
+    return mb200_check_launch();
+}
+
+}  // extern "C"

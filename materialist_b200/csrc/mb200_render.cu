@@ -1,0 +1,524 @@
+// mb200_render.cu — fused forward / adjoint envmap shading kernels (sm_100a) + their C-ABI entry points.
+//
+// Mapping: ONE WARP PER PIXEL, lanes stride over the pixel's samples (lane l takes s = l, l+32, ...).
+// All per-pixel data (G-buffer, texel fetch, frames) is warp-uniform, so the samples of a pixel never
+// diverge on geometry; per-sample state (PCG32 stream, hierarchy descent, BSDF evals) lives in registers.
+//
+// Forward (gaussian film): every sample contributes to a 5x5 pixel footprint.  Instead of 100 float
+// atomics per sample the warp stages (wx[5], wy[5], L.rgb) of its 32 in-flight samples in shared memory
+// and lanes 0..24 each own one tap: the pixel's 25 (rgb,w) tap sums are written once, coalesced, to
+// `partials` and mb200_film_develop gathers them in a fixed order -> bitwise deterministic and
+// shard-invariant.  Forward (box film): 3 warp-shuffle reductions per pixel.
+//
+// Adjoint: second render with seed_grad.  Film adjoint is a 5x5 gather of
+// G = grad/W staged per warp in shared memory; material gradients are reduced per pixel in registers
+// with warp shuffles and leave as one RED per channel; envmap gradients leave as 16-byte vector
+// reductions (red.global.add.v4.f32) into a float4 texel grid.
+#include "mb200_device.cuh"
+#include "mb200_host.h"
+
+using namespace mb;
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kThreads = kWarpsPerBlock * 32;
+constexpr int kRecStride = 20;            // floats per staged sample record (bank-conflict-free for 16B stores)
+
+struct RenderParams {
+    CamView cam; HierView hier; EnvView env;
+    const float4* gpos; const float4* gnrm;
+    const float* a; const float* r; const float* m; const float* n_opt;
+    int H, W, spp; uint32_t seed; int flags; int use_mesh_normal; int max_depth;
+    int prow0, prows;                    // rows this launch processes (shard rows + film halo)
+    // forward
+    float* partials;
+    // adjoint
+    const float4* gadj; int grow0, grows; // G image rows
+    float* g_a; float* g_r; float* g_m; float* g_n; float4* g_env4;
+};
+
+struct PixelCtx {
+    bool valid; long long flat; Material mt; float3 view; Frame fgeo, fshade;
+};
+
+__device__ __forceinline__ PixelCtx load_pixel(const RenderParams& P, int gpix) {
+    PixelCtx c;
+    const float4 gp = __ldg(P.gpos + gpix), gn = __ldg(P.gnrm + gpix);
+    c.valid = gp.w != 0.f;
+    const float3 p = f3(gp.x, gp.y, gp.z), ng = f3(gn.x, gn.y, gn.z);
+    c.flat = 0; c.mt.a = f3(0, 0, 0); c.mt.r = 1.f; c.mt.m = 0.f; c.mt.n = ng; c.view = f3(0, 0, 1);
+    if (c.valid) {
+        c.flat = texel_index(P.cam, p);
+        c.mt.a = f3(__ldg(P.a + 3 * c.flat), __ldg(P.a + 3 * c.flat + 1), __ldg(P.a + 3 * c.flat + 2));
+        c.mt.r = __ldg(P.r + c.flat); c.mt.m = __ldg(P.m + c.flat);
+        if (!P.use_mesh_normal && P.n_opt)
+            c.mt.n = f3(__ldg(P.n_opt + 3 * c.flat), __ldg(P.n_opt + 3 * c.flat + 1), __ldg(P.n_opt + 3 * c.flat + 2));
+        c.view = normalize(f3(P.cam.c2w[3], P.cam.c2w[7], P.cam.c2w[11]) - p);
+    }
+    c.fgeo = make_frame(ng); c.fshade = make_frame(c.mt.n);
+    return c;
+}
+
+// ---------------------------------------------------------------- one forward sample
+template <bool AD_W>
+__device__ __forceinline__ float3 shade_sample(const RenderParams& P, const PixelCtx& c, int px, int py, uint32_t lane_id,
+                                               float& jx, float& jy) {
+    Pcg32 rng; rng.seed(P.seed, lane_id);
+    jx = rng.next_float(); jy = rng.next_float();
+    if (!c.valid) {
+        const float3 d = primary_dir(P.cam, (float)px + jx, (float)py + jy);
+        float u, v; dir_to_uv(d, u, v);
+        return env_value(P.env, env_lookup<false>(P.env, u, v));
+    }
+    float3 L = f3(0.f, 0.f, 0.f);
+    if (P.max_depth < 2) return L;
+    const float uex = rng.next_float(), uey = rng.next_float();
+    const float s1 = rng.next_float();
+    const float s2x = rng.next_float(), s2y = rng.next_float();
+    // (the russian-roulette draw that follows is never consumed: rr_depth 5 > max_depth)
+    // ---- emitter sampling
+    const EmSample em = env_sample_direction(P.hier, P.env, uex, uey);
+    if (em.pdf != 0.f) {
+        const float3 le = env_value(P.env, em.b);
+        const BsdfVal fv = eval_brdf(em.d, c.view, c.mt);
+        const float k = mis_weight(em.pdf, fv.pdf) / em.pdf;
+        L = fv.f * le * k;
+    }
+    // ---- BSDF sampling
+    const BsdfSample bs = sample_brdf(s1, s2x, s2y, c.view, c.mt, c.fshade);
+    const float3 d_bs = (P.flags & MB200_FLAG_WO_WORLD_QUIRK) ? to_world(c.fgeo, bs.wi) : bs.wi;
+    float3 w_bs = bs.weight;
+    if (AD_W) {
+        const BsdfVal b2 = eval_brdf(d_bs, c.view, c.mt);
+        if (b2.pdf > 0.f) w_bs = b2.f * (1.f / b2.pdf);
+    }
+    if (fmax3(w_bs.x, w_bs.y, w_bs.z) != 0.f && bs.pdf > 0.f) {
+        float u, v; dir_to_uv(d_bs, u, v);
+        const float em_pdf = env_pdf_direction(P.hier, P.env, d_bs, u, v);
+        const float3 le = env_value(P.env, env_lookup<false>(P.env, u, v));
+        L = L + w_bs * le * mis_weight(bs.pdf, em_pdf);
+    }
+    return L;
+}
+
+// ---------------------------------------------------------------- forward kernel
+template <int FILTER, bool AD_W>
+__global__ void __launch_bounds__(kThreads) shade_fwd_kernel(const __grid_constant__ RenderParams P) {
+    __shared__ __align__(16) float s_rec[FILTER == MB200_FILTER_GAUSSIAN ? kWarpsPerBlock * 32 * kRecStride : 4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* rec = s_rec + (FILTER == MB200_FILTER_GAUSSIAN ? warp * 32 * kRecStride : 0);
+    const int npix = P.prows * P.W;
+    const int ti = lane % 5, tj = lane / 5;              // tap owned by this lane (lanes 0..24)
+    for (int pix = blockIdx.x * kWarpsPerBlock + warp; pix < npix; pix += gridDim.x * kWarpsPerBlock) {
+        const int py = P.prow0 + pix / P.W, px = pix % P.W;
+        const int gpix = py * P.W + px;
+        const PixelCtx c = load_pixel(P, gpix);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s0 = 0; s0 < P.spp; s0 += 32) {
+            const int s = s0 + lane;
+            float3 L = f3(0.f, 0.f, 0.f); float jx = 0.f, jy = 0.f;
+            const bool act = s < P.spp;
+            if (act) L = shade_sample<AD_W>(P, c, px, py, (uint32_t)gpix * (uint32_t)P.spp + (uint32_t)s, jx, jy);
+            if (FILTER == MB200_FILTER_GAUSSIAN) {
+                float wx[5], wy[5]; film_taps(jx, wx); film_taps(jy, wy);
+                if (!act) { wx[0] = wx[1] = wx[2] = wx[3] = wx[4] = 0.f; }
+                float4* r4 = reinterpret_cast<float4*>(rec + lane * kRecStride);
+                r4[0] = make_float4(wx[0], wx[1], wx[2], wx[3]);
+                r4[1] = make_float4(wx[4], wy[0], wy[1], wy[2]);
+                r4[2] = make_float4(wy[3], wy[4], 0.f, 0.f);
+                r4[3] = make_float4(L.x, L.y, L.z, 1.f);
+                __syncwarp();
+                if (lane < MB200_FILM_TAPS) {
+                    const int n = min(32, P.spp - s0);
+                    for (int k = 0; k < n; ++k) {
+                        const float* rk = rec + k * kRecStride;
+                        const float w = rk[ti] * rk[5 + tj];
+                        const float4 l4 = *reinterpret_cast<const float4*>(rk + 12);
+                        acc.x = fmaf(w, l4.x, acc.x); acc.y = fmaf(w, l4.y, acc.y); acc.z = fmaf(w, l4.z, acc.z); acc.w += w;
+                    }
+                }
+                __syncwarp();
+            } else {
+                acc.x += L.x; acc.y += L.y; acc.z += L.z;
+            }
+        }
+        if (FILTER == MB200_FILTER_GAUSSIAN) {
+            if (lane < MB200_FILM_TAPS)
+                reinterpret_cast<float4*>(P.partials)[(size_t)pix * MB200_FILM_TAPS + lane] = acc;
+        } else {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+                acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+            }
+            if (lane == 0) reinterpret_cast<float4*>(P.partials)[pix] = make_float4(acc.x, acc.y, acc.z, (float)P.spp);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- develop: gather taps in a fixed order, rgb / w
+template <int FILTER>
+__global__ void film_develop_kernel(const float4* __restrict__ partials, int H, int W, int prow0, int prows,
+                                    int row0, int rows, float* __restrict__ img) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * W) return;
+    const int qy = row0 + i / W, qx = i % W;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (FILTER == MB200_FILTER_GAUSSIAN) {
+#pragma unroll
+        for (int t = 0; t < MB200_FILM_TAPS; ++t) {
+            const int sy = qy - (t / 5 - 2), sx = qx - (t % 5 - 2);
+            if (sx < 0 || sx >= W || sy < prow0 || sy >= prow0 + prows) continue;
+            const float4 q = __ldg(partials + ((size_t)(sy - prow0) * W + sx) * MB200_FILM_TAPS + t);
+            acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+        }
+    } else {
+        acc = __ldg(partials + (size_t)(qy - prow0) * W + qx);
+    }
+    const float ws = acc.w == 0.f ? 1.f : acc.w;
+    img[3 * (size_t)i] = __fdiv_rn(acc.x, ws); img[3 * (size_t)i + 1] = __fdiv_rn(acc.y, ws); img[3 * (size_t)i + 2] = __fdiv_rn(acc.z, ws);
+}
+
+// ---------------------------------------------------------------- film weights of a render (RNG only)
+__global__ void __launch_bounds__(kThreads) film_weights_kernel(int W, int spp, uint32_t seed, int wrow0, int wrows, float* __restrict__ wpart) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int npix = wrows * W;
+    for (int pix = blockIdx.x * kWarpsPerBlock + warp; pix < npix; pix += gridDim.x * kWarpsPerBlock) {
+        const int gpix = (wrow0 + pix / W) * W + pix % W;
+        float acc[MB200_FILM_TAPS];
+#pragma unroll
+        for (int t = 0; t < MB200_FILM_TAPS; ++t) acc[t] = 0.f;
+        for (int s = lane; s < spp; s += 32) {
+            Pcg32 rng; rng.seed(seed, (uint32_t)gpix * (uint32_t)spp + (uint32_t)s);
+            const float jx = rng.next_float(), jy = rng.next_float();
+            float wx[5], wy[5]; film_taps(jx, wx); film_taps(jy, wy);
+#pragma unroll
+            for (int t = 0; t < MB200_FILM_TAPS; ++t) acc[t] = fmaf(wx[t % 5], wy[t / 5], acc[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < MB200_FILM_TAPS; ++t) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int t = 0; t < MB200_FILM_TAPS; ++t) wpart[(size_t)pix * MB200_FILM_TAPS + t] = acc[t];
+        }
+    }
+}
+// G[q] = grad[q] / W_q
+template <int FILTER>
+__global__ void film_adjoint_kernel(const float* __restrict__ wpart, int H, int W, int wrow0, int wrows, int grow0, int grows,
+                                    float inv_spp, const float* __restrict__ grad, float4* __restrict__ gadj) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= grows * W) return;
+    const int qy = grow0 + i / W, qx = i % W;
+    float inv = inv_spp;
+    if (FILTER == MB200_FILTER_GAUSSIAN) {
+        float ws = 0.f;
+#pragma unroll
+        for (int t = 0; t < MB200_FILM_TAPS; ++t) {
+            const int sy = qy - (t / 5 - 2), sx = qx - (t % 5 - 2);
+            if (sx < 0 || sx >= W || sy < wrow0 || sy >= wrow0 + wrows) continue;
+            ws += __ldg(wpart + ((size_t)(sy - wrow0) * W + sx) * MB200_FILM_TAPS + t);
+        }
+        inv = 1.f / (ws == 0.f ? 1.f : ws);
+    }
+    gadj[i] = make_float4(grad[3 * (size_t)i] * inv, grad[3 * (size_t)i + 1] * inv, grad[3 * (size_t)i + 2] * inv, 0.f);
+}
+
+// ---------------------------------------------------------------- adjoint kernel
+__device__ __forceinline__ void env_scatter(float4* g, int Wi, const Bilerp& b, float3 cot) {
+    const float w00 = b.w0y * b.w0x, w10 = b.w0y * b.w1x, w01 = b.w1y * b.w0x, w11 = b.w1y * b.w1x;
+    atomicAdd(g + b.i00,          make_float4(w00 * cot.x, w00 * cot.y, w00 * cot.z, 0.f));
+    atomicAdd(g + b.i00 + 1,      make_float4(w10 * cot.x, w10 * cot.y, w10 * cot.z, 0.f));
+    atomicAdd(g + b.i00 + Wi,     make_float4(w01 * cot.x, w01 * cot.y, w01 * cot.z, 0.f));
+    atomicAdd(g + b.i00 + Wi + 1, make_float4(w11 * cot.x, w11 * cot.y, w11 * cot.z, 0.f));
+}
+
+template <int FILTER, bool WANT_MAT, bool WANT_N, bool WANT_ENV>
+__global__ void __launch_bounds__(kThreads) shade_bwd_kernel(const __grid_constant__ RenderParams P) {
+    __shared__ float4 s_g[FILTER == MB200_FILTER_GAUSSIAN ? kWarpsPerBlock * MB200_FILM_TAPS : 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4* gt = s_g + (FILTER == MB200_FILTER_GAUSSIAN ? warp * MB200_FILM_TAPS : 0);
+    const int npix = P.prows * P.W;
+    for (int pix = blockIdx.x * kWarpsPerBlock + warp; pix < npix; pix += gridDim.x * kWarpsPerBlock) {
+        const int py = P.prow0 + pix / P.W, px = pix % P.W;
+        const int gpix = py * P.W + px;
+        const PixelCtx c = load_pixel(P, gpix);
+        float3 gbox = f3(0, 0, 0);
+        if (FILTER == MB200_FILTER_GAUSSIAN) {
+            __syncwarp();
+            if (lane < MB200_FILM_TAPS) {
+                const int qy = py + (lane / 5 - 2), qx = px + (lane % 5 - 2);
+                float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (qx >= 0 && qx < P.W && qy >= P.grow0 && qy < P.grow0 + P.grows && qy >= 0 && qy < P.H)
+                    g = __ldg(P.gadj + (size_t)(qy - P.grow0) * P.W + qx);
+                gt[lane] = g;
+            }
+            __syncwarp();
+        } else {
+            const float4 g = __ldg(P.gadj + (size_t)(py - P.grow0) * P.W + px);
+            gbox = f3(g.x, g.y, g.z);
+        }
+        float3 ga = f3(0, 0, 0), gn = f3(0, 0, 0); float gr = 0.f, gm = 0.f;
+        for (int s = lane; s < P.spp; s += 32) {
+            Pcg32 rng; rng.seed(P.seed, (uint32_t)gpix * (uint32_t)P.spp + (uint32_t)s);
+            const float jx = rng.next_float(), jy = rng.next_float();
+            // film adjoint: dl = sum_taps wx_i wy_j G[p + (i,j)]
+            float3 dl = gbox;
+            if (FILTER == MB200_FILTER_GAUSSIAN) {
+                float wx[5], wy[5]; film_taps(jx, wx); film_taps(jy, wy);
+                dl = f3(0, 0, 0);
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    float3 row = f3(0, 0, 0);
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) {
+                        const float4 g = gt[j * 5 + i];
+                        row.x = fmaf(wx[i], g.x, row.x); row.y = fmaf(wx[i], g.y, row.y); row.z = fmaf(wx[i], g.z, row.z);
+                    }
+                    dl.x = fmaf(wy[j], row.x, dl.x); dl.y = fmaf(wy[j], row.y, dl.y); dl.z = fmaf(wy[j], row.z, dl.z);
+                }
+            }
+            if (!c.valid) {
+                if (WANT_ENV) {
+                    const float3 d = primary_dir(P.cam, (float)px + jx, (float)py + jy);
+                    float u, v; dir_to_uv(d, u, v);
+                    env_scatter(P.g_env4, P.env.Wi, env_lookup<false>(P.env, u, v), dl);
+                }
+                continue;
+            }
+            if (P.max_depth < 2) continue;
+            const float uex = rng.next_float(), uey = rng.next_float();
+            const float s1 = rng.next_float();
+            const float s2x = rng.next_float(), s2y = rng.next_float();
+            // ---- emitter term: L1 = f(d_em) * Le/pdf * mis
+            const EmSample em = env_sample_direction(P.hier, P.env, uex, uey);
+            if (em.pdf != 0.f) {
+                const BsdfVal fv = eval_brdf(em.d, c.view, c.mt);
+                const float k = mis_weight(em.pdf, fv.pdf) / em.pdf;
+                if (WANT_MAT) {
+                    const float3 le = env_value(P.env, em.b);
+                    const BsdfGrad bg = eval_brdf_grad<WANT_N>(em.d, c.view, c.mt, dl * le * k);
+                    ga = ga + bg.ga; gr += bg.gr; gm += bg.gm; if (WANT_N) gn = gn + bg.gn;
+                }
+                if (WANT_ENV) env_scatter(P.g_env4, P.env.Wi, em.b, dl * fv.f * k);
+            }
+            // ---- BSDF term: L2 = f(d_bs)/detach(p2) * Le(d_bs) * mis
+            const BsdfSample bs = sample_brdf(s1, s2x, s2y, c.view, c.mt, c.fshade);
+            const float3 d_bs = (P.flags & MB200_FLAG_WO_WORLD_QUIRK) ? to_world(c.fgeo, bs.wi) : bs.wi;
+            const BsdfVal b2 = eval_brdf(d_bs, c.view, c.mt);
+            const float3 w_bs = b2.pdf > 0.f ? b2.f * (1.f / b2.pdf) : bs.weight;
+            if (fmax3(w_bs.x, w_bs.y, w_bs.z) != 0.f && bs.pdf > 0.f) {
+                float u, v; dir_to_uv(d_bs, u, v);
+                const float mis = mis_weight(bs.pdf, env_pdf_direction(P.hier, P.env, d_bs, u, v));
+                const Bilerp bb = env_lookup<false>(P.env, u, v);
+                if (WANT_MAT && b2.pdf > 0.f) {
+                    const float3 le = env_value(P.env, bb);
+                    const BsdfGrad bg = eval_brdf_grad<WANT_N>(d_bs, c.view, c.mt, dl * le * (mis / b2.pdf));
+                    ga = ga + bg.ga; gr += bg.gr; gm += bg.gm; if (WANT_N) gn = gn + bg.gn;
+                }
+                if (WANT_ENV) env_scatter(P.g_env4, P.env.Wi, bb, dl * w_bs * mis);
+            }
+        }
+        if (WANT_MAT) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                ga.x += __shfl_xor_sync(0xffffffffu, ga.x, o); ga.y += __shfl_xor_sync(0xffffffffu, ga.y, o);
+                ga.z += __shfl_xor_sync(0xffffffffu, ga.z, o);
+                gr += __shfl_xor_sync(0xffffffffu, gr, o); gm += __shfl_xor_sync(0xffffffffu, gm, o);
+                if (WANT_N) {
+                    gn.x += __shfl_xor_sync(0xffffffffu, gn.x, o); gn.y += __shfl_xor_sync(0xffffffffu, gn.y, o);
+                    gn.z += __shfl_xor_sync(0xffffffffu, gn.z, o);
+                }
+            }
+            if (lane == 0 && c.valid && P.max_depth >= 2) {
+                if (P.g_a) { atomicAdd(P.g_a + 3 * c.flat, ga.x); atomicAdd(P.g_a + 3 * c.flat + 1, ga.y); atomicAdd(P.g_a + 3 * c.flat + 2, ga.z); }
+                if (P.g_r) atomicAdd(P.g_r + c.flat, gr);
+                if (P.g_m) atomicAdd(P.g_m + c.flat, gm);
+                if (WANT_N && P.g_n) { atomicAdd(P.g_n + 3 * c.flat, gn.x); atomicAdd(P.g_n + 3 * c.flat + 1, gn.y); atomicAdd(P.g_n + 3 * c.flat + 2, gn.z); }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- debug: integer decisions per lane
+__global__ void sample_indices_kernel(const __grid_constant__ RenderParams P, int32_t* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = (long long)P.prows * P.W * P.spp;
+    if (i >= n) return;
+    const int s = (int)(i % P.spp); const long long pix = i / P.spp;
+    const int py = P.prow0 + (int)(pix / P.W), px = (int)(pix % P.W);
+    const int gpix = py * P.W + px;
+    const float4 gp = __ldg(P.gpos + gpix);
+    int32_t o0 = 0, o1 = 0, o2 = -1, o3 = -1;
+    if (gp.w != 0.f && P.max_depth >= 2) {
+        Pcg32 rng; rng.seed(P.seed, (uint32_t)gpix * (uint32_t)P.spp + (uint32_t)s);
+        rng.next_float(); rng.next_float();
+        const float uex = rng.next_float(), uey = rng.next_float();
+        const float s1 = rng.next_float();
+        const HSample hs = hier_sample(P.hier, uex, uey);
+        o0 = (int32_t)hs.ox; o1 = (int32_t)hs.oy;
+        o2 = (int32_t)texel_index(P.cam, f3(gp.x, gp.y, gp.z));
+        o3 = s1 > 0.5f ? 1 : 0;
+    }
+    reinterpret_cast<int4*>(out)[i] = make_int4(o0, o1, o2, o3);
+}
+
+// ---------------------------------------------------------------- host side
+int fill_params(const mb200_cfg* c, const float* gpos, const float* gnrm, const float* a, const float* r, const float* m,
+                const float* n_opt, const float* env4, const float* hier, const mb200_hier_desc* d, RenderParams& P) {
+    if (!c || !gpos || !gnrm || !a || !r || !m || !env4 || !hier || !d) return MB200_EINVAL;
+    if (c->H <= 0 || c->W <= 0 || c->spp <= 0 || c->rows <= 0 || c->row0 < 0 || c->row0 + c->rows > c->H) return MB200_EINVAL;
+    if (c->filter != MB200_FILTER_BOX && c->filter != MB200_FILTER_GAUSSIAN) return MB200_EINVAL;
+    if (!c->use_mesh_normal && !n_opt) return MB200_EINVAL;
+    if ((double)c->H * (double)c->W * (double)c->spp >= 4294967296.0) return MB200_ERANGE;
+    if (d->n_levels < 2 || d->n_levels > MB200_MAX_LEVELS) return MB200_EINVAL;
+    memset(&P, 0, sizeof(P));
+    for (int i = 0; i < 16; ++i) { P.cam.view[i] = c->view[i]; P.cam.proj[i] = c->proj[i]; P.cam.c2w[i] = c->cam_to_world[i]; }
+    P.cam.tan_half_fov_x = c->tan_half_fov_x; P.cam.H = c->H; P.cam.W = c->W;
+    P.cam.stride = (c->flags & MB200_FLAG_ROW_STRIDE_H) ? c->H : c->W;
+    P.hier.data = hier; P.hier.res_x = d->res_x; P.hier.res_y = d->res_y; P.hier.n_levels = d->n_levels;
+    for (int l = 0; l < d->n_levels; ++l) { P.hier.lvl_off[l] = d->lvl_off[l]; P.hier.lvl_w[l] = d->lvl_w[l]; }
+    P.env.tex = reinterpret_cast<const float4*>(env4); P.env.Wi = d->res_x; P.env.He = d->res_y; P.env.u_shift = c->env_u_shift;
+    P.gpos = reinterpret_cast<const float4*>(gpos); P.gnrm = reinterpret_cast<const float4*>(gnrm);
+    P.a = a; P.r = r; P.m = m; P.n_opt = n_opt;
+    P.H = c->H; P.W = c->W; P.spp = c->spp; P.seed = c->seed; P.flags = c->flags; P.use_mesh_normal = c->use_mesh_normal;
+    P.max_depth = c->max_depth;
+    return MB200_OK;
+}
+
+void halo_rows(const mb200_cfg* c, int halo, int* first, int* count) {
+    int r0 = c->row0 - halo, r1 = c->row0 + c->rows + halo;
+    if (r0 < 0) r0 = 0; if (r1 > c->H) r1 = c->H;
+    *first = r0; *count = r1 - r0;
+}
+
+int grid_for(int npix) {
+    const int blocks_needed = (npix + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const int cap = mb200_sm_count() * 8;           // persistent-style grid: a multiple of the SM count
+    return blocks_needed < cap ? blocks_needed : cap;
+}
+
+template <int FILTER>
+int launch_bwd(const RenderParams& P, bool want_mat, bool want_n, bool want_env, cudaStream_t st) {
+    const int grid = grid_for(P.prows * P.W);
+#define MB_BWD(M, N, E) shade_bwd_kernel<FILTER, M, N, E><<<grid, kThreads, 0, st>>>(P)
+    if (want_mat && want_n && want_env) MB_BWD(true, true, true);
+    else if (want_mat && want_n) MB_BWD(true, true, false);
+    else if (want_mat && want_env) MB_BWD(true, false, true);
+    else if (want_mat) MB_BWD(true, false, false);
+    else if (want_env) MB_BWD(false, false, true);
+#undef MB_BWD
+    return mb200_check_launch();
+}
+
+}  // namespace
+
+extern "C" {
+
+int mb200_partial_stride(int filter) { return filter == MB200_FILTER_GAUSSIAN ? MB200_FILM_TAPS * 4 : 4; }
+
+int mb200_fwd_partial_rows(const mb200_cfg* c, int* first_row) {
+    int f, n; halo_rows(c, c->filter == MB200_FILTER_GAUSSIAN ? 2 : 0, &f, &n);
+    if (first_row) *first_row = f; return n;
+}
+int mb200_bwd_wpart_rows(const mb200_cfg* c, int* first_row) {
+    int f, n; halo_rows(c, c->filter == MB200_FILTER_GAUSSIAN ? 4 : 0, &f, &n);
+    if (first_row) *first_row = f; return n;
+}
+int mb200_bwd_gadj_rows(const mb200_cfg* c, int* first_row) {
+    int f, n; halo_rows(c, c->filter == MB200_FILTER_GAUSSIAN ? 2 : 0, &f, &n);
+    if (first_row) *first_row = f; return n;
+}
+
+int mb200_shade_fwd(const mb200_cfg* c, const float* gpos, const float* gnrm, const float* a, const float* r, const float* m,
+                    const float* n_opt, const float* env4, const float* hier, const mb200_hier_desc* d,
+                    float* partials, void* stream) {
+    RenderParams P; int rc = fill_params(c, gpos, gnrm, a, r, m, n_opt, env4, hier, d, P);
+    if (rc) return rc;
+    if (!partials) return MB200_EINVAL;
+    P.prows = mb200_fwd_partial_rows(c, &P.prow0); P.partials = partials;
+    const int grid = grid_for(P.prows * P.W);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool ad = (c->flags & MB200_FLAG_AD_WEIGHTS) != 0;
+    if (c->filter == MB200_FILTER_GAUSSIAN) {
+        if (ad) shade_fwd_kernel<MB200_FILTER_GAUSSIAN, true><<<grid, kThreads, 0, st>>>(P);
+        else    shade_fwd_kernel<MB200_FILTER_GAUSSIAN, false><<<grid, kThreads, 0, st>>>(P);
+    } else {
+        if (ad) shade_fwd_kernel<MB200_FILTER_BOX, true><<<grid, kThreads, 0, st>>>(P);
+        else    shade_fwd_kernel<MB200_FILTER_BOX, false><<<grid, kThreads, 0, st>>>(P);
+    }
+    return mb200_check_launch();
+}
+
+int mb200_film_develop(const mb200_cfg* c, const float* partials, float* img, void* stream) {
+    if (!c || !partials || !img) return MB200_EINVAL;
+    int prow0; const int prows = mb200_fwd_partial_rows(c, &prow0);
+    const int n = c->rows * c->W, tb = 256;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (c->filter == MB200_FILTER_GAUSSIAN)
+        film_develop_kernel<MB200_FILTER_GAUSSIAN><<<(n + tb - 1) / tb, tb, 0, st>>>(reinterpret_cast<const float4*>(partials), c->H, c->W, prow0, prows, c->row0, c->rows, img);
+    else
+        film_develop_kernel<MB200_FILTER_BOX><<<(n + tb - 1) / tb, tb, 0, st>>>(reinterpret_cast<const float4*>(partials), c->H, c->W, prow0, prows, c->row0, c->rows, img);
+    return mb200_check_launch();
+}
+
+int mb200_film_weights(const mb200_cfg* c, float* wpart, void* stream) {
+    if (!c) return MB200_EINVAL;
+    if (c->filter != MB200_FILTER_GAUSSIAN) return MB200_OK;
+    if (!wpart) return MB200_EINVAL;
+    if ((double)c->H * (double)c->W * (double)c->spp >= 4294967296.0) return MB200_ERANGE;
+    int wrow0; const int wrows = mb200_bwd_wpart_rows(c, &wrow0);
+    film_weights_kernel<<<grid_for(wrows * c->W), kThreads, 0, (cudaStream_t)stream>>>(c->W, c->spp, c->seed, wrow0, wrows, wpart);
+    return mb200_check_launch();
+}
+
+int mb200_film_adjoint(const mb200_cfg* c, const float* wpart, const float* grad_img_halo, float* gadj, void* stream) {
+    if (!c || !grad_img_halo || !gadj) return MB200_EINVAL;
+    int grow0; const int grows = mb200_bwd_gadj_rows(c, &grow0);
+    const int n = grows * c->W, tb = 256;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (c->filter == MB200_FILTER_GAUSSIAN) {
+        if (!wpart) return MB200_EINVAL;
+        int wrow0; const int wrows = mb200_bwd_wpart_rows(c, &wrow0);
+        film_adjoint_kernel<MB200_FILTER_GAUSSIAN><<<(n + tb - 1) / tb, tb, 0, st>>>(wpart, c->H, c->W, wrow0, wrows, grow0, grows, 0.f, grad_img_halo, reinterpret_cast<float4*>(gadj));
+    } else {
+        film_adjoint_kernel<MB200_FILTER_BOX><<<(n + tb - 1) / tb, tb, 0, st>>>(nullptr, c->H, c->W, 0, 0, grow0, grows, 1.f / (float)c->spp, grad_img_halo, reinterpret_cast<float4*>(gadj));
+    }
+    return mb200_check_launch();
+}
+
+int mb200_shade_bwd(const mb200_cfg* c, const float* gpos, const float* gnrm, const float* a, const float* r, const float* m,
+                    const float* n_opt, const float* env4, const float* hier, const mb200_hier_desc* d, const float* gadj,
+                    float* g_a, float* g_r, float* g_m, float* g_n, float* g_env4, void* stream) {
+    RenderParams P; int rc = fill_params(c, gpos, gnrm, a, r, m, n_opt, env4, hier, d, P);
+    if (rc) return rc;
+    if (!gadj) return MB200_EINVAL;
+    P.prow0 = c->row0; P.prows = c->rows;
+    P.gadj = reinterpret_cast<const float4*>(gadj); P.grows = mb200_bwd_gadj_rows(c, &P.grow0);
+    P.g_a = g_a; P.g_r = g_r; P.g_m = g_m; P.g_n = g_n; P.g_env4 = reinterpret_cast<float4*>(g_env4);
+    const bool want_n = g_n != nullptr && !c->use_mesh_normal;
+    const bool want_mat = g_a || g_r || g_m || want_n;
+    const bool want_env = g_env4 != nullptr;
+    if (!want_mat && !want_env) return MB200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    return c->filter == MB200_FILTER_GAUSSIAN ? launch_bwd<MB200_FILTER_GAUSSIAN>(P, want_mat, want_n, want_env, st)
+                                              : launch_bwd<MB200_FILTER_BOX>(P, want_mat, want_n, want_env, st);
+}
+
+int mb200_debug_sample_indices(const mb200_cfg* c, const float* gpos, const float* r, const float* hier,
+                               const mb200_hier_desc* d, int32_t* out, void* stream) {
+    if (!out) return MB200_EINVAL;
+    RenderParams P; int rc = fill_params(c, gpos, gpos, r, r, r, r, hier, hier, d, P);   // only gpos/hier/cam are read
+    if (rc) return rc;
+    P.prow0 = c->row0; P.prows = c->rows;
+    const long long n = (long long)P.prows * P.W * P.spp; const int tb = 256;
+    sample_indices_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, (cudaStream_t)stream>>>(P, out);
+    return mb200_check_launch();
+}
+
+}  // extern "C"

@@ -1,0 +1,221 @@
+"""Scene handle of the B200 render operator — the replacement for the `mi.load_dict({...})` scene of
+inverse_img_w_mi.py:30-56 / render_final.py:19-97 and for `mi.traverse(scene)`.
+
+A scene is: a per-pixel G-buffer (position, geometric normal, validity) in place of the ray-traced PLY
+height field, the camera meta MatDiffBSDF reads (myutils/default_cam.json, mi_plugin.py:1259-1275), the
+material maps a/r/m/n exposed by MatDiffBSDF.traverse (mi_plugin.py:1464-1469), the envmap emitter data,
+and the integrator / film settings (path max_depth, hdrfilm gaussian rfilter — all Mitsuba defaults).
+"""
+import ctypes as C
+import json
+import math
+import os
+
+import numpy as np
+import torch
+
+from . import _abi
+
+_DEFAULT_CAM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "myutils", "default_cam.json")
+
+
+class Camera:
+    """Perspective sensor + the matrices MatDiffBSDF.__init__ derives from the camera JSON
+    (mi_plugin.py:1259-1275: view = inverse(to_world), persp_proj_matx(fov, W/H, near, far))."""
+
+    def __init__(self, to_world=None, x_fov=35.0, near=0.009999999776482582, far=10000.0, width=512, height=512,
+                 ref_exact_proj=None):
+        if to_world is None:
+            to_world = np.diag([-1.0, 1.0, -1.0, 1.0])
+        self.to_world = np.asarray(to_world, dtype=np.float64).reshape(4, 4)
+        self.x_fov, self.near, self.far = float(x_fov), float(near), float(far)
+        self.width, self.height = int(width), int(height)
+        # mi_plugin.py:585-595 uses f/aspect for x and f for y with f = 1/tan(x_fov/2): exact for square films only.
+        # For W != H the intended (sensor-consistent) matrix is x: f, y: f*aspect.
+        if ref_exact_proj is None:
+            ref_exact_proj = self.width == self.height
+        self.ref_exact_proj = bool(ref_exact_proj)
+
+    @classmethod
+    def from_json(cls, path=None, width=None, height=None):
+        meta = json.load(open(path or _DEFAULT_CAM))
+        w, h = meta["film.size"]
+        return cls(np.array(meta["to_world"])[0], meta["x_fov"][0], meta["near_clip"], meta["far_clip"],
+                   width or w, height or h)
+
+    @property
+    def view_matrix(self):
+        return torch.inverse(torch.tensor(self.to_world, dtype=torch.float32)).numpy().astype(np.float32)
+
+    @property
+    def proj_matrix(self):
+        fov = torch.deg2rad(torch.tensor(self.x_fov))
+        f = float(1.0 / torch.tan(fov / 2.0))
+        aspect = self.width / self.height
+        near, far = self.near, self.far
+        fx, fy = (f / aspect, f) if self.ref_exact_proj else (f, f * aspect)
+        return np.array([[fx, 0, 0, 0], [0, fy, 0, 0],
+                         [0, 0, (far + near) / (near - far), (2 * far * near) / (near - far)],
+                         [0, 0, -1, 0]], dtype=np.float32)
+
+    @property
+    def tan_half_fov_x(self):
+        return math.tan(math.radians(self.x_fov) / 2.0)
+
+    def pixel_ray_dirs(self, sx, sy):
+        """World-space directions of the sensor rays through film positions (sx, sy) in pixel units (numpy)."""
+        t, aspect = self.tan_half_fov_x, self.width / self.height
+        l = np.stack([(1 - 2 * sx / self.width) * t, (1 - 2 * sy / self.height) * t / aspect, np.ones_like(sx)], -1)
+        l = l / np.linalg.norm(l, axis=-1, keepdims=True)
+        return l @ self.to_world[:3, :3].T
+
+
+class Scene:
+    """G-buffer scene handle. Tensors live on one CUDA device; everything is fp32 and contiguous."""
+
+    def __init__(self, pos, nrm, valid=None, camera=None, envmap=None, use_mesh_normal=True, max_depth=4,
+                 rfilter="gaussian", device=None, flags=None):
+        pos = torch.as_tensor(pos, dtype=torch.float32)
+        nrm = torch.as_tensor(nrm, dtype=torch.float32)
+        if pos.ndim != 3 or pos.shape[-1] != 3 or nrm.shape != pos.shape:
+            raise ValueError("pos and nrm must be (H, W, 3)")
+        H, W, _ = pos.shape
+        self.device = torch.device(device if device is not None else "cuda")
+        if self.device.type != "cuda":
+            raise ValueError("materialist_b200 scenes live on a CUDA device (no CPU fallback)")
+        self.H, self.W = H, W
+        self.camera = camera or Camera(width=W, height=H)
+        if (self.camera.width, self.camera.height) != (W, H):
+            raise ValueError("camera film size does not match the G-buffer")
+        v = torch.ones(H, W, 1) if valid is None else torch.as_tensor(valid).reshape(H, W, 1).float()
+        self.gpos = torch.cat([pos, v], -1).contiguous().to(self.device)
+        self.gnrm = torch.cat([nrm, torch.zeros(H, W, 1)], -1).contiguous().to(self.device)
+        # MatDiffBSDF placeholders (mi_plugin.py:1238-1241)
+        self.a = torch.full((H, W, 3), 0.5, device=self.device)
+        self.r = torch.full((H, W, 1), 0.5, device=self.device)
+        self.m = torch.full((H, W, 1), 0.5, device=self.device)
+        self.n = torch.full((H, W, 3), 0.5, device=self.device)
+        self.use_mesh_normal = bool(use_mesh_normal)
+        self.max_depth = int(max_depth)
+        if rfilter not in ("gaussian", "box"):
+            raise ValueError("rfilter must be 'gaussian' or 'box'")
+        self.filter = _abi.FILTER_GAUSSIAN if rfilter == "gaussian" else _abi.FILTER_BOX
+        if flags is None:   # reference-exact defaults; the row-stride quirk is only meaningful (and harmless) for square maps
+            flags = _abi.FLAG_WO_WORLD_QUIRK | _abi.FLAG_ENV_HALF_TEXEL | (_abi.FLAG_ROW_STRIDE_H if H == W else 0)
+        self.flags = int(flags)
+        self.row0, self.rows = 0, H            # pixel shard (whole image by default)
+        self._env = None
+        if envmap is None:
+            envmap = torch.ones(16, 32, 3)
+        self.set_envmap(envmap, _abi.ENV_FILE)
+
+    # ---------------------------------------------------------------- shard
+    def set_shard(self, row0, rows):
+        if row0 < 0 or rows <= 0 or row0 + rows > self.H:
+            raise ValueError("shard rows out of range")
+        self.row0, self.rows = int(row0), int(rows)
+
+    # ---------------------------------------------------------------- envmap
+    def set_envmap(self, env, mode):
+        """env: (He, We, 3). mode ENV_FILE = bitmap loaded from file (column appended), ENV_ASSIGNED = tensor
+        assigned through params['emitter.data'] (first/last column averaged)."""
+        env = torch.as_tensor(env, dtype=torch.float32)
+        if env.ndim != 3 or env.shape[-1] != 3 or env.shape[0] < 2 or env.shape[1] < 2:
+            raise ValueError("envmap must be (He, We, 3) with He, We >= 2")
+        self.env_user = env.detach().contiguous().to(self.device)
+        self.env_mode = mode
+        self._env = None                        # hierarchy rebuilt lazily on the next render
+
+    def prepared_env(self, env_tensor=None, mode=None):
+        """Returns (env4, hier, desc, He, We, mode) for the current (or the given) envmap; runs the ingest +
+        Hierarchical2D build kernels on the current stream."""
+        cache = env_tensor is None
+        if cache:
+            if self._env is not None:
+                return self._env
+            env_tensor, mode = self.env_user, self.env_mode
+        env_tensor = env_tensor.detach().contiguous().float()
+        He, We, _ = env_tensor.shape
+        Wi = _abi.lib.mb200_env_internal_width(We, mode)
+        desc = _abi.hier_describe(Wi, He)
+        env4 = torch.empty(He, Wi, 4, device=self.device)
+        hier = torch.empty(desc.total_floats, device=self.device)
+        scratch = torch.empty(_abi.lib.mb200_env_scratch_bytes(Wi, He) // 8 + 1, dtype=torch.float64, device=self.device)
+        _abi.check(_abi.lib.mb200_env_prepare(_abi.ptr(env_tensor), He, We, mode, _abi.ptr(env4), _abi.ptr(hier),
+                                              C.byref(desc), _abi.ptr(scratch), _abi.stream_ptr()), "mb200_env_prepare")
+        out = (env4, hier, desc, He, We, mode)
+        if cache:
+            self._env = out
+        return out
+
+    # ---------------------------------------------------------------- cfg
+    def make_cfg(self, spp, seed, res_x, extra_flags=0, row0=None, rows=None):
+        cam = self.camera
+        c = _abi.Cfg()
+        c.H, c.W, c.spp, c.max_depth = self.H, self.W, int(spp), self.max_depth
+        c.seed = int(seed) & 0xFFFFFFFF
+        c.filter, c.flags, c.use_mesh_normal = self.filter, self.flags | extra_flags, int(self.use_mesh_normal)
+        c.row0 = self.row0 if row0 is None else row0
+        c.rows = self.rows if rows is None else rows
+        c.view[:] = cam.view_matrix.reshape(-1).tolist()
+        c.proj[:] = cam.proj_matrix.reshape(-1).tolist()
+        c.cam_to_world[:] = cam.to_world.astype(np.float32).reshape(-1).tolist()
+        c.tan_half_fov_x = cam.tan_half_fov_x
+        c.env_u_shift = (np.float32(0.5) / np.float32(res_x - 1)) if (c.flags & _abi.FLAG_ENV_HALF_TEXEL) else 0.0
+        return c
+
+
+class SceneParameters(dict):
+    """`mi.traverse(scene)` stand-in with the keys the reference touches (inverse_img_w_mi.py:61-64, :72-78,
+    :216-220, :334-342; render_final.py:182-192).  Assign, then call update()."""
+    KEYS = ("shape.bsdf.a", "shape.bsdf.r", "shape.bsdf.m", "shape.bsdf.n", "shape.bsdf.use_mesh_normal",
+            "emitter.data", "integrator.max_depth")
+
+    def __init__(self, scene):
+        super().__init__()
+        self._scene = scene
+        self._dirty = set()
+        dict.__setitem__(self, "shape.bsdf.a", scene.a)
+        dict.__setitem__(self, "shape.bsdf.r", scene.r)
+        dict.__setitem__(self, "shape.bsdf.m", scene.m)
+        dict.__setitem__(self, "shape.bsdf.n", scene.n)
+        dict.__setitem__(self, "shape.bsdf.use_mesh_normal", scene.use_mesh_normal)
+        dict.__setitem__(self, "emitter.data", scene.env_user)
+        dict.__setitem__(self, "integrator.max_depth", scene.max_depth)
+
+    def __setitem__(self, key, value):
+        if key not in self.KEYS:
+            raise KeyError(f"unknown scene parameter {key!r}; known: {self.KEYS}")
+        dict.__setitem__(self, key, value)
+        self._dirty.add(key)
+
+    def update(self):
+        s = self._scene
+        H, W = s.H, s.W
+        shapes = {"shape.bsdf.a": (H, W, 3), "shape.bsdf.r": (H, W, 1), "shape.bsdf.m": (H, W, 1), "shape.bsdf.n": (H, W, 3)}
+        for key in sorted(self._dirty):
+            v = self[key]
+            if key in shapes:
+                if not isinstance(v, torch.Tensor):
+                    raise TypeError(f"{key} must be a torch.Tensor")
+                if tuple(v.shape) != shapes[key]:
+                    if key in ("shape.bsdf.r", "shape.bsdf.m") and tuple(v.shape) == (H, W):
+                        v = v.unsqueeze(-1)
+                    else:
+                        raise ValueError(f"{key} must have shape {shapes[key]}, got {tuple(v.shape)}")
+                if v.dtype != torch.float32:
+                    raise TypeError(f"{key} must be float32")
+                if not v.is_cuda:
+                    raise ValueError(f"{key} must be a CUDA tensor (no CPU fallback)")
+                setattr(s, key.rsplit(".", 1)[1], v.detach().contiguous())
+            elif key == "shape.bsdf.use_mesh_normal":
+                s.use_mesh_normal = bool(v)
+            elif key == "emitter.data":
+                s.set_envmap(v, _abi.ENV_ASSIGNED)
+            elif key == "integrator.max_depth":
+                s.max_depth = int(v)
+        self._dirty.clear()
+
+
+def traverse(scene):
+    return SceneParameters(scene)
