@@ -220,6 +220,12 @@ int mb200_cdf_sample(const float* c_cdf, const float* m_cdf, int h, int w, const
 int mb200_sh_project(const double* im, int h, int w, const double* angles, int64_t n, double* coef, void* stream);
 int mb200_sh_reconstruct(const double* coef, int nrows, int ncols, int clip, double* img /*(nrows,ncols,3)*/, void* stream);
 
+/* ---------------------------------------------------------------- measurement aid (bench.py only) */
+/* Runs `iters` rounds of 16 independent FFMA chains per thread on SMs*8 blocks of 256 threads and writes a
+ * checksum to out[0..]; returns the number of FLOPs issued (2 per FFMA) through *flops_host.  Used to MEASURE
+ * the non-tensor FP32 peak that the shading kernels are bounded by. */
+int mb200_probe_ffma(float* out, int iters, double* flops_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,7 +3,7 @@ plugin / operator surface of lez-s/Materialist.  Importing this package loads th
 library (libmaterialist_b200.so); there is no CPU fallback."""
 from . import _abi
 from .scene import Camera, Scene, SceneParameters, traverse
-from .render import render, render_envmap, render_w_brdf, default_seed_grad, sample_indices, tea32
+from .renderop import render, render_envmap, render_w_brdf, default_seed_grad, sample_indices, tea32
 from . import synthetic
 
 __all__ = ["Camera", "Scene", "SceneParameters", "traverse", "render", "render_envmap", "render_w_brdf",

@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmaterialist_b200.so")
+LIB_PATH = os.environ.get("MB200_LIB") or os.path.join(_HERE, "libmaterialist_b200.so")   # MB200_LIB: tuning builds only
 
 MAX_LEVELS = 24
 FILM_TAPS = 25
@@ -81,6 +81,7 @@ def _load():
         "mb200_cdf_sample": (i32, [vp, vp, i32, i32, vp, i64, vp, vp, vp, vp, vp]),
         "mb200_sh_project": (i32, [vp, i32, i32, vp, i64, vp, vp]),
         "mb200_sh_reconstruct": (i32, [vp, i32, i32, i32, vp, vp]),
+        "mb200_probe_ffma": (i32, [vp, i32, C.POINTER(C.c_double), vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)           # AttributeError here = header / library mismatch

@@ -21,6 +21,13 @@ using namespace mb;
 
 namespace {
 
+// resident CTAs per SM the shade kernels are compiled for (register cap = 65536 / (256 * N)); tuned in profiles/
+#ifndef MB_MIN_BLOCKS_FWD
+#define MB_MIN_BLOCKS_FWD 4
+#endif
+#ifndef MB_MIN_BLOCKS_BWD
+#define MB_MIN_BLOCKS_BWD 3
+#endif
 constexpr int kWarpsPerBlock = 8;
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr int kRecStride = 20;            // floats per staged sample record (bank-conflict-free for 16B stores)
@@ -104,7 +111,7 @@ __device__ __forceinline__ float3 shade_sample(const RenderParams& P, const Pixe
 
 // ---------------------------------------------------------------- forward kernel
 template <int FILTER, bool AD_W>
-__global__ void __launch_bounds__(kThreads) shade_fwd_kernel(const __grid_constant__ RenderParams P) {
+__global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_FWD) shade_fwd_kernel(const __grid_constant__ RenderParams P) {
     __shared__ __align__(16) float s_rec[FILTER == MB200_FILTER_GAUSSIAN ? kWarpsPerBlock * 32 * kRecStride : 4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* rec = s_rec + (FILTER == MB200_FILTER_GAUSSIAN ? warp * 32 * kRecStride : 0);
@@ -239,7 +246,7 @@ __device__ __forceinline__ void env_scatter(float4* g, int Wi, const Bilerp& b, 
 }
 
 template <int FILTER, bool WANT_MAT, bool WANT_N, bool WANT_ENV>
-__global__ void __launch_bounds__(kThreads) shade_bwd_kernel(const __grid_constant__ RenderParams P) {
+__global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_BWD) shade_bwd_kernel(const __grid_constant__ RenderParams P) {
     __shared__ float4 s_g[FILTER == MB200_FILTER_GAUSSIAN ? kWarpsPerBlock * MB200_FILM_TAPS : 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float4* gt = s_g + (FILTER == MB200_FILTER_GAUSSIAN ? warp * MB200_FILM_TAPS : 0);
@@ -382,6 +389,7 @@ int fill_params(const mb200_cfg* c, const float* gpos, const float* gnrm, const 
     P.cam.tan_half_fov_x = c->tan_half_fov_x; P.cam.H = c->H; P.cam.W = c->W;
     P.cam.stride = (c->flags & MB200_FLAG_ROW_STRIDE_H) ? c->H : c->W;
     P.hier.data = hier; P.hier.res_x = d->res_x; P.hier.res_y = d->res_y; P.hier.n_levels = d->n_levels;
+    P.hier.psx = 1.f / (float)(d->res_x - 1); P.hier.psy = 1.f / (float)(d->res_y - 1);
     for (int l = 0; l < d->n_levels; ++l) { P.hier.lvl_off[l] = d->lvl_off[l]; P.hier.lvl_w[l] = d->lvl_w[l]; }
     P.env.tex = reinterpret_cast<const float4*>(env4); P.env.Wi = d->res_x; P.env.He = d->res_y; P.env.u_shift = c->env_u_shift;
     P.gpos = reinterpret_cast<const float4*>(gpos); P.gnrm = reinterpret_cast<const float4*>(gnrm);

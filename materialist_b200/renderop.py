@@ -16,6 +16,26 @@ from .scene import Scene, traverse
 
 _MASK32 = 0xFFFFFFFF
 
+# Measurement hook (bench.py): when set to a list, every shade kernel launch is bracketed by CUDA events
+# recorded on the launching stream and (name, start, end) is appended.
+KERNEL_EVENTS = None
+
+
+class _ktime:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if KERNEL_EVENTS is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True); self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if KERNEL_EVENTS is not None:
+            self.e1.record()
+            KERNEL_EVENTS.append((self.name, self.e0, self.e1))
+        return False
+
 
 def tea32(v0, v1, rounds=4):
     """mitsuba.sample_tea_32 (host-side scalar; integer-exact)."""
@@ -53,9 +73,10 @@ def _forward(scene, spp, seed, a, r, m, n, env_pack, extra_flags=0):
     partials = torch.empty(prows, scene.W, stride, device=scene.device)
     st = _abi.stream_ptr()
     nmap = None if scene.use_mesh_normal else n
-    _abi.check(_abi.lib.mb200_shade_fwd(C.byref(cfg), _abi.ptr(scene.gpos), _abi.ptr(scene.gnrm), _abi.ptr(a), _abi.ptr(r),
-                                        _abi.ptr(m), _abi.ptr(nmap), _abi.ptr(env4), _abi.ptr(hier), C.byref(desc),
-                                        _abi.ptr(partials), st), "mb200_shade_fwd")
+    with _ktime("shade_fwd"):
+        _abi.check(_abi.lib.mb200_shade_fwd(C.byref(cfg), _abi.ptr(scene.gpos), _abi.ptr(scene.gnrm), _abi.ptr(a), _abi.ptr(r),
+                                            _abi.ptr(m), _abi.ptr(nmap), _abi.ptr(env4), _abi.ptr(hier), C.byref(desc),
+                                            _abi.ptr(partials), st), "mb200_shade_fwd")
     img = torch.empty(cfg.rows, scene.W, 3, device=scene.device)
     _abi.check(_abi.lib.mb200_film_develop(C.byref(cfg), _abi.ptr(partials), _abi.ptr(img), st), "mb200_film_develop")
     return img
@@ -86,10 +107,11 @@ def _backward(scene, spp, seed_grad, a, r, m, n, env_pack, grad_img_halo, want_a
     g_n = torch.zeros(H, W, 3, device=dev) if (want_n and not scene.use_mesh_normal) else None
     g_env4 = torch.zeros_like(env4) if want_env else None
     nmap = None if scene.use_mesh_normal else n
-    _abi.check(_abi.lib.mb200_shade_bwd(C.byref(cfg), _abi.ptr(scene.gpos), _abi.ptr(scene.gnrm), _abi.ptr(a), _abi.ptr(r),
-                                        _abi.ptr(m), _abi.ptr(nmap), _abi.ptr(env4), _abi.ptr(hier), C.byref(desc),
-                                        _abi.ptr(gadj), _abi.ptr(g_a), _abi.ptr(g_r), _abi.ptr(g_m), _abi.ptr(g_n),
-                                        _abi.ptr(g_env4), st), "mb200_shade_bwd")
+    with _ktime("shade_bwd"):
+        _abi.check(_abi.lib.mb200_shade_bwd(C.byref(cfg), _abi.ptr(scene.gpos), _abi.ptr(scene.gnrm), _abi.ptr(a), _abi.ptr(r),
+                                            _abi.ptr(m), _abi.ptr(nmap), _abi.ptr(env4), _abi.ptr(hier), C.byref(desc),
+                                            _abi.ptr(gadj), _abi.ptr(g_a), _abi.ptr(g_r), _abi.ptr(g_m), _abi.ptr(g_n),
+                                            _abi.ptr(g_env4), st), "mb200_shade_bwd")
     g_env = None
     if want_env:
         g_env = torch.empty(He, We, 3, device=dev)
