@@ -1,0 +1,469 @@
+// mb200_posmlp.cu — fused PosMLP forward / backward (mymodels/mlps.py:129-251) as instantiated by the reference:
+//   brdf_net   inverse_img_w_mi.py:163  in_dims=7, out=5, color_ch=5, dims=[256]*4, skip=[1,3], multires_view=2, 'arm'
+//   envmap_net inverse_img_w_mi.py:117  in_dims=5, out=3, color_ch=3, same topology, 'envmap' (softplus)
+//
+//   pts   = [row, col, sin r, sin c, cos r, cos c, sin 2r, sin 2c, cos 2r, cos 2c | colour]      d0 = 10 + n_color
+//   lin0: d0 -> h0 = 256 - d0 (sin)   x1 = [h | pts]        lin1: 256 -> 256 (sin)
+//   lin2: 256 -> h0 (sin)             x3 = [h | pts]        lin3: 256 -> 256 (sin)      lin4: 256 -> n_out
+//   'arm': y = clamp(1.3 tanh(o) + img, 0, 1) with a straight-through clamp; 'envmap': y = softplus(o)
+//
+// One CTA owns a tile of 64 pixels and walks all five layers with the activations resident in shared memory
+// (transposed, [feature][pixel]); weights stream from L2 in 16-deep chunks, double-buffered.  FP32 FFMA: the
+// reference runs these GEMMs in FP32 (TF32 off), and the parity bar is 1e-4; whether to move the contraction to
+// tcgen05 (3xTF32) is decided from the ncu profile.  Backward = data pass (same tiling, reversed) that
+// also reduces the small lin0 / lin4 / bias gradients in shared memory, + a split-K weight-gradient pass.
+#include "mb200_device.cuh"
+#include "mb200_host.h"
+
+namespace {
+
+constexpr int TM = 64;            // pixels per tile
+constexpr int HID = 256;
+constexpr int XS = TM + 4;        // row stride of the transposed activation tile (floats)
+constexpr int KC = 16;            // reduction chunk
+constexpr int NT = 256;           // threads per CTA
+constexpr int ZSTRIDE = 4 * HID;  // cached pre-activations per pixel (lin0..lin3)
+constexpr int OSTRIDE = 8;        // cached lin4 outputs per pixel
+constexpr long long GCHUNK = 1ll << 20;   // pixels per backward chunk (bounds the dL/dz workspace to 4 GB)
+
+struct Dims {
+    int n_color, n_out, d0, h0, H, W, otype;
+    int oW[5], ob[5];             // offsets into the packed parameter vector
+};
+
+Dims make_dims(const mb200_posmlp_desc* d) {
+    Dims D; D.n_color = d->n_color; D.n_out = d->n_out; D.d0 = 2 + 4 * d->n_freq + d->n_color; D.h0 = HID - D.d0;
+    D.H = d->H; D.W = d->W; D.otype = d->output_type;
+    const int in[5] = {D.d0, HID, HID, HID, HID}, out[5] = {D.h0, HID, D.h0, HID, D.n_out};
+    int off = 0;
+    for (int l = 0; l < 5; ++l) { D.oW[l] = off; off += in[l] * out[l]; D.ob[l] = off; off += out[l]; }
+    return D;
+}
+bool valid_desc(const mb200_posmlp_desc* d) {
+    return d && d->hidden == HID && d->n_freq == 2 && d->n_color >= 1 && d->n_color <= 6 && d->n_out >= 1 && d->n_out <= OSTRIDE &&
+           d->H > 0 && d->W > 0 && (d->output_type == 0 || d->output_type == 1) && (d->output_type == 0 || d->n_out == d->n_color);
+}
+
+// ---------------------------------------------------------------- shared helpers
+// Embedding of a tile's pixels: PT[k][r], k < 16 (zero padded), r < TM
+__device__ __forceinline__ void load_points(const Dims& D, const float* __restrict__ img, long long n0, long long N, float* PT) {
+    const int r = threadIdx.x;
+    if (r < TM) {
+        const long long n = n0 + r;
+        float f[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) f[k] = 0.f;
+        if (n < N) {
+            const float row = (float)(n / D.W), col = (float)(n % D.W);
+            f[0] = row; f[1] = col;
+            f[2] = sinf(row); f[3] = sinf(col); f[4] = cosf(row); f[5] = cosf(col);
+            f[6] = sinf(row * 2.f); f[7] = sinf(col * 2.f); f[8] = cosf(row * 2.f); f[9] = cosf(col * 2.f);
+            for (int c = 0; c < D.n_color; ++c) f[10 + c] = img[n * D.n_color + c];
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) PT[k * XS + r] = f[k];
+    }
+}
+
+// acc[r][4j+i] (+)= sum_red A[red][row ty*4+r] * Wt(red, col 64j+4tx+i)
+//   TRANS = false: Wt(k, c) = Wg[c*ldw + k]   (forward:  reduce over inputs k, outputs c)
+//   TRANS = true : Wt(c, k) = Wg[c*ldw + k]   (backward: reduce over outputs c, outputs are inputs k)
+template <bool TRANS>
+__device__ __forceinline__ void tile_gemm(float acc[4][16], const float* __restrict__ AT, const float* __restrict__ Wg, int ldw,
+                                          int n_red, int n_out, float* __restrict__ Ws) {
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int nch = (n_red + KC - 1) / KC;
+    float pre[KC];
+    auto fetch = [&](int ch) {
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) {
+            const int red = ch * KC + kk;
+            float v = 0.f;
+            if (red < n_red && tid < n_out) v = TRANS ? __ldg(Wg + (size_t)red * ldw + tid) : __ldg(Wg + (size_t)tid * ldw + red);
+            pre[kk] = v;
+        }
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) Ws[(buf * KC + kk) * HID + tid] = pre[kk];
+    };
+    fetch(0); stash(0);
+    __syncthreads();
+    for (int ch = 0; ch < nch; ++ch) {
+        if (ch + 1 < nch) fetch(ch + 1);
+        const float* wb = Ws + (ch & 1) * KC * HID;
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) {
+            const float4 a = *reinterpret_cast<const float4*>(AT + (ch * KC + kk) * XS + ty * 4);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 w = *reinterpret_cast<const float4*>(wb + kk * HID + 64 * j + 4 * tx);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    acc[r][4 * j] = fmaf(av[r], w.x, acc[r][4 * j]); acc[r][4 * j + 1] = fmaf(av[r], w.y, acc[r][4 * j + 1]);
+                    acc[r][4 * j + 2] = fmaf(av[r], w.z, acc[r][4 * j + 2]); acc[r][4 * j + 3] = fmaf(av[r], w.w, acc[r][4 * j + 3]);
+                }
+            }
+        }
+        if (ch + 1 < nch) stash((ch + 1) & 1);
+        __syncthreads();
+    }
+}
+__device__ __forceinline__ int col_of(int j, int i) { return 64 * j + 4 * (threadIdx.x & 15) + i; }
+
+// ---------------------------------------------------------------- forward
+__global__ void __launch_bounds__(NT) posmlp_fwd_kernel(const Dims D, const float* __restrict__ params, const float* __restrict__ img,
+                                                        long long N, float* __restrict__ out, float* __restrict__ zc, float* __restrict__ oc) {
+    extern __shared__ __align__(16) float sm[];
+    float* XT = sm; float* PT = XT + HID * XS; float* Ws = PT + 16 * XS;
+    const int tid = threadIdx.x, ty = tid >> 4;
+    const long long ntiles = (N + TM - 1) / TM;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long n0 = tile * TM;
+        __syncthreads();
+        load_points(D, img, n0, N, PT);
+        __syncthreads();
+        float acc[4][16];
+        for (int l = 0; l < 4; ++l) {
+            const int n_out = (l == 0 || l == 2) ? D.h0 : HID;
+            const float* W = params + D.oW[l]; const float* b = params + D.ob[l];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 16; ++c) acc[r][c] = 0.f;
+            if (l == 0) tile_gemm<false>(acc, PT, W, D.d0, D.d0, n_out, Ws);
+            else        tile_gemm<false>(acc, XT, W, HID, HID, n_out, Ws);
+            // bias, cache z, activation -> XT (all reads of XT finished at the last barrier of tile_gemm)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int c = col_of(j, i);
+                    const float bias = c < n_out ? __ldg(b + c) : 0.f;
+                    float4 s4;
+                    float* sp = &s4.x;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const float z = acc[r][4 * j + i] + bias;
+                        acc[r][4 * j + i] = z;
+                        sp[r] = c < n_out ? sinf(z) : PT[(c - n_out) * XS + ty * 4 + r];     // skip concat: [h | pts]
+                    }
+                    *reinterpret_cast<float4*>(XT + c * XS + ty * 4) = s4;
+                }
+                if (zc) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const long long n = n0 + ty * 4 + r;
+                        if (n < N) *reinterpret_cast<float4*>(zc + n * ZSTRIDE + l * HID + col_of(j, 0)) =
+                            make_float4(acc[r][4 * j], acc[r][4 * j + 1], acc[r][4 * j + 2], acc[r][4 * j + 3]);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // lin4 + output activation: thread -> (pixel r = tid % 64, k-quarter q = tid / 64)
+        {
+            const int r = tid & 63, q = tid >> 6;
+            float part[OSTRIDE];
+#pragma unroll
+            for (int o = 0; o < OSTRIDE; ++o) part[o] = 0.f;
+            const float* W4 = params + D.oW[4];
+            for (int k = q * 64; k < q * 64 + 64; ++k) {
+                const float x = XT[k * XS + r];
+#pragma unroll
+                for (int o = 0; o < OSTRIDE; ++o) if (o < D.n_out) part[o] = fmaf(x, __ldg(W4 + o * HID + k), part[o]);
+            }
+            float* red = Ws;                                     // [4][OSTRIDE][64]
+#pragma unroll
+            for (int o = 0; o < OSTRIDE; ++o) red[(q * OSTRIDE + o) * TM + r] = part[o];
+            __syncthreads();
+            if (q == 0) {
+                const long long n = n0 + r;
+                if (n < N) {
+                    for (int o = 0; o < D.n_out; ++o) {
+                        const float v = ((red[o * TM + r] + red[(OSTRIDE + o) * TM + r]) + red[(2 * OSTRIDE + o) * TM + r]) + red[(3 * OSTRIDE + o) * TM + r]
+                                        + __ldg(params + D.ob[4] + o);
+                        if (oc) oc[n * OSTRIDE + o] = v;
+                        float y;
+                        if (D.otype == 0) y = v > 20.f ? v : log1pf(expf(v));                       // nn.Softplus (threshold 20)
+                        else y = fminf(fmaxf(1.3f * tanhf(v) + img[n * D.n_color + o], 0.f), 1.f);   // straight-through clamp: value
+                        out[n * D.n_out + o] = y;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- backward: data pass
+struct BwdAcc { float* gW0; float* gW4; float* gb; };   // shared-memory accumulators: [256][16], [8][256], [5][256]
+
+__global__ void __launch_bounds__(NT) posmlp_bwd_data_kernel(const Dims D, const float* __restrict__ params, const float* __restrict__ img,
+                                                             long long n_begin, long long n_end, long long N,
+                                                             const float* __restrict__ zc, const float* __restrict__ oc,
+                                                             const float* __restrict__ g_out, float* __restrict__ gbuf /* chunk-local (n - n_begin) */,
+                                                             float* __restrict__ g_params, float* __restrict__ g_img) {
+    extern __shared__ __align__(16) float sm[];
+    float* GT = sm; float* PT = GT + HID * XS; float* Ws = PT + 16 * XS; float* gPT = Ws + 2 * KC * HID;
+    float* sGo = gPT + 16 * XS;                    // [8][XS]
+    float* aW0 = sGo + OSTRIDE * XS;               // [256][16]
+    float* aW4 = aW0 + HID * 16;                   // [8][256]
+    float* ab = aW4 + OSTRIDE * HID;               // [5][256]
+    const int tid = threadIdx.x, ty = tid >> 4;
+    for (int i = tid; i < HID * 16 + OSTRIDE * HID + 5 * HID; i += NT) aW0[i] = 0.f;
+    const long long ntiles = (n_end - n_begin + TM - 1) / TM;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long n0 = n_begin + tile * TM;
+        __syncthreads();
+        load_points(D, img, n0, n_end, PT);
+        for (int i = tid; i < 16 * XS; i += NT) gPT[i] = 0.f;
+        // dL/do = g_out * act'(o)
+        for (int i = tid; i < OSTRIDE * TM; i += NT) {
+            const int o = i / TM, r = i % TM; const long long n = n0 + r;
+            float g = 0.f;
+            if (o < D.n_out && n < n_end) {
+                const float v = oc[n * OSTRIDE + o], gy = g_out[n * D.n_out + o];
+                if (D.otype == 0) g = gy * (v > 20.f ? 1.f : 1.f / (1.f + expf(-v)));
+                else { const float t = tanhf(v); g = gy * 1.3f * (1.f - t * t); }
+            }
+            sGo[o * XS + r] = g;
+        }
+        __syncthreads();
+        if (tid < OSTRIDE && tid < D.n_out) { float s = 0.f; for (int r = 0; r < TM; ++r) s += sGo[tid * XS + r]; ab[4 * HID + tid] += s; }
+        float acc[4][16];
+        // ---- lin4 backward: gx[r][k] = sum_o go[r][o] W4[o][k]
+        {
+            const float* W4 = params + D.oW[4];
+            float go[4][OSTRIDE];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int o = 0; o < OSTRIDE; ++o) go[r][o] = sGo[o * XS + ty * 4 + r];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int k = col_of(j, i);
+                    float w[OSTRIDE];
+#pragma unroll
+                    for (int o = 0; o < OSTRIDE; ++o) w[o] = o < D.n_out ? __ldg(W4 + o * HID + k) : 0.f;
+                    float gw[OSTRIDE];
+#pragma unroll
+                    for (int o = 0; o < OSTRIDE; ++o) gw[o] = 0.f;
+                    float4 g4; float* gp = &g4.x; float bsum = 0.f;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const long long n = n0 + ty * 4 + r;
+                        float gx = 0.f;
+#pragma unroll
+                        for (int o = 0; o < OSTRIDE; ++o) gx = fmaf(go[r][o], w[o], gx);
+                        float s = 0.f, c = 0.f;
+                        if (n < n_end) sincosf(zc[n * ZSTRIDE + 3 * HID + k], &s, &c);
+                        const float gz = gx * c;                                   // dL/dz3
+#pragma unroll
+                        for (int o = 0; o < OSTRIDE; ++o) gw[o] = fmaf(go[r][o], s, gw[o]);   // x4 = sin(z3)
+                        gp[r] = gz; bsum += gz;
+                        if (n < n_end) gbuf[(n - n_begin) * ZSTRIDE + 3 * HID + k] = gz;
+                    }
+                    *reinterpret_cast<float4*>(GT + k * XS + ty * 4) = g4;
+                    atomicAdd(ab + 3 * HID + k, bsum);
+#pragma unroll
+                    for (int o = 0; o < OSTRIDE; ++o) if (o < D.n_out) atomicAdd(aW4 + o * HID + k, gw[o]);
+                }
+        }
+        __syncthreads();
+        // ---- lin3, lin2, lin1 backward (data): gx = G W_l ; then through the sine of layer l-1
+        for (int l = 3; l >= 1; --l) {
+            const int n_red = (l == 2) ? D.h0 : HID;               // outputs of layer l
+            const int h_prev = (l == 3 || l == 1) ? D.h0 : HID;    // sine units feeding layer l (the rest of its input is pts)
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 16; ++c) acc[r][c] = 0.f;
+            tile_gemm<true>(acc, GT, params + D.oW[l], HID, n_red, HID, Ws);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int k = col_of(j, i);
+                    float4 g4; float* gp = &g4.x; float bsum = 0.f;
+                    if (k < h_prev) {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const long long n = n0 + ty * 4 + r;
+                            const float gz = n < n_end ? acc[r][4 * j + i] * cosf(zc[n * ZSTRIDE + (l - 1) * HID + k]) : 0.f;
+                            gp[r] = gz; bsum += gz;
+                            if (n < n_end) gbuf[(n - n_begin) * ZSTRIDE + (l - 1) * HID + k] = gz;
+                        }
+                        atomicAdd(ab + (l - 1) * HID + k, bsum);
+                    } else {                                         // gradient of the concatenated points
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            gPT[(k - h_prev) * XS + ty * 4 + r] += acc[r][4 * j + i];
+                            gp[r] = 0.f;
+                            const long long n = n0 + ty * 4 + r;
+                            if (n < n_end) gbuf[(n - n_begin) * ZSTRIDE + (l - 1) * HID + k] = 0.f;
+                        }
+                    }
+                    *reinterpret_cast<float4*>(GT + k * XS + ty * 4) = g4;
+                }
+            __syncthreads();
+        }
+        // ---- lin0: weight gradient (h0 x d0, reduced in shared memory) and data gradient into gPT
+        {
+            for (int idx = tid; idx < D.h0 * D.d0; idx += NT) {
+                const int c = idx / D.d0, k = idx % D.d0;
+                float s = 0.f;
+                for (int r = 0; r < TM; ++r) s = fmaf(GT[c * XS + r], PT[k * XS + r], s);
+                aW0[c * 16 + k] += s;
+            }
+            const int r = tid & 63, q = tid >> 6;
+            const float* W0 = params + D.oW[0];
+            for (int k = q; k < D.d0; k += 4) {
+                float s = 0.f;
+                for (int c = 0; c < D.h0; ++c) s = fmaf(GT[c * XS + r], __ldg(W0 + c * D.d0 + k), s);
+                gPT[k * XS + r] += s;
+            }
+        }
+        __syncthreads();
+        if (g_img) {
+            for (int i = tid; i < D.n_color * TM; i += NT) {
+                const int ch = i / TM, r = i % TM; const long long n = n0 + r;
+                if (n < n_end) {
+                    float g = gPT[(10 + ch) * XS + r];
+                    if (D.otype == 1) g += g_out[n * D.n_out + ch];          // y = 1.3 tanh(o) + img
+                    g_img[n * D.n_color + ch] = g;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // flush the shared-memory accumulators
+    for (int idx = tid; idx < D.h0 * D.d0; idx += NT) atomicAdd(g_params + D.oW[0] + idx, aW0[(idx / D.d0) * 16 + idx % D.d0]);
+    for (int idx = tid; idx < D.n_out * HID; idx += NT) atomicAdd(g_params + D.oW[4] + idx, aW4[idx]);
+    for (int l = 0; l < 5; ++l) {
+        const int n = (l == 0 || l == 2) ? D.h0 : (l == 4 ? D.n_out : HID);
+        for (int c = tid; c < n; c += NT) atomicAdd(g_params + D.ob[l] + c, ab[l * HID + c]);
+    }
+}
+
+// ---------------------------------------------------------------- backward: weight gradients of lin1..lin3 (split-K)
+// gW_l[c][k] += sum_n G_l[n][c] * X_l[n][k],  X_l = input of layer l rebuilt from the cached pre-activations.
+__global__ void __launch_bounds__(NT) posmlp_wgrad_kernel(const Dims D, const float* __restrict__ img, long long n_begin, long long n_end,
+                                                          const float* __restrict__ zc, const float* __restrict__ gbuf, int ksplit,
+                                                          float* __restrict__ g_params) {
+    __shared__ __align__(16) float Gs[KC][128];
+    __shared__ __align__(16) float Xs[KC][128];
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int l = 1 + blockIdx.y / 4, sub = blockIdx.y % 4, c0 = (sub >> 1) * 128, k0 = (sub & 1) * 128;
+    const int n_out = (l == 2) ? D.h0 : HID;
+    const int h_in = (l == 1 || l == 3) ? D.h0 : HID;            // sine units in the layer input; the rest is pts
+    const long long span = n_end - n_begin, per = (span + ksplit - 1) / ksplit;
+    const long long p0 = n_begin + per * blockIdx.x, p1 = p0 + per < n_end ? p0 + per : n_end;
+    if (p0 >= p1) return;
+    float acc[8][8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+    for (long long p = p0; p < p1; p += KC) {
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < (KC * 128) / NT; ++it) {
+            const int e = it * NT + tid, rr = e >> 7, cc = e & 127;
+            const long long n = p + rr;
+            float g = 0.f, x = 0.f;
+            if (n < p1) {
+                g = gbuf[(n - n_begin) * ZSTRIDE + l * HID + c0 + cc];
+                const int k = k0 + cc;
+                if (k < h_in) x = sinf(zc[n * ZSTRIDE + (l - 1) * HID + k]);
+                else {
+                    const int f = k - h_in;                              // point feature
+                    const float row = (float)(n / D.W), col = (float)(n % D.W);
+                    x = f == 0 ? row : f == 1 ? col : f == 2 ? sinf(row) : f == 3 ? sinf(col) : f == 4 ? cosf(row) : f == 5 ? cosf(col)
+                      : f == 6 ? sinf(row * 2.f) : f == 7 ? sinf(col * 2.f) : f == 8 ? cosf(row * 2.f) : f == 9 ? cosf(col * 2.f)
+                      : img[n * D.n_color + (f - 10)];
+                }
+            }
+            Gs[rr][cc] = g; Xs[rr][cc] = x;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < KC; ++rr) {
+            const float4 ga = *reinterpret_cast<const float4*>(&Gs[rr][4 * ty]), gb = *reinterpret_cast<const float4*>(&Gs[rr][64 + 4 * ty]);
+            const float4 xa = *reinterpret_cast<const float4*>(&Xs[rr][4 * tx]), xb = *reinterpret_cast<const float4*>(&Xs[rr][64 + 4 * tx]);
+            const float gv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w}, xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(gv[a], xv[b], acc[a][b]);
+        }
+    }
+    float* gW = g_params + D.oW[l];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int c = c0 + (a < 4 ? 4 * ty + a : 64 + 4 * ty + (a - 4));
+        if (c >= n_out) continue;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int k = k0 + (b < 4 ? 4 * tx + b : 64 + 4 * tx + (b - 4));
+            atomicAdd(gW + (size_t)c * HID + k, acc[a][b]);
+        }
+    }
+}
+
+constexpr size_t kFwdSmem = sizeof(float) * (HID * XS + 16 * XS + 2 * KC * HID);
+constexpr size_t kBwdSmem = kFwdSmem + sizeof(float) * (16 * XS + OSTRIDE * XS + HID * 16 + OSTRIDE * HID + 5 * HID);
+
+}  // namespace
+
+extern "C" {
+
+int64_t mb200_posmlp_param_count(const mb200_posmlp_desc* d) {
+    if (!valid_desc(d)) return -1;
+    const Dims D = make_dims(d);
+    return (int64_t)D.ob[4] + D.n_out;
+}
+
+size_t mb200_posmlp_cache_bytes(const mb200_posmlp_desc* d, int64_t N) {
+    if (!valid_desc(d) || N <= 0) return 0;
+    const long long g = N < GCHUNK ? N : GCHUNK;
+    return sizeof(float) * ((size_t)N * ZSTRIDE + (size_t)N * OSTRIDE + (size_t)g * ZSTRIDE);
+}
+
+int mb200_posmlp_fwd(const mb200_posmlp_desc* d, const float* params, const float* img, int64_t N, float* out, void* cache, void* stream) {
+    if (!valid_desc(d) || !params || !img || !out || N <= 0) return MB200_EINVAL;
+    const Dims D = make_dims(d);
+    float* zc = reinterpret_cast<float*>(cache);
+    float* oc = zc ? zc + (size_t)N * ZSTRIDE : nullptr;
+    int rc = mb200_check(cudaFuncSetAttribute(posmlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
+    if (rc) return rc;
+    const long long ntiles = (N + TM - 1) / TM;
+    const int grid = (int)(ntiles < 2ll * mb200_sm_count() ? ntiles : 2ll * mb200_sm_count());
+    posmlp_fwd_kernel<<<grid, NT, kFwdSmem, (cudaStream_t)stream>>>(D, params, img, N, out, zc, oc);
+    return mb200_check_launch();
+}
+
+int mb200_posmlp_bwd(const mb200_posmlp_desc* d, const float* params, const float* img, int64_t N, const void* cache,
+                     const float* g_out, float* g_params, float* g_img, void* stream) {
+    if (!valid_desc(d) || !params || !img || !cache || !g_out || !g_params || N <= 0) return MB200_EINVAL;
+    const Dims D = make_dims(d);
+    const float* zc = reinterpret_cast<const float*>(cache);
+    const float* oc = zc + (size_t)N * ZSTRIDE;
+    float* gbuf = const_cast<float*>(oc) + (size_t)N * OSTRIDE;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = mb200_check(cudaFuncSetAttribute(posmlp_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
+    if (rc) return rc;
+    for (long long b = 0; b < N; b += GCHUNK) {
+        const long long e = b + GCHUNK < N ? b + GCHUNK : N;
+        const long long ntiles = (e - b + TM - 1) / TM;
+        const int grid = (int)(ntiles < (long long)mb200_sm_count() ? ntiles : (long long)mb200_sm_count());
+        posmlp_bwd_data_kernel<<<grid, NT, kBwdSmem, st>>>(D, params, img, b, e, N, zc, oc, g_out, gbuf, g_params, g_img);
+        long long ks = (e - b + 4095) / 4096; if (ks > 40) ks = 40; if (ks < 1) ks = 1;
+        posmlp_wgrad_kernel<<<dim3((unsigned)ks, 12), NT, 0, st>>>(D, img, b, e, zc, gbuf, (int)ks, g_params);
+    }
+    return mb200_check_launch();
+}
+
+}  // extern "C"
