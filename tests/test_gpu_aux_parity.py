@@ -169,8 +169,11 @@ def test_matdiffbsdf_lanes_vs_oracle(oracle32):
     bs, w = bsdf.sample(None, si, torch.from_numpy(s1).cuda(), torch.from_numpy(s2).cuda())
     wo_ref, pdf_s_ref, w_ref = O.bsdf_sample(cfg, p, n, wi_w, s1, s2, c.a, c.r, c.m)
     assert rel_l2(bs.wo.cpu().numpy(), wo_ref) < 1e-4, rel_l2(bs.wo.cpu().numpy(), wo_ref)
-    assert rel_l2(bs.pdf.cpu().numpy(), pdf_s_ref) < 1e-3, rel_l2(bs.pdf.cpu().numpy(), pdf_s_ref)
-    assert rel_l2(w.cpu().numpy(), w_ref) < 1e-3, rel_l2(w.cpu().numpy(), w_ref)
+    # the pdf of a sampled glossy direction sits ON the GGX peak (D up to 1e4 at r = 0.07): a 1-ulp difference in the
+    # sampled half-vector moves it by ~1e-3 relative, and those few lanes dominate any L2 norm -> per-lane statistics
+    for got, ref, name in ((bs.pdf.cpu().numpy(), pdf_s_ref, "pdf"), (w.cpu().numpy(), w_ref, "weight")):
+        e = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-4)
+        assert np.median(e) < 5e-6 and np.percentile(e, 99) < 2e-3 and e.max() < 5e-2, (name, np.median(e), np.percentile(e, 99), e.max())
 
 
 # ---------------------------------------------------------------- relighting a shipped scene (C1, statistical)
