@@ -220,6 +220,40 @@ int mb200_cdf_sample(const float* c_cdf, const float* m_cdf, int h, int w, const
 int mb200_sh_project(const double* im, int h, int w, const double* angles, int64_t n, double* coef, void* stream);
 int mb200_sh_reconstruct(const double* coef, int nrows, int ncols, int clip, double* img /*(nrows,ncols,3)*/, void* stream);
 
+/* ---------------------------------------------------------------- fused loss + optimiser step (BRDF phase) */
+/* What sits between the forward and the adjoint render of one iteration of `optimize_envmap_ARMN`
+ * (inverse_img_w_mi.py:388-432, model_name == 'none'), as four streaming kernels with fixed-order reductions
+ * and device-resident scalars (no `.item()` host syncs):
+ *   mb200_image_sum       Σ pred                   -> ratio = gt.mean() / pred.detach().mean()            (:388)
+ *   mb200_loss_srgb_sums  Σ diff², Σ|diff|, diff = (pred*ratio)^(1/2.2) - gt_srgb  (misc.py:167-170; :391-395)
+ *   mb200_loss_srgb_grad  d/d pred of  3*(S1/S0).detach()*mse + l1                                       (:415-419)
+ *   mb200_adam_clamped    clamp backward (:370-376) + aux L1 gradient NF.l1_loss(mat, ori)*scale_delta (:398-417)
+ *                         + torch.optim.Adam step (:428) + the clamp of the next iteration's maps.
+ * `scratch` = mb200_reduce_scratch_bytes() bytes, zero-initialised ONCE by the caller, reusable launch after launch
+ * on one stream.  gt_pred_sums = device float[2] = (Σ gt, Σ pred) over ALL ranks; sums2 = device float[2] =
+ * (Σ diff², Σ|diff|) over ALL ranks (the caller all-reduces between the calls when the image is sharded);
+ * n = this rank's element count, n_total = elements of the whole image. */
+#define MB200_ADAM_MAX_SEGS 4
+typedef struct mb200_adam_seg {
+    float*       p;          /* parameter (updated in place)                                  */
+    float*       mat;        /* out: clamp(p_new, lo, hi) — what the next iteration renders   */
+    const float* g;          /* gradient of the render loss w.r.t. mat (from mb200_shade_bwd) */
+    const float* ori;        /* the map the aux L1 term pulls towards (may be NULL if aux_coeff == 0) */
+    float*       m;          /* Adam exp_avg                                                  */
+    float*       v;          /* Adam exp_avg_sq                                               */
+    int64_t      n;          /* elements                                                      */
+    float        lo, hi;     /* clamp range (albedo/metallic 0..1, roughness 0.07..1)         */
+    float        aux_coeff;  /* scale_delta / (H*W*C): d(aux L1 mean * scale_delta)/d element */
+} mb200_adam_seg;
+size_t mb200_reduce_scratch_bytes(void);
+int mb200_image_sum(const float* img, int64_t n, float* out /*1*/, void* scratch, void* stream);
+int mb200_loss_srgb_sums(const float* img, const float* gt_srgb, int64_t n, const float* gt_pred_sums, float* out2,
+                         float* pred_srgb_opt /* (n) or NULL */, void* scratch, void* stream);
+int mb200_loss_srgb_grad(const float* img, const float* gt_srgb, int64_t n, const float* gt_pred_sums, const float* sums2,
+                         int64_t n_total, float* grad /*(n)*/, void* stream);
+int mb200_adam_clamped(const mb200_adam_seg* segs_host, int nseg, float lr, float beta1, float beta2, float eps,
+                       int step /* 1-based */, void* stream);
+
 /* ---------------------------------------------------------------- measurement aid (bench.py only) */
 /* Runs `iters` rounds of 16 independent FFMA chains per thread on SMs*8 blocks of 256 threads and writes a
  * checksum to out[0..]; returns the number of FLOPs issued (2 per FFMA) through *flops_host.  Used to MEASURE

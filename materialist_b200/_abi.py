@@ -40,6 +40,11 @@ class PosMLPDesc(C.Structure):
                 ("output_type", C.c_int32), ("H", C.c_int32), ("W", C.c_int32)]
 
 
+class AdamSeg(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("mat", C.c_void_p), ("g", C.c_void_p), ("ori", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p),
+                ("n", C.c_int64), ("lo", C.c_float), ("hi", C.c_float), ("aux_coeff", C.c_float)]
+
+
 class MB200Error(RuntimeError):
     pass
 
@@ -81,6 +86,11 @@ def _load():
         "mb200_cdf_sample": (i32, [vp, vp, i32, i32, vp, i64, vp, vp, vp, vp, vp]),
         "mb200_sh_project": (i32, [vp, i32, i32, vp, i64, vp, vp]),
         "mb200_sh_reconstruct": (i32, [vp, i32, i32, i32, vp, vp]),
+        "mb200_reduce_scratch_bytes": (sz, []),
+        "mb200_image_sum": (i32, [vp, i64, vp, vp, vp]),
+        "mb200_loss_srgb_sums": (i32, [vp, vp, i64, vp, vp, vp, vp, vp]),
+        "mb200_loss_srgb_grad": (i32, [vp, vp, i64, vp, vp, i64, vp, vp]),
+        "mb200_adam_clamped": (i32, [C.POINTER(AdamSeg), i32, C.c_float, C.c_float, C.c_float, C.c_float, i32, vp]),
         "mb200_probe_ffma": (i32, [vp, i32, C.POINTER(C.c_double), vp]),
     }
     for name, (res, args) in sig.items():

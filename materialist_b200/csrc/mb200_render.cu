@@ -137,11 +137,12 @@ __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_FWD) shade_fwd_kernel(
                 r4[3] = make_float4(L.x, L.y, L.z, 1.f);
                 __syncwarp();
                 if (lane < MB200_FILM_TAPS) {
-                    const int n = min(32, P.spp - s0);
-                    for (int k = 0; k < n; ++k) {
-                        const float* rk = rec + k * kRecStride;
-                        const float w = rk[ti] * rk[5 + tj];
-                        const float4 l4 = *reinterpret_cast<const float4*>(rk + 12);
+                    // inactive lanes of a ragged last batch staged wx = 0 -> w = 0: always 32 records, fully unrollable
+                    const float* rt = rec + ti; const float* ru = rec + 5 + tj;
+#pragma unroll 8
+                    for (int k = 0; k < 32; ++k) {
+                        const float w = rt[k * kRecStride] * ru[k * kRecStride];
+                        const float4 l4 = *reinterpret_cast<const float4*>(rec + k * kRecStride + 12);
                         acc.x = fmaf(w, l4.x, acc.x); acc.y = fmaf(w, l4.y, acc.y); acc.z = fmaf(w, l4.z, acc.z); acc.w += w;
                     }
                 }

@@ -3,9 +3,13 @@
 (:237-256), minus file I/O, tqdm and the per-iteration `.item()` host syncs.  Everything stays on the device;
 with a ShardContext the three scalar sums and the image-gradient halo are exchanged between ranks.
 """
+import ctypes as C
+
 import torch
 import torch.nn.functional as NF
 
+from . import _abi
+from . import renderop as _rop
 from .parallel import ShardContext
 from .renderop import render
 
@@ -13,6 +17,19 @@ from .renderop import render
 def linear_to_srgb(image):
     """myutils/misc.py:167-170"""
     return image ** (1.0 / 2.2)
+
+
+def brdf_phase_lr(k, lr0=3e-4, step_size=100, gamma=0.8, floor=1.5e-4):
+    """Learning rate of iteration k (0-based) of the BRDF phase: StepLR(step_size=100, gamma=0.8) that the reference
+    only advances while `current_lr > 1.5e-4` (inverse_img_w_mi.py:359, :424-432) — a pure function of k, so the
+    host never reads the device."""
+    lr, epoch = lr0, 0
+    for _ in range(k):
+        if lr > floor:
+            epoch += 1
+            if epoch % step_size == 0:
+                lr *= gamma
+    return lr
 
 
 class DirectBRDFOptimizer:
@@ -68,9 +85,104 @@ class DirectBRDFOptimizer:
         loss.backward()
         self.opt.step()
         self.opt.zero_grad(set_to_none=True)
-        self.sched.step()          # the reference stops decaying below lr 1.5e-4 (:432) through a host-side read
+        if self.opt.param_groups[0]["lr"] > 1.5e-4:            # :431-432 (a host-side float, no device read)
+            self.sched.step()
         self.last = {"loss_mse": sums[0] / self.n_img, "loss_l1": sums[1] / self.n_img, "pred": pred_srgb}
         return loss.detach()
+
+
+class FusedBRDFOptimizer:
+    """Same iteration as DirectBRDFOptimizer (inverse_img_w_mi.py:346-446, `model_name == 'none'`), with everything
+    between the two render kernels done by the fused loss / Adam kernels of csrc/mb200_optim.cu instead of ~100
+    elementwise torch launches + autograd: 9 kernel launches per iteration, no host sync, scalars stay on the device.
+
+    Per iteration: shade_fwd -> film_develop -> image_sum [all-reduce] -> loss_srgb_sums [all-reduce] ->
+    loss_srgb_grad [halo exchange] -> film_weights -> film_adjoint -> shade_bwd -> adam_clamped.
+    """
+
+    _RANGE = {"albedo": (0.0, 1.0), "roughness": (0.07, 1.0), "metallic": (0.0, 1.0)}
+
+    def __init__(self, scene, mat, gt_image, optimize_part="arm", spp=64, lr=3e-4, scale_delta=0.1, shard=None,
+                 betas=(0.9, 0.999), eps=1e-8):
+        if not scene.use_mesh_normal:
+            raise ValueError("FusedBRDFOptimizer covers the use_mesh_normal=True schedule (a/r/m); use DirectBRDFOptimizer for 'n'")
+        self.scene, self.spp, self.scale_delta, self.part = scene, spp, scale_delta, optimize_part
+        self.lr0, self.betas, self.eps = lr, betas, eps
+        self.shard = sh = shard or ShardContext(scene.H, scene.W)
+        scene.set_shard(sh.row0, sh.rows)
+        dev, H, W = scene.device, scene.H, scene.W
+        self.names = [n for n, k in (("albedo", "a"), ("roughness", "r"), ("metallic", "m")) if k in optimize_part]
+        # the maps the kernels render with (full image; this rank only ever touches its own rows)
+        self.mat = {k: mat[k].detach().clone().contiguous() for k in ("albedo", "roughness", "metallic")}
+        for k in self.names:
+            self.mat[k].clamp_(*self._RANGE[k])
+        self.ori = {k: mat[k].detach().clone().contiguous() for k in self.names}
+        self.params = {k: mat[k].detach().clone().contiguous() for k in self.names}
+        ch = {"albedo": 3, "roughness": 1, "metallic": 1}
+        # one flat gradient buffer (one memset per iteration) and one flat Adam state
+        sizes = [H * W * ch[k] for k in ("albedo", "roughness", "metallic")]
+        self.gflat = torch.zeros(sum(sizes), device=dev)
+        ga, gr, gm = torch.split(self.gflat, sizes)
+        self.grads = {"albedo": ga.view(H, W, 3), "roughness": gr.view(H, W, 1), "metallic": gm.view(H, W, 1)}
+        self.exp_avg = {k: torch.zeros_like(self.params[k]) for k in self.names}
+        self.exp_avg_sq = {k: torch.zeros_like(self.params[k]) for k in self.names}
+        self.rows = slice(sh.row0, sh.row0 + sh.rows)
+        self.gt = gt_image[self.rows].contiguous()
+        self.gt_srgb = linear_to_srgb(self.gt)
+        self.n_total = H * W * 3
+        # device scalars: scal = (Σ gt, Σ pred), sums2 = (Σ diff², Σ |diff|)
+        self.scal = torch.zeros(2, device=dev)
+        self.scal[0:1] = sh.all_reduce_sum(self.gt.sum().reshape(1).clone())
+        self.sums2 = torch.zeros(2, device=dev)
+        self.scratch = torch.zeros(_abi.lib.mb200_reduce_scratch_bytes() // 4 + 1, dtype=torch.int32, device=dev)
+        self.grad_img = torch.empty(sh.rows, W, 3, device=dev)
+        self.pred_srgb = torch.empty(sh.rows, W, 3, device=dev)
+        self.k, self._lr, self._epoch = 0, lr, 0
+        self.last = {}
+        # Adam segments over this rank's rows (contiguous in the row-major maps)
+        segs = (_abi.AdamSeg * len(self.names))()
+        npx = float(H * W)
+        for i, k in enumerate(self.names):
+            c = ch[k]
+            off = sh.row0 * W * c * 4
+            n = sh.rows * W * c
+            segs[i].p = self.params[k].data_ptr() + off; segs[i].mat = self.mat[k].data_ptr() + off
+            segs[i].g = self.grads[k].data_ptr() + off; segs[i].ori = self.ori[k].data_ptr() + off
+            segs[i].m = self.exp_avg[k].data_ptr() + off; segs[i].v = self.exp_avg_sq[k].data_ptr() + off
+            segs[i].n = n; segs[i].lo, segs[i].hi = self._RANGE[k]
+            segs[i].aux_coeff = scale_delta / (npx * c)
+        self.segs = segs
+
+    def step(self, seed):
+        sc, sh, lib, st = self.scene, self.shard, _abi.lib, _abi.stream_ptr()
+        a, r, m = self.mat["albedo"], self.mat["roughness"], self.mat["metallic"]
+        env_pack = sc.prepared_env()
+        img = _rop._forward(sc, self.spp, int(seed), a, r, m, None, env_pack)
+        n = img.numel()
+        _abi.check(lib.mb200_image_sum(_abi.ptr(img), n, C.c_void_p(self.scal.data_ptr() + 4), _abi.ptr(self.scratch), st), "mb200_image_sum")
+        if sh.world_size > 1:
+            sh.all_reduce_sum(self.scal[1:2])
+        _abi.check(lib.mb200_loss_srgb_sums(_abi.ptr(img), _abi.ptr(self.gt_srgb), n, _abi.ptr(self.scal), _abi.ptr(self.sums2),
+                                            _abi.ptr(self.pred_srgb), _abi.ptr(self.scratch), st), "mb200_loss_srgb_sums")
+        if sh.world_size > 1:
+            sh.all_reduce_sum(self.sums2)
+        _abi.check(lib.mb200_loss_srgb_grad(_abi.ptr(img), _abi.ptr(self.gt_srgb), n, _abi.ptr(self.scal), _abi.ptr(self.sums2),
+                                            self.n_total, _abi.ptr(self.grad_img), st), "mb200_loss_srgb_grad")
+        grad = sh.halo_exchange(self.grad_img) if sh.world_size > 1 else self.grad_img
+        self.gflat.zero_()
+        _rop._backward(sc, self.spp, _rop.default_seed_grad(int(seed)), a, r, m, None, env_pack, grad,
+                       "albedo" in self.names, "roughness" in self.names, "metallic" in self.names, False, False,
+                       out=(self.grads["albedo"], self.grads["roughness"], self.grads["metallic"]))
+        self.k += 1
+        lr = self._lr
+        if self._lr > 1.5e-4:                                  # StepLR(100, 0.8), advanced only above the floor (:431-432)
+            self._epoch += 1
+            if self._epoch % 100 == 0:
+                self._lr *= 0.8
+        _abi.check(lib.mb200_adam_clamped(self.segs, len(self.names), lr, self.betas[0], self.betas[1], self.eps, self.k, st),
+                   "mb200_adam_clamped")
+        self.last = {"loss_mse": self.sums2[0] / self.n_total, "loss_l1": self.sums2[1] / self.n_total, "pred": self.pred_srgb}
+        return self.last["loss_mse"]
 
 
 class EnvmapOptimizer:

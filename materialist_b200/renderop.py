@@ -82,8 +82,9 @@ def _forward(scene, spp, seed, a, r, m, n, env_pack, extra_flags=0):
     return img
 
 
-def _backward(scene, spp, seed_grad, a, r, m, n, env_pack, grad_img_halo, want_a, want_r, want_m, want_n, want_env):
-    """grad_img_halo: (gadj_rows, W, 3) — gradient w.r.t. the image for the shard rows plus the film halo."""
+def _backward(scene, spp, seed_grad, a, r, m, n, env_pack, grad_img_halo, want_a, want_r, want_m, want_n, want_env, out=None):
+    """grad_img_halo: (gadj_rows, W, 3) — gradient w.r.t. the image for the shard rows plus the film halo.
+    out: optional pre-zeroed (g_a, g_r, g_m) full-image buffers to accumulate into (fused optimiser path)."""
     env4, hier, desc, He, We, mode = env_pack
     cfg = scene.make_cfg(spp, seed_grad, desc.res_x)
     st = _abi.stream_ptr()
@@ -101,9 +102,12 @@ def _backward(scene, spp, seed_grad, a, r, m, n, env_pack, grad_img_halo, want_a
     gadj = torch.empty(grows, scene.W, 4, device=dev)
     _abi.check(_abi.lib.mb200_film_adjoint(C.byref(cfg), _abi.ptr(wpart), _abi.ptr(grad_img_halo), _abi.ptr(gadj), st), "mb200_film_adjoint")
     H, W = scene.H, scene.W
-    g_a = torch.zeros(H, W, 3, device=dev) if want_a else None
-    g_r = torch.zeros(H, W, 1, device=dev) if want_r else None
-    g_m = torch.zeros(H, W, 1, device=dev) if want_m else None
+    if out is not None:
+        g_a, g_r, g_m = (o if w else None for o, w in zip(out, (want_a, want_r, want_m)))
+    else:
+        g_a = torch.zeros(H, W, 3, device=dev) if want_a else None
+        g_r = torch.zeros(H, W, 1, device=dev) if want_r else None
+        g_m = torch.zeros(H, W, 1, device=dev) if want_m else None
     g_n = torch.zeros(H, W, 3, device=dev) if (want_n and not scene.use_mesh_normal) else None
     g_env4 = torch.zeros_like(env4) if want_env else None
     nmap = None if scene.use_mesh_normal else n

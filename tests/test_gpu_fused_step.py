@@ -1,0 +1,100 @@
+"""GPU: the fused loss / Adam kernels (csrc/mb200_optim.cu) against torch autograd + torch.optim.Adam, and the
+fused BRDF-phase iteration (FusedBRDFOptimizer) against the autograd iteration (DirectBRDFOptimizer) — the body of
+inverse_img_w_mi.py:368-432 with model_name == 'none'."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import Case
+
+pytestmark = pytest.mark.gpu
+
+
+def _scratch(abi):
+    return torch.zeros(abi.lib.mb200_reduce_scratch_bytes() // 4 + 1, dtype=torch.int32, device="cuda")
+
+
+@pytest.mark.parametrize("n", [3, 1000, 512 * 512 * 3, 1237 * 811 * 3])
+def test_loss_kernels_vs_autograd(n):
+    from materialist_b200 import _abi as abi
+    g = torch.Generator().manual_seed(n)
+    img = (torch.rand(n, generator=g) * 2 + 1e-3).cuda()
+    img[::97] = 0.0                                         # black pixels: gradient defined as 0 (torch gives inf)
+    gt = torch.rand(n, generator=g).cuda()
+    gt_srgb = gt ** (1 / 2.2)
+    sc, st = _scratch(abi), abi.stream_ptr()
+    scal = torch.zeros(2, device="cuda"); scal[0] = gt.sum()
+    for _ in range(2):                                      # twice: the ticket of the scratch must re-arm itself
+        abi.check(abi.lib.mb200_image_sum(abi.ptr(img), n, C.c_void_p(scal.data_ptr() + 4), abi.ptr(sc), st))
+    assert abs(scal[1].item() - img.double().sum().item()) <= 2e-6 * img.double().sum().item()
+    sums2 = torch.zeros(2, device="cuda"); srgb = torch.empty(n, device="cuda")
+    abi.check(abi.lib.mb200_loss_srgb_sums(abi.ptr(img), abi.ptr(gt_srgb), n, abi.ptr(scal), abi.ptr(sums2), abi.ptr(srgb), abi.ptr(sc), st))
+    x = img.clone().requires_grad_(True)
+    ratio = (scal[0] / scal[1]).detach()
+    y = (x * ratio) ** (1 / 2.2)
+    d = y - gt_srgb
+    S0, S1 = (d * d).sum(), d.abs().sum()
+    assert abs(sums2[0].item() - S0.item()) <= 1e-5 * S0.item() and abs(sums2[1].item() - S1.item()) <= 1e-5 * S1.item()
+    assert torch.allclose(srgb, y.detach(), rtol=2e-6, atol=1e-7)
+    n_total = 4 * n
+    loss = 3 * (S1 / S0).detach() * S0 / n_total + S1 / n_total
+    loss.backward()
+    grad = torch.empty(n, device="cuda")
+    abi.check(abi.lib.mb200_loss_srgb_grad(abi.ptr(img), abi.ptr(gt_srgb), n, abi.ptr(scal), abi.ptr(sums2), n_total, abi.ptr(grad), st))
+    ok = img > 0
+    ref = x.grad
+    assert torch.isfinite(grad).all() and (grad[~ok] == 0).all()
+    err = (grad[ok] - ref[ok]).abs() / ref[ok].abs().clamp_min(1e-12)
+    # |diff| ~ 1 ulp flips sign(diff) in a handful of elements; everywhere else the two agree to float rounding
+    assert (err < 2e-5).float().mean() > 0.999, err.max()
+
+
+def test_adam_clamped_vs_torch():
+    from materialist_b200 import _abi as abi
+    g = torch.Generator().manual_seed(3)
+    n = 100_003
+    lo, hi, aux = 0.07, 1.0, 0.1 / n
+    p0 = (torch.rand(n, generator=g) * 1.2 - 0.1).cuda()        # some outside the clamp range
+    ori = torch.rand(n, generator=g).cuda()
+    p_ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([p_ref], lr=3e-4)
+    p, m, v, mat = p0.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda"), torch.empty(n, device="cuda")
+    seg = (abi.AdamSeg * 1)()
+    gr = torch.empty(n, device="cuda")
+    seg[0].p, seg[0].mat, seg[0].g, seg[0].ori, seg[0].m, seg[0].v = (t.data_ptr() for t in (p, mat, gr, ori, m, v))
+    seg[0].n, seg[0].lo, seg[0].hi, seg[0].aux_coeff = n, lo, hi, aux
+    for step in range(1, 6):
+        g_render = (torch.randn(n, generator=g) * 1e-4).cuda()
+        gr.copy_(g_render)
+        abi.check(abi.lib.mb200_adam_clamped(seg, 1, 3e-4, 0.9, 0.999, 1e-8, step, abi.stream_ptr()))
+        matr = p_ref.clamp(lo, hi)
+        loss = (matr * g_render).sum() + (matr - ori).abs().sum() * aux
+        loss.backward(); opt.step(); opt.zero_grad()
+        assert torch.allclose(p, p_ref.detach(), rtol=0, atol=2e-7), (step, (p - p_ref.detach()).abs().max())
+        assert torch.equal(mat, p.clamp(lo, hi))
+
+
+@pytest.mark.parametrize("part", ["arm", "rm"])
+def test_fused_iteration_matches_autograd_iteration(part):
+    import materialist_b200 as mb
+    from materialist_b200.inverse import DirectBRDFOptimizer, FusedBRDFOptimizer
+    c = Case(H=64, W=64, spp=32, He=16, We=32)
+    s = c.scene()
+    a, r, m, _ = c.torch_maps()
+    c2 = Case(H=64, W=64, spp=32, He=16, We=32, mat_seed=5)
+    a2, r2, m2, _ = c2.torch_maps()
+    gt = mb.render(s, spp=32, seed=999, albedo=a2, roughness=r2, metallic=m2)
+    mat = {"albedo": a, "roughness": r, "metallic": m}
+    d = DirectBRDFOptimizer(s, mat, gt, part, spp=c.spp)
+    f = FusedBRDFOptimizer(s, mat, gt, part, spp=c.spp)
+    for i in range(4):
+        d.step(10 + i); f.step(10 + i)
+        assert torch.allclose(f.last["loss_mse"], d.last["loss_mse"], rtol=1e-5), i
+        assert torch.allclose(f.last["loss_l1"], d.last["loss_l1"], rtol=1e-5), i
+    for k in f.names:
+        diff = (f.params[k] - d.params[k].detach()).abs()
+        # Adam's first steps are ~lr * sign(g): a gradient that is 0 up to rounding may step either way (<= 4 lr)
+        assert (diff < 1e-6).float().mean() > 0.995 and diff.max() < 4 * 4 * 3e-4, (k, diff.max(), (diff < 1e-6).float().mean())
+        assert torch.equal(f.mat[k], f.params[k].clamp(*f._RANGE[k]))
