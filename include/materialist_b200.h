@@ -193,6 +193,8 @@ int mb200_bsdf_sample(const mb200_cfg* cfg_host, int64_t L,
                       void* stream);
 
 /* ---------------------------------------------------------------- PosMLP */
+#define MB200_POSMLP_TCGEN05 0   /* 256-wide layers on tcgen05 tensor cores, FP16x2-split operands, FP32 TMEM accumulators */
+#define MB200_POSMLP_FFMA    1   /* all layers in FP32 FFMA (first-generation kernels; kept for A/B measurement)           */
 typedef struct mb200_posmlp_desc {
     int32_t n_color;      /* colour / feature channels of the input image (5 for 'arm', 3 for envmap_net) */
     int32_t n_out;        /* output channels                                                   */
@@ -200,12 +202,15 @@ typedef struct mb200_posmlp_desc {
     int32_t n_freq;       /* multires_view (2)                                                 */
     int32_t output_type;  /* 0 = 'envmap' (softplus), 1 = 'arm' (1.3*tanh + img, STE clamp)    */
     int32_t H, W;         /* pixel grid the N rows enumerate (row-major)                       */
+    int32_t impl;         /* MB200_POSMLP_*                                                    */
 } mb200_posmlp_desc;
 /* parameter packing: [W0 (h0 x d0) | b0 | W1 | b1 | W2 | b2 | W3 | b3 | W4 | b4], nn.Linear row-major (out,in) */
 int64_t mb200_posmlp_param_count(const mb200_posmlp_desc* d_host);
 size_t  mb200_posmlp_cache_bytes(const mb200_posmlp_desc* d_host, int64_t N);
+/* device scratch (16-byte aligned) the forward needs for the pre-split weight images; 0 for MB200_POSMLP_FFMA */
+size_t  mb200_posmlp_workspace_bytes(const mb200_posmlp_desc* d_host);
 int mb200_posmlp_fwd(const mb200_posmlp_desc* d_host, const float* params, const float* img /*(N,n_color)*/,
-                     int64_t N, float* out /*(N,n_out)*/, void* cache /* or NULL: inference */, void* stream);
+                     int64_t N, float* out /*(N,n_out)*/, void* cache /* or NULL: inference */, void* workspace, void* stream);
 int mb200_posmlp_bwd(const mb200_posmlp_desc* d_host, const float* params, const float* img, int64_t N,
                      const void* cache, const float* g_out /*(N,n_out)*/,
                      float* g_params /* += */, float* g_img /*(N,n_color) or NULL*/, void* stream);

@@ -19,6 +19,7 @@ OK, EINVAL, ERANGE, ELAUNCH, EUNSUPPORTED = 0, -1, -2, -3, -4
 FLAG_WO_WORLD_QUIRK, FLAG_ROW_STRIDE_H, FLAG_ENV_HALF_TEXEL, FLAG_AD_WEIGHTS = 1, 2, 4, 8
 FILTER_BOX, FILTER_GAUSSIAN = 0, 1
 ENV_ASSIGNED, ENV_FILE = 0, 1
+POSMLP_TCGEN05, POSMLP_FFMA = 0, 1
 
 
 class Cfg(C.Structure):
@@ -37,7 +38,7 @@ class HierDesc(C.Structure):
 
 class PosMLPDesc(C.Structure):
     _fields_ = [("n_color", C.c_int32), ("n_out", C.c_int32), ("hidden", C.c_int32), ("n_freq", C.c_int32),
-                ("output_type", C.c_int32), ("H", C.c_int32), ("W", C.c_int32)]
+                ("output_type", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("impl", C.c_int32)]
 
 
 class AdamSeg(C.Structure):
@@ -80,7 +81,8 @@ def _load():
         "mb200_bsdf_sample": (i32, [pc, i64] + [vp] * 13),
         "mb200_posmlp_param_count": (i64, [pm]),
         "mb200_posmlp_cache_bytes": (sz, [pm, i64]),
-        "mb200_posmlp_fwd": (i32, [pm, vp, vp, i64, vp, vp, vp]),
+        "mb200_posmlp_workspace_bytes": (sz, [pm]),
+        "mb200_posmlp_fwd": (i32, [pm, vp, vp, i64, vp, vp, vp, vp]),
         "mb200_posmlp_bwd": (i32, [pm, vp, vp, i64, vp, vp, vp, vp, vp]),
         "mb200_cdf_build": (i32, [vp, i32, i32, vp, vp, vp]),
         "mb200_cdf_sample": (i32, [vp, vp, i32, i32, vp, i64, vp, vp, vp, vp, vp]),

@@ -13,36 +13,17 @@
 // tcgen05 (3xTF32) is decided from the ncu profile.  Backward = data pass (same tiling, reversed) that
 // also reduces the small lin0 / lin4 / bias gradients in shared memory, + a split-K weight-gradient pass.
 #include "mb200_device.cuh"
-#include "mb200_host.h"
+#include "mb200_posmlp.h"
+
+using namespace posmlp;
 
 namespace {
 
 constexpr int TM = 64;            // pixels per tile
-constexpr int HID = 256;
 constexpr int XS = TM + 4;        // row stride of the transposed activation tile (floats)
 constexpr int KC = 16;            // reduction chunk
 constexpr int NT = 256;           // threads per CTA
-constexpr int ZSTRIDE = 4 * HID;  // cached pre-activations per pixel (lin0..lin3)
-constexpr int OSTRIDE = 8;        // cached lin4 outputs per pixel
 constexpr long long GCHUNK = 1ll << 20;   // pixels per backward chunk (bounds the dL/dz workspace to 4 GB)
-
-struct Dims {
-    int n_color, n_out, d0, h0, H, W, otype;
-    int oW[5], ob[5];             // offsets into the packed parameter vector
-};
-
-Dims make_dims(const mb200_posmlp_desc* d) {
-    Dims D; D.n_color = d->n_color; D.n_out = d->n_out; D.d0 = 2 + 4 * d->n_freq + d->n_color; D.h0 = HID - D.d0;
-    D.H = d->H; D.W = d->W; D.otype = d->output_type;
-    const int in[5] = {D.d0, HID, HID, HID, HID}, out[5] = {D.h0, HID, D.h0, HID, D.n_out};
-    int off = 0;
-    for (int l = 0; l < 5; ++l) { D.oW[l] = off; off += in[l] * out[l]; D.ob[l] = off; off += out[l]; }
-    return D;
-}
-bool valid_desc(const mb200_posmlp_desc* d) {
-    return d && d->hidden == HID && d->n_freq == 2 && d->n_color >= 1 && d->n_color <= 6 && d->n_out >= 1 && d->n_out <= OSTRIDE &&
-           d->H > 0 && d->W > 0 && (d->output_type == 0 || d->output_type == 1) && (d->output_type == 0 || d->n_out == d->n_color);
-}
 
 // ---------------------------------------------------------------- shared helpers
 // Embedding of a tile's pixels: PT[k][r], k < 16 (zero padded), r < TM
@@ -432,11 +413,21 @@ size_t mb200_posmlp_cache_bytes(const mb200_posmlp_desc* d, int64_t N) {
     return sizeof(float) * ((size_t)N * ZSTRIDE + (size_t)N * OSTRIDE + (size_t)g * ZSTRIDE);
 }
 
-int mb200_posmlp_fwd(const mb200_posmlp_desc* d, const float* params, const float* img, int64_t N, float* out, void* cache, void* stream) {
+size_t mb200_posmlp_workspace_bytes(const mb200_posmlp_desc* d) {
+    if (!valid_desc(d)) return 0;
+    return d->impl == MB200_POSMLP_TCGEN05 ? tc_workspace_bytes() : 0;
+}
+
+int mb200_posmlp_fwd(const mb200_posmlp_desc* d, const float* params, const float* img, int64_t N, float* out, void* cache,
+                     void* workspace, void* stream) {
     if (!valid_desc(d) || !params || !img || !out || N <= 0) return MB200_EINVAL;
     const Dims D = make_dims(d);
     float* zc = reinterpret_cast<float*>(cache);
     float* oc = zc ? zc + (size_t)N * ZSTRIDE : nullptr;
+    if (d->impl == MB200_POSMLP_TCGEN05) {
+        if (!workspace) return MB200_EINVAL;
+        return tc_forward(D, params, img, N, out, zc, oc, workspace, (cudaStream_t)stream);
+    }
     int rc = mb200_check(cudaFuncSetAttribute(posmlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
     if (rc) return rc;
     const long long ntiles = (N + TM - 1) / TM;

@@ -54,8 +54,10 @@ class _PosMLPFn(torch.autograd.Function):
         if need_grad:
             nbytes = _abi.lib.mb200_posmlp_cache_bytes(C.byref(desc), N)
             cache = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=img.device)
+        wbytes = _abi.lib.mb200_posmlp_workspace_bytes(C.byref(desc))
+        work = torch.empty((wbytes + 3) // 4, dtype=torch.float32, device=img.device) if wbytes else None
         _abi.check(_abi.lib.mb200_posmlp_fwd(C.byref(desc), _abi.ptr(flat), _abi.ptr(img), N, _abi.ptr(out), _abi.ptr(cache),
-                                             _abi.stream_ptr()), "mb200_posmlp_fwd")
+                                             _abi.ptr(work), _abi.stream_ptr()), "mb200_posmlp_fwd")
         ctx.desc, ctx.cache, ctx.N = desc, cache, N
         ctx.save_for_backward(img, flat)
         return out
@@ -98,6 +100,7 @@ class PosMLP(nn.Module):
                 nn.init.zeros_(lin.weight); nn.init.zeros_(lin.bias)          # mlps.py:174-176
             setattr(self, "lin" + str(l), lin)
         self.last_active_fun = nn.Softplus()
+        self.impl = _abi.POSMLP_TCGEN05            # _abi.POSMLP_FFMA selects the FP32-FFMA kernels (A/B measurement only)
 
     # ------------------------------------------------------------------
     def _linears(self):
@@ -128,6 +131,7 @@ class PosMLP(nn.Module):
         d.n_color, d.n_out, d.hidden, d.n_freq = self.color_ch, self.out_dims, 256, 2
         d.output_type = 0 if self.output_type == "envmap" else 1
         d.H, d.W = hw
+        d.impl = self.impl
         return d
 
     def forward(self, img, hw=None):
