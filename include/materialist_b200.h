@@ -213,7 +213,7 @@ int mb200_posmlp_fwd(const mb200_posmlp_desc* d_host, const float* params, const
                      int64_t N, float* out /*(N,n_out)*/, void* cache /* or NULL: inference */, void* workspace, void* stream);
 int mb200_posmlp_bwd(const mb200_posmlp_desc* d_host, const float* params, const float* img, int64_t N,
                      const void* cache, const float* g_out /*(N,n_out)*/,
-                     float* g_params /* += */, float* g_img /*(N,n_color) or NULL*/, void* stream);
+                     float* g_params /* += */, float* g_img /*(N,n_color) or NULL*/, void* workspace, void* stream);
 
 /* ---------------------------------------------------------------- envmap_utils / computeSH */
 /* build_envmap: env (h,w,3) -> c_cdf (h,w), m_cdf (h) */

@@ -83,7 +83,7 @@ def _load():
         "mb200_posmlp_cache_bytes": (sz, [pm, i64]),
         "mb200_posmlp_workspace_bytes": (sz, [pm]),
         "mb200_posmlp_fwd": (i32, [pm, vp, vp, i64, vp, vp, vp, vp]),
-        "mb200_posmlp_bwd": (i32, [pm, vp, vp, i64, vp, vp, vp, vp, vp]),
+        "mb200_posmlp_bwd": (i32, [pm, vp, vp, i64, vp, vp, vp, vp, vp, vp]),
         "mb200_cdf_build": (i32, [vp, i32, i32, vp, vp, vp]),
         "mb200_cdf_sample": (i32, [vp, vp, i32, i32, vp, i64, vp, vp, vp, vp, vp]),
         "mb200_sh_project": (i32, [vp, i32, i32, vp, i64, vp, vp]),

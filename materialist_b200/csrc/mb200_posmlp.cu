@@ -407,10 +407,18 @@ int64_t mb200_posmlp_param_count(const mb200_posmlp_desc* d) {
     return (int64_t)D.ob[4] + D.n_out;
 }
 
+// cache layout: [zc N x 1024 f32][oc N x 8 f32][pad to 128 B][scratch]
+//   FFMA   : scratch = dL/dz workspace of one backward chunk (min(N, 2^20) x 1024 f32)
+//   tcgen05: scratch = [ximg | gimg], tc_image_bytes(N) each (>= the FFMA scratch, which the g_img path reuses)
+static size_t cache_head_bytes(int64_t N) { return (sizeof(float) * ((size_t)N * ZSTRIDE + (size_t)N * OSTRIDE) + 127) & ~(size_t)127; }
+
 size_t mb200_posmlp_cache_bytes(const mb200_posmlp_desc* d, int64_t N) {
     if (!valid_desc(d) || N <= 0) return 0;
     const long long g = N < GCHUNK ? N : GCHUNK;
-    return sizeof(float) * ((size_t)N * ZSTRIDE + (size_t)N * OSTRIDE + (size_t)g * ZSTRIDE);
+    const size_t ffma = sizeof(float) * (size_t)g * ZSTRIDE;
+    if (d->impl == MB200_POSMLP_FFMA) return cache_head_bytes(N) + ffma;
+    const size_t tc = 2 * tc_image_bytes(N);
+    return cache_head_bytes(N) + (tc > ffma ? tc : ffma);
 }
 
 size_t mb200_posmlp_workspace_bytes(const mb200_posmlp_desc* d) {
@@ -426,7 +434,8 @@ int mb200_posmlp_fwd(const mb200_posmlp_desc* d, const float* params, const floa
     float* oc = zc ? zc + (size_t)N * ZSTRIDE : nullptr;
     if (d->impl == MB200_POSMLP_TCGEN05) {
         if (!workspace) return MB200_EINVAL;
-        return tc_forward(D, params, img, N, out, zc, oc, workspace, (cudaStream_t)stream);
+        void* ximg = cache ? reinterpret_cast<uint8_t*>(cache) + cache_head_bytes(N) : nullptr;
+        return tc_forward(D, params, img, N, out, zc, oc, ximg, workspace, (cudaStream_t)stream);
     }
     int rc = mb200_check(cudaFuncSetAttribute(posmlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
     if (rc) return rc;
@@ -437,13 +446,20 @@ int mb200_posmlp_fwd(const mb200_posmlp_desc* d, const float* params, const floa
 }
 
 int mb200_posmlp_bwd(const mb200_posmlp_desc* d, const float* params, const float* img, int64_t N, const void* cache,
-                     const float* g_out, float* g_params, float* g_img, void* stream) {
+                     const float* g_out, float* g_params, float* g_img, void* workspace, void* stream) {
     if (!valid_desc(d) || !params || !img || !cache || !g_out || !g_params || N <= 0) return MB200_EINVAL;
     const Dims D = make_dims(d);
     const float* zc = reinterpret_cast<const float*>(cache);
     const float* oc = zc + (size_t)N * ZSTRIDE;
-    float* gbuf = const_cast<float*>(oc) + (size_t)N * OSTRIDE;
+    uint8_t* scratch = const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(cache)) + cache_head_bytes(N);
     cudaStream_t st = (cudaStream_t)stream;
+    // The tensor-core backward produces the parameter gradients; the gradient w.r.t. the input image (never requested by the
+    // reference: brdf_net / envmap_net inputs are constants) is served by the FP32 data pass below.
+    if (d->impl == MB200_POSMLP_TCGEN05 && !g_img) {
+        if (!workspace) return MB200_EINVAL;
+        return tc_backward(D, params, img, N, zc, oc, scratch, scratch + tc_image_bytes(N), g_out, g_params, workspace, st);
+    }
+    float* gbuf = reinterpret_cast<float*>(scratch);
     int rc = mb200_check(cudaFuncSetAttribute(posmlp_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
     if (rc) return rc;
     for (long long b = 0; b < N; b += GCHUNK) {

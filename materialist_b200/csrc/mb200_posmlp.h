@@ -27,9 +27,13 @@ inline bool valid_desc(const mb200_posmlp_desc* d) {
            (d->impl == MB200_POSMLP_TCGEN05 || d->impl == MB200_POSMLP_FFMA);
 }
 
-// tcgen05 forward (mb200_posmlp_tc.cu): wprep = mb200_posmlp_workspace_bytes() bytes of device scratch
+// tcgen05 path (mb200_posmlp_tc.cu).  workspace = tc_workspace_bytes() bytes of device scratch (pre-split weight images);
+// ximg / gimg = tc_image_bytes(N) bytes each: the FP16-split activation / gradient images kept for the weight-gradient GEMM.
 size_t tc_workspace_bytes();
-int tc_forward(const Dims& D, const float* params, const float* img, long long N, float* out, float* zc, float* oc,
-               void* wprep, cudaStream_t st);
+size_t tc_image_bytes(long long N);
+int tc_forward(const Dims& D, const float* params, const float* img, long long N, float* out, float* zc, float* oc, void* ximg,
+               void* workspace, cudaStream_t st);
+int tc_backward(const Dims& D, const float* params, const float* img, long long N, const float* zc, const float* oc, const void* ximg,
+                void* gimg, const float* g_out, float* g_params, void* workspace, cudaStream_t st);
 
 }  // namespace posmlp

@@ -30,12 +30,19 @@ def _net_from_golden(g, tag, n_color, n_out, otype):
     return net
 
 
+@pytest.mark.parametrize("impl", ["tcgen05", "ffma"])
+@pytest.mark.parametrize("want_gx", [False, True])
 @pytest.mark.parametrize("tag,n_color,n_out,otype", [("arm", 5, 5, "arm"), ("envmap", 3, 3, "envmap")])
-def test_posmlp_matches_reference_golden(tag, n_color, n_out, otype):
+def test_posmlp_matches_reference_golden(tag, n_color, n_out, otype, want_gx, impl):
+    """Forward + backward against outputs / autograd gradients of the REFERENCE PosMLP (tests/golden/make_golden.py).
+    want_gx=False is the reference's own use (network inputs are constants): with impl=tcgen05 the whole backward runs on
+    the tensor cores; want_gx=True additionally asks for d/d(input image), served by the FP32 data pass."""
+    from materialist_b200 import _abi
     g = load("posmlp.npz")
     net = _net_from_golden(g, tag, n_color, n_out, otype)
+    net.impl = _abi.POSMLP_TCGEN05 if impl == "tcgen05" else _abi.POSMLP_FFMA
     assert sum(p.numel() for p in net.parameters()) == int(g[f"{tag}_nparams"])
-    x = torch.from_numpy(g[f"{tag}_x"]).cuda().requires_grad_(True)
+    x = torch.from_numpy(g[f"{tag}_x"]).cuda().requires_grad_(want_gx)
     y = net(x)
     assert rel_l2(y.detach().cpu().numpy(), g[f"{tag}_y"]) < 1e-5
     y.backward(torch.from_numpy(g[f"{tag}_gy"]).cuda())
@@ -43,28 +50,54 @@ def test_posmlp_matches_reference_golden(tag, n_color, n_out, otype):
         lin = getattr(net, f"lin{l}").linear if l < 4 else net.lin4
         assert rel_l2(lin.weight.grad.cpu().numpy(), g[f"{tag}_gW{l}"]) < 1e-4, l
         assert rel_l2(lin.bias.grad.cpu().numpy(), g[f"{tag}_gb{l}"]) < 1e-4, l
-    assert rel_l2(x.grad.cpu().numpy(), g[f"{tag}_gx"]) < 1e-4
+    if want_gx:
+        assert rel_l2(x.grad.cpu().numpy(), g[f"{tag}_gx"]) < 1e-4
 
 
-def test_posmlp_ragged_size_vs_oracle():
-    """N not a multiple of the 64-pixel tile, explicit non-square grid, against the numpy oracle."""
+@pytest.mark.parametrize("impl", ["tcgen05", "ffma"])
+@pytest.mark.parametrize("H,W", [(37, 53), (3, 5), (128, 129)])
+def test_posmlp_ragged_size_vs_oracle(H, W, impl):
+    """N not a multiple of the pixel tile (128 / 64), explicit non-square grid, tiny and multi-tile sizes, against the numpy oracle."""
+    from materialist_b200 import _abi
     g = load("posmlp.npz")
     net = _net_from_golden(g, "arm", 5, 5, "arm")
-    H, W = 37, 53
+    net.impl = _abi.POSMLP_TCGEN05 if impl == "tcgen05" else _abi.POSMLP_FFMA
     x = torch.rand(H * W, 5, generator=torch.Generator().manual_seed(5))
     o = aux.PosMLPOracle([g[f"arm_W{l}"] for l in range(5)], [g[f"arm_b{l}"] for l in range(5)], 5, 5, "arm")
     y_ref = o.forward(x.numpy(), H, W)
     gy = torch.randn(H * W, 5, generator=torch.Generator().manual_seed(6))
     gW, gb, gx = o.backward(gy.numpy())
-    xc = x.cuda().requires_grad_(True)
-    y = net(xc, hw=(H, W))
-    assert rel_l2(y.detach().cpu().numpy(), y_ref) < 1e-5
-    y.backward(gy.cuda())
-    assert rel_l2(xc.grad.cpu().numpy(), gx) < 1e-4
-    for l in range(5):
-        lin = getattr(net, f"lin{l}").linear if l < 4 else net.lin4
-        assert rel_l2(lin.weight.grad.cpu().numpy(), gW[l]) < 1e-4, l
-        assert rel_l2(lin.bias.grad.cpu().numpy(), gb[l]) < 1e-4, l
+    for want_gx in (False, True):
+        net.zero_grad(set_to_none=True)
+        xc = x.cuda().requires_grad_(want_gx)
+        y = net(xc, hw=(H, W))
+        assert rel_l2(y.detach().cpu().numpy(), y_ref) < 1e-5
+        y.backward(gy.cuda())
+        if want_gx:
+            assert rel_l2(xc.grad.cpu().numpy(), gx) < 1e-4
+        for l in range(5):
+            lin = getattr(net, f"lin{l}").linear if l < 4 else net.lin4
+            assert rel_l2(lin.weight.grad.cpu().numpy(), gW[l]) < 1e-4, (l, want_gx)
+            assert rel_l2(lin.bias.grad.cpu().numpy(), gb[l]) < 1e-4, (l, want_gx)
+
+
+def test_posmlp_gradient_scale_invariance():
+    """The tensor-core backward carries gradients scaled by a power of two chosen from max|g_out|: results must not depend on
+    the magnitude of the incoming gradient (1e-12 .. 1e+6 here)."""
+    g = load("posmlp.npz")
+    net = _net_from_golden(g, "arm", 5, 5, "arm")
+    x = torch.from_numpy(g["arm_x"]).cuda()
+    gy = torch.from_numpy(g["arm_gy"]).cuda()
+    ref = None
+    for scale in (1.0, 1e-12, 1e6):
+        net.zero_grad(set_to_none=True)
+        net(x).backward(gy * scale)
+        got = torch.cat([p.grad.reshape(-1) for p in net.parameters()]) / scale
+        assert torch.isfinite(got).all()
+        if ref is None:
+            ref = got
+        else:
+            assert float((got - ref).norm() / ref.norm()) < 2e-6, scale
 
 
 def test_posmlp_zero_init_envmap_is_ln2():

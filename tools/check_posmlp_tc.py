@@ -34,15 +34,28 @@ def main():
                 res[name + "_maxabs"] = float((y - y_ref64).abs().max().item())
                 res[name + "_ms"] = timeit(lambda: net(img, hw=(H, W)), n=5, warm=2)
             res["torch32_err_vs_f64"] = float(((y_t - y_ref64).norm() / y_ref64.norm()).item())
-        # cached pre-activations feed the backward: compare grads of the TC forward + FFMA backward against FFMA/FFMA
-        gy = torch.randn(H * W, 5, device="cuda")
-        grads = {}
+        # gradients: tcgen05 backward and FFMA backward against float64 autograd of the plain-torch network
+        gy = torch.randn(H * W, 5, device="cuda") * 1e-4
+        net.double(); net.zero_grad(set_to_none=True)
+        torch_forward(net, img.double(), H, W).backward(gy.double())
+        ref = [p.grad.float().clone() for p in net.parameters()]
+        net.float()
+        names = [n for n, _ in net.named_parameters()]
         for name, impl in (("tc", _abi.POSMLP_TCGEN05), ("ffma", _abi.POSMLP_FFMA)):
             net.impl = impl
             net.zero_grad(set_to_none=True)
             net(img, hw=(H, W)).backward(gy)
-            grads[name] = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
-        res["grad_tc_vs_ffma"] = float(((grads["tc"] - grads["ffma"]).norm() / grads["ffma"].norm()).item())
+            torch.cuda.synchronize()
+            errs = {n: float(((p.grad - r).norm() / r.norm().clamp_min(1e-30)).item()) for n, p, r in zip(names, net.parameters(), ref)}
+            res[name + "_grad_err_max"] = max(errs.values())
+            res[name + "_grad_err_worst"] = max(errs, key=errs.get)
+            if impl == _abi.POSMLP_TCGEN05:
+                res["tc_grad_errs"] = {k: round(v, 9) for k, v in errs.items()}
+
+            def fb():
+                net.zero_grad(set_to_none=True)
+                net(img, hw=(H, W)).backward(gy)
+            res[name + "_fwd_bwd_ms"] = timeit(fb, n=5, warm=2)
         flops = H * W * 2 * (15 * 241 + 256 * 256 + 256 * 241 + 256 * 256 + 256 * 5)
         res["tc_fwd_tflops"] = flops / res["tc_ms"] / 1e9
         print(json.dumps(res), flush=True)
