@@ -31,6 +31,8 @@ WORKLOADS = {
                desc="inverse_img_w_mi.py --model_name=none --opt_src=arm --opt_order=arm, synthetic 512x512 G-buffer, 64 spp, 256x128 envmap"),
     "c5": dict(H=2160, W=3840, spp=256, He=1024, We=2048, scaling="strong",
                desc="synthetic 4K (3840x2160) G-buffer inverse optimisation, 2048x1024 envmap, 256 spp, rows sharded"),
+    "c3": dict(H=768, W=1024, spp=64, He=16, We=32, scaling="weak", pos_mlp=True,
+               desc="inverse_img_w_mi.py --model_name=pos_mlp --opt_src=a --opt_order='rm a', synthetic 1024x768 G-buffer, 64 spp, 16x32 envmap, brdf_net = PosMLP"),
     "tiny": dict(H=64, W=64, spp=32, He=16, We=32, scaling="weak", desc="tiny self-test workload"),
 }
 METRIC = "fwd+adjoint shaded samples/s (inverse-optimisation iteration)"
@@ -181,7 +183,7 @@ def run_b200(args, wl):
     import torch.distributed as dist
     import materialist_b200 as mb
     from materialist_b200 import _abi, renderop as mbr
-    from materialist_b200.inverse import DirectBRDFOptimizer, FusedBRDFOptimizer
+    from materialist_b200.inverse import DirectBRDFOptimizer, FusedBRDFOptimizer, PosMLPBRDFOptimizer
     from materialist_b200.parallel import ShardContext
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -202,7 +204,17 @@ def run_b200(args, wl):
     scene.set_shard(0, H)
     gt = mb.render(scene, spp=min(spp, 64), seed=999, albedo=to(case["a2"]), roughness=to(case["r2"]), metallic=to(case["m2"]))
     mat = {"albedo": to(case["a"]), "roughness": to(case["r"]), "metallic": to(case["m"])}
-    opt = (FusedBRDFOptimizer if args.optimizer == "fused" else DirectBRDFOptimizer)(scene, mat, gt, "arm", spp=spp, shard=shard)
+    if wl.get("pos_mlp"):
+        if world > 1:
+            raise SystemExit("the pos_mlp workload is single-GPU (brdf_net sees every pixel)")
+        torch.manual_seed(0)
+        opt = PosMLPBRDFOptimizer(scene, mat, gt, "arm", spp=spp)
+        with torch.no_grad():                          # lin4 is zero-initialised (mlps.py:174-176): perturb so the timed steps do real work
+            opt.net.lin4.weight.normal_(0, 0.02)
+        args.optimizer = "autograd+posmlp"
+        args.no_e2e = True
+    else:
+        opt = (FusedBRDFOptimizer if args.optimizer == "fused" else DirectBRDFOptimizer)(scene, mat, gt, "arm", spp=spp, shard=shard)
     samples_per_step = H * W * spp                       # whole job (all ranks)
 
     def sync():

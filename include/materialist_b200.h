@@ -134,8 +134,13 @@ int mb200_env_prepare(const float* env_in, int He, int We, int mode,
                       float* env4, float* hier, const mb200_hier_desc* desc_host,
                       void* scratch, void* stream);
 
-/* g_env4 (He, Wi, 4) -> g_env (He, We, 3), adjoint of the ingest map; g_env is OVERWRITTEN */
-int mb200_env_grad_finish(const float* g_env4, int He, int We, int mode, float* g_env, void* stream);
+/* Number of privatised copies ("slabs") of the envmap-gradient grid mb200_shade_bwd should scatter into: the CTAs of the
+ * adjoint kernel spread over them (slab = blockIdx % n) so that hot texels (a sun) are n L2 addresses instead of one.
+ * Sized to keep n * He * Wi * 16 bytes <= 64 MB (L2-resident). */
+int mb200_env_grad_slabs(int He, int We, int mode);
+/* g_env4 (n_slabs, He, Wi, 4) -> g_env (He, We, 3): sums the slabs in a fixed order, then the adjoint of the ingest map;
+ * g_env is OVERWRITTEN */
+int mb200_env_grad_finish(const float* g_env4, int n_slabs, int He, int We, int mode, float* g_env, void* stream);
 
 /* ---------------------------------------------------------------- render */
 /* G-buffer: gpos (H,W,4) = (x,y,z,valid?1:0), gnrm (H,W,4) = (nx,ny,nz,0)  — full image, fp32.
@@ -164,13 +169,13 @@ int mb200_bwd_gadj_rows(const mb200_cfg* cfg_host, int* first_row_host);
 
 /* Adjoint render (cfg.seed = seed_grad).  Accumulates (+=) into the gradient buffers:
  * g_a (H,W,3), g_r (H,W,1), g_m (H,W,1), g_n (H,W,3) full-image, any may be NULL;
- * g_env4 (He, Wi, 4) or NULL.  Caller zeroes them. */
+ * g_env4 (n_env_slabs, He, Wi, 4) or NULL (n_env_slabs from mb200_env_grad_slabs, >= 1).  Caller zeroes them. */
 int mb200_shade_bwd(const mb200_cfg* cfg_host,
                     const float* gpos, const float* gnrm,
                     const float* a, const float* r, const float* m, const float* n_opt,
                     const float* env4, const float* hier, const mb200_hier_desc* desc_host,
                     const float* gadj,
-                    float* g_a, float* g_r, float* g_m, float* g_n, float* g_env4,
+                    float* g_a, float* g_r, float* g_m, float* g_n, float* g_env4, int n_env_slabs,
                     void* stream);
 
 /* (S,4) int32 per lane: (hier off.x, off.y, texel flat index, lobe 0=specular 1=diffuse); shard rows only */

@@ -68,14 +68,15 @@ def _load():
         "mb200_fwd_partial_rows": (i32, [pc, C.POINTER(C.c_int)]),
         "mb200_partial_stride": (i32, [i32]),
         "mb200_env_prepare": (i32, [vp, i32, i32, i32, vp, vp, ph, vp, vp]),
-        "mb200_env_grad_finish": (i32, [vp, i32, i32, i32, vp, vp]),
+        "mb200_env_grad_slabs": (i32, [i32, i32, i32]),
+        "mb200_env_grad_finish": (i32, [vp, i32, i32, i32, i32, vp, vp]),
         "mb200_shade_fwd": (i32, [pc] + [vp] * 8 + [ph, vp, vp]),
         "mb200_film_develop": (i32, [pc, vp, vp, vp]),
         "mb200_film_weights": (i32, [pc, vp, vp]),
         "mb200_film_adjoint": (i32, [pc, vp, vp, vp, vp]),
         "mb200_bwd_wpart_rows": (i32, [pc, C.POINTER(C.c_int)]),
         "mb200_bwd_gadj_rows": (i32, [pc, C.POINTER(C.c_int)]),
-        "mb200_shade_bwd": (i32, [pc] + [vp] * 8 + [ph] + [vp] * 7),
+        "mb200_shade_bwd": (i32, [pc] + [vp] * 8 + [ph] + [vp] * 6 + [i32, vp]),
         "mb200_debug_sample_indices": (i32, [pc, vp, vp, vp, ph, vp, vp]),
         "mb200_bsdf_eval_pdf": (i32, [pc, i64] + [vp] * 11),
         "mb200_bsdf_sample": (i32, [pc, i64] + [vp] * 13),

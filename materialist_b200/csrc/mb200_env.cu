@@ -75,16 +75,23 @@ __global__ void env_upper_level_kernel(const float* __restrict__ child, int cw, 
     parent[lvl_index((uint32_t)x, (uint32_t)y, (uint32_t)pw)] = XADD(XADD(XADD(q.x, q.y), q.z), q.w);
 }
 
-__global__ void env_grad_finish_kernel(const float4* __restrict__ g4, int He, int We, int Wi, int mode, float* __restrict__ g) {
+// sums the privatised slabs (fixed order) and applies the adjoint of the ingest map
+__global__ void env_grad_finish_kernel(const float4* __restrict__ g4, int n_slabs, int He, int We, int Wi, int mode, float* __restrict__ g) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= He * We) return;
     const int y = i / We, x = i % We;
-    float4 v = g4[(size_t)y * Wi + x];
+    const size_t stride = (size_t)He * Wi;
+    auto texel = [&](size_t idx) {
+        float3 a = make_float3(0.f, 0.f, 0.f);
+        for (int s = 0; s < n_slabs; ++s) { const float4 t = __ldg(g4 + (size_t)s * stride + idx); a.x += t.x; a.y += t.y; a.z += t.z; }
+        return a;
+    };
+    float3 v = texel((size_t)y * Wi + x);
     if (mode == MB200_ENV_FILE) {
-        if (x == 0) { const float4 e = g4[(size_t)y * Wi + We]; v.x += e.x; v.y += e.y; v.z += e.z; }
+        if (x == 0) { const float3 e = texel((size_t)y * Wi + We); v.x += e.x; v.y += e.y; v.z += e.z; }
     } else if (x == 0 || x == We - 1) {
-        const float4 p = g4[(size_t)y * Wi], q = g4[(size_t)y * Wi + Wi - 1];
-        v = make_float4(.5f * (p.x + q.x), .5f * (p.y + q.y), .5f * (p.z + q.z), 0.f);
+        const float3 p = texel((size_t)y * Wi), q = texel((size_t)y * Wi + Wi - 1);
+        v = make_float3(.5f * (p.x + q.x), .5f * (p.y + q.y), .5f * (p.z + q.z));
     }
     g[3 * (size_t)i] = v.x; g[3 * (size_t)i + 1] = v.y; g[3 * (size_t)i + 2] = v.z;
 }
@@ -118,10 +125,22 @@ int mb200_env_prepare(const float* env_in, int He, int We, int mode, float* env4
     return mb200_check_launch();
 }
 
-int mb200_env_grad_finish(const float* g_env4, int He, int We, int mode, float* g_env, void* stream) {
-    if (!g_env4 || !g_env || He < 2 || We < 2) return MB200_EINVAL;
-    const int Wi = mb200_env_internal_width(We, mode), n = He * We, tb = 256;
-    env_grad_finish_kernel<<<(n + tb - 1) / tb, tb, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(g_env4), He, We, Wi, mode, g_env);
+int mb200_env_grad_slabs(int He, int We, int mode) {
+    // privatised copies of the envmap-gradient grid, sized to stay L2-resident (<= 64 MB in total): the adjoint kernel's
+    // CTAs spread their texel updates over them (slab = blockIdx % n), so a sun texel that attracts half of all emitter
+    // samples is n different L2 addresses instead of one serialised atomic.
+    if (He < 2 || We < 2) return 1;
+    const long long bytes = (long long)He * mb200_env_internal_width(We, mode) * 16;
+    long long n = (64ll << 20) / bytes;
+    const long long cap = (long long)mb200_sm_count() * 8;
+    if (n > cap) n = cap;
+    return n < 1 ? 1 : (int)n;
+}
+
+int mb200_env_grad_finish(const float* g_env4, int n_slabs, int He, int We, int mode, float* g_env, void* stream) {
+    if (!g_env4 || !g_env || He < 2 || We < 2 || n_slabs < 1) return MB200_EINVAL;
+    const int Wi = mb200_env_internal_width(We, mode), n = He * We, tb = 128;
+    env_grad_finish_kernel<<<(n + tb - 1) / tb, tb, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(g_env4), n_slabs, He, We, Wi, mode, g_env);
     return mb200_check_launch();
 }
 

@@ -42,7 +42,7 @@ struct RenderParams {
     float* partials;
     // adjoint
     const float4* gadj; int grow0, grows; // G image rows
-    float* g_a; float* g_r; float* g_m; float* g_n; float4* g_env4;
+    float* g_a; float* g_r; float* g_m; float* g_n; float4* g_env4; int env_slabs; long long env_slab_stride;
 };
 
 struct PixelCtx {
@@ -252,6 +252,8 @@ __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_BWD) shade_bwd_kernel(
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float4* gt = s_g + (FILTER == MB200_FILTER_GAUSSIAN ? warp * MB200_FILM_TAPS : 0);
     const int npix = P.prows * P.W;
+    // this CTA's privatised copy of the envmap-gradient grid (mb200_env_grad_slabs)
+    float4* const genv = WANT_ENV ? P.g_env4 + (long long)(blockIdx.x % P.env_slabs) * P.env_slab_stride : nullptr;
     for (int pix = blockIdx.x * kWarpsPerBlock + warp; pix < npix; pix += gridDim.x * kWarpsPerBlock) {
         const int py = P.prow0 + pix / P.W, px = pix % P.W;
         const int gpix = py * P.W + px;
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_BWD) shade_bwd_kernel(
                 if (WANT_ENV) {
                     const float3 d = primary_dir(P.cam, (float)px + jx, (float)py + jy);
                     float u, v; dir_to_uv(d, u, v);
-                    env_scatter(P.g_env4, P.env.Wi, env_lookup<false>(P.env, u, v), dl);
+                    env_scatter(genv, P.env.Wi, env_lookup<false>(P.env, u, v), dl);
                 }
                 continue;
             }
@@ -313,7 +315,7 @@ __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_BWD) shade_bwd_kernel(
                     const BsdfGrad bg = eval_brdf_grad<WANT_N>(em.d, c.view, c.mt, dl * le * k);
                     ga = ga + bg.ga; gr += bg.gr; gm += bg.gm; if (WANT_N) gn = gn + bg.gn;
                 }
-                if (WANT_ENV) env_scatter(P.g_env4, P.env.Wi, em.b, dl * fv.f * k);
+                if (WANT_ENV) env_scatter(genv, P.env.Wi, em.b, dl * fv.f * k);
             }
             // ---- BSDF term: L2 = f(d_bs)/detach(p2) * Le(d_bs) * mis
             const BsdfSample bs = sample_brdf(s1, s2x, s2y, c.view, c.mt, c.fshade);
@@ -329,7 +331,7 @@ __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_BWD) shade_bwd_kernel(
                     const BsdfGrad bg = eval_brdf_grad<WANT_N>(d_bs, c.view, c.mt, dl * le * (mis / b2.pdf));
                     ga = ga + bg.ga; gr += bg.gr; gm += bg.gm; if (WANT_N) gn = gn + bg.gn;
                 }
-                if (WANT_ENV) env_scatter(P.g_env4, P.env.Wi, bb, dl * w_bs * mis);
+                if (WANT_ENV) env_scatter(genv, P.env.Wi, bb, dl * w_bs * mis);
             }
         }
         if (WANT_MAT) {
@@ -503,10 +505,11 @@ int mb200_film_adjoint(const mb200_cfg* c, const float* wpart, const float* grad
 
 int mb200_shade_bwd(const mb200_cfg* c, const float* gpos, const float* gnrm, const float* a, const float* r, const float* m,
                     const float* n_opt, const float* env4, const float* hier, const mb200_hier_desc* d, const float* gadj,
-                    float* g_a, float* g_r, float* g_m, float* g_n, float* g_env4, void* stream) {
+                    float* g_a, float* g_r, float* g_m, float* g_n, float* g_env4, int n_env_slabs, void* stream) {
     RenderParams P; int rc = fill_params(c, gpos, gnrm, a, r, m, n_opt, env4, hier, d, P);
     if (rc) return rc;
-    if (!gadj) return MB200_EINVAL;
+    if (!gadj || (g_env4 && n_env_slabs < 1)) return MB200_EINVAL;
+    P.env_slabs = g_env4 ? n_env_slabs : 1; P.env_slab_stride = (long long)d->res_x * d->res_y;
     P.prow0 = c->row0; P.prows = c->rows;
     P.gadj = reinterpret_cast<const float4*>(gadj); P.grows = mb200_bwd_gadj_rows(c, &P.grow0);
     P.g_a = g_a; P.g_r = g_r; P.g_m = g_m; P.g_n = g_n; P.g_env4 = reinterpret_cast<float4*>(g_env4);

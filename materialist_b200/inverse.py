@@ -185,6 +185,54 @@ class FusedBRDFOptimizer:
         return self.last["loss_mse"]
 
 
+class PosMLPBRDFOptimizer:
+    """BRDF phase with `model_name == 'pos_mlp'` (inverse_img_w_mi.py:471-552): the maps are the output of `brdf_net`
+    (PosMLP on the tensor cores, mymodels/mlps.py) applied to the initial estimate `start_arm`; the network weights are
+    optimised with AdamW(lr=3e-4) + the guarded StepLR(100, 0.8).  Single-GPU (the network sees every pixel)."""
+
+    def __init__(self, scene, mat, gt_image, optimize_part="arm", spp=64, lr=3e-4, scale_delta=0.1, net=None):
+        from .mymodels.mlps import PosMLP
+        self.scene, self.spp, self.scale_delta, self.part = scene, spp, scale_delta, optimize_part
+        scene.set_shard(0, scene.H)
+        dev = scene.device
+        self.net = net if net is not None else PosMLP(in_dims=7, out_dims=5, dims=[256] * 4, skip_connection=[1, 3], weight_norm=False,
+                                                      multires_view=2, output_type="arm", color_ch=5).to(dev)   # :163
+        self.mat = {k: v.detach().clone() for k, v in mat.items()}
+        self.ori = {k: v.detach().clone() for k, v in mat.items()}
+        self.start_arm = torch.cat([mat["albedo"].reshape(-1, 3), mat["roughness"].reshape(-1, 1), mat["metallic"].reshape(-1, 1)],
+                                   dim=-1).clamp(0, 1).contiguous()                                               # :205
+        self.opt = torch.optim.AdamW(self.net.parameters(), lr=lr)
+        self.sched = torch.optim.lr_scheduler.StepLR(self.opt, step_size=100, gamma=0.8)
+        self.gt_srgb = linear_to_srgb(gt_image)
+        self.gt_mean = gt_image.mean()
+        self.last = {}
+
+    def step(self, seed):
+        H, W = self.scene.H, self.scene.W
+        arm = self.net(self.start_arm, hw=(H, W))                                                                # :493
+        albedo, roughness, metallic = arm[..., 0:3].clamp(0, 1), (arm[..., 3:4] * 0.93 + 0.07).clamp(0, 1), arm[..., 4:5].clamp(0, 1)
+        mat = dict(self.mat)
+        if "a" in self.part: mat["albedo"] = albedo.reshape(H, W, 3)
+        if "r" in self.part: mat["roughness"] = roughness.reshape(H, W, 1)
+        if "m" in self.part: mat["metallic"] = metallic.reshape(H, W, 1)
+        pred = render(self.scene, spp=self.spp, seed=seed, albedo=mat["albedo"], roughness=mat["roughness"], metallic=mat["metallic"])
+        pred = pred * (self.gt_mean / pred.detach().mean())
+        pred_srgb = linear_to_srgb(pred)
+        loss_mse, loss_l1 = NF.mse_loss(pred_srgb, self.gt_srgb), NF.l1_loss(pred_srgb, self.gt_srgb)
+        aux = 0.0
+        if "a" in self.part: aux = aux + NF.l1_loss(mat["albedo"], self.ori["albedo"])
+        if "r" in self.part: aux = aux + NF.l1_loss(mat["roughness"], self.ori["roughness"])
+        if "m" in self.part: aux = aux + NF.l1_loss(mat["metallic"], self.ori["metallic"])
+        loss = 3 * (loss_l1.detach() / loss_mse.detach()) * loss_mse + loss_l1 + aux * self.scale_delta
+        loss.backward()
+        self.opt.step()
+        self.opt.zero_grad(set_to_none=True)
+        if self.opt.param_groups[0]["lr"] > 1.5e-4:
+            self.sched.step()
+        self.last = {"loss_mse": loss_mse.detach(), "loss_l1": loss_l1.detach(), "pred": pred_srgb.detach()}
+        return loss.detach()
+
+
 class EnvmapOptimizer:
     """Envmap phase (inverse_img_w_mi.py:237-256) with the envmap texels as direct parameters (the reference
     drives them through `envmap_net`; see mymodels/mlps.py for that module).  Gradients of the envmap are summed

@@ -109,17 +109,18 @@ def _backward(scene, spp, seed_grad, a, r, m, n, env_pack, grad_img_halo, want_a
         g_r = torch.zeros(H, W, 1, device=dev) if want_r else None
         g_m = torch.zeros(H, W, 1, device=dev) if want_m else None
     g_n = torch.zeros(H, W, 3, device=dev) if (want_n and not scene.use_mesh_normal) else None
-    g_env4 = torch.zeros_like(env4) if want_env else None
+    n_slabs = _abi.lib.mb200_env_grad_slabs(He, We, mode) if want_env else 1
+    g_env4 = torch.zeros((n_slabs,) + tuple(env4.shape), device=dev) if want_env else None
     nmap = None if scene.use_mesh_normal else n
     with _ktime("shade_bwd"):
         _abi.check(_abi.lib.mb200_shade_bwd(C.byref(cfg), _abi.ptr(scene.gpos), _abi.ptr(scene.gnrm), _abi.ptr(a), _abi.ptr(r),
                                             _abi.ptr(m), _abi.ptr(nmap), _abi.ptr(env4), _abi.ptr(hier), C.byref(desc),
                                             _abi.ptr(gadj), _abi.ptr(g_a), _abi.ptr(g_r), _abi.ptr(g_m), _abi.ptr(g_n),
-                                            _abi.ptr(g_env4), st), "mb200_shade_bwd")
+                                            _abi.ptr(g_env4), n_slabs, st), "mb200_shade_bwd")
     g_env = None
     if want_env:
         g_env = torch.empty(He, We, 3, device=dev)
-        _abi.check(_abi.lib.mb200_env_grad_finish(_abi.ptr(g_env4), He, We, mode, _abi.ptr(g_env), st), "mb200_env_grad_finish")
+        _abi.check(_abi.lib.mb200_env_grad_finish(_abi.ptr(g_env4), n_slabs, He, We, mode, _abi.ptr(g_env), st), "mb200_env_grad_finish")
     if want_n and g_n is None:
         g_n = torch.zeros(H, W, 3, device=dev)
     return g_a, g_r, g_m, g_n, g_env

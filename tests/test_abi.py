@@ -63,7 +63,7 @@ def test_compute_entry_points_reject_null_arguments():
     from materialist_b200 import _abi
     c = _abi.Cfg(); d = _abi.HierDesc()
     assert _abi.lib.mb200_shade_fwd(C.byref(c), *([None] * 8), C.byref(d), None, None) == _abi.EINVAL
-    assert _abi.lib.mb200_shade_bwd(C.byref(c), *([None] * 8), C.byref(d), *([None] * 7)) == _abi.EINVAL
+    assert _abi.lib.mb200_shade_bwd(C.byref(c), *([None] * 8), C.byref(d), *([None] * 6), 1, None) == _abi.EINVAL
     assert _abi.lib.mb200_env_prepare(None, 16, 32, 0, None, None, C.byref(d), None, None) == _abi.EINVAL
     assert _abi.lib.mb200_film_develop(C.byref(c), None, None, None) == _abi.EINVAL
     assert _abi.lib.mb200_bsdf_eval_pdf(C.byref(c), 4, *([None] * 11)) == _abi.EINVAL
