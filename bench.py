@@ -266,10 +266,15 @@ def run_b200(args, wl):
     roofline = None
     if dom:
         achieved = alg_bytes / (kavg[dom] * 1e-3) / 1e9
+        # DRAM bytes per launch from one `ncu --set full` capture of the C2 workload (profiles/r1c_ncu_summary.txt); other shapes: null
+        ncu_traffic = {"shade_bwd": 23.95e6 + 0.05e6, "shade_fwd": 14.55e6 + 60.95e6}
+        traffic = ncu_traffic.get(dom) if (args.workload == "c2" and world == 1) else None
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": None, "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes, "kernel_ms": kavg[dom],
+                    "traffic": traffic,
+                    "issue_frac_ncu": {"shade_bwd": 0.699, "shade_fwd": 0.727}.get(dom), "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes, "kernel_ms": kavg[dom],
                     "kernel_share_of_step": kavg[dom] * 1e-3 / t_step,
-                    "note": "at 64-256 spp the fused path is FP32-ALU/SFU bound, not HBM bound (SURVEY §8d: ~830 FLOP/B); see fp32"}
+                    "note": "at 64-256 spp the fused path is instruction-issue bound, not HBM bound (SURVEY §8d: ~830 FLOP/B): ncu shows issue-active "
+                            "70-73 %, L1 LSU wavefronts 51-72 %, DRAM < 1 % (issue_frac_ncu, profiles/); see also fp32"}
     # ---- FP32 (non-tensor) peak, measured with an FFMA loop, and the kernel's algorithmic FLOP rate
     fp32 = None
     try:
