@@ -233,6 +233,60 @@ class PosMLPBRDFOptimizer:
         return loss.detach()
 
 
+class _SumGradOverRanks(torch.autograd.Function):
+    """Identity whose backward all-reduces (sums) the gradient over the ranks of a ShardContext: every rank renders its own
+    rows, the envmap they all share receives the sum of their texel gradients (exchange step 3)."""
+
+    @staticmethod
+    def forward(ctx, x, shard):
+        ctx.shard = shard
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        ctx.shard.all_reduce_sum(g)
+        return g, None
+
+
+class EnvmapNetOptimizer:
+    """Envmap phase exactly as the reference runs it (inverse_img_w_mi.py:117-124, :222-256): `envmap_net` = PosMLP(in_dims=5,
+    out_dims=3, 'envmap') applied to a constant all-ones (env_h*env_w, 3) input gives the (16, 32, 3) envmap that
+    `render_envmap` shades with; loss = mse + l1 in sRGB; Adam(lr=1e-3) + StepLR(100, 0.8) in the first outer loop.
+    With the image sharded, every rank holds a replica of the network; the texel gradients are summed over ranks before they
+    enter the (replicated, therefore identical) network backward."""
+
+    def __init__(self, scene, gt_image, env_h=16, env_w=32, spp=64, lr=1e-3, shard=None, net=None):
+        from .mymodels.mlps import PosMLP
+        self.scene, self.spp, self.env_h, self.env_w = scene, spp, env_h, env_w
+        self.shard = shard or ShardContext(scene.H, scene.W)
+        scene.set_shard(self.shard.row0, self.shard.rows)
+        dev = scene.device
+        self.net = net if net is not None else PosMLP(in_dims=5, out_dims=3, dims=[256] * 4, skip_connection=[1, 3], weight_norm=False,
+                                                      multires_view=2, output_type="envmap", color_ch=3).to(dev)      # :117-124
+        self.start_envmap = torch.ones(env_h * env_w, 3, device=dev)
+        self.opt = torch.optim.Adam(self.net.parameters(), lr=lr)
+        self.sched = torch.optim.lr_scheduler.StepLR(self.opt, step_size=100, gamma=0.8)
+        rows = slice(self.shard.row0, self.shard.row0 + self.shard.rows)
+        self.gt_srgb = linear_to_srgb(gt_image[rows].contiguous())
+        self.n_img = float(scene.H * scene.W * 3)
+        self.last = {}
+
+    def step(self, seed):
+        sh = self.shard
+        envmap_pred = self.net(self.start_envmap, hw=(self.env_h, self.env_w)).reshape(self.env_h, self.env_w, 3)           # :238-239
+        env = _SumGradOverRanks.apply(envmap_pred, sh) if sh.world_size > 1 else envmap_pred
+        pred = render(self.scene, spp=self.spp, seed=seed, envmap=env, halo_exchange=sh.halo_exchange if sh.world_size > 1 else None)
+        diff = linear_to_srgb(pred) - self.gt_srgb
+        loss = (diff * diff).sum() / self.n_img + diff.abs().sum() / self.n_img          # this rank's share of mse + l1 (:243-245)
+        loss.backward()
+        self.opt.step()
+        self.opt.zero_grad(set_to_none=True)
+        self.sched.step()
+        self.last = {"loss": loss.detach(), "envmap": envmap_pred.detach()}
+        return loss.detach()
+
+
 class EnvmapOptimizer:
     """Envmap phase (inverse_img_w_mi.py:237-256) with the envmap texels as direct parameters (the reference
     drives them through `envmap_net`; see mymodels/mlps.py for that module).  Gradients of the envmap are summed

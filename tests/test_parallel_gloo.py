@@ -40,7 +40,11 @@ def _worker(rank, world, port, H, W, out):
         ok_halo = torch.equal(halo, full[lo:hi])
         # 3. gradient all-reduce
         g = sh.all_reduce_sum(torch.full((4,), float(rank + 1)))
-        out[rank] = (float(s.item()), bool(ok_halo), g.tolist())
+        # 4. shared envmap, per-rank image rows: the envmap gradient every rank sees is the sum over ranks
+        from materialist_b200.inverse import _SumGradOverRanks
+        env = torch.ones(3, requires_grad=True)
+        (_SumGradOverRanks.apply(env, sh) * float(rank + 1)).sum().backward()
+        out[rank] = (float(s.item()), bool(ok_halo), g.tolist(), env.grad.tolist())
     finally:
         dist.destroy_process_group()
 
@@ -53,5 +57,5 @@ def test_two_rank_collectives_gloo():
     mp.spawn(_worker, args=(world, port, H, W, out), nprocs=world, join=True)
     total = float(np.arange(H * W * 3, dtype=np.float64).sum())
     for r in range(world):
-        s, ok_halo, g = out[r]
-        assert s == total and ok_halo and g == [3.0] * 4
+        s, ok_halo, g, ge = out[r]
+        assert s == total and ok_halo and g == [3.0] * 4 and ge == [3.0] * 3
