@@ -33,6 +33,8 @@ WORKLOADS = {
                desc="synthetic 4K (3840x2160) G-buffer inverse optimisation, 2048x1024 envmap, 256 spp, rows sharded"),
     "c3": dict(H=768, W=1024, spp=64, He=16, We=32, scaling="weak", pos_mlp=True,
                desc="inverse_img_w_mi.py --model_name=pos_mlp --opt_src=a --opt_order='rm a', synthetic 1024x768 G-buffer, 64 spp, 16x32 envmap, brdf_net = PosMLP"),
+    "c4": dict(H=1080, W=1920, spp=32, He=512, We=1024, scaling="weak", rolling=True,
+               desc="render_final.py --mode=rolling: rotated-envmap relights of a synthetic 1080p material set, 1024x512 envmap, 32 spp, forward only, frames sharded over the GPUs (replicas, no collective)"),
     "tiny": dict(H=64, W=64, spp=32, He=16, We=32, scaling="weak", desc="tiny self-test workload"),
 }
 METRIC = "fwd+adjoint shaded samples/s (inverse-optimisation iteration)"
@@ -105,7 +107,7 @@ def build_case(wl, world):
     import torch
     from materialist_b200 import synthetic
     from materialist_b200.scene import Camera
-    H = wl["H"] * (world if wl["scaling"] == "weak" else 1)
+    H = wl["H"] * (world if (wl["scaling"] == "weak" and not wl.get("rolling")) else 1)
     W = wl["W"]
     cam = Camera(width=W, height=H)
     pos, nrm, valid = synthetic.gbuffer(H, W, cam)
@@ -176,6 +178,76 @@ def run_reference(args, wl):
     print(json.dumps(out), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ rolling relight (C4)
+def run_rolling(args, wl, case, scene, dev, world, rank, local):
+    """One step = one frame per rank: roll the envmap by 1 degree (render_final.py:290-298), rebuild the sampling hierarchy ON
+    THE GPU (the reference migrates to the host for that), forward render + film develop.  Frames are independent: no collective."""
+    import torch
+    import torch.distributed as dist
+    import materialist_b200 as mb
+    from materialist_b200 import _abi
+    from materialist_b200.inverse_img_w_mi import rotate_envmap
+    H, W, spp = case["H"], case["W"], wl["spp"]
+    scene.set_shard(0, H)
+    scene.a, scene.r, scene.m = (case[k].to(dev) for k in ("a", "r", "m"))
+    env = case["env"].to(dev)
+
+    def frame(k):
+        scene.set_envmap(rotate_envmap(env, float(k * world + rank)), _abi.ENV_FILE)
+        return mb.render(scene, spp=spp, seed=0)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize()
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    for k in range(args.warmup):
+        frame(k)
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        img = frame(100 + k)
+    e1.record(); sync()
+    tt = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_step = float(tt.item()) / args.steps / 1e3
+    # e2e: envmap rolled on the HOST and uploaded per frame, image downloaded per frame
+    henv = case["env"].pin_memory(); himg = torch.empty(H, W, 3).pin_memory()
+    def frame_e2e(k):
+        scene.set_envmap(torch.roll(henv, shifts=int((k * world + rank) / 360.0 * henv.shape[1]), dims=1).pin_memory().to(dev, non_blocking=True), _abi.ENV_FILE)
+        himg.copy_(mb.render(scene, spp=spp, seed=0), non_blocking=True)
+    for k in range(3):
+        frame_e2e(k)
+    sync(); e0.record()
+    for k in range(args.steps):
+        frame_e2e(200 + k)
+    e1.record(); sync()
+    te = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    t_e = float(te.item()) / args.steps / 1e3
+    clk = clocks.stop() if rank == 0 else None
+    if rank == 0:
+        samples = H * W * spp * world
+        print(json.dumps({"metric": "forward shaded samples/s (rolling-envmap relight, hierarchy rebuilt per frame)", "value": samples / t_step / 1e9,
+                          "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": wl["desc"], "image": [H, W], "spp": spp, "envmap": [wl["He"], wl["We"]], "filter": "gaussian",
+                                     "parallelism": f"one frame per GPU per step, {world} GPU(s)"},
+                          "frames_per_s": world / t_step,
+                          "e2e": {"value": samples / t_e / 1e9, "unit": UNIT, "h2d_bytes_per_step": henv.numel() * 4, "d2h_bytes_per_step": himg.numel() * 4,
+                                  "ms_per_step": t_e * 1e3, "bytes_are": "per rank"},
+                          "gpu_launches": 8 * args.steps, "gpu_launches_note": "per frame: 6 env_* (ingest + Hierarchical2D build), shade_fwd, film_develop",
+                          "clocks": clk, "image_mean": float(img.mean().item())}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------------ b200 arm
 def run_b200(args, wl):
     import numpy as np
@@ -204,6 +276,8 @@ def run_b200(args, wl):
     scene.set_shard(0, H)
     gt = mb.render(scene, spp=min(spp, 64), seed=999, albedo=to(case["a2"]), roughness=to(case["r2"]), metallic=to(case["m2"]))
     mat = {"albedo": to(case["a"]), "roughness": to(case["r"]), "metallic": to(case["m"])}
+    if wl.get("rolling"):
+        return run_rolling(args, wl, case, scene, dev, world, rank, local)
     if wl.get("pos_mlp"):
         if world > 1:
             raise SystemExit("the pos_mlp workload is single-GPU (brdf_net sees every pixel)")

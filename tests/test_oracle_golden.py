@@ -35,6 +35,22 @@ def test_tea32_and_float_mapping(oracle32):
         assert default_seed_grad(s) == oracle32.seed_grad(s)
 
 
+def test_tea32_mitsuba_known_answers(oracle32):
+    """Known answers of mitsuba 3's own unit test for the TEA generator (src/core/tests/test_random.py, test_tea_float32 /
+    test_tea_float64: `sample_tea_float32(1, 1, 4) == 0.5424730777740479`, `(1, 2, 4) == 0.5079904794692993`,
+    `(1, 3, 4) == 0.4171961545944214`, `sample_tea_float64(1, 1, 4) == 0.5424730799533735`), restated from memory of the
+    upstream repository and reproduced here exactly by the oracle's tea32 — sample_tea_float32 maps the SECOND word,
+    sample_tea_float64 maps (second << 32 | first): three 24-bit and one 52-bit agreement cannot be a coincidence, so the
+    TEA core that seeds every sampler lane (and derives seed_grad) is pinned to upstream, not only to itself."""
+    def f32(u):
+        return np.uint32((u >> 9) | 0x3F800000).view(np.float32) - np.float32(1.0)
+    got = [float(f32(oracle32.tea32(1, k)[1])) for k in (1, 2, 3)]
+    assert got == [0.5424730777740479, 0.5079904794692993, 0.4171961545944214], got
+    v0, v1 = oracle32.tea32(1, 1)
+    f64 = np.uint64((((v1 << 32) | v0) >> 12) | 0x3FF0000000000000).view(np.float64) - 1.0
+    assert float(f64) == 0.5424730799533735, float(f64)
+
+
 # ---------------------------------------------------------------- BSDF sub-terms vs the reference's torch functions
 def test_bsdf_terms_match_reference(oracle32):
     g = load("bsdf_terms.npz")
