@@ -64,6 +64,68 @@ def reconstImageFromSH(coef, nrows, ncols, K=None, isClip=True):
     return img.cpu().numpy()
 
 
+# ------------------------------------------------------------------ S4: the "AfterRotate" variants (:242-297, :349-391)
+def uvToEnvmap(envmap, u, v):
+    """:75-85, vectorised over arrays of (u, v): bilinear fetch with c = u (W-1), r = (1-v)(H-1), int() truncation and the
+    clamped +1 neighbour."""
+    envmap = np.asarray(envmap)
+    height, width = envmap.shape[0], envmap.shape[1]
+    u = np.asarray(u, dtype=np.float64); v = np.asarray(v, dtype=np.float64)
+    c, r = u * (width - 1), (1 - v) * (height - 1)
+    cs, rs = c.astype(np.int64), r.astype(np.int64)                 # int(): truncation towards zero
+    ce, re = np.minimum(width - 1, cs + 1), np.minimum(height - 1, rs + 1)
+    wc, wr = (c - cs)[..., None], (r - rs)[..., None]
+    color1 = (1 - wc) * envmap[rs, cs, :] + wc * envmap[rs, ce, :]
+    color2 = (1 - wc) * envmap[re, cs, :] + wc * envmap[re, ce, :]
+    return (1 - wr) * color1 + wr * color2
+
+
+def _camera_frame(cameraLoc, cameraUp, isInv):
+    cameraLoc = np.asarray(cameraLoc, dtype=np.float32); cameraUp = np.asarray(cameraUp, dtype=np.float32)
+    cameraLoc = cameraLoc / np.sqrt(np.sum(cameraLoc * cameraLoc), dtype=np.float32)
+    cameraUp = cameraUp / np.sqrt(np.sum(cameraUp * cameraUp), dtype=np.float32)
+    rz, ry = cameraLoc, cameraUp
+    rx = np.cross(ry, rz); rx = rx / np.sqrt(np.sum(rx * rx))
+    ry = np.cross(rz, rx); ry = ry / np.sqrt(np.sum(ry * ry))
+    if isInv:
+        rot = np.stack([rx, ry, rz], axis=1).transpose([1, 0])
+        rx, ry, rz = rot[:, 0], rot[:, 1], rot[:, 2]
+    return rx, ry, rz
+
+
+def _rotate_latlong(envmap, cameraLoc, cameraUp, isInv):
+    """The per-texel loop shared by :272-295 and :366-388, vectorised: direction of texel (r, c) in the camera frame ->
+    (theta, phi) in the world frame -> bilinear fetch.  float64 like the reference's Python scalars, float32 result."""
+    envmap = np.asarray(envmap)
+    rx, ry, rz = _camera_frame(cameraLoc, cameraUp, isInv)
+    height, width = envmap.shape[0], envmap.shape[1]
+    r, c = np.meshgrid(np.arange(height), np.arange(width), indexing="ij")
+    theta = r / float(height - 1) * np.pi
+    phi = c / float(width) * np.pi * 2 - np.pi
+    x, y, z = np.sin(theta) * np.cos(phi), np.sin(theta) * np.sin(phi), np.cos(theta)
+    coord = x[..., None] * rx + y[..., None] * ry + z[..., None] * rz
+    nx, ny, nz = coord[..., 0], coord[..., 1], coord[..., 2]
+    with np.errstate(invalid="ignore"):
+        thetaNew = np.arccos(nz)
+        den = np.sqrt(1 - nz * nz) + 1e-12
+    nx = np.clip(nx / den, -1, 1); ny = np.clip(ny / den, -1, 1)
+    phiNew = np.arccos(nx)
+    phiNew = np.where(ny < 0, -phiNew, phiNew)
+    u, v = angleToUV(thetaNew, phiNew)
+    return uvToEnvmap(envmap, u, v).astype(np.float32)
+
+
+def reconstImageFromSHAfterRotate(coef, cameraLoc, cameraUp, nrows=512, ncols=1024, K=None, isClip=True, isInv=False):
+    """:242-297 — reconstruct the lat-long map from the 25 coefficients (CUDA), then resample it into the camera frame."""
+    envmap = reconstImageFromSH(coef, nrows, ncols, K, isClip)
+    return _rotate_latlong(envmap, cameraLoc, cameraUp, isInv)
+
+
+def computeSHFromImageAfterRotate(envmap, cameraLoc, cameraUp, isInv=False, jitter=None):
+    """:349-391 — resample the map into the camera frame, then project (CUDA; jitter as in computeSHFromImage)."""
+    return computeSHFromImage(_rotate_latlong(envmap, cameraLoc, cameraUp, isInv), jitter=jitter)
+
+
 # ------------------------------------------------------------------ intended behaviour of the broken torch variants
 def _assoc_legendre(l, m, x):
     """P_l^m(x) with the Condon-Shortley phase, elementwise (the recurrence legendre_polynomial :458-466 intends)."""

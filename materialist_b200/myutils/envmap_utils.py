@@ -109,3 +109,68 @@ def sample_brdf1(wo, normals, mat, use_mesh_normals, device):
     sample1 = torch.rand(len(normals), device=device)
     sample2 = torch.rand(len(normals), 2, device=device)
     return sample_brdf(sample1, sample2, wo, normals, mat, use_mesh_normals)
+
+
+# ------------------------------------------------------------------ small CDF helpers of the reference, same semantics
+def cdf_search_1d(cdf, x):
+    """:131-132"""
+    return torch.searchsorted(cdf, x)
+
+
+def cdf_search_2d(cdf, x, row_offset):
+    """:135-136"""
+    return torch.searchsorted(cdf[row_offset, :], x)
+
+
+def get_pdf_from_cdf_1d(cdf, idx):
+    """:109-113 — cdf[idx] - cdf[idx-1] (cdf[idx] at idx 0)."""
+    mask = (idx > 0).float()
+    return mask * (cdf[idx] - cdf[(idx - 1).clamp_min(0)]) + (1 - mask) * cdf[idx]
+
+
+def get_pdf_from_cdf_2d(cdf, idx, row_offset=0):
+    """:115-124 — per-row variant; like the reference, indices equal to the row length are clamped to the last column
+    (the reference hard-codes 32 / 31, :120)."""
+    mask = (idx > 0).float()
+    idx = idx.clamp_max(cdf.shape[1] - 1)
+    idx1 = (idx - 1).clamp_min(0)
+    return mask * (cdf[row_offset, idx] - cdf[row_offset, idx1]) + (1 - mask) * cdf[row_offset, idx]
+
+
+def interp_1d(buf, x, index):
+    """:92-97 — position of x inside CDF bin `index`, in [0, 1]."""
+    mask = (index > 0).float()
+    lo = buf[(index - 1).clamp_min(0)]
+    interp_if = (x - lo) / (buf[index] - lo)
+    interp_else = x / buf[index]
+    return torch.where(mask > 0, interp_if, interp_else)
+
+
+def interp_2d(buf, x, index, row=0, ref_exact_nan=False):
+    """:99-107.  The reference evaluates BOTH branches and blends them with a 0/1 mask, so index 0 yields 0 * (x - c) / (c - c)
+    = NaN; `ref_exact_nan=True` reproduces that, the default selects the valid branch."""
+    mask = (index > 0).float()
+    index = index.clamp_max(buf.shape[1] - 1)
+    index1 = (index - 1).clamp_min(0)
+    interp_if = (x - buf[row, index1]) / (buf[row, index] - buf[row, index1])
+    interp_else = x / buf[row, index]
+    if ref_exact_nan:
+        return mask * interp_if + (1 - mask) * interp_else
+    return torch.where(mask > 0, interp_if, interp_else)
+
+
+def build_envmap_np(envmap):
+    """:68-90 — numpy-input variant of build_envmap.  NOTE it differs from build_envmap exactly as in the reference:
+    Rec.601 luminance via `luminance`, NO +1e-6 in the normalisation, marginal from the sum of the CUMULATIVE rows."""
+    envmap = np.asarray(envmap)
+    h, w, _ = envmap.shape
+    h01 = (np.arange(h) + 0.5) / h
+    lum = 0.299 * envmap[..., 0] + 0.587 * envmap[..., 1] + 0.114 * envmap[..., 2]     # np.apply_along_axis(luminance, 2, envmap)
+    lum_sin = lum * np.sin(np.pi * h01).reshape(h, 1)
+    c_cdf = np.cumsum(lum_sin, axis=1)
+    m_cdf = np.cumsum(np.sum(c_cdf, axis=1))
+    c_cdf = c_cdf / c_cdf[:, -1].reshape(h, 1)
+    m_cdf = m_cdf / m_cdf[-1]
+    if not torch.cuda.is_available():
+        raise RuntimeError("build_envmap_np places its tables on the GPU like the reference (.cuda()); no CUDA device")
+    return {"envmap": torch.from_numpy(envmap).cuda(), "c_cdf": torch.from_numpy(c_cdf).cuda(), "m_cdf": torch.from_numpy(m_cdf).cuda()}

@@ -142,6 +142,37 @@ def compute_sh(sh):
     np.savez_compressed(os.path.join(HERE, "compute_sh.npz"), im=im, jitter=jit, coef=coef, K=K, rec=rec, rec_clip=rec_clip)
 
 
+def helpers_and_rotate(sh, eu):
+    """S4 (computeSH 'AfterRotate' variants) and the small CDF helpers of envmap_utils, from the reference's own code."""
+    rs = np.random.RandomState(400)
+    out = {}
+    env = rs.rand(12, 24, 3).astype(np.float32)
+    cams = [((0.3, -0.5, 0.8), (0.1, 1.0, 0.05), False), ((1.0, 0.2, -0.4), (0.0, 0.3, 1.0), True)]
+    for k, (loc, up, inv) in enumerate(cams):
+        np.random.seed(500 + k)
+        out[f"rot{k}_coef"] = sh.computeSHFromImageAfterRotate(env, loc, up, isInv=inv)
+        np.random.seed(500 + k)
+        out[f"rot{k}_jitter"] = np.random.random(12 * 24 * 2).reshape(12 * 24, 2)
+        out[f"rot{k}_rec"] = sh.reconstImageFromSHAfterRotate(out[f"rot{k}_coef"], loc, up, nrows=10, ncols=20, isClip=False, isInv=inv)
+        out[f"rot{k}_cam"] = np.array([loc, up], np.float64); out[f"rot{k}_inv"] = np.array(inv)
+    out["env"] = env
+    u, v = rs.rand(50), rs.rand(50)
+    out["uv"] = np.stack([u, v]); out["uv_color"] = np.stack([sh.uvToEnvmap(env, a, b) for a, b in zip(u, v)])
+    # CDF helpers on a (16, 32) map: torch CPU
+    e = torch.rand(16, 32, 3, generator=g(401))
+    d = eu.build_envmap(e)
+    x = torch.rand(200, generator=g(402))
+    vi = eu.cdf_search_1d(d["m_cdf"], x)
+    out["cdf_env"] = e.numpy(); out["cdf_x"] = x.numpy(); out["cdf_vi"] = vi.numpy()
+    out["pdf1d"] = eu.get_pdf_from_cdf_1d(d["m_cdf"], vi.clamp_max(15)).numpy()
+    out["interp1d"] = eu.interp_1d(d["m_cdf"], x, vi.clamp_max(15)).numpy()
+    ui = eu.cdf_search_2d(d["c_cdf"], x, 5)
+    out["cdf_ui"] = ui.numpy()
+    out["pdf2d"] = eu.get_pdf_from_cdf_2d(d["c_cdf"], ui.clone(), 5).numpy()
+    out["interp2d"] = eu.interp_2d(d["c_cdf"], x, ui.clone(), 5).numpy()          # NaN where ui == 0 (reference behaviour)
+    np.savez_compressed(os.path.join(HERE, "helpers_rotate.npz"), **out)
+
+
 def main():
     install_stubs()
     import myutils.mi_plugin as mp
@@ -152,6 +183,7 @@ def main():
     posmlp(mlps); print("posmlp.npz")
     envmap_utils(eu); print("envmap_utils.npz")
     compute_sh(sh); print("compute_sh.npz")
+    helpers_and_rotate(sh, eu); print("helpers_rotate.npz")
 
 
 if __name__ == "__main__":

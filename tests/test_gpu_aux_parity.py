@@ -233,3 +233,17 @@ def test_relight_shipped_scene_statistical():
     assert 0.3 < ratio < 3.0, ratio
     cc = np.corrcoef((img * ratio).reshape(-1), ref.reshape(-1))[0, 1]
     assert cc > 0.8, cc
+
+
+def test_compute_sh_after_rotate_matches_reference_golden():
+    """S4: computeSHFromImageAfterRotate / reconstImageFromSHAfterRotate (computeSH.py:242-297, :349-391) against the
+    reference's own per-texel loops (golden: tests/golden/make_golden.py, two camera frames incl. isInv)."""
+    from materialist_b200.myutils import computeSH as sh
+    g = load("helpers_rotate.npz")
+    for k in range(2):
+        loc, up = g[f"rot{k}_cam"]
+        inv = bool(g[f"rot{k}_inv"])
+        coef = sh.computeSHFromImageAfterRotate(g["env"], loc, up, isInv=inv, jitter=g[f"rot{k}_jitter"])
+        assert rel_l2(coef, g[f"rot{k}_coef"]) < 1e-6, k
+        rec = sh.reconstImageFromSHAfterRotate(g[f"rot{k}_coef"], loc, up, nrows=10, ncols=20, isClip=False, isInv=inv)
+        assert rel_l2(rec, g[f"rot{k}_rec"]) < 1e-6, k
