@@ -66,3 +66,32 @@ def envmap(He, We, seed=4, sun=2000.0):
         y0, x0 = He // 4, (3 * We) // 8
         e[y0:y0 + 5, x0:x0 + 5] *= sun
     return e.contiguous()
+
+
+def grid_mesh(pos, valid=None):
+    """Triangle mesh over a (H,W,3) position grid with the connectivity of the reference's depth-derived PLY
+    (myutils/mesh_recon.py:184-258: vertex k = row*W + col; faces [k, k+W, k+1] and [k+1, k+W, k+W+1], which face the
+    camera of default_cam.json).  Quads touching an invalid vertex are dropped, like the reference's zero-depth test.
+    Returns (verts (H*W,3) float32, tris (nt,3) int32)."""
+    pos = np.asarray(pos, dtype=np.float32)
+    H, W, _ = pos.shape
+    k = (np.arange(H - 1)[:, None] * W + np.arange(W - 1)[None, :]).reshape(-1)
+    t0 = np.stack([k, k + W, k + 1], -1)
+    t1 = np.stack([k + 1, k + W, k + W + 1], -1)
+    tris = np.stack([t0, t1], 1).reshape(-1, 3)
+    if valid is not None:
+        ok = np.asarray(valid).reshape(-1).astype(bool)
+        tris = tris[ok[tris].all(-1)]
+    return np.ascontiguousarray(pos.reshape(-1, 3)), np.ascontiguousarray(tris.astype(np.int32))
+
+
+def bumpy_positions(H, W, camera=None, amp=3.0, freq=3.0):
+    """Positions on the pixel-centre rays of a height field with enough relief for self-occlusion and interreflection:
+    depth = 20 + 4 cos(pi u) cos(pi v) - amp * max(0, sin(freq 2 pi u) sin(freq 2 pi v))."""
+    cam = camera or Camera(width=W, height=H)
+    t, aspect = cam.tan_half_fov_x, W / H
+    sx, sy = np.meshgrid(np.arange(W, dtype=np.float64) + 0.5, np.arange(H, dtype=np.float64) + 0.5)
+    u, v = sx / W, sy / H
+    depth = 20.0 + 4.0 * np.cos(np.pi * u) * np.cos(np.pi * v) - amp * np.maximum(0.0, np.sin(freq * 2 * np.pi * u) * np.sin(freq * 2 * np.pi * v))
+    l = np.stack([(1 - 2 * sx / W) * t, (1 - 2 * sy / H) * t / aspect, np.ones_like(sx)], -1) * depth[..., None]
+    return (l @ cam.to_world[:3, :3].T + cam.to_world[:3, 3]).astype(np.float32)

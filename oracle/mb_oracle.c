@@ -887,3 +887,6 @@ int mbo_is_double(void) {
     return 0;
 #endif
 }
+
+/* ======================================================================== mesh mode */
+#include "mb_oracle_mesh.c"

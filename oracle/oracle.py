@@ -37,7 +37,7 @@ class HierDesc(C.Structure):
 def build(force=False):
     """Compile the oracle with gcc (Makefile in this directory)."""
     so = os.path.join(_HERE, "libmb_oracle.so")
-    src_m = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("mb_oracle.c", "mb_oracle_aux.c", "Makefile"))
+    src_m = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("mb_oracle.c", "mb_oracle_mesh.c", "mb_oracle_aux.c", "Makefile"))
     if force or not os.path.exists(so) or os.path.getmtime(so) < src_m:
         subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
     return so
@@ -190,3 +190,57 @@ class Oracle:
         if rc != 0:
             raise RuntimeError(f"mbo_render_bwd rc={rc}")
         return g
+
+    # ------------------------------------------------------------------ mesh mode (oracle/mb_oracle_mesh.c)
+    def mesh_create(self, verts, tris, face_normals=False):
+        """verts (nv,3) float, tris (nt,3) int -> opaque handle (median-split BVH inside)."""
+        verts = _f32(verts); tris = np.ascontiguousarray(tris, dtype=np.int32)
+        self.lib.mbo_mesh_create.restype = C.c_void_p
+        h = self.lib.mbo_mesh_create(_p(verts), C.c_int(verts.shape[0]), _p(tris, C.c_int32), C.c_int(tris.shape[0]), C.c_int(int(face_normals)))
+        return C.c_void_p(h)
+
+    def mesh_destroy(self, mesh):
+        self.lib.mbo_mesh_destroy(mesh)
+
+    def mesh_render_fwd(self, cfg, mesh, a, r, m, n_opt, env_int, hier, d, want_stats=False):
+        img = np.zeros((cfg.rows, cfg.W, 3), np.float32)
+        stats = np.zeros(5, np.int64)
+        rc = self.lib.mbo_mesh_render_fwd(C.byref(cfg), mesh, _p(a), _p(r), _p(m), _p(n_opt), _p(env_int), _p(hier), C.byref(d),
+                                          _p(img), _p(stats, C.c_int64))
+        if rc != 0:
+            raise RuntimeError(f"mbo_mesh_render_fwd rc={rc}")
+        return (img, stats) if want_stats else img
+
+    def mesh_render_bwd(self, cfg, mesh, a, r, m, n_opt, env_int, hier, d, grad_img, want=("a", "r", "m", "env")):
+        H, W = cfg.H, cfg.W
+        grad_img = _f32(grad_img)
+        assert grad_img.shape == (H, W, 3)
+        g = {}
+        if "a" in want: g["a"] = np.zeros((H, W, 3), np.float32)
+        if "r" in want: g["r"] = np.zeros((H, W, 1), np.float32)
+        if "m" in want: g["m"] = np.zeros((H, W, 1), np.float32)
+        if "n" in want: g["n"] = np.zeros((H, W, 3), np.float32)
+        if "env" in want: g["env_int"] = np.zeros_like(env_int)
+        rc = self.lib.mbo_mesh_render_bwd(C.byref(cfg), mesh, _p(a), _p(r), _p(m), _p(n_opt), _p(env_int), _p(hier), C.byref(d),
+                                          _p(grad_img), _p(g.get("a")), _p(g.get("r")), _p(g.get("m")), _p(g.get("n")), _p(g.get("env_int")))
+        if rc != 0:
+            raise RuntimeError(f"mbo_mesh_render_bwd rc={rc}")
+        return g
+
+    def mesh_primary(self, cfg, mesh, jx=0.5, jy=0.5):
+        H, W = cfg.H, cfg.W
+        pos = np.zeros((H, W, 3), np.float32); nrm = np.zeros((H, W, 3), np.float32); tri = np.zeros((H, W), np.int32)
+        self.lib.mbo_mesh_primary(C.byref(cfg), mesh, C.c_float(jx), C.c_float(jy), _p(pos), _p(nrm), _p(tri, C.c_int32))
+        return pos, nrm, tri
+
+    def mesh_intersect(self, mesh, o, d, maxt=None, brute=False, any_hit=False):
+        o, d = _f32(o), _f32(d); n = o.shape[0]
+        maxt = None if maxt is None else _f32(maxt)
+        tri = np.zeros(n, np.int32); tuv = np.zeros((n, 3), np.float32)
+        self.lib.mbo_mesh_intersect_n(mesh, _p(o), _p(d), _p(maxt), C.c_int(n), C.c_int(int(brute)), C.c_int(int(any_hit)),
+                                      _p(tri, C.c_int32), _p(tuv))
+        return tri, tuv
+
+    def mesh_vertex_normals(self, mesh, nv):
+        out = np.zeros((nv, 3), np.float32)
+        return out if self.lib.mbo_mesh_vertex_normals(mesh, _p(out)) else None

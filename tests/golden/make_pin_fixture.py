@@ -1,0 +1,35 @@
+"""Builds tests/golden/indoor_pin.npz from the reference's SHIPPED scene output_imgs/indoor (run in the container that has
+/root/reference; the fixture travels, the reference does not).
+
+Contents = the exact inputs of the reference's own saved render best_results/rendered_img.exr:
+  verts/tris  indoor.ply (vertex doubles rounded to float32 as Mitsuba's PLY loader does), 268 041 vertices / 522 220 faces
+  a, r, m     best_results/{albedo,roughness,metallic}.exr (float32, what SaveBest.update cloned together with the render)
+  env         best_results/envmap.hdr (16x32 RGBE; the float envmap the reference rendered with is NOT available, only this
+              8-bit-mantissa copy: measured effect on the image 1e-3 rel-L2)
+  ref         rows [row0, row0+rows) of rendered_img.exr: LINEAR radiance of `pred_image = render_envmap(scene, envmap, 64)`
+              (inverse_img_w_mi.py:238,247 — the envmap phase saves the un-rescaled, un-gamma'd image), Mitsuba cuda_ad_rgb
+  seed        993 — NOT stored by the reference (np.random.randint(0,1000), inverse_img_w_mi.py:62); recovered by
+              tools/ref_render_pin.py: the sampler is seeded per lane from (seed, lane), so only the right seed
+              reproduces the reference's noise pattern (rel-L2 0.020 for 993 vs 0.064-0.071 for the 999 others on a
+              6-row crop with the first version of the mesh oracle; see tests/golden/pin_search_*.txt).
+Known input mismatch: the albedo the scene held in that envmap phase is the LAST iterate of the preceding 'a' stage
+(render_w_brdf assigns params['shape.bsdf.a'] every iteration), the saved albedo.exr is the BEST iterate
+(inverse_img_w_mi.py:575-579) -> smooth, channel-dependent albedo differences (R, B >> G); the green channel is the clean one.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(ROOT, "tools")); sys.path.insert(0, ROOT)
+import ref_render_pin as rp  # noqa: E402
+
+if __name__ == "__main__":
+    S = rp.load_scene("indoor")
+    row0, rows = 240, 32
+    out = os.path.join(ROOT, "tests", "golden", "indoor_pin.npz")
+    np.savez_compressed(out, verts=S["verts"], tris=S["tris"], a=S["a"], r=S["r"], m=S["m"], env=S["env"],
+                        ref=S["ref_srgb"][row0:row0 + rows], row0=np.int32(row0), seed=np.int32(993),
+                        gt_mean=np.float32(S["gt"].mean()))
+    print(out, os.path.getsize(out) / 1e6, "MB")
