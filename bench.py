@@ -35,6 +35,10 @@ WORKLOADS = {
                desc="inverse_img_w_mi.py --model_name=pos_mlp --opt_src=a --opt_order='rm a', synthetic 1024x768 G-buffer, 64 spp, 16x32 envmap, brdf_net = PosMLP"),
     "c4": dict(H=1080, W=1920, spp=32, He=512, We=1024, scaling="weak", rolling=True,
                desc="render_final.py --mode=rolling: rotated-envmap relights of a synthetic 1080p material set, 1024x512 envmap, 32 spp, forward only, frames sharded over the GPUs (replicas, no collective)"),
+    "c2m": dict(H=512, W=512, spp=64, He=128, We=256, scaling="weak", mesh=True,
+                desc="inverse_img_w_mi.py --model_name=none --opt_src=arm --opt_order=arm with the scene TRACED as the reference does (521 k-triangle "
+                     "synthetic height-field mesh, per-sample hits, shadow rays, max_depth 4 bounces), 512x512, 64 spp, 256x128 envmap"),
+    "tinym": dict(H=64, W=64, spp=32, He=16, We=32, scaling="weak", mesh=True, desc="tiny self-test workload, mesh mode"),
     "tiny": dict(H=64, W=64, spp=32, He=16, We=32, scaling="weak", desc="tiny self-test workload"),
 }
 METRIC = "fwd+adjoint shaded samples/s (inverse-optimisation iteration)"
@@ -110,11 +114,14 @@ def build_case(wl, world):
     H = wl["H"] * (world if (wl["scaling"] == "weak" and not wl.get("rolling")) else 1)
     W = wl["W"]
     cam = Camera(width=W, height=H)
+    mesh = None
+    if wl.get("mesh"):
+        mesh = synthetic.grid_mesh(synthetic.bumpy_positions(H, W, cam))
     pos, nrm, valid = synthetic.gbuffer(H, W, cam)
     a, r, m = synthetic.materials(H, W, seed_base=1)
     a2, r2, m2 = synthetic.materials(H, W, seed_base=5)       # the material set behind gt_image
     env = synthetic.envmap(wl["He"], wl["We"], seed=4)
-    return dict(H=H, W=W, cam=cam, pos=pos, nrm=nrm, valid=valid, a=a, r=r, m=m, a2=a2, r2=r2, m2=m2, env=env)
+    return dict(mesh=mesh, H=H, W=W, cam=cam, pos=pos, nrm=nrm, valid=valid, a=a, r=r, m=m, a2=a2, r2=r2, m2=m2, env=env)
 
 
 def alg_bytes_per_pixel():
@@ -155,8 +162,13 @@ def run_reference(args, wl):
         return c
 
     G = np.ones((H, W, 3), np.float32)
+    om = O.mesh_create(*case["mesh"]) if case["mesh"] is not None else None
 
     def step(i):
+        if om is not None:
+            O.mesh_render_fwd(cfg(i), om, a, r, m, None, env_int, hier, d)
+            O.mesh_render_bwd(cfg(O.seed_grad(i)), om, a, r, m, None, env_int, hier, d, G, want=("a", "r", "m"))
+            return
         O.render_fwd(cfg(i), gpos, gnrm, a, r, m, None, env_int, hier, d)
         O.render_bwd(cfg(O.seed_grad(i)), gpos, gnrm, a, r, m, None, env_int, hier, d, G, want=("a", "r", "m"))
 
@@ -270,7 +282,10 @@ def run_b200(args, wl):
     case = build_case(wl, world)
     H, W, spp = case["H"], case["W"], wl["spp"]
     shard = ShardContext(H, W, rank, world)
-    scene = mb.Scene(case["pos"], case["nrm"], case["valid"], camera=case["cam"], envmap=case["env"], device=dev)
+    if case["mesh"] is not None:
+        scene = mb.Scene.from_mesh(case["mesh"][0], case["mesh"][1], case["cam"], device=dev, envmap=case["env"])
+    else:
+        scene = mb.Scene(case["pos"], case["nrm"], case["valid"], camera=case["cam"], envmap=case["env"], device=dev)
     to = lambda t: t.to(dev)
     # gt_image = render of the second material set, seed 999
     scene.set_shard(0, H)
@@ -335,8 +350,10 @@ def run_b200(args, wl):
     npix_rank = shard.rows * W
     env_bytes = wl["He"] * (wl["We"] + 1) * 16 + scene.prepared_env()[2].total_floats * 4
     # bytes one launch of the dominant kernel must move (SURVEY §8d itemisation): bwd 88 B/px, fwd 96 B/px, + envmap + hierarchy once
-    per_px = {"shade_bwd": 88.0, "shade_fwd": 96.0}.get(dom, 184.0)
+    per_px = {"shade_bwd": 88.0, "shade_fwd": 96.0, "mesh_bwd": 88.0 - 32.0, "mesh_fwd": 96.0 - 32.0}.get(dom, 184.0)
     alg_bytes = npix_rank * per_px + env_bytes
+    if scene.mesh is not None:       # mesh mode: no G-buffer (-32 B/px); sorted triangles (+ normals) and BVH boxes read once
+        alg_bytes += scene.mesh.desc.total_bytes
     roofline = None
     if dom:
         achieved = alg_bytes / (kavg[dom] * 1e-3) / 1e9
@@ -345,7 +362,7 @@ def run_b200(args, wl):
         traffic = ncu_traffic.get(dom) if (args.workload == "c2" and world == 1) else None
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                     "traffic": traffic,
-                    "issue_frac_ncu": {"shade_bwd": 0.699, "shade_fwd": 0.727}.get(dom), "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes, "kernel_ms": kavg[dom],
+                    "issue_frac_ncu": {"shade_bwd": 0.699, "shade_fwd": 0.727}.get(dom) if scene.mesh is None else None, "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes, "kernel_ms": kavg[dom],
                     "kernel_share_of_step": kavg[dom] * 1e-3 / t_step,
                     "note": "at 64-256 spp the fused path is instruction-issue bound, not HBM bound (SURVEY §8d: ~830 FLOP/B): ncu shows issue-active "
                             "70-73 %, L1 LSU wavefronts 51-72 %, DRAM < 1 % (issue_frac_ncu, profiles/); see also fp32"}
@@ -361,8 +378,10 @@ def run_b200(args, wl):
         _abi.check(_abi.lib.mb200_probe_ffma(_abi.ptr(buf), 16384, _abi.C.byref(fl), _abi.stream_ptr()), "probe")
         p1.record(); torch.cuda.synchronize()
         peak_tf = fl.value / (p0.elapsed_time(p1) * 1e-3) / 1e12
-        flops_sample = {"shade_bwd": 1600.0, "shade_fwd": 800.0}     # SURVEY §8d estimate (2.4 kFLOP fwd+adjoint)
-        if dom:
+        flops_sample = {"shade_bwd": 1600.0, "shade_fwd": 800.0, "mesh_bwd": None, "mesh_fwd": None}     # SURVEY §8d estimate (2.4 kFLOP fwd+adjoint)
+        if dom and flops_sample.get(dom, 2400.0) is None:
+            fp32 = {"peak_tflops": peak_tf, "note": "no algorithmic FLOP figure for traced paths (data-dependent traversal length)"}
+        elif dom:
             ach = npix_rank * spp * flops_sample.get(dom, 2400.0) / (kavg[dom] * 1e-3) / 1e12
             fp32 = {"achieved_tflops": ach, "peak_tflops": peak_tf, "frac": ach / peak_tf,
                     "alg_flops_per_sample": flops_sample.get(dom), "peak_source": "measured here: FFMA loop (mb200_probe_ffma)"}
@@ -423,7 +442,8 @@ def run_b200(args, wl):
                           "max_depth": 4, "parallelism": f"rows sharded over {world} GPU(s)",
                           "l2": f"no explicit flush: each step streams {(shard.rows * W * (400 + 100 + 32 + 20 + 16 + 12 + 12 + 40)) / 1e6:.0f} MB of inputs + per-step intermediates (film tap partials 400 B/px, weight partials 100 B/px, G-buffer, maps, gradients) per rank; >126 MB L2 for C2/C5. The 0.6 MB envmap + hierarchy is L2/L1-resident by design"},
                "iters_per_s": 1.0 / t_step, "e2e": e2e, "gpu_launches": (9 if args.optimizer == "fused" else 5) * args.steps,
-               "gpu_launches_note": "own kernels per step: shade_fwd, film_develop, film_weights, film_adjoint, shade_bwd"
+               "gpu_launches_note": "own kernels per step: " + ("mesh_fwd" if scene.mesh is not None else "shade_fwd") + ", film_develop, film_weights, film_adjoint, "
+                                    + ("mesh_bwd" if scene.mesh is not None else "shade_bwd")
                                     + (", image_sum, loss_srgb_sums, loss_srgb_grad, adam_clamped" if args.optimizer == "fused"
                                        else " (+ ~100 torch elementwise/reduce launches for loss and Adam)"),
                "optimizer": args.optimizer,

@@ -33,6 +33,18 @@
  *   mb200_debug_sample_indices
  *                          not in the reference: exposes the integer decisions of the path
  *                          (hierarchy offsets, texel index, lobe) so tests can assert them bit-exact.
+ *   mb200_mesh_build       the scene side of mi.load_dict({... 'shape': {'type': 'ply', 'filename': mesh_path}})
+ *                          inverse_img_w_mi.py:40-56 / render_final.py:32-53: Mitsuba's PLY loader (vertex normals
+ *                          recomputed, angle-weighted) + the OptiX acceleration structure, here a GPU-built
+ *                          Morton-ordered implicit 4-ary BVH.
+ *   mb200_mesh_shade_fwd / _bwd
+ *                          the same mi.render / render_backward calls as mb200_shade_fwd / _bwd, but tracing the
+ *                          triangle mesh the reference really renders: per-sample primary hits, shadow rays, up to
+ *                          max_depth-1 bounces with the material fetched at every vertex through
+ *                          mi_world_to_screen(si.p) (mi_plugin.py:1435,1456).  Same film kernels either way.
+ *   mb200_mesh_primary     primary visibility of the mesh -> the G-buffer mb200_shade_* consume (the fast path);
+ *                          also exposes the primary triangle / texel indices so tests can assert them bit-exact.
+ *   mb200_mesh_intersect   debug: closest / any hit for caller-supplied rays (bit-exact vs the oracle).
  *   mb200_posmlp_*         PosMLP.forward (+autograd backward) mymodels/mlps.py:211-251 as used at
  *                          inverse_img_w_mi.py:163,:493 (brdf_net) and :117,:238 (envmap_net).
  *   mb200_cdf_build        build_envmap   myutils/envmap_utils.py:43-66
@@ -182,6 +194,51 @@ int mb200_shade_bwd(const mb200_cfg* cfg_host,
 int mb200_debug_sample_indices(const mb200_cfg* cfg_host, const float* gpos, const float* r,
                                const float* hier, const mb200_hier_desc* desc_host,
                                int32_t* out, void* stream);
+
+/* ---------------------------------------------------------------- mesh mode (triangle mesh instead of a G-buffer) */
+#define MB200_MESH_LEAF        4    /* triangles per BVH leaf */
+#define MB200_MESH_MAX_LEVELS  16
+/* Layout of a built mesh inside ONE device buffer `mesh_buf` (byte offsets), filled by mb200_mesh_describe:
+ *   header : centre.xyz, radius of the scene bounding sphere, bbox lo.xyz, hi.xyz (written by the build, read by kernels)
+ *   tv     : (n_slots, 3) float4 — triangles in Morton order: (p0.xyz, triangle id as int bits), (p1.xyz,0), (p2.xyz,0)
+ *   tn     : (n_slots, 3) float4 — their three vertex normals (absent when face_normals)
+ *   nodes  : n_groups x 6 float4 — implicit 4-ary tree: group g of level l holds the boxes of nodes 4g..4g+3 of level l
+ *            as (lo.x[4], lo.y[4], lo.z[4], hi.x[4], hi.y[4], hi.z[4]); node i of level l has children = group i of
+ *            level l-1; level 0 nodes are leaves of MB200_MESH_LEAF consecutive slots. */
+typedef struct mb200_mesh_desc {
+    int32_t nv, nt;
+    int32_t face_normals;      /* 1: flat shading frames; 0: Mitsuba's default for a PLY without normals (angle-weighted vertex normals) */
+    int32_t n_slots, n_levels, n_groups;
+    int32_t lvl_nodes[MB200_MESH_MAX_LEVELS];
+    int32_t lvl_group_off[MB200_MESH_MAX_LEVELS];
+    int64_t off_header, off_tv, off_tn, off_nodes, total_bytes;
+} mb200_mesh_desc;
+int    mb200_mesh_describe(int nv, int nt, int face_normals, mb200_mesh_desc* out_host);        /* host only */
+size_t mb200_mesh_scratch_bytes(int nv, int nt, int face_normals);                             /* needs a CUDA device; 0 on error */
+/* verts (nv,3) fp32, tris (nt,3) int32 (device) -> mesh_buf (desc.total_bytes, 256-byte aligned); scratch may be freed
+ * once the stream has passed the call.  Everything runs on the GPU (bounds, Morton sort, vertex normals, boxes). */
+int mb200_mesh_build(const float* verts, const int32_t* tris, const mb200_mesh_desc* desc_host,
+                     void* mesh_buf, void* scratch, void* stream);
+/* as mb200_shade_fwd / mb200_shade_bwd with the mesh in place of the G-buffer; n_opt may be NULL (geometric normal).
+ * cfg.max_depth <= 8.  Film buffers (partials, gadj) and mb200_film_* are shared with the G-buffer path. */
+int mb200_mesh_shade_fwd(const mb200_cfg* cfg_host, const mb200_mesh_desc* desc_host, const void* mesh_buf,
+                         const float* a, const float* r, const float* m, const float* n_opt,
+                         const float* env4, const float* hier, const mb200_hier_desc* hdesc_host,
+                         float* partials, void* stream);
+int mb200_mesh_shade_bwd(const mb200_cfg* cfg_host, const mb200_mesh_desc* desc_host, const void* mesh_buf,
+                         const float* a, const float* r, const float* m, const float* n_opt,
+                         const float* env4, const float* hier, const mb200_hier_desc* hdesc_host,
+                         const float* gadj,
+                         float* g_a, float* g_r, float* g_m, float* g_n, float* g_env4, int n_env_slabs,
+                         void* stream);
+/* closest hit (out_tri = triangle id or -1, out_tuv (n,3) = t,u,v) or any hit (out_tri = 1/0) for n rays (o, d: (n,3));
+ * maxt (n) or NULL = infinity */
+int mb200_mesh_intersect(const mb200_mesh_desc* desc_host, const void* mesh_buf, const float* o, const float* d,
+                         const float* maxt, int n, int any_hit, int32_t* out_tri, float* out_tuv, void* stream);
+/* primary visibility through film offset (jx, jy) of every pixel: gpos (H,W,4) = (p, hit?1:0), gnrm (H,W,4) = (n_geo, 0),
+ * tri (H,W) int32 or NULL, flat (H,W) int32 texel index of the hit point or NULL */
+int mb200_mesh_primary(const mb200_cfg* cfg_host, const mb200_mesh_desc* desc_host, const void* mesh_buf, float jx, float jy,
+                       float* gpos, float* gnrm, int32_t* tri, int32_t* flat, void* stream);
 
 /* ---------------------------------------------------------------- BSDF plugin on lanes */
 /* All lane arrays are (L,3) / (L) fp32.  cfg supplies view/proj/H/W/flags/use_mesh_normal.

@@ -5,6 +5,7 @@ from . import _abi
 from .scene import Camera, Scene, SceneParameters, traverse
 from .renderop import render, render_envmap, render_w_brdf, default_seed_grad, sample_indices, tea32
 from . import synthetic
+from .mesh import Mesh, read_ply_mesh
 
 __all__ = ["Camera", "Scene", "SceneParameters", "traverse", "render", "render_envmap", "render_w_brdf",
-           "default_seed_grad", "sample_indices", "tea32", "synthetic"]
+           "default_seed_grad", "sample_indices", "tea32", "synthetic", "Mesh", "read_ply_mesh"]

@@ -36,6 +36,17 @@ class HierDesc(C.Structure):
                 ("total_floats", C.c_int32)]
 
 
+MESH_MAX_LEVELS, MESH_LEAF = 16, 4
+
+
+class MeshDesc(C.Structure):
+    _fields_ = [("nv", C.c_int32), ("nt", C.c_int32), ("face_normals", C.c_int32),
+                ("n_slots", C.c_int32), ("n_levels", C.c_int32), ("n_groups", C.c_int32),
+                ("lvl_nodes", C.c_int32 * MESH_MAX_LEVELS), ("lvl_group_off", C.c_int32 * MESH_MAX_LEVELS),
+                ("off_header", C.c_int64), ("off_tv", C.c_int64), ("off_tn", C.c_int64), ("off_nodes", C.c_int64),
+                ("total_bytes", C.c_int64)]
+
+
 class PosMLPDesc(C.Structure):
     _fields_ = [("n_color", C.c_int32), ("n_out", C.c_int32), ("hidden", C.c_int32), ("n_freq", C.c_int32),
                 ("output_type", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("impl", C.c_int32)]
@@ -57,7 +68,7 @@ def _load():
             "or `make -C materialist_b200/csrc`. There is no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
     vp, i32, i64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
-    pc, ph, pm = C.POINTER(Cfg), C.POINTER(HierDesc), C.POINTER(PosMLPDesc)
+    pc, ph, pm, pd = C.POINTER(Cfg), C.POINTER(HierDesc), C.POINTER(PosMLPDesc), C.POINTER(MeshDesc)
     sig = {
         "mb200_strerror": (C.c_char_p, [i32]),
         "mb200_last_cuda_error": (C.c_char_p, []),
@@ -78,6 +89,13 @@ def _load():
         "mb200_bwd_gadj_rows": (i32, [pc, C.POINTER(C.c_int)]),
         "mb200_shade_bwd": (i32, [pc] + [vp] * 8 + [ph] + [vp] * 6 + [i32, vp]),
         "mb200_debug_sample_indices": (i32, [pc, vp, vp, vp, ph, vp, vp]),
+        "mb200_mesh_describe": (i32, [i32, i32, i32, pd]),
+        "mb200_mesh_scratch_bytes": (sz, [i32, i32, i32]),
+        "mb200_mesh_build": (i32, [vp, vp, pd, vp, vp, vp]),
+        "mb200_mesh_shade_fwd": (i32, [pc, pd] + [vp] * 7 + [ph, vp, vp]),
+        "mb200_mesh_shade_bwd": (i32, [pc, pd] + [vp] * 7 + [ph] + [vp] * 6 + [i32, vp]),
+        "mb200_mesh_intersect": (i32, [pd, vp, vp, vp, vp, i32, i32, vp, vp, vp]),
+        "mb200_mesh_primary": (i32, [pc, pd, vp, C.c_float, C.c_float, vp, vp, vp, vp, vp]),
         "mb200_bsdf_eval_pdf": (i32, [pc, i64] + [vp] * 11),
         "mb200_bsdf_sample": (i32, [pc, i64] + [vp] * 13),
         "mb200_posmlp_param_count": (i64, [pm]),

@@ -1,0 +1,861 @@
+// mb200_mesh.cu — mesh mode of the render operator (sm_100a): what the reference REALLY renders for its scene
+// (inverse_img_w_mi.py:30-56: one `ply` shape with MatDiffBSDF, `path` integrator max_depth 4, envmap emitter):
+// jittered primary rays against the depth-derived triangle mesh (myutils/mesh_recon.py:86-331), per-sample triangle
+// hits, shadow rays for the emitter samples, up to max_depth-1 scattering vertices with the material looked up at
+// EVERY vertex through mi_world_to_screen(si.p) (mi_plugin.py:1435,1456), forward and adjoint.
+//
+// Upstream units restated (mitsuba==3.5.2, un-vendored): src/integrators/path.cpp (loop, draw order, MIS, AD-pass
+// weight), render/mesh.h (Moeller-Trumbore ray_intersect_triangle, compute_surface_interaction without UVs),
+// render/interaction.h (offset_p / spawn_ray / spawn_ray_to, RayEpsilon, ShadowEpsilon), emitters/envmap.cpp
+// (sample_direction target point), render/scene.cpp (sample_emitter_direction visibility test),
+// Mesh::recompute_vertex_normals (angle-weighted).
+//
+// Acceleration structure (this file's own, built ON THE GPU, no pointers): triangles are sorted by the 30-bit Morton
+// code of their bounding-box centre (cub radix sort), 4 consecutive sorted triangles form a leaf, and an IMPLICIT
+// complete 4-ary tree is laid over the leaves: node i of level l has children 4i..4i+3 of level l-1.  The four
+// child boxes of a node are stored together as six float4 (lo.x[4], lo.y[4], lo.z[4], hi.x[4], hi.y[4], hi.z[4])
+// = 96 contiguous bytes, so one traversal step is six 16-byte loads and four slab tests.  Sorted triangles carry
+// their vertices (3 float4 per slot, original triangle id in p0.w) and, for smooth shading frames, their three
+// vertex normals.  The closest hit is defined as (smallest t, then smallest triangle id) — independent of traversal
+// order and of the BVH — and the Moeller-Trumbore test is written with non-contracted IEEE operations in exactly the
+// oracle's order, so for bit-identical rays (all primary rays) the hit triangle, t, u, v are bit-identical to the CPU
+// oracle's (tests/test_gpu_mesh_parity.py).
+//
+// Shading kernels: ONE WARP PER PIXEL, lanes stride over the pixel's samples, exactly as the G-buffer kernels, same
+// film partials / develop / adjoint kernels.  The adjoint walks the path forward (emitter-term and miss-term envmap
+// gradients scattered on the way), keeps a 30-word record per scattering vertex in local memory, then walks back
+// with the suffix radiance R_{k+1} to add the BSDF-weight term; material gradients of lanes that hit the same texel
+// are combined with match.any + a peer reduction before they leave as REDs.
+#include <cub/device/device_radix_sort.cuh>
+#include "mb200_render_common.cuh"
+
+namespace {
+
+constexpr int kLeaf = MB200_MESH_LEAF;          // triangles per leaf
+constexpr int kMaxVerts = 7;                    // scattering vertices per path (max_depth <= 8), as the oracle
+constexpr int kStack = 56;
+constexpr float kRayEps = 1500.f * 5.9604644775390625e-08f;
+constexpr float kShadowEps = 15000.f * 5.9604644775390625e-08f;
+constexpr float kInf = __builtin_huge_valf();
+
+struct MeshView {
+    const float4* tv;        // (slots, 3): (p0.xyz, tri id as int bits), (p1.xyz, 0), (p2.xyz, 0)
+    const float4* tn;        // (slots, 3) vertex normals of the slot's triangle, or nullptr (flat shading frames)
+    const float4* nodes;     // child-box groups, 6 float4 each
+    const float* header;     // centre.xyz, radius (scene bounding sphere)
+    int n_levels;            // group levels 0 .. n_levels-1 (level 0 = leaves)
+    int lvl_off[MB200_MESH_MAX_LEVELS];   // first group of each level
+};
+
+struct Hit { int slot, tri; float t, u, v; };
+
+// ---------------------------------------------------------------- exact (non-contracted) vector helpers
+__device__ __forceinline__ float3 xsub3(float3 a, float3 b) { return f3(XSUB(a.x, b.x), XSUB(a.y, b.y), XSUB(a.z, b.z)); }
+__device__ __forceinline__ float xdot3(float3 a, float3 b) { return XADD(XADD(XMUL(a.x, b.x), XMUL(a.y, b.y)), XMUL(a.z, b.z)); }
+__device__ __forceinline__ float3 xcross3(float3 a, float3 b) {
+    return f3(XSUB(XMUL(a.y, b.z), XMUL(a.z, b.y)), XSUB(XMUL(a.z, b.x), XMUL(a.x, b.z)), XSUB(XMUL(a.x, b.y), XMUL(a.y, b.x)));
+}
+__device__ __forceinline__ float3 xnormalize3(float3 a) {
+    const float inv = XDIV(1.f, XSQRT(xdot3(a, a)));
+    return f3(XMUL(a.x, inv), XMUL(a.y, inv), XMUL(a.z, inv));
+}
+__device__ __forceinline__ float3 cross3(float3 a, float3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+
+// perspective sensor ray, bit-identical to the oracle's primary_dir (oracle/mb_oracle.c)
+__device__ __forceinline__ float3 primary_dir_exact(const CamView& c, float sx, float sy) {
+    const float t = c.tan_half_fov_x, aspect = XDIV((float)c.W, (float)c.H);
+    float3 l = f3(XMUL(XSUB(1.f, XDIV(XMUL(2.f, sx), (float)c.W)), t), XDIV(XMUL(XSUB(1.f, XDIV(XMUL(2.f, sy), (float)c.H)), t), aspect), 1.f);
+    l = xnormalize3(l);
+    return f3(XADD(XADD(XMUL(c.c2w[0], l.x), XMUL(c.c2w[1], l.y)), XMUL(c.c2w[2], l.z)),
+              XADD(XADD(XMUL(c.c2w[4], l.x), XMUL(c.c2w[5], l.y)), XMUL(c.c2w[6], l.z)),
+              XADD(XADD(XMUL(c.c2w[8], l.x), XMUL(c.c2w[9], l.y)), XMUL(c.c2w[10], l.z)));
+}
+
+// Mesh::ray_intersect_triangle (Moeller-Trumbore), operation order of the oracle's tri_intersect
+__device__ __forceinline__ bool tri_intersect(float3 p0, float3 p1, float3 p2, float3 o, float3 d, float maxt, float& tt, float& uu, float& vv) {
+    const float3 e1 = xsub3(p1, p0), e2 = xsub3(p2, p0);
+    const float3 pvec = xcross3(d, e2);
+    const float inv_det = XDIV(1.f, xdot3(e1, pvec));
+    const float3 tvec = xsub3(o, p0);
+    const float u = XMUL(xdot3(tvec, pvec), inv_det);
+    if (!(u >= 0.f && u <= 1.f)) return false;
+    const float3 qvec = xcross3(tvec, e1);
+    const float v = XMUL(xdot3(d, qvec), inv_det);
+    if (!(v >= 0.f && XADD(u, v) <= 1.f)) return false;
+    const float th = XMUL(xdot3(e2, qvec), inv_det);
+    if (!(th >= 0.f && th <= maxt)) return false;
+    tt = th; uu = u; vv = v; return true;
+}
+
+#define MB_CSWAP(i, j) { if (ct[j] < ct[i]) { float tf = ct[i]; ct[i] = ct[j]; ct[j] = tf; uint32_t tc = cc[i]; cc[i] = cc[j]; cc[j] = tc; } }
+
+// closest hit = (smallest t, then smallest triangle id); ANY: true as soon as one triangle is hit within maxt
+template <bool ANY>
+__device__ __forceinline__ bool mesh_intersect(const MeshView& M, float3 o, float3 d, float maxt, Hit& h) {
+    const float3 inv = f3(__fdiv_rn(1.f, d.x), __fdiv_rn(1.f, d.y), __fdiv_rn(1.f, d.z));
+    const float3 oi = f3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
+    uint2 stack[kStack]; int sp = 0;
+    float best = maxt; bool found = false;
+    h.slot = -1; h.tri = -1; h.t = maxt; h.u = h.v = 0.f;
+    uint32_t cur = (uint32_t)M.n_levels << 27;          // virtual root: its children are group 0 of the top level
+    for (;;) {
+        const uint32_t level = cur >> 27, idx = cur & 0x7ffffffu;
+        if (level == 0) {
+#pragma unroll
+            for (int k = 0; k < kLeaf; ++k) {
+                const int slot = (int)idx * kLeaf + k;
+                const float4 q0 = __ldg(M.tv + 3 * (size_t)slot);
+                const int tri = __float_as_int(q0.w);
+                if (tri < 0) continue;
+                const float4 q1 = __ldg(M.tv + 3 * (size_t)slot + 1), q2 = __ldg(M.tv + 3 * (size_t)slot + 2);
+                float tt, uu, vv;
+                if (!tri_intersect(f3(q0.x, q0.y, q0.z), f3(q1.x, q1.y, q1.z), f3(q2.x, q2.y, q2.z), o, d, best, tt, uu, vv)) continue;
+                if (ANY) return true;
+                if (!found || tt < h.t || (tt == h.t && tri < h.tri)) { h.slot = slot; h.tri = tri; h.t = tt; h.u = uu; h.v = vv; best = tt; found = true; }
+            }
+        } else {
+            const float4* g = M.nodes + (size_t)(M.lvl_off[level - 1] + (int)idx) * 6;
+            const float4 lx = __ldg(g), ly = __ldg(g + 1), lz = __ldg(g + 2), hx = __ldg(g + 3), hy = __ldg(g + 4), hz = __ldg(g + 5);
+            const float lox[4] = {lx.x, lx.y, lx.z, lx.w}, loy[4] = {ly.x, ly.y, ly.z, ly.w}, loz[4] = {lz.x, lz.y, lz.z, lz.w};
+            const float hix[4] = {hx.x, hx.y, hx.z, hx.w}, hiy[4] = {hy.x, hy.y, hy.z, hy.w}, hiz[4] = {hz.x, hz.y, hz.z, hz.w};
+            float ct[4]; uint32_t cc[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                // slab test; a NaN (0 * inf) is ignored by fminf / fmaxf, i.e. treated conservatively
+                const float ax = fmaf(lox[k], inv.x, -oi.x), bx = fmaf(hix[k], inv.x, -oi.x);
+                const float ay = fmaf(loy[k], inv.y, -oi.y), by = fmaf(hiy[k], inv.y, -oi.y);
+                const float az = fmaf(loz[k], inv.z, -oi.z), bz = fmaf(hiz[k], inv.z, -oi.z);
+                const float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
+                const float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.0000004f;
+                const bool hit = t0 <= fminf(t1, best) && lox[k] <= hix[k];
+                ct[k] = hit ? t0 : kInf;
+                cc[k] = ((level - 1) << 27) | (idx * 4u + (uint32_t)k);
+            }
+            MB_CSWAP(0, 1) MB_CSWAP(2, 3) MB_CSWAP(0, 2) MB_CSWAP(1, 3) MB_CSWAP(1, 2)
+            if (ct[0] < kInf) {
+                if (ct[1] < kInf) {
+                    if (ct[2] < kInf) {
+                        if (ct[3] < kInf) stack[sp++] = make_uint2(cc[3], __float_as_uint(ct[3]));
+                        stack[sp++] = make_uint2(cc[2], __float_as_uint(ct[2]));
+                    }
+                    stack[sp++] = make_uint2(cc[1], __float_as_uint(ct[1]));
+                }
+                cur = cc[0];
+                continue;
+            }
+        }
+        // pop the next node that can still contain a closer (or equally close) hit
+        bool got = false;
+        while (sp > 0) {
+            const uint2 e = stack[--sp];
+            if (__uint_as_float(e.y) <= best) { cur = e.x; got = true; break; }
+        }
+        if (!got) break;
+    }
+    return found;
+}
+
+struct SurfacePoint { float3 p, ng; Frame sh; };
+// Mesh::compute_surface_interaction for a mesh without UVs; shading frame from interpolated vertex normals when present
+__device__ __forceinline__ SurfacePoint hit_point(const MeshView& M, const Hit& h) {
+    const float4 q0 = __ldg(M.tv + 3 * (size_t)h.slot), q1 = __ldg(M.tv + 3 * (size_t)h.slot + 1), q2 = __ldg(M.tv + 3 * (size_t)h.slot + 2);
+    const float b1 = h.u, b2 = h.v, b0 = XSUB(XSUB(1.f, b1), b2);
+    SurfacePoint s;
+    s.p = f3(XFMA(q0.x, b0, XFMA(q1.x, b1, XMUL(q2.x, b2))), XFMA(q0.y, b0, XFMA(q1.y, b1, XMUL(q2.y, b2))), XFMA(q0.z, b0, XFMA(q1.z, b1, XMUL(q2.z, b2))));
+    const float3 p0 = f3(q0.x, q0.y, q0.z);
+    s.ng = xnormalize3(xcross3(xsub3(f3(q1.x, q1.y, q1.z), p0), xsub3(f3(q2.x, q2.y, q2.z), p0)));
+    const Frame g = make_frame(s.ng);
+    if (!M.tn) { s.sh = g; return s; }
+    const float4 a0 = __ldg(M.tn + 3 * (size_t)h.slot), a1 = __ldg(M.tn + 3 * (size_t)h.slot + 1), a2 = __ldg(M.tn + 3 * (size_t)h.slot + 2);
+    float3 ns = f3(fmaf(a0.x, b0, fmaf(a1.x, b1, a2.x * b2)), fmaf(a0.y, b0, fmaf(a1.y, b1, a2.y * b2)), fmaf(a0.z, b0, fmaf(a1.z, b1, a2.z * b2)));
+    ns = ns * (1.f / sqrtf(dot(ns, ns)));
+    // SurfaceInteraction::initialize_sh_frame: Gram-Schmidt of dp_du (= coordinate_system(n).s) against the shading normal
+    const float dd = dot(ns, g.s);
+    float3 ss = f3(fmaf(-ns.x, dd, g.s.x), fmaf(-ns.y, dd, g.s.y), fmaf(-ns.z, dd, g.s.z));
+    ss = ss * (1.f / sqrtf(dot(ss, ss)));
+    s.sh.n = ns; s.sh.s = ss; s.sh.t = cross3(ns, ss);
+    return s;
+}
+// SurfaceInteraction::offset_p
+__device__ __forceinline__ float3 offset_p(float3 p, float3 n, float3 d) {
+    float mag = (1.f + fmaxf(fabsf(p.x), fmaxf(fabsf(p.y), fabsf(p.z)))) * kRayEps;
+    if (dot(n, d) < 0.f) mag = -mag;
+    return f3(fmaf(mag, n.x, p.x), fmaf(mag, n.y, p.y), fmaf(mag, n.z, p.z));
+}
+// Scene::sample_emitter_direction(test_visibility) for an envmap: ray_test towards it.p + d * 2 * max(radius, |it.p - centre|)
+__device__ __forceinline__ bool shadow_visible(const MeshView& M, float3 p, float3 n, float3 d) {
+    const float3 c = f3(__ldg(M.header), __ldg(M.header + 1), __ldg(M.header + 2));
+    const float3 pc = p - c;
+    const float rad = fmaxf(__ldg(M.header + 3), sqrtf(dot(pc, pc)));
+    const float3 target = p + d * (2.f * rad);
+    const float3 o = offset_p(p, n, target - p);
+    float3 dd = target - o;
+    const float dist = sqrtf(dot(dd, dd));
+    dd = dd * (1.f / dist);
+    Hit h;
+    return !mesh_intersect<true>(M, o, dd, dist * (1.f - kShadowEps), h);
+}
+
+__device__ __forceinline__ Material fetch_material(const RenderParams& P, float3 p, float3 ng, long long& flat) {
+    Material mt; flat = texel_index(P.cam, p);
+    mt.a = f3(__ldg(P.a + 3 * flat), __ldg(P.a + 3 * flat + 1), __ldg(P.a + 3 * flat + 2));
+    mt.r = __ldg(P.r + flat); mt.m = __ldg(P.m + flat);
+    mt.n = (P.use_mesh_normal || !P.n_opt) ? ng : f3(__ldg(P.n_opt + 3 * flat), __ldg(P.n_opt + 3 * flat + 1), __ldg(P.n_opt + 3 * flat + 2));
+    return mt;
+}
+
+// ---------------------------------------------------------------- forward: PathIntegrator::sample for one lane
+template <bool AD_W>
+__device__ __forceinline__ float3 trace_path_fwd(const RenderParams& P, const MeshView& M, int px, int py, uint32_t lane_id, float& jx, float& jy) {
+    Pcg32 rng; rng.seed(P.seed, lane_id);
+    jx = rng.next_float(); jy = rng.next_float();
+    float3 ro = f3(P.cam.c2w[3], P.cam.c2w[7], P.cam.c2w[11]);
+    float3 rd = primary_dir_exact(P.cam, XADD((float)px, jx), XADD((float)py, jy));
+    float3 beta = f3(1.f, 1.f, 1.f), L = f3(0.f, 0.f, 0.f);
+    float prev_pdf = 1.f; bool prev_delta = true;
+    const int max_verts = min(P.max_depth - 1, kMaxVerts);
+    for (int nv = 0;; ++nv) {
+        Hit h;
+        if (!mesh_intersect<false>(M, ro, rd, kInf, h)) {          // direct emission: the environment
+            float u, v; dir_to_uv(rd, u, v);
+            const float em_pdf = prev_delta ? 0.f : env_pdf_direction(P.hier, P.env, rd, u, v);
+            if (prev_pdf > 0.f) L = L + beta * env_value(P.env, env_lookup<false>(P.env, u, v)) * mis_weight(prev_pdf, em_pdf);
+            break;
+        }
+        if (nv >= max_verts) break;                                 // depth + 1 >= max_depth
+        const SurfacePoint sp = hit_point(M, h);
+        const float3 view = f3(-rd.x, -rd.y, -rd.z);
+        long long flat; const Material mt = fetch_material(P, sp.p, sp.ng, flat);
+        // ---- emitter sampling
+        const float uex = rng.next_float(), uey = rng.next_float();
+        const EmSample em = env_sample_direction(P.hier, P.env, uex, uey);
+        const bool visible = em.pdf != 0.f && shadow_visible(M, sp.p, sp.ng, em.d);
+        const float s1 = rng.next_float();
+        const float s2x = rng.next_float(), s2y = rng.next_float();
+        if (visible) {
+            const BsdfVal fv = eval_brdf(em.d, view, mt);
+            L = L + beta * fv.f * env_value(P.env, em.b) * (mis_weight(em.pdf, fv.pdf) / em.pdf);
+        }
+        // ---- BSDF sampling
+        const BsdfSample bs = sample_brdf(s1, s2x, s2y, view, mt, make_frame(mt.n));
+        const float3 d_bs = (P.flags & MB200_FLAG_WO_WORLD_QUIRK) ? to_world(sp.sh, bs.wi) : bs.wi;     // mi_plugin.py:1444
+        float3 w = bs.weight;
+        if (AD_W) {
+            const BsdfVal b2 = eval_brdf(d_bs, view, mt);
+            if (b2.pdf > 0.f) w = b2.f * (1.f / b2.pdf);
+        }
+        ro = offset_p(sp.p, sp.ng, d_bs); rd = d_bs;
+        beta = beta * w; prev_pdf = bs.pdf; prev_delta = false;
+        rng.next_float();                                           // russian-roulette draw (rr_depth 5: never applied)
+        if (fmax3(beta.x, beta.y, beta.z) == 0.f) break;
+    }
+    return L;
+}
+
+template <int FILTER, bool AD_W>
+__global__ void __launch_bounds__(kThreads, 2) mesh_fwd_kernel(const __grid_constant__ RenderParams P, const __grid_constant__ MeshView M) {
+    __shared__ __align__(16) float s_rec[FILTER == MB200_FILTER_GAUSSIAN ? kWarpsPerBlock * 32 * kRecStride : 4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* rec = s_rec + (FILTER == MB200_FILTER_GAUSSIAN ? warp * 32 * kRecStride : 0);
+    const int npix = P.prows * P.W;
+    const int ti = lane % 5, tj = lane / 5;
+    for (int pix = blockIdx.x * kWarpsPerBlock + warp; pix < npix; pix += gridDim.x * kWarpsPerBlock) {
+        const int py = P.prow0 + pix / P.W, px = pix % P.W;
+        const int gpix = py * P.W + px;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s0 = 0; s0 < P.spp; s0 += 32) {
+            const int s = s0 + lane;
+            float3 L = f3(0.f, 0.f, 0.f); float jx = 0.f, jy = 0.f;
+            const bool act = s < P.spp;
+            if (act) L = trace_path_fwd<AD_W>(P, M, px, py, (uint32_t)gpix * (uint32_t)P.spp + (uint32_t)s, jx, jy);
+            __syncwarp();
+            if (FILTER == MB200_FILTER_GAUSSIAN) {
+                float wx[5], wy[5]; film_taps(jx, wx); film_taps(jy, wy);
+                if (!act) { wx[0] = wx[1] = wx[2] = wx[3] = wx[4] = 0.f; }
+                float4* r4 = reinterpret_cast<float4*>(rec + lane * kRecStride);
+                r4[0] = make_float4(wx[0], wx[1], wx[2], wx[3]);
+                r4[1] = make_float4(wx[4], wy[0], wy[1], wy[2]);
+                r4[2] = make_float4(wy[3], wy[4], 0.f, 0.f);
+                r4[3] = make_float4(L.x, L.y, L.z, 1.f);
+                __syncwarp();
+                if (lane < MB200_FILM_TAPS) {
+                    const float* rt = rec + ti; const float* ru = rec + 5 + tj;
+#pragma unroll 8
+                    for (int k = 0; k < 32; ++k) {
+                        const float w = rt[k * kRecStride] * ru[k * kRecStride];
+                        const float4 l4 = *reinterpret_cast<const float4*>(rec + k * kRecStride + 12);
+                        acc.x = fmaf(w, l4.x, acc.x); acc.y = fmaf(w, l4.y, acc.y); acc.z = fmaf(w, l4.z, acc.z); acc.w += w;
+                    }
+                }
+                __syncwarp();
+            } else {
+                acc.x += L.x; acc.y += L.y; acc.z += L.z;
+            }
+        }
+        if (FILTER == MB200_FILTER_GAUSSIAN) {
+            if (lane < MB200_FILM_TAPS)
+                reinterpret_cast<float4*>(P.partials)[(size_t)pix * MB200_FILM_TAPS + lane] = acc;
+        } else {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+                acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+            }
+            if (lane == 0) reinterpret_cast<float4*>(P.partials)[pix] = make_float4(acc.x, acc.y, acc.z, (float)P.spp);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- adjoint
+struct VRec {                       // what the backward walk needs of one scattering vertex (30 words, local memory)
+    Material mt; float3 view, em_d, cem, d_bs, cpre, w, E; int flat;
+};
+
+// sums x over the lanes of `peers` (all lanes of the warp must call); result valid in the lowest lane of each group
+template <int N>
+__device__ __forceinline__ void reduce_peers(unsigned peers, float (&x)[N]) {
+    const int lane = threadIdx.x & 31;
+    int rel_pos = __popc(peers << (32 - lane)) ;
+    if (lane == 0) rel_pos = 0;
+    peers &= (0xfffffffeu << lane);
+    while (__any_sync(0xffffffffu, peers)) {
+        const int next = __ffs(peers);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const float t = __shfl_sync(0xffffffffu, x[i], (next - 1) & 31);
+            if (next) x[i] += t;
+        }
+        const unsigned done = rel_pos & 1;
+        peers &= ~__ballot_sync(0xffffffffu, done);
+        rel_pos >>= 1;
+    }
+}
+
+template <int FILTER, bool WANT_MAT, bool WANT_N, bool WANT_ENV>
+__global__ void __launch_bounds__(kThreads, 2) mesh_bwd_kernel(const __grid_constant__ RenderParams P, const __grid_constant__ MeshView M) {
+    __shared__ float4 s_g[FILTER == MB200_FILTER_GAUSSIAN ? kWarpsPerBlock * MB200_FILM_TAPS : 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4* gt = s_g + (FILTER == MB200_FILTER_GAUSSIAN ? warp * MB200_FILM_TAPS : 0);
+    const int npix = P.prows * P.W;
+    float4* const genv = WANT_ENV ? P.g_env4 + (long long)(blockIdx.x % P.env_slabs) * P.env_slab_stride : nullptr;
+    const int max_verts = min(P.max_depth - 1, kMaxVerts);
+    const float3 cam_o = f3(P.cam.c2w[3], P.cam.c2w[7], P.cam.c2w[11]);
+    VRec recs[WANT_MAT ? kMaxVerts : 1];
+    for (int pix = blockIdx.x * kWarpsPerBlock + warp; pix < npix; pix += gridDim.x * kWarpsPerBlock) {
+        const int py = P.prow0 + pix / P.W, px = pix % P.W;
+        const int gpix = py * P.W + px;
+        float3 gbox = f3(0, 0, 0);
+        if (FILTER == MB200_FILTER_GAUSSIAN) {
+            __syncwarp();
+            if (lane < MB200_FILM_TAPS) {
+                const int qy = py + (lane / 5 - 2), qx = px + (lane % 5 - 2);
+                float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (qx >= 0 && qx < P.W && qy >= P.grow0 && qy < P.grow0 + P.grows && qy >= 0 && qy < P.H)
+                    g = __ldg(P.gadj + (size_t)(qy - P.grow0) * P.W + qx);
+                gt[lane] = g;
+            }
+            __syncwarp();
+        } else {
+            const float4 g = __ldg(P.gadj + (size_t)(py - P.grow0) * P.W + px);
+            gbox = f3(g.x, g.y, g.z);
+        }
+        for (int s0 = 0; s0 < P.spp; s0 += 32) {
+            const int s = s0 + lane;
+            bool alive = s < P.spp;
+            Pcg32 rng; rng.seed(P.seed, (uint32_t)gpix * (uint32_t)P.spp + (uint32_t)s);
+            const float jx = rng.next_float(), jy = rng.next_float();
+            float3 dl = gbox;
+            if (FILTER == MB200_FILTER_GAUSSIAN) {
+                float wx[5], wy[5]; film_taps(jx, wx); film_taps(jy, wy);
+                dl = f3(0, 0, 0);
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    float3 row = f3(0, 0, 0);
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) {
+                        const float4 g = gt[j * 5 + i];
+                        row.x = fmaf(wx[i], g.x, row.x); row.y = fmaf(wx[i], g.y, row.y); row.z = fmaf(wx[i], g.z, row.z);
+                    }
+                    dl.x = fmaf(wy[j], row.x, dl.x); dl.y = fmaf(wy[j], row.y, dl.y); dl.z = fmaf(wy[j], row.z, dl.z);
+                }
+            }
+            // ---- forward walk (per lane; no warp-level operation inside)
+            float3 ro = cam_o, rd = primary_dir_exact(P.cam, XADD((float)px, jx), XADD((float)py, jy));
+            float3 beta = f3(1.f, 1.f, 1.f), R = f3(0.f, 0.f, 0.f);
+            float prev_pdf = 1.f; bool prev_delta = true; int nv = 0;
+            while (alive) {
+                Hit h;
+                if (!mesh_intersect<false>(M, ro, rd, kInf, h)) {
+                    if (prev_pdf > 0.f) {
+                        float u, v; dir_to_uv(rd, u, v);
+                        const float mis = mis_weight(prev_pdf, prev_delta ? 0.f : env_pdf_direction(P.hier, P.env, rd, u, v));
+                        const Bilerp bb = env_lookup<false>(P.env, u, v);
+                        if (WANT_MAT) R = env_value(P.env, bb) * mis;
+                        if (WANT_ENV) env_scatter(genv, P.env.Wi, bb, dl * beta * mis);
+                    }
+                    break;
+                }
+                if (nv >= max_verts) break;
+                const SurfacePoint sp = hit_point(M, h);
+                const float3 view = f3(-rd.x, -rd.y, -rd.z);
+                long long flat; const Material mt = fetch_material(P, sp.p, sp.ng, flat);
+                const float uex = rng.next_float(), uey = rng.next_float();
+                const EmSample em = env_sample_direction(P.hier, P.env, uex, uey);
+                const bool visible = em.pdf != 0.f && shadow_visible(M, sp.p, sp.ng, em.d);
+                const float s1 = rng.next_float();
+                const float s2x = rng.next_float(), s2y = rng.next_float();
+                float3 E = f3(0.f, 0.f, 0.f), cem = f3(0.f, 0.f, 0.f);
+                if (visible) {
+                    const BsdfVal fv = eval_brdf(em.d, view, mt);
+                    const float k = mis_weight(em.pdf, fv.pdf) / em.pdf;
+                    if (WANT_MAT) { const float3 lek = env_value(P.env, em.b) * k; E = fv.f * lek; cem = dl * beta * lek; }
+                    if (WANT_ENV) env_scatter(genv, P.env.Wi, em.b, dl * beta * fv.f * k);
+                }
+                const BsdfSample bs = sample_brdf(s1, s2x, s2y, view, mt, make_frame(mt.n));
+                const float3 d_bs = (P.flags & MB200_FLAG_WO_WORLD_QUIRK) ? to_world(sp.sh, bs.wi) : bs.wi;
+                const BsdfVal b2 = eval_brdf(d_bs, view, mt);
+                const float3 w = b2.pdf > 0.f ? b2.f * (1.f / b2.pdf) : bs.weight;
+                if (WANT_MAT) {
+                    VRec& V = recs[nv];
+                    V.mt = mt; V.view = view; V.em_d = em.d; V.cem = cem; V.d_bs = d_bs; V.w = w; V.E = E; V.flat = (int)flat;
+                    V.cpre = b2.pdf > 0.f ? dl * beta * (1.f / b2.pdf) : f3(0.f, 0.f, 0.f);
+                }
+                ro = offset_p(sp.p, sp.ng, d_bs); rd = d_bs;
+                beta = beta * w; prev_pdf = bs.pdf; prev_delta = false; nv += 1;
+                rng.next_float();
+                if (fmax3(beta.x, beta.y, beta.z) == 0.f) break;
+            }
+            // ---- backward walk, warp-synchronous: R = radiance leaving vertex k+1 towards vertex k
+            if (WANT_MAT) {
+                __syncwarp();
+                const int max_nv = __reduce_max_sync(0xffffffffu, nv);
+                for (int k = max_nv - 1; k >= 0; --k) {
+                    float g[WANT_N ? 8 : 5];
+#pragma unroll
+                    for (int i = 0; i < (WANT_N ? 8 : 5); ++i) g[i] = 0.f;
+                    int flat = -1 - lane;                       // unique: lanes without vertex k form singleton groups
+                    if (k < nv) {
+                        const VRec& V = recs[k];
+                        flat = V.flat;
+                        if (V.cem.x != 0.f || V.cem.y != 0.f || V.cem.z != 0.f) {
+                            const BsdfGrad bg = eval_brdf_grad<WANT_N>(V.em_d, V.view, V.mt, V.cem);
+                            g[0] += bg.ga.x; g[1] += bg.ga.y; g[2] += bg.ga.z; g[3] += bg.gr; g[4] += bg.gm;
+                            if (WANT_N) { g[5] += bg.gn.x; g[6] += bg.gn.y; g[7] += bg.gn.z; }
+                        }
+                        const float3 cw = V.cpre * R;
+                        if (cw.x != 0.f || cw.y != 0.f || cw.z != 0.f) {
+                            const BsdfGrad bg = eval_brdf_grad<WANT_N>(V.d_bs, V.view, V.mt, cw);
+                            g[0] += bg.ga.x; g[1] += bg.ga.y; g[2] += bg.ga.z; g[3] += bg.gr; g[4] += bg.gm;
+                            if (WANT_N) { g[5] += bg.gn.x; g[6] += bg.gn.y; g[7] += bg.gn.z; }
+                        }
+                        R = V.E + V.w * R;
+                    }
+                    const unsigned peers = __match_any_sync(0xffffffffu, flat);
+                    reduce_peers(peers, g);
+                    if (flat >= 0 && lane == __ffs(peers) - 1) {
+                        if (P.g_a) { atomicAdd(P.g_a + 3 * (size_t)flat, g[0]); atomicAdd(P.g_a + 3 * (size_t)flat + 1, g[1]); atomicAdd(P.g_a + 3 * (size_t)flat + 2, g[2]); }
+                        if (P.g_r) atomicAdd(P.g_r + flat, g[3]);
+                        if (P.g_m) atomicAdd(P.g_m + flat, g[4]);
+                        if (WANT_N && P.g_n) { atomicAdd(P.g_n + 3 * (size_t)flat, g[5]); atomicAdd(P.g_n + 3 * (size_t)flat + 1, g[6]); atomicAdd(P.g_n + 3 * (size_t)flat + 2, g[7]); }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- debug / G-buffer extraction kernels
+__global__ void mesh_intersect_kernel(const __grid_constant__ MeshView M, const float* __restrict__ o, const float* __restrict__ d,
+                                      const float* __restrict__ maxt, int n, int any_hit, int32_t* __restrict__ out_tri, float* __restrict__ out_tuv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float3 ro = f3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), rd = f3(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
+    const float mt = maxt ? maxt[i] : kInf;
+    Hit h; bool found;
+    if (any_hit) found = mesh_intersect<true>(M, ro, rd, mt, h); else found = mesh_intersect<false>(M, ro, rd, mt, h);
+    out_tri[i] = any_hit ? (found ? 1 : 0) : (found ? h.tri : -1);
+    if (out_tuv) { out_tuv[3 * i] = found && !any_hit ? h.t : 0.f; out_tuv[3 * i + 1] = found && !any_hit ? h.u : 0.f; out_tuv[3 * i + 2] = found && !any_hit ? h.v : 0.f; }
+}
+// primary visibility at film offset (jx, jy) inside every pixel: gpos (H,W,4) = (p, hit?1:0), gnrm (H,W,4), tri (H,W), flat (H,W)
+__global__ void mesh_primary_kernel(const __grid_constant__ RenderParams P, const __grid_constant__ MeshView M, float jx, float jy,
+                                    float4* __restrict__ gpos, float4* __restrict__ gnrm, int32_t* __restrict__ tri, int32_t* __restrict__ flat_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.H * P.W) return;
+    const int py = i / P.W, px = i % P.W;
+    const float3 ro = f3(P.cam.c2w[3], P.cam.c2w[7], P.cam.c2w[11]);
+    const float3 rd = primary_dir_exact(P.cam, XADD((float)px, jx), XADD((float)py, jy));
+    Hit h;
+    if (mesh_intersect<false>(M, ro, rd, kInf, h)) {
+        const SurfacePoint sp = hit_point(M, h);
+        gpos[i] = make_float4(sp.p.x, sp.p.y, sp.p.z, 1.f); gnrm[i] = make_float4(sp.ng.x, sp.ng.y, sp.ng.z, 0.f);
+        if (tri) tri[i] = h.tri;
+        if (flat_out) flat_out[i] = (int32_t)texel_index(P.cam, sp.p);
+    } else {
+        gpos[i] = make_float4(0.f, 0.f, 0.f, 0.f); gnrm[i] = make_float4(0.f, 0.f, 1.f, 0.f);
+        if (tri) tri[i] = -1;
+        if (flat_out) flat_out[i] = -1;
+    }
+}
+
+// ================================================================ BVH build (GPU)
+__device__ __forceinline__ int f2ord(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void mesh_init_kernel(int* bbox_ord) {
+    if (threadIdx.x < 3) bbox_ord[threadIdx.x] = 0x7fffffff;
+    else if (threadIdx.x < 6) bbox_ord[threadIdx.x] = (int)0x80000000;
+}
+__device__ __forceinline__ void tri_bounds(const float* __restrict__ verts, const int32_t* __restrict__ tris, int t, float lo[3], float hi[3]) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { lo[k] = 1e30f; hi[k] = -1e30f; }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int vi = tris[3 * (size_t)t + j];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { const float x = verts[3 * (size_t)vi + k]; lo[k] = fminf(lo[k], x); hi[k] = fmaxf(hi[k], x); }
+    }
+}
+__global__ void mesh_scene_bounds_kernel(const float* __restrict__ verts, const int32_t* __restrict__ tris, int nt, int* bbox_ord) {
+    float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
+        float l[3], h[3]; tri_bounds(verts, tris, t, l, h);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], l[k]); hi[k] = fmaxf(hi[k], h[k]); }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o)); hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o)); }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { atomicMin(bbox_ord + k, f2ord(lo[k])); atomicMax(bbox_ord + 3 + k, f2ord(hi[k])); }
+    }
+}
+// header: centre.xyz, radius = |bbox.max - centre|, then bbox lo.xyz, hi.xyz  (operation order of the oracle's mbo_mesh_create)
+__global__ void mesh_header_kernel(const int* bbox_ord, float* header) {
+    float r2 = 0.f;
+    for (int k = 0; k < 3; ++k) {
+        const float lo = ord2f(bbox_ord[k]), hi = ord2f(bbox_ord[3 + k]);
+        const float c = XMUL(0.5f, XADD(lo, hi)), e = XSUB(hi, c);
+        header[k] = c; r2 = XADD(r2, XMUL(e, e));
+        header[4 + k] = lo; header[8 + k] = hi;
+    }
+    header[3] = XSQRT(r2); header[7] = 0.f; header[11] = 0.f;
+}
+__device__ __forceinline__ uint32_t expand10(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu; v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u; v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+__global__ void mesh_morton_kernel(const float* __restrict__ verts, const int32_t* __restrict__ tris, int nt, const float* __restrict__ header,
+                                   uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    float lo[3], hi[3]; tri_bounds(verts, tris, t, lo, hi);
+    uint32_t q[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float blo = header[4 + k], ext = header[8 + k] - blo;
+        const float x = ext > 0.f ? (0.5f * (lo[k] + hi[k]) - blo) / ext : 0.f;
+        q[k] = (uint32_t)fminf(fmaxf(x * 1024.f, 0.f), 1023.f);
+    }
+    keys[t] = (expand10(q[0]) << 2) | (expand10(q[1]) << 1) | expand10(q[2]);
+    vals[t] = t;
+}
+// Mesh::recompute_vertex_normals: face normals weighted by the corner angle, accumulated in double
+__device__ __forceinline__ float unit_angle(float3 u, float3 v) {
+    const float3 dm = v - u, dp = v + u;
+    const float t = 2.f * asinf(fminf(0.5f * sqrtf(dot(dm, dm)), 1.f));
+    return dot(u, v) >= 0.f ? t : MB_PI - 2.f * asinf(fminf(0.5f * sqrtf(dot(dp, dp)), 1.f));
+}
+__global__ void mesh_vn_accum_kernel(const float* __restrict__ verts, const int32_t* __restrict__ tris, int nt, double* __restrict__ acc) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    int vi[3]; float3 p[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { vi[j] = tris[3 * (size_t)t + j]; p[j] = f3(verts[3 * (size_t)vi[j]], verts[3 * (size_t)vi[j] + 1], verts[3 * (size_t)vi[j] + 2]); }
+    float3 n = xcross3(xsub3(p[1], p[0]), xsub3(p[2], p[0]));
+    const float l2 = xdot3(n, n);
+    if (l2 == 0.f) return;
+    const float il = XDIV(1.f, XSQRT(l2));
+    n = f3(XMUL(n.x, il), XMUL(n.y, il), XMUL(n.z, il));
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float3 d0 = xnormalize3(xsub3(p[(i + 1) % 3], p[i])), d1 = xnormalize3(xsub3(p[(i + 2) % 3], p[i]));
+        const float w = unit_angle(d0, d1);
+        atomicAdd(acc + 3 * (size_t)vi[i], (double)XMUL(n.x, w));
+        atomicAdd(acc + 3 * (size_t)vi[i] + 1, (double)XMUL(n.y, w));
+        atomicAdd(acc + 3 * (size_t)vi[i] + 2, (double)XMUL(n.z, w));
+    }
+}
+__global__ void mesh_vn_finish_kernel(const double* __restrict__ acc, int nv, float4* __restrict__ vn) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nv) return;
+    const double x = acc[3 * (size_t)i], y = acc[3 * (size_t)i + 1], z = acc[3 * (size_t)i + 2];
+    const double l = sqrt(x * x + y * y + z * z);
+    vn[i] = l > 0.0 ? make_float4((float)(x / l), (float)(y / l), (float)(z / l), 0.f) : make_float4(1.f, 0.f, 0.f, 0.f);
+}
+__global__ void mesh_gather_kernel(const float* __restrict__ verts, const int32_t* __restrict__ tris, int nt, int n_slots,
+                                   const int32_t* __restrict__ order, const float4* __restrict__ vn, float4* __restrict__ tv, float4* __restrict__ tn) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    if (s >= nt) {
+        tv[3 * (size_t)s] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)); tv[3 * (size_t)s + 1] = tv[3 * (size_t)s + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tn) tn[3 * (size_t)s] = tn[3 * (size_t)s + 1] = tn[3 * (size_t)s + 2] = make_float4(0.f, 0.f, 1.f, 0.f);
+        return;
+    }
+    const int t = order[s];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int vi = tris[3 * (size_t)t + j];
+        tv[3 * (size_t)s + j] = make_float4(verts[3 * (size_t)vi], verts[3 * (size_t)vi + 1], verts[3 * (size_t)vi + 2], j == 0 ? __int_as_float(t) : 0.f);
+        if (tn) tn[3 * (size_t)s + j] = vn[vi];
+    }
+}
+// box of node i at some level is component (i & 3) of the six float4 of group (i >> 2)
+__device__ __forceinline__ void store_box(float4* nodes, int group_off, int i, const float lo[3], const float hi[3]) {
+    float* g = reinterpret_cast<float*>(nodes + (size_t)(group_off + (i >> 2)) * 6);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { g[4 * k + (i & 3)] = lo[k]; g[12 + 4 * k + (i & 3)] = hi[k]; }
+}
+__global__ void mesh_leaf_bounds_kernel(const float4* __restrict__ tv, int n_leaves, int n_padded, float4* __restrict__ nodes, int group_off) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_padded) return;
+    float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+    if (i < n_leaves) {
+        for (int k = 0; k < kLeaf; ++k) {
+            const float4 q0 = tv[3 * ((size_t)i * kLeaf + k)];
+            if (__float_as_int(q0.w) < 0) continue;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const float4 q = tv[3 * ((size_t)i * kLeaf + k) + j];
+                lo[0] = fminf(lo[0], q.x); lo[1] = fminf(lo[1], q.y); lo[2] = fminf(lo[2], q.z);
+                hi[0] = fmaxf(hi[0], q.x); hi[1] = fmaxf(hi[1], q.y); hi[2] = fmaxf(hi[2], q.z);
+            }
+        }
+        // conservative padding: Moeller-Trumbore hits are not exactly on the triangle's plane in float
+        const float pad = 3.814697265625e-06f * (1.f + fmaxf(fmaxf(fmaxf(fabsf(lo[0]), fabsf(hi[0])), fmaxf(fabsf(lo[1]), fabsf(hi[1]))), fmaxf(fabsf(lo[2]), fabsf(hi[2]))));
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { lo[k] -= pad; hi[k] += pad; }
+    }
+    store_box(nodes, group_off, i, lo, hi);
+}
+__global__ void mesh_level_kernel(float4* __restrict__ nodes, int child_group_off, int n_nodes, int n_padded, int group_off) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_padded) return;
+    float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+    if (i < n_nodes) {
+        const float4* g = nodes + (size_t)(child_group_off + i) * 6;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float4 l = g[k], h = g[3 + k];
+            lo[k] = fminf(fminf(l.x, l.y), fminf(l.z, l.w)); hi[k] = fmaxf(fmaxf(h.x, h.y), fmaxf(h.z, h.w));
+        }
+    }
+    store_box(nodes, group_off, i, lo, hi);
+}
+
+// ---------------------------------------------------------------- host side
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int make_view(const mb200_mesh_desc* md, const void* mesh_buf, MeshView& M) {
+    if (!md || !mesh_buf || md->nt <= 0 || md->n_levels < 1 || md->n_levels > MB200_MESH_MAX_LEVELS) return MB200_EINVAL;
+    const char* b = reinterpret_cast<const char*>(mesh_buf);
+    M.header = reinterpret_cast<const float*>(b + md->off_header);
+    M.tv = reinterpret_cast<const float4*>(b + md->off_tv);
+    M.tn = md->face_normals ? nullptr : reinterpret_cast<const float4*>(b + md->off_tn);
+    M.nodes = reinterpret_cast<const float4*>(b + md->off_nodes);
+    M.n_levels = md->n_levels;
+    for (int l = 0; l < MB200_MESH_MAX_LEVELS; ++l) M.lvl_off[l] = l < md->n_levels ? md->lvl_group_off[l] : 0;
+    return MB200_OK;
+}
+
+struct ScratchLayout { size_t bbox, keys0, keys1, vals0, vals1, vnacc, vn, cub, cub_bytes, total; };
+int scratch_layout(int nv, int nt, int face_normals, ScratchLayout& S) {
+    size_t off = 0;
+    S.bbox = off; off += 256;
+    S.keys0 = off; off += align_up(sizeof(uint32_t) * (size_t)nt, 256);
+    S.keys1 = off; off += align_up(sizeof(uint32_t) * (size_t)nt, 256);
+    S.vals0 = off; off += align_up(sizeof(int32_t) * (size_t)nt, 256);
+    S.vals1 = off; off += align_up(sizeof(int32_t) * (size_t)nt, 256);
+    S.vnacc = off; off += face_normals ? 0 : align_up(sizeof(double) * 3 * (size_t)nv, 256);
+    S.vn = off; off += face_normals ? 0 : align_up(sizeof(float4) * (size_t)nv, 256);
+    size_t cub_bytes = 0;
+    cub::DoubleBuffer<uint32_t> k(nullptr, nullptr); cub::DoubleBuffer<int32_t> v(nullptr, nullptr);
+    if (cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, k, v, nt, 0, 30) != cudaSuccess) { cudaGetLastError(); return MB200_ELAUNCH; }
+    S.cub = off; S.cub_bytes = cub_bytes; off += align_up(cub_bytes, 256);
+    S.total = off;
+    return MB200_OK;
+}
+
+int mesh_render_params(const mb200_cfg* c, const float* a, const float* r, const float* m, const float* n_opt, const float* env4,
+                       const float* hier, const mb200_hier_desc* d, RenderParams& P) {
+    int rc = fill_params(c, nullptr, nullptr, a, r, m, n_opt, env4, hier, d, P, false);
+    if (rc) return rc;
+    if (c->max_depth - 1 > kMaxVerts) return MB200_ERANGE;
+    return MB200_OK;
+}
+
+template <int FILTER>
+int launch_mesh_bwd(const RenderParams& P, const MeshView& M, bool want_mat, bool want_n, bool want_env, cudaStream_t st) {
+    const int grid = grid_for(P.prows * P.W);
+#define MB_BWD(MT, N, E) mesh_bwd_kernel<FILTER, MT, N, E><<<grid, kThreads, 0, st>>>(P, M)
+    if (want_mat && want_n && want_env) MB_BWD(true, true, true);
+    else if (want_mat && want_n) MB_BWD(true, true, false);
+    else if (want_mat && want_env) MB_BWD(true, false, true);
+    else if (want_mat) MB_BWD(true, false, false);
+    else if (want_env) MB_BWD(false, false, true);
+#undef MB_BWD
+    return mb200_check_launch();
+}
+
+}  // namespace
+
+extern "C" {
+
+int mb200_mesh_describe(int nv, int nt, int face_normals, mb200_mesh_desc* out) {
+    if (!out || nv <= 0 || nt <= 0) return MB200_EINVAL;
+    memset(out, 0, sizeof(*out));
+    out->nv = nv; out->nt = nt; out->face_normals = face_normals ? 1 : 0;
+    long long n = ((long long)nt + kLeaf - 1) / kLeaf;          // leaves
+    if (n >= (1ll << 27)) return MB200_ERANGE;
+    out->n_slots = (int32_t)(n * kLeaf);
+    int L = 0; int goff = 0;
+    for (;;) {
+        if (L >= MB200_MESH_MAX_LEVELS) return MB200_ERANGE;
+        out->lvl_nodes[L] = (int32_t)n; out->lvl_group_off[L] = goff;
+        const long long groups = (n + 3) / 4;
+        goff += (int)groups; ++L;
+        if (n <= 4) break;
+        n = groups;
+    }
+    out->n_levels = L; out->n_groups = goff;
+    size_t off = 0;
+    out->off_header = (int64_t)off; off += 256;
+    out->off_tv = (int64_t)off; off += align_up(sizeof(float4) * 3 * (size_t)out->n_slots, 256);
+    out->off_tn = (int64_t)off; off += face_normals ? 0 : align_up(sizeof(float4) * 3 * (size_t)out->n_slots, 256);
+    out->off_nodes = (int64_t)off; off += align_up(sizeof(float4) * 6 * (size_t)goff, 256);
+    out->total_bytes = (int64_t)off;
+    return MB200_OK;
+}
+
+size_t mb200_mesh_scratch_bytes(int nv, int nt, int face_normals) {
+    ScratchLayout S;
+    if (nv <= 0 || nt <= 0 || scratch_layout(nv, nt, face_normals, S) != MB200_OK) return 0;
+    return S.total;
+}
+
+int mb200_mesh_build(const float* verts, const int32_t* tris, const mb200_mesh_desc* md, void* mesh_buf, void* scratch, void* stream) {
+    if (!verts || !tris || !md || !mesh_buf || !scratch) return MB200_EINVAL;
+    mb200_mesh_desc chk;
+    int rc = mb200_mesh_describe(md->nv, md->nt, md->face_normals, &chk);
+    if (rc) return rc;
+    if (chk.total_bytes != md->total_bytes || chk.n_levels != md->n_levels) return MB200_EINVAL;
+    ScratchLayout S; rc = scratch_layout(md->nv, md->nt, md->face_normals, S);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* sb = reinterpret_cast<char*>(scratch); char* mb = reinterpret_cast<char*>(mesh_buf);
+    const int nt = md->nt, nv = md->nv, tb = 256;
+    int* bbox = reinterpret_cast<int*>(sb + S.bbox);
+    float* header = reinterpret_cast<float*>(mb + md->off_header);
+    float4* tv = reinterpret_cast<float4*>(mb + md->off_tv);
+    float4* tn = md->face_normals ? nullptr : reinterpret_cast<float4*>(mb + md->off_tn);
+    float4* nodes = reinterpret_cast<float4*>(mb + md->off_nodes);
+    mesh_init_kernel<<<1, 32, 0, st>>>(bbox);
+    int grid = (nt + tb - 1) / tb; const int cap = mb200_sm_count() * 8;
+    mesh_scene_bounds_kernel<<<grid < cap ? grid : cap, tb, 0, st>>>(verts, tris, nt, bbox);
+    mesh_header_kernel<<<1, 1, 0, st>>>(bbox, header);
+    uint32_t* k0 = reinterpret_cast<uint32_t*>(sb + S.keys0); uint32_t* k1 = reinterpret_cast<uint32_t*>(sb + S.keys1);
+    int32_t* v0 = reinterpret_cast<int32_t*>(sb + S.vals0); int32_t* v1 = reinterpret_cast<int32_t*>(sb + S.vals1);
+    mesh_morton_kernel<<<grid, tb, 0, st>>>(verts, tris, nt, header, k0, v0);
+    cub::DoubleBuffer<uint32_t> kb(k0, k1); cub::DoubleBuffer<int32_t> vb(v0, v1);
+    size_t cub_bytes = S.cub_bytes;
+    if (cub::DeviceRadixSort::SortPairs(sb + S.cub, cub_bytes, kb, vb, nt, 0, 30, st) != cudaSuccess) return mb200_check_launch();
+    float4* vn = nullptr;
+    if (!md->face_normals) {
+        double* acc = reinterpret_cast<double*>(sb + S.vnacc); vn = reinterpret_cast<float4*>(sb + S.vn);
+        if (mb200_check(cudaMemsetAsync(acc, 0, sizeof(double) * 3 * (size_t)nv, st)) != MB200_OK) return MB200_ELAUNCH;
+        mesh_vn_accum_kernel<<<grid, tb, 0, st>>>(verts, tris, nt, acc);
+        mesh_vn_finish_kernel<<<(nv + tb - 1) / tb, tb, 0, st>>>(acc, nv, vn);
+    }
+    mesh_gather_kernel<<<(md->n_slots + tb - 1) / tb, tb, 0, st>>>(verts, tris, nt, md->n_slots, vb.Current(), vn, tv, tn);
+    for (int l = 0; l < md->n_levels; ++l) {
+        const int n = md->lvl_nodes[l], padded = (n + 3) / 4 * 4;
+        if (l == 0) mesh_leaf_bounds_kernel<<<(padded + tb - 1) / tb, tb, 0, st>>>(tv, n, padded, nodes, md->lvl_group_off[0]);
+        else mesh_level_kernel<<<(padded + tb - 1) / tb, tb, 0, st>>>(nodes, md->lvl_group_off[l - 1], n, padded, md->lvl_group_off[l]);
+    }
+    return mb200_check_launch();
+}
+
+int mb200_mesh_shade_fwd(const mb200_cfg* c, const mb200_mesh_desc* md, const void* mesh_buf,
+                         const float* a, const float* r, const float* m, const float* n_opt,
+                         const float* env4, const float* hier, const mb200_hier_desc* d, float* partials, void* stream) {
+    RenderParams P; int rc = mesh_render_params(c, a, r, m, n_opt, env4, hier, d, P);
+    if (rc) return rc;
+    MeshView M; rc = make_view(md, mesh_buf, M);
+    if (rc) return rc;
+    if (!partials) return MB200_EINVAL;
+    P.prows = mb200_fwd_partial_rows(c, &P.prow0); P.partials = partials;
+    const int grid = grid_for(P.prows * P.W);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool ad = (c->flags & MB200_FLAG_AD_WEIGHTS) != 0;
+    if (c->filter == MB200_FILTER_GAUSSIAN) {
+        if (ad) mesh_fwd_kernel<MB200_FILTER_GAUSSIAN, true><<<grid, kThreads, 0, st>>>(P, M);
+        else    mesh_fwd_kernel<MB200_FILTER_GAUSSIAN, false><<<grid, kThreads, 0, st>>>(P, M);
+    } else {
+        if (ad) mesh_fwd_kernel<MB200_FILTER_BOX, true><<<grid, kThreads, 0, st>>>(P, M);
+        else    mesh_fwd_kernel<MB200_FILTER_BOX, false><<<grid, kThreads, 0, st>>>(P, M);
+    }
+    return mb200_check_launch();
+}
+
+int mb200_mesh_shade_bwd(const mb200_cfg* c, const mb200_mesh_desc* md, const void* mesh_buf,
+                         const float* a, const float* r, const float* m, const float* n_opt,
+                         const float* env4, const float* hier, const mb200_hier_desc* d, const float* gadj,
+                         float* g_a, float* g_r, float* g_m, float* g_n, float* g_env4, int n_env_slabs, void* stream) {
+    RenderParams P; int rc = mesh_render_params(c, a, r, m, n_opt, env4, hier, d, P);
+    if (rc) return rc;
+    MeshView M; rc = make_view(md, mesh_buf, M);
+    if (rc) return rc;
+    if (!gadj || (g_env4 && n_env_slabs < 1)) return MB200_EINVAL;
+    P.env_slabs = g_env4 ? n_env_slabs : 1; P.env_slab_stride = (long long)d->res_x * d->res_y;
+    P.prow0 = c->row0; P.prows = c->rows;
+    P.gadj = reinterpret_cast<const float4*>(gadj); P.grows = mb200_bwd_gadj_rows(c, &P.grow0);
+    P.g_a = g_a; P.g_r = g_r; P.g_m = g_m; P.g_n = g_n; P.g_env4 = reinterpret_cast<float4*>(g_env4);
+    const bool want_n = g_n != nullptr && !c->use_mesh_normal && n_opt != nullptr;
+    const bool want_mat = g_a || g_r || g_m || want_n;
+    const bool want_env = g_env4 != nullptr;
+    if (!want_mat && !want_env) return MB200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    return c->filter == MB200_FILTER_GAUSSIAN ? launch_mesh_bwd<MB200_FILTER_GAUSSIAN>(P, M, want_mat, want_n, want_env, st)
+                                              : launch_mesh_bwd<MB200_FILTER_BOX>(P, M, want_mat, want_n, want_env, st);
+}
+
+int mb200_mesh_intersect(const mb200_mesh_desc* md, const void* mesh_buf, const float* o, const float* d, const float* maxt,
+                         int n, int any_hit, int32_t* out_tri, float* out_tuv, void* stream) {
+    MeshView M; int rc = make_view(md, mesh_buf, M);
+    if (rc) return rc;
+    if (!o || !d || !out_tri || n < 0) return MB200_EINVAL;
+    if (n == 0) return MB200_OK;
+    mesh_intersect_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(M, o, d, maxt, n, any_hit, out_tri, out_tuv);
+    return mb200_check_launch();
+}
+
+int mb200_mesh_primary(const mb200_cfg* c, const mb200_mesh_desc* md, const void* mesh_buf, float jx, float jy,
+                       float* gpos, float* gnrm, int32_t* tri, int32_t* flat, void* stream) {
+    if (!c || !gpos || !gnrm || c->H <= 0 || c->W <= 0) return MB200_EINVAL;
+    MeshView M; int rc = make_view(md, mesh_buf, M);
+    if (rc) return rc;
+    RenderParams P; memset(&P, 0, sizeof(P));
+    for (int i = 0; i < 16; ++i) { P.cam.view[i] = c->view[i]; P.cam.proj[i] = c->proj[i]; P.cam.c2w[i] = c->cam_to_world[i]; }
+    P.cam.tan_half_fov_x = c->tan_half_fov_x; P.cam.H = c->H; P.cam.W = c->W;
+    P.cam.stride = (c->flags & MB200_FLAG_ROW_STRIDE_H) ? c->H : c->W;
+    P.H = c->H; P.W = c->W;
+    const int n = c->H * c->W;
+    mesh_primary_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, M, jx, jy, reinterpret_cast<float4*>(gpos), reinterpret_cast<float4*>(gnrm), tri, flat);
+    return mb200_check_launch();
+}
+
+}  // extern "C"

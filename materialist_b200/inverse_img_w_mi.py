@@ -22,17 +22,26 @@ from .scene import Camera, Scene, traverse  # noqa: F401
 _ENV0 = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "envmaps", "0.hdr")
 
 
-def load_estimated_mesh(mesh_path, use_mesh_normal, max_path=4, envmap=None, width=512, height=512, device="cuda"):
-    """Scene handle for a depth-derived height-field PLY (vertex k <-> pixel k).  `envmap`: (He,We,3) array/tensor or a
-    path to a .hdr/.exr; the reference hard-wires 'envmaps/0.hdr' (inverse_img_w_mi.py:54) — pass it explicitly here."""
+def load_estimated_mesh(mesh_path, use_mesh_normal, max_path=4, envmap=None, width=512, height=512, device="cuda", mode="mesh"):
+    """Scene handle for the depth-derived PLY.  `envmap`: (He,We,3) array/tensor or a path to a .hdr/.exr; the reference
+    hard-wires 'envmaps/0.hdr' (inverse_img_w_mi.py:54) — pass it explicitly here.
+    mode='mesh' (default): the triangle mesh is traced like the reference does (per-sample hits, shadow rays, max_path-1
+    bounces; csrc/mb200_mesh.cu).  mode='gbuffer': the fast approximation — per-pixel G-buffer (vertex k <-> pixel k),
+    no occlusion / interreflection."""
     cam = Camera.from_json(width=width, height=height)
-    pos, nrm, valid = gbuffer_from_ply(mesh_path, height, width, cam)
     if isinstance(envmap, str):
         envmap = read_image(envmap)[..., :3]
     if envmap is None:
         envmap = np.ones((16, 32, 3), np.float32)
-    return Scene(pos, nrm, valid, camera=cam, envmap=torch.as_tensor(np.ascontiguousarray(envmap)), use_mesh_normal=use_mesh_normal,
-                 max_depth=max_path, device=device)
+    envmap = torch.as_tensor(np.ascontiguousarray(envmap))
+    if mode == "mesh":
+        from .mesh import read_ply_mesh
+        verts, tris = read_ply_mesh(mesh_path)
+        return Scene.from_mesh(verts, tris, cam, device=device, envmap=envmap, use_mesh_normal=use_mesh_normal, max_depth=max_path)
+    if mode != "gbuffer":
+        raise ValueError("mode must be 'mesh' or 'gbuffer'")
+    pos, nrm, valid = gbuffer_from_ply(mesh_path, height, width, cam)
+    return Scene(pos, nrm, valid, camera=cam, envmap=envmap, use_mesh_normal=use_mesh_normal, max_depth=max_path, device=device)
 
 
 def load_estimated_mesh_w_env(mesh_path, envmap_path, bsdf="matDiffBSDF", max_depth=4, **kw):

@@ -73,10 +73,16 @@ def _forward(scene, spp, seed, a, r, m, n, env_pack, extra_flags=0):
     partials = torch.empty(prows, scene.W, stride, device=scene.device)
     st = _abi.stream_ptr()
     nmap = None if scene.use_mesh_normal else n
-    with _ktime("shade_fwd"):
-        _abi.check(_abi.lib.mb200_shade_fwd(C.byref(cfg), _abi.ptr(scene.gpos), _abi.ptr(scene.gnrm), _abi.ptr(a), _abi.ptr(r),
-                                            _abi.ptr(m), _abi.ptr(nmap), _abi.ptr(env4), _abi.ptr(hier), C.byref(desc),
-                                            _abi.ptr(partials), st), "mb200_shade_fwd")
+    if scene.mesh is not None:
+        with _ktime("mesh_fwd"):
+            _abi.check(_abi.lib.mb200_mesh_shade_fwd(C.byref(cfg), C.byref(scene.mesh.desc), _abi.ptr(scene.mesh.buf), _abi.ptr(a), _abi.ptr(r),
+                                                     _abi.ptr(m), _abi.ptr(nmap), _abi.ptr(env4), _abi.ptr(hier), C.byref(desc),
+                                                     _abi.ptr(partials), st), "mb200_mesh_shade_fwd")
+    else:
+        with _ktime("shade_fwd"):
+            _abi.check(_abi.lib.mb200_shade_fwd(C.byref(cfg), _abi.ptr(scene.gpos), _abi.ptr(scene.gnrm), _abi.ptr(a), _abi.ptr(r),
+                                                _abi.ptr(m), _abi.ptr(nmap), _abi.ptr(env4), _abi.ptr(hier), C.byref(desc),
+                                                _abi.ptr(partials), st), "mb200_shade_fwd")
     img = torch.empty(cfg.rows, scene.W, 3, device=scene.device)
     _abi.check(_abi.lib.mb200_film_develop(C.byref(cfg), _abi.ptr(partials), _abi.ptr(img), st), "mb200_film_develop")
     return img
@@ -112,11 +118,18 @@ def _backward(scene, spp, seed_grad, a, r, m, n, env_pack, grad_img_halo, want_a
     n_slabs = _abi.lib.mb200_env_grad_slabs(He, We, mode) if want_env else 1
     g_env4 = torch.zeros((n_slabs,) + tuple(env4.shape), device=dev) if want_env else None
     nmap = None if scene.use_mesh_normal else n
-    with _ktime("shade_bwd"):
-        _abi.check(_abi.lib.mb200_shade_bwd(C.byref(cfg), _abi.ptr(scene.gpos), _abi.ptr(scene.gnrm), _abi.ptr(a), _abi.ptr(r),
-                                            _abi.ptr(m), _abi.ptr(nmap), _abi.ptr(env4), _abi.ptr(hier), C.byref(desc),
-                                            _abi.ptr(gadj), _abi.ptr(g_a), _abi.ptr(g_r), _abi.ptr(g_m), _abi.ptr(g_n),
-                                            _abi.ptr(g_env4), n_slabs, st), "mb200_shade_bwd")
+    if scene.mesh is not None:
+        with _ktime("mesh_bwd"):
+            _abi.check(_abi.lib.mb200_mesh_shade_bwd(C.byref(cfg), C.byref(scene.mesh.desc), _abi.ptr(scene.mesh.buf), _abi.ptr(a), _abi.ptr(r),
+                                                     _abi.ptr(m), _abi.ptr(nmap), _abi.ptr(env4), _abi.ptr(hier), C.byref(desc),
+                                                     _abi.ptr(gadj), _abi.ptr(g_a), _abi.ptr(g_r), _abi.ptr(g_m), _abi.ptr(g_n),
+                                                     _abi.ptr(g_env4), n_slabs, st), "mb200_mesh_shade_bwd")
+    else:
+        with _ktime("shade_bwd"):
+            _abi.check(_abi.lib.mb200_shade_bwd(C.byref(cfg), _abi.ptr(scene.gpos), _abi.ptr(scene.gnrm), _abi.ptr(a), _abi.ptr(r),
+                                                _abi.ptr(m), _abi.ptr(nmap), _abi.ptr(env4), _abi.ptr(hier), C.byref(desc),
+                                                _abi.ptr(gadj), _abi.ptr(g_a), _abi.ptr(g_r), _abi.ptr(g_m), _abi.ptr(g_n),
+                                                _abi.ptr(g_env4), n_slabs, st), "mb200_shade_bwd")
     g_env = None
     if want_env:
         g_env = torch.empty(He, We, 3, device=dev)

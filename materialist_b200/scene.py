@@ -74,7 +74,9 @@ class Scene:
     """G-buffer scene handle. Tensors live on one CUDA device; everything is fp32 and contiguous."""
 
     def __init__(self, pos, nrm, valid=None, camera=None, envmap=None, use_mesh_normal=True, max_depth=4,
-                 rfilter="gaussian", device=None, flags=None):
+                 rfilter="gaussian", device=None, flags=None, mesh=None):
+        """mesh: optional materialist_b200.mesh.Mesh.  With a mesh the operator TRACES it (per-sample triangle hits,
+        shadow rays, bounces — what the reference renders); without, it shades the per-pixel G-buffer (pos, nrm)."""
         pos = torch.as_tensor(pos, dtype=torch.float32)
         nrm = torch.as_tensor(nrm, dtype=torch.float32)
         if pos.ndim != 3 or pos.shape[-1] != 3 or nrm.shape != pos.shape:
@@ -88,8 +90,11 @@ class Scene:
         if (self.camera.width, self.camera.height) != (W, H):
             raise ValueError("camera film size does not match the G-buffer")
         v = torch.ones(H, W, 1) if valid is None else torch.as_tensor(valid).reshape(H, W, 1).float()
-        self.gpos = torch.cat([pos, v], -1).contiguous().to(self.device)
-        self.gnrm = torch.cat([nrm, torch.zeros(H, W, 1)], -1).contiguous().to(self.device)
+        self.gpos = torch.cat([pos.to(self.device), v.to(self.device)], -1).contiguous()
+        self.gnrm = torch.cat([nrm.to(self.device), torch.zeros(H, W, 1, device=self.device)], -1).contiguous()
+        self.mesh = mesh
+        if mesh is not None and mesh.buf.device != self.gpos.device:
+            raise ValueError("mesh and scene must live on the same device")
         # MatDiffBSDF placeholders (mi_plugin.py:1238-1241)
         self.a = torch.full((H, W, 3), 0.5, device=self.device)
         self.r = torch.full((H, W, 1), 0.5, device=self.device)
@@ -108,6 +113,24 @@ class Scene:
         if envmap is None:
             envmap = torch.ones(16, 32, 3)
         self.set_envmap(envmap, _abi.ENV_FILE)
+
+    @classmethod
+    def from_mesh(cls, verts, tris, camera, face_normals=False, device="cuda", trace=True, **kw):
+        """Scene for a triangle mesh (the reference's depth-derived PLY).  The G-buffer of the fast path is the mesh's
+        primary visibility through the pixel centres (mb200_mesh_primary); `trace=False` drops the mesh afterwards
+        (G-buffer shading only)."""
+        from .mesh import Mesh
+        mesh = Mesh(verts, tris, face_normals=face_normals, device=device)
+        c = _abi.Cfg()
+        c.H, c.W = camera.height, camera.width
+        c.view[:] = camera.view_matrix.reshape(-1).tolist()
+        c.proj[:] = camera.proj_matrix.reshape(-1).tolist()
+        c.cam_to_world[:] = camera.to_world.astype(np.float32).reshape(-1).tolist()
+        c.tan_half_fov_x = camera.tan_half_fov_x
+        # slightly off-centre: rays through the exact pixel centres pass through the mesh vertices (vertex k <-> pixel k) and
+        # ~7 % of them slip between the triangles in float
+        gpos, gnrm, _, _ = mesh.primary(c, 0.47, 0.53)
+        return cls(gpos[..., :3], gnrm[..., :3], gpos[..., 3:], camera=camera, device=device, mesh=mesh if trace else None, **kw)
 
     # ---------------------------------------------------------------- shard
     def set_shard(self, row0, rows):

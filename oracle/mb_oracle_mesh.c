@@ -67,6 +67,11 @@ static int bvh_build(mbo_mesh* M, const real* cen, int first, int count) {
     for (int k = 0; k < 3; ++k) { nd->lo[k] = (real)1e30; nd->hi[k] = (real)-1e30; }
     for (int i = first; i < first + count; ++i) {
         real lo[3], hi[3]; tri_bounds(M, M->order[i], lo, hi);
+        /* conservative padding: Moeller-Trumbore accepts hits (u, v rounded to exactly 0, e.g. pixel-centre rays through a
+         * shared vertex) that an exact slab test of the unpadded box rejects; with it BVH == brute force (tests) */
+        real mx = 0; for (int k = 0; k < 3; ++k) { if (FABS(lo[k]) > mx) mx = FABS(lo[k]); if (FABS(hi[k]) > mx) mx = FABS(hi[k]); }
+        const real pad = (real)3.814697265625e-06 * (R(1.0) + mx);
+        for (int k = 0; k < 3; ++k) { lo[k] -= pad; hi[k] += pad; }
         for (int k = 0; k < 3; ++k) {
             if (lo[k] < nd->lo[k]) nd->lo[k] = lo[k]; if (hi[k] > nd->hi[k]) nd->hi[k] = hi[k];
             real c = cen[3 * (size_t)M->order[i] + k]; if (c < clo[k]) clo[k] = c; if (c > chi[k]) chi[k] = c;
