@@ -17,20 +17,28 @@ from test_reference_render_pin import FIX, REF_FLAGS, pin_cfg, rel_l2
 pytestmark = pytest.mark.gpu
 
 
-def assert_radiance_parity(img, ref, spp):
+def assert_radiance_parity(img, ref, spp, shape=None):
     """Traced paths are bit-identical to the oracle's up to and including the primary hit; from the first sampled direction
     on, CUDA's sincospif / rsqrt / fast division differ from glibc's by ulps, and about one path in 10^5 takes a different
     DISCRETE decision at a secondary ray (grazing shadow ray, hit next to an edge, offset side of a tangent direction): one
     whole sample of one pixel changes (measured: 1-2 pixels of 1600-4096, everything else agrees to ~1e-6).  So the 1e-4 bar
     is asserted on all but the worst 0.5 % of the pixels, the flipped ones are bounded in number, and the full-image
-    rel-L2 is bounded loosely."""
+    rel-L2 is bounded loosely.  With the gaussian film ONE flipped sample moves the up-to-5x5 pixels of its footprint, so
+    when `shape` = (H, W) is given the flipped pixels are counted as footprint clusters (greedy: worst pixel first, everything
+    within 4 pixels of it belongs to the same event)."""
     img = np.asarray(img, np.float64).reshape(-1, 3); ref = np.asarray(ref, np.float64).reshape(-1, 3)
     err = np.abs(img - ref).sum(-1)
     n = len(err); k = max(1, n // 200)
     order = np.argsort(-err); keep = np.ones(n, bool); keep[order[:k]] = False
     e_core = np.linalg.norm((img - ref)[keep]) / np.linalg.norm(ref[keep])
     assert e_core <= 1e-4, e_core
-    flipped = int((err > 0.05 * ref.mean() * 3 / spp).sum())          # moved by more than 5 % of one mean-valued sample
+    bad = err > 0.05 * ref.mean() * 3 / spp                            # moved by more than 5 % of one mean-valued sample
+    flipped = int(bad.sum())
+    if shape is not None and flipped:
+        Wd = shape[1]; todo = [int(i) for i in order if bad[i]]; flipped = 0
+        while todo:
+            y0, x0 = divmod(todo[0], Wd); flipped += 1
+            todo = [i for i in todo if max(abs(i // Wd - y0), abs(i % Wd - x0)) > 4]
     assert flipped <= max(2, n // 400), flipped
     assert rel_l2(img, ref) <= 2e-2
     return e_core
@@ -121,7 +129,7 @@ def test_mesh_forward_matches_oracle(oracle32, max_depth, flags, gaussian, face_
     from materialist_b200 import renderop
     img = renderop._forward(s, 32, 5, ta, tr, tm, None, s.prepared_env(), extra_flags=flags & orc.FLAG_AD_WEIGHTS)
     assert st[2] > 0                     # the case has occluded emitter samples
-    assert_radiance_parity(img.cpu().numpy(), ref, 32)
+    assert_radiance_parity(img.cpu().numpy(), ref, 32, shape=(H, W) if gaussian else None)
     oracle32.mesh_destroy(om)
 
 
@@ -203,5 +211,5 @@ def test_cuda_mesh_matches_oracle_on_reference_scene(oracle32):
     om = oracle32.mesh_create(g["verts"], g["tris"])
     env_int, hier, d = oracle32.env_prepare(g["env"], orc.ENV_ASSIGNED)
     ref = oracle32.mesh_render_fwd(pin_cfg(d, 993, 250, 8), om, g["a"], g["r"], g["m"], None, env_int, hier, d)
-    assert_radiance_parity(img, ref, 64)
+    assert_radiance_parity(img, ref, 64, shape=img.shape[:2])
     oracle32.mesh_destroy(om)
