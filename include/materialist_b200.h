@@ -30,6 +30,8 @@
  *                          parameters_changed.
  *   mb200_bsdf_eval_pdf    MatDiffBSDF.eval_pdf  (myutils/mi_plugin.py:1449-1460) on an array of lanes.
  *   mb200_bsdf_sample      MatDiffBSDF.sample    (myutils/mi_plugin.py:1429-1446) on an array of lanes.
+ *   mb200_trans_*          TransBSDF (myutils/mi_plugin.py:1477-1770), the transparency-editing plugin of
+ *                          trans_edit.py:16-49: forward render in G-buffer and mesh mode + lane-level eval_pdf / sample.
  *   mb200_debug_sample_indices
  *                          not in the reference: exposes the integer decisions of the path
  *                          (hierarchy offsets, texel index, lobe) so tests can assert them bit-exact.
@@ -196,7 +198,9 @@ int mb200_debug_sample_indices(const mb200_cfg* cfg_host, const float* gpos, con
                                int32_t* out, void* stream);
 
 /* ---------------------------------------------------------------- mesh mode (triangle mesh instead of a G-buffer) */
-#define MB200_MESH_LEAF        4    /* triangles per BVH leaf */
+#ifndef MB200_MESH_LEAF
+#define MB200_MESH_LEAF        1    /* triangles per BVH leaf (compile-time; mb200_mesh_describe reports the layout) */
+#endif
 #define MB200_MESH_MAX_LEVELS  16
 /* Layout of a built mesh inside ONE device buffer `mesh_buf` (byte offsets), filled by mb200_mesh_describe:
  *   header : centre.xyz, radius of the scene bounding sphere, bbox lo.xyz, hi.xyz (written by the build, read by kernels)
@@ -253,6 +257,46 @@ int mb200_bsdf_sample(const mb200_cfg* cfg_host, int64_t L,
                       const float* a, const float* r, const float* m, const float* n_opt,
                       float* out_wo /*(L,3) world*/, float* out_pdf /*(L)*/, float* out_weight /*(L,3)*/,
                       void* stream);
+
+/* ---------------------------------------------------------------- TransBSDF (transparency editing; forward only) */
+/* Replaces the `TransBSDF` plugin (myutils/mi_plugin.py:1477-1770) that trans_edit.py:16-49 renders with: texels under
+ * `mask` get the edited (diffuse + metal + glass reflection / transmission) BSDF with the background `bg` looked up at
+ * the twice-refracted screen position (calculate_refracted_screen_coor, :1503-1519); all other texels keep the
+ * MatDiffBSDF value.  pdf clamps VoH at 1e-4 and the sample weight is f / (pdf + 1e-4) (:1610, :1659).  The reference
+ * never differentiates this plugin, so there is no adjoint entry point. */
+typedef struct mb200_trans {
+    float ior;               /* 'shape.bsdf.ior' (props['ior'], default 1.3)                                  */
+    float spec_trans;        /* 'shape.bsdf.specTrans' (default 0.8)                                          */
+    float refract_distance;  /* 100 when the plugin was given keep_albedo_color, else 1 (mi_plugin.py:1484-1489) */
+    int32_t reserved;
+    const float*   bg;       /* (H,W,3) fp32 'shape.bsdf.bg'                                                   */
+    const uint8_t* mask;     /* (H,W) bytes, nonzero = edited texel ('shape.bsdf.mask')                        */
+} mb200_trans;
+/* as mb200_shade_fwd / mb200_mesh_shade_fwd with the TransBSDF in place of MatDiffBSDF */
+int mb200_trans_shade_fwd(const mb200_cfg* cfg_host, const mb200_trans* trans_host,
+                          const float* gpos, const float* gnrm,
+                          const float* a, const float* r, const float* m, const float* n_opt,
+                          const float* env4, const float* hier, const mb200_hier_desc* desc_host,
+                          float* partials, void* stream);
+int mb200_trans_mesh_shade_fwd(const mb200_cfg* cfg_host, const mb200_trans* trans_host,
+                               const mb200_mesh_desc* desc_host, const void* mesh_buf,
+                               const float* a, const float* r, const float* m, const float* n_opt,
+                               const float* env4, const float* hier, const mb200_hier_desc* hdesc_host,
+                               float* partials, void* stream);
+/* TransBSDF.eval_pdf (:1748-1761) / .sample (:1521-1544) on arrays of lanes, arguments as mb200_bsdf_eval_pdf / _sample */
+int mb200_trans_eval_pdf(const mb200_cfg* cfg_host, const mb200_trans* trans_host, int64_t L,
+                         const float* p, const float* n_geo, const float* wi_world, const float* wo_world,
+                         const float* a, const float* r, const float* m, const float* n_opt,
+                         float* out_f, float* out_pdf, void* stream);
+int mb200_trans_sample(const mb200_cfg* cfg_host, const mb200_trans* trans_host, int64_t L,
+                       const float* p, const float* n_geo, const float* wi_world,
+                       const float* sample1, const float* sample2,
+                       const float* a, const float* r, const float* m, const float* n_opt,
+                       float* out_wo, float* out_pdf, float* out_weight, void* stream);
+/* calculate_refracted_screen_coor on lanes: out_screen (L,2) fp32, out_flat (L) int64 = x + y*stride of the bg texel */
+int mb200_trans_refracted_texel(const mb200_cfg* cfg_host, const mb200_trans* trans_host, int64_t L,
+                                const float* p, const float* n_geo, const float* wi_world,
+                                float* out_screen, int64_t* out_flat, void* stream);
 
 /* ---------------------------------------------------------------- PosMLP */
 #define MB200_POSMLP_TCGEN05 0   /* 256-wide layers on tcgen05 tensor cores, FP16x2-split operands, FP32 TMEM accumulators */

@@ -36,7 +36,7 @@ class HierDesc(C.Structure):
                 ("total_floats", C.c_int32)]
 
 
-MESH_MAX_LEVELS, MESH_LEAF = 16, 4
+MESH_MAX_LEVELS = 16
 
 
 class MeshDesc(C.Structure):
@@ -45,6 +45,12 @@ class MeshDesc(C.Structure):
                 ("lvl_nodes", C.c_int32 * MESH_MAX_LEVELS), ("lvl_group_off", C.c_int32 * MESH_MAX_LEVELS),
                 ("off_header", C.c_int64), ("off_tv", C.c_int64), ("off_tn", C.c_int64), ("off_nodes", C.c_int64),
                 ("total_bytes", C.c_int64)]
+
+
+class Trans(C.Structure):
+    """mb200_trans: TransBSDF parameters (device pointers)."""
+    _fields_ = [("ior", C.c_float), ("spec_trans", C.c_float), ("refract_distance", C.c_float), ("reserved", C.c_int32),
+                ("bg", C.c_void_p), ("mask", C.c_void_p)]
 
 
 class PosMLPDesc(C.Structure):
@@ -68,7 +74,7 @@ def _load():
             "or `make -C materialist_b200/csrc`. There is no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
     vp, i32, i64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
-    pc, ph, pm, pd = C.POINTER(Cfg), C.POINTER(HierDesc), C.POINTER(PosMLPDesc), C.POINTER(MeshDesc)
+    pc, ph, pm, pd, pt = C.POINTER(Cfg), C.POINTER(HierDesc), C.POINTER(PosMLPDesc), C.POINTER(MeshDesc), C.POINTER(Trans)
     sig = {
         "mb200_strerror": (C.c_char_p, [i32]),
         "mb200_last_cuda_error": (C.c_char_p, []),
@@ -98,6 +104,11 @@ def _load():
         "mb200_mesh_primary": (i32, [pc, pd, vp, C.c_float, C.c_float, vp, vp, vp, vp, vp]),
         "mb200_bsdf_eval_pdf": (i32, [pc, i64] + [vp] * 11),
         "mb200_bsdf_sample": (i32, [pc, i64] + [vp] * 13),
+        "mb200_trans_shade_fwd": (i32, [pc, pt] + [vp] * 8 + [ph, vp, vp]),
+        "mb200_trans_mesh_shade_fwd": (i32, [pc, pt, pd] + [vp] * 7 + [ph, vp, vp]),
+        "mb200_trans_eval_pdf": (i32, [pc, pt, i64] + [vp] * 11),
+        "mb200_trans_sample": (i32, [pc, pt, i64] + [vp] * 13),
+        "mb200_trans_refracted_texel": (i32, [pc, pt, i64] + [vp] * 6),
         "mb200_posmlp_param_count": (i64, [pm]),
         "mb200_posmlp_cache_bytes": (sz, [pm, i64]),
         "mb200_posmlp_workspace_bytes": (sz, [pm]),

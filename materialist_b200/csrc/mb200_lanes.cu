@@ -12,6 +12,7 @@ struct LaneParams {
     CamView cam; int use_mesh_normal; long long L;
     const float *p, *n_geo, *wi, *wo, *s1, *s2, *a, *r, *m, *n_opt;
     float *o3, *o1, *ow;
+    TransView trans; long long* oflat;          // mb200_trans_* only
 };
 __device__ __forceinline__ float3 ld3(const float* q, long long i) { return f3(q[3 * i], q[3 * i + 1], q[3 * i + 2]); }
 __device__ __forceinline__ void st3(float* q, long long i, float3 v) { q[3 * i] = v.x; q[3 * i + 1] = v.y; q[3 * i + 2] = v.z; }
@@ -35,6 +36,37 @@ __global__ void bsdf_sample_kernel(const __grid_constant__ LaneParams P) {
     const Frame fs = make_frame(mt.n);
     const BsdfSample s = sample_brdf(P.s1[i], P.s2[2 * i], P.s2[2 * i + 1], ld3(P.wi, i), mt, fs);
     st3(P.o3, i, s.wi); P.o1[i] = s.pdf; st3(P.ow, i, s.weight);
+}
+// TransBSDF.eval_pdf / .sample / calculate_refracted_screen_coor on lanes (mi_plugin.py:1503-1544, 1748-1761)
+__global__ void trans_eval_pdf_kernel(const __grid_constant__ LaneParams P) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.L) return;
+    const Material mt = lane_material(P, i);
+    const float3 p = ld3(P.p, i), view = ld3(P.wi, i);
+    const TransMat tm = trans_fetch(P.cam, P.trans, texel_index(P.cam, p), view, ld3(P.n_geo, i), p);
+    const BsdfVal v = trans_eval_brdf(ld3(P.wo, i), view, mt, tm, P.trans);
+    st3(P.o3, i, v.f); P.o1[i] = v.pdf;
+}
+__global__ void trans_sample_kernel(const __grid_constant__ LaneParams P) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.L) return;
+    const Material mt = lane_material(P, i);
+    const float3 p = ld3(P.p, i), view = ld3(P.wi, i);
+    const TransMat tm = trans_fetch(P.cam, P.trans, texel_index(P.cam, p), view, ld3(P.n_geo, i), p);
+    const BsdfSample s = trans_sample_brdf(P.s1[i], P.s2[2 * i], P.s2[2 * i + 1], view, mt, tm, P.trans, make_frame(mt.n));
+    st3(P.o3, i, s.wi); P.o1[i] = s.pdf; st3(P.ow, i, s.weight);
+}
+__global__ void trans_refracted_kernel(const __grid_constant__ LaneParams P) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.L) return;
+    float sx, sy; trans_refracted_screen(P.cam, P.trans, ld3(P.wi, i), ld3(P.n_geo, i), ld3(P.p, i), sx, sy);
+    P.o3[2 * i] = sx; P.o3[2 * i + 1] = sy;
+    P.oflat[i] = trans_refracted_index(P.cam, P.trans, ld3(P.wi, i), ld3(P.n_geo, i), ld3(P.p, i));
+}
+int fill_trans_lanes(const mb200_trans* t, LaneParams& P) {
+    if (!t || !(t->ior > 0.f)) return MB200_EINVAL;
+    P.trans.bg = t->bg; P.trans.mask = t->mask; P.trans.ior = t->ior; P.trans.spec_trans = t->spec_trans; P.trans.refract_dist = t->refract_distance;
+    return MB200_OK;
 }
 int fill(const mb200_cfg* c, LaneParams& P) {
     if (!c || c->H <= 0 || c->W <= 0) return MB200_EINVAL;
@@ -70,6 +102,43 @@ int mb200_bsdf_sample(const mb200_cfg* c, int64_t L, const float* p, const float
     P.L = L; P.p = p; P.n_geo = n_geo; P.wi = wi_world; P.s1 = sample1; P.s2 = sample2; P.a = a; P.r = r; P.m = m; P.n_opt = n_opt;
     P.o3 = out_wo; P.o1 = out_pdf; P.ow = out_weight;
     bsdf_sample_kernel<<<(unsigned)((L + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P);
+    return mb200_check_launch();
+}
+
+int mb200_trans_eval_pdf(const mb200_cfg* c, const mb200_trans* t, int64_t L, const float* p, const float* n_geo, const float* wi_world,
+                         const float* wo_world, const float* a, const float* r, const float* m, const float* n_opt,
+                         float* out_f, float* out_pdf, void* stream) {
+    LaneParams P; int rc = fill(c, P); if (rc) return rc;
+    if ((rc = fill_trans_lanes(t, P)) != MB200_OK) return rc;
+    if (L < 0 || !t->bg || !t->mask || !p || !n_geo || !wi_world || !wo_world || !a || !r || !m || !out_f || !out_pdf) return MB200_EINVAL;
+    if (L == 0) return MB200_OK;
+    P.L = L; P.p = p; P.n_geo = n_geo; P.wi = wi_world; P.wo = wo_world; P.a = a; P.r = r; P.m = m; P.n_opt = n_opt;
+    P.o3 = out_f; P.o1 = out_pdf;
+    trans_eval_pdf_kernel<<<(unsigned)((L + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P);
+    return mb200_check_launch();
+}
+
+int mb200_trans_sample(const mb200_cfg* c, const mb200_trans* t, int64_t L, const float* p, const float* n_geo, const float* wi_world,
+                       const float* sample1, const float* sample2, const float* a, const float* r, const float* m,
+                       const float* n_opt, float* out_wo, float* out_pdf, float* out_weight, void* stream) {
+    LaneParams P; int rc = fill(c, P); if (rc) return rc;
+    if ((rc = fill_trans_lanes(t, P)) != MB200_OK) return rc;
+    if (L < 0 || !t->bg || !t->mask || !p || !n_geo || !wi_world || !sample1 || !sample2 || !a || !r || !m || !out_wo || !out_pdf || !out_weight) return MB200_EINVAL;
+    if (L == 0) return MB200_OK;
+    P.L = L; P.p = p; P.n_geo = n_geo; P.wi = wi_world; P.s1 = sample1; P.s2 = sample2; P.a = a; P.r = r; P.m = m; P.n_opt = n_opt;
+    P.o3 = out_wo; P.o1 = out_pdf; P.ow = out_weight;
+    trans_sample_kernel<<<(unsigned)((L + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P);
+    return mb200_check_launch();
+}
+
+int mb200_trans_refracted_texel(const mb200_cfg* c, const mb200_trans* t, int64_t L, const float* p, const float* n_geo,
+                                const float* wi_world, float* out_screen, int64_t* out_flat, void* stream) {
+    LaneParams P; int rc = fill(c, P); if (rc) return rc;
+    if ((rc = fill_trans_lanes(t, P)) != MB200_OK) return rc;
+    if (L < 0 || !p || !n_geo || !wi_world || !out_screen || !out_flat) return MB200_EINVAL;
+    if (L == 0) return MB200_OK;
+    P.L = L; P.p = p; P.n_geo = n_geo; P.wi = wi_world; P.o3 = out_screen; P.oflat = (long long*)out_flat;
+    trans_refracted_kernel<<<(unsigned)((L + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P);
     return mb200_check_launch();
 }
 

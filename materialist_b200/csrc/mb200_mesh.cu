@@ -89,7 +89,10 @@ __device__ __forceinline__ bool tri_intersect(float3 p0, float3 p1, float3 p2, f
 
 #define MB_CSWAP(i, j) { if (ct[j] < ct[i]) { float tf = ct[i]; ct[i] = ct[j]; ct[j] = tf; uint32_t tc = cc[i]; cc[i] = cc[j]; cc[j] = tc; } }
 
-// closest hit = (smallest t, then smallest triangle id); ANY: true as soon as one triangle is hit within maxt
+// closest hit = (smallest t, then smallest triangle id); ANY: true as soon as one triangle is hit within maxt.
+// Measured alternatives (profiles/r1r_mesh_traversal_variants.log, C2m step): 4-triangle leaves 549 ms, 2-triangle 433 ms,
+// 1-triangle leaves (every triangle has its own box in a level-0 group) 380 ms; a "while-while" loop that postpones the
+// leaf tests until every lane holds one: 780-790 ms for all leaf sizes (lanes with long inner descents stall the rest)
 template <bool ANY>
 __device__ __forceinline__ bool mesh_intersect(const MeshView& M, float3 o, float3 d, float maxt, Hit& h) {
     const float3 inv = f3(__fdiv_rn(1.f, d.x), __fdiv_rn(1.f, d.y), __fdiv_rn(1.f, d.z));
@@ -205,7 +208,7 @@ __device__ __forceinline__ Material fetch_material(const RenderParams& P, float3
 }
 
 // ---------------------------------------------------------------- forward: PathIntegrator::sample for one lane
-template <bool AD_W>
+template <bool AD_W, bool TRANS = false>
 __device__ __forceinline__ float3 trace_path_fwd(const RenderParams& P, const MeshView& M, int px, int py, uint32_t lane_id, float& jx, float& jy) {
     Pcg32 rng; rng.seed(P.seed, lane_id);
     jx = rng.next_float(); jy = rng.next_float();
@@ -226,6 +229,7 @@ __device__ __forceinline__ float3 trace_path_fwd(const RenderParams& P, const Me
         const SurfacePoint sp = hit_point(M, h);
         const float3 view = f3(-rd.x, -rd.y, -rd.z);
         long long flat; const Material mt = fetch_material(P, sp.p, sp.ng, flat);
+        TransMat tm; if (TRANS) tm = trans_fetch(P.cam, P.trans, flat, view, sp.ng, sp.p);
         // ---- emitter sampling
         const float uex = rng.next_float(), uey = rng.next_float();
         const EmSample em = env_sample_direction(P.hier, P.env, uex, uey);
@@ -233,11 +237,11 @@ __device__ __forceinline__ float3 trace_path_fwd(const RenderParams& P, const Me
         const float s1 = rng.next_float();
         const float s2x = rng.next_float(), s2y = rng.next_float();
         if (visible) {
-            const BsdfVal fv = eval_brdf(em.d, view, mt);
+            const BsdfVal fv = TRANS ? trans_eval_brdf(em.d, view, mt, tm, P.trans) : eval_brdf(em.d, view, mt);
             L = L + beta * fv.f * env_value(P.env, em.b) * (mis_weight(em.pdf, fv.pdf) / em.pdf);
         }
         // ---- BSDF sampling
-        const BsdfSample bs = sample_brdf(s1, s2x, s2y, view, mt, make_frame(mt.n));
+        const BsdfSample bs = TRANS ? trans_sample_brdf(s1, s2x, s2y, view, mt, tm, P.trans, make_frame(mt.n)) : sample_brdf(s1, s2x, s2y, view, mt, make_frame(mt.n));
         const float3 d_bs = (P.flags & MB200_FLAG_WO_WORLD_QUIRK) ? to_world(sp.sh, bs.wi) : bs.wi;     // mi_plugin.py:1444
         float3 w = bs.weight;
         if (AD_W) {
@@ -252,7 +256,7 @@ __device__ __forceinline__ float3 trace_path_fwd(const RenderParams& P, const Me
     return L;
 }
 
-template <int FILTER, bool AD_W>
+template <int FILTER, bool AD_W, bool TRANS = false>
 __global__ void __launch_bounds__(kThreads, 2) mesh_fwd_kernel(const __grid_constant__ RenderParams P, const __grid_constant__ MeshView M) {
     __shared__ __align__(16) float s_rec[FILTER == MB200_FILTER_GAUSSIAN ? kWarpsPerBlock * 32 * kRecStride : 4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -267,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 2) mesh_fwd_kernel(const __grid_cons
             const int s = s0 + lane;
             float3 L = f3(0.f, 0.f, 0.f); float jx = 0.f, jy = 0.f;
             const bool act = s < P.spp;
-            if (act) L = trace_path_fwd<AD_W>(P, M, px, py, (uint32_t)gpix * (uint32_t)P.spp + (uint32_t)s, jx, jy);
+            if (act) L = trace_path_fwd<AD_W, TRANS>(P, M, px, py, (uint32_t)gpix * (uint32_t)P.spp + (uint32_t)s, jx, jy);
             __syncwarp();
             if (FILTER == MB200_FILTER_GAUSSIAN) {
                 float wx[5], wy[5]; film_taps(jx, wx); film_taps(jy, wy);
@@ -808,6 +812,24 @@ int mb200_mesh_shade_fwd(const mb200_cfg* c, const mb200_mesh_desc* md, const vo
         if (ad) mesh_fwd_kernel<MB200_FILTER_BOX, true><<<grid, kThreads, 0, st>>>(P, M);
         else    mesh_fwd_kernel<MB200_FILTER_BOX, false><<<grid, kThreads, 0, st>>>(P, M);
     }
+    return mb200_check_launch();
+}
+
+int mb200_trans_mesh_shade_fwd(const mb200_cfg* c, const mb200_trans* t, const mb200_mesh_desc* md, const void* mesh_buf,
+                               const float* a, const float* r, const float* m, const float* n_opt,
+                               const float* env4, const float* hier, const mb200_hier_desc* d, float* partials, void* stream) {
+    RenderParams P; int rc = mesh_render_params(c, a, r, m, n_opt, env4, hier, d, P);
+    if (rc) return rc;
+    if ((rc = fill_trans(t, P)) != MB200_OK) return rc;
+    MeshView M; rc = make_view(md, mesh_buf, M);
+    if (rc) return rc;
+    if (!partials) return MB200_EINVAL;
+    if (c->flags & MB200_FLAG_AD_WEIGHTS) return MB200_EUNSUPPORTED;      // the reference never differentiates TransBSDF
+    P.prows = mb200_fwd_partial_rows(c, &P.prow0); P.partials = partials;
+    const int grid = grid_for(P.prows * P.W);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (c->filter == MB200_FILTER_GAUSSIAN) mesh_fwd_kernel<MB200_FILTER_GAUSSIAN, false, true><<<grid, kThreads, 0, st>>>(P, M);
+    else                                    mesh_fwd_kernel<MB200_FILTER_BOX, false, true><<<grid, kThreads, 0, st>>>(P, M);
     return mb200_check_launch();
 }
 

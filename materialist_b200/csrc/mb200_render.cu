@@ -20,9 +20,10 @@ namespace {
 
 
 struct PixelCtx {
-    bool valid; long long flat; Material mt; float3 view; Frame fgeo, fshade;
+    bool valid; long long flat; Material mt; float3 view; Frame fgeo, fshade; TransMat tm;
 };
 
+template <bool TRANS = false>
 __device__ __forceinline__ PixelCtx load_pixel(const RenderParams& P, int gpix) {
     PixelCtx c;
     const float4 gp = __ldg(P.gpos + gpix), gn = __ldg(P.gnrm + gpix);
@@ -36,13 +37,14 @@ __device__ __forceinline__ PixelCtx load_pixel(const RenderParams& P, int gpix) 
         if (!P.use_mesh_normal && P.n_opt)
             c.mt.n = f3(__ldg(P.n_opt + 3 * c.flat), __ldg(P.n_opt + 3 * c.flat + 1), __ldg(P.n_opt + 3 * c.flat + 2));
         c.view = normalize(f3(P.cam.c2w[3], P.cam.c2w[7], P.cam.c2w[11]) - p);
+        if (TRANS) c.tm = trans_fetch(P.cam, P.trans, c.flat, c.view, ng, p);
     }
     c.fgeo = make_frame(ng); c.fshade = make_frame(c.mt.n);
     return c;
 }
 
 // ---------------------------------------------------------------- one forward sample
-template <bool AD_W>
+template <bool AD_W, bool TRANS = false>
 __device__ __forceinline__ float3 shade_sample(const RenderParams& P, const PixelCtx& c, int px, int py, uint32_t lane_id,
                                                float& jx, float& jy) {
     Pcg32 rng; rng.seed(P.seed, lane_id);
@@ -62,12 +64,12 @@ __device__ __forceinline__ float3 shade_sample(const RenderParams& P, const Pixe
     const EmSample em = env_sample_direction(P.hier, P.env, uex, uey);
     if (em.pdf != 0.f) {
         const float3 le = env_value(P.env, em.b);
-        const BsdfVal fv = eval_brdf(em.d, c.view, c.mt);
+        const BsdfVal fv = TRANS ? trans_eval_brdf(em.d, c.view, c.mt, c.tm, P.trans) : eval_brdf(em.d, c.view, c.mt);
         const float k = mis_weight(em.pdf, fv.pdf) / em.pdf;
         L = fv.f * le * k;
     }
     // ---- BSDF sampling
-    const BsdfSample bs = sample_brdf(s1, s2x, s2y, c.view, c.mt, c.fshade);
+    const BsdfSample bs = TRANS ? trans_sample_brdf(s1, s2x, s2y, c.view, c.mt, c.tm, P.trans, c.fshade) : sample_brdf(s1, s2x, s2y, c.view, c.mt, c.fshade);
     const float3 d_bs = (P.flags & MB200_FLAG_WO_WORLD_QUIRK) ? to_world(c.fgeo, bs.wi) : bs.wi;
     float3 w_bs = bs.weight;
     if (AD_W) {
@@ -84,7 +86,7 @@ __device__ __forceinline__ float3 shade_sample(const RenderParams& P, const Pixe
 }
 
 // ---------------------------------------------------------------- forward kernel
-template <int FILTER, bool AD_W>
+template <int FILTER, bool AD_W, bool TRANS = false>
 __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_FWD) shade_fwd_kernel(const __grid_constant__ RenderParams P) {
     __shared__ __align__(16) float s_rec[FILTER == MB200_FILTER_GAUSSIAN ? kWarpsPerBlock * 32 * kRecStride : 4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -94,13 +96,13 @@ __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_FWD) shade_fwd_kernel(
     for (int pix = blockIdx.x * kWarpsPerBlock + warp; pix < npix; pix += gridDim.x * kWarpsPerBlock) {
         const int py = P.prow0 + pix / P.W, px = pix % P.W;
         const int gpix = py * P.W + px;
-        const PixelCtx c = load_pixel(P, gpix);
+        const PixelCtx c = load_pixel<TRANS>(P, gpix);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int s0 = 0; s0 < P.spp; s0 += 32) {
             const int s = s0 + lane;
             float3 L = f3(0.f, 0.f, 0.f); float jx = 0.f, jy = 0.f;
             const bool act = s < P.spp;
-            if (act) L = shade_sample<AD_W>(P, c, px, py, (uint32_t)gpix * (uint32_t)P.spp + (uint32_t)s, jx, jy);
+            if (act) L = shade_sample<AD_W, TRANS>(P, c, px, py, (uint32_t)gpix * (uint32_t)P.spp + (uint32_t)s, jx, jy);
             if (FILTER == MB200_FILTER_GAUSSIAN) {
                 float wx[5], wy[5]; film_taps(jx, wx); film_taps(jy, wy);
                 if (!act) { wx[0] = wx[1] = wx[2] = wx[3] = wx[4] = 0.f; }
@@ -395,6 +397,22 @@ int mb200_shade_fwd(const mb200_cfg* c, const float* gpos, const float* gnrm, co
         if (ad) shade_fwd_kernel<MB200_FILTER_BOX, true><<<grid, kThreads, 0, st>>>(P);
         else    shade_fwd_kernel<MB200_FILTER_BOX, false><<<grid, kThreads, 0, st>>>(P);
     }
+    return mb200_check_launch();
+}
+
+int mb200_trans_shade_fwd(const mb200_cfg* c, const mb200_trans* t, const float* gpos, const float* gnrm, const float* a, const float* r,
+                          const float* m, const float* n_opt, const float* env4, const float* hier, const mb200_hier_desc* d,
+                          float* partials, void* stream) {
+    RenderParams P; int rc = fill_params(c, gpos, gnrm, a, r, m, n_opt, env4, hier, d, P);
+    if (rc) return rc;
+    if ((rc = fill_trans(t, P)) != MB200_OK) return rc;
+    if (!partials) return MB200_EINVAL;
+    if (c->flags & MB200_FLAG_AD_WEIGHTS) return MB200_EUNSUPPORTED;      // the reference never differentiates TransBSDF
+    P.prows = mb200_fwd_partial_rows(c, &P.prow0); P.partials = partials;
+    const int grid = grid_for(P.prows * P.W);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (c->filter == MB200_FILTER_GAUSSIAN) shade_fwd_kernel<MB200_FILTER_GAUSSIAN, false, true><<<grid, kThreads, 0, st>>>(P);
+    else                                    shade_fwd_kernel<MB200_FILTER_BOX, false, true><<<grid, kThreads, 0, st>>>(P);
     return mb200_check_launch();
 }
 

@@ -31,7 +31,14 @@ struct RenderParams {
     // adjoint
     const float4* gadj; int grow0, grows; // G image rows
     float* g_a; float* g_r; float* g_m; float* g_n; float4* g_env4; int env_slabs; long long env_slab_stride;
+    TransView trans;                     // TransBSDF kernels only (mb200_trans_*)
 };
+
+inline int fill_trans(const mb200_trans* t, RenderParams& P) {
+    if (!t || !t->bg || !t->mask || !(t->ior > 0.f)) return MB200_EINVAL;
+    P.trans.bg = t->bg; P.trans.mask = t->mask; P.trans.ior = t->ior; P.trans.spec_trans = t->spec_trans; P.trans.refract_dist = t->refract_distance;
+    return MB200_OK;
+}
 
 __device__ __forceinline__ void env_scatter(float4* g, int Wi, const Bilerp& b, float3 cot) {
     const float w00 = b.w0y * b.w0x, w10 = b.w0y * b.w1x, w01 = b.w1y * b.w0x, w11 = b.w1y * b.w1x;

@@ -44,11 +44,18 @@ def load_estimated_mesh(mesh_path, use_mesh_normal, max_path=4, envmap=None, wid
     return Scene(pos, nrm, valid, camera=cam, envmap=envmap, use_mesh_normal=use_mesh_normal, max_depth=max_path, device=device)
 
 
-def load_estimated_mesh_w_env(mesh_path, envmap_path, bsdf="matDiffBSDF", max_depth=4, **kw):
-    """render_final.py:19-97 for bsdf='matDiffBSDF' (the only type that function accepts, :95-96)."""
-    if bsdf not in ("matDiffBSDF", "MatDiffBSDF"):
+def load_estimated_mesh_w_env(mesh_path, envmap_path, mat_dir=None, bsdf="matDiffBSDF", max_depth=4, **kw):
+    """render_final.py:19-97: bsdf = 'matDiffBSDF' / {'name': 'matDiffBSDF'}, or {'name': 'TransBSDF', 'ior': ..,
+    'keep_albedo_color': ..} as trans_edit.py:18 passes it (`mat_dir` is accepted for signature compatibility: maps are
+    assigned through traverse(), as both callers do)."""
+    if isinstance(bsdf, str):
+        bsdf = {"name": bsdf}
+    if bsdf.get("name") in ("MatDiffBSDF",):
+        bsdf = dict(bsdf, name="matDiffBSDF")
+    if bsdf.get("name") not in ("matDiffBSDF", "TransBSDF"):
         raise ValueError("Invalid bsdf type")
-    return load_estimated_mesh(mesh_path, True, max_depth, envmap=envmap_path, **kw)
+    scene = load_estimated_mesh(mesh_path, True, max_depth, envmap=envmap_path, **kw)
+    return scene.set_bsdf(bsdf)
 
 
 def render_w_mi(scene, mat_dir, n_iter=10, spp=64):

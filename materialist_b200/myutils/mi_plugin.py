@@ -10,7 +10,11 @@
 * the torch 'scratch' BRDF (:26-58, :136-177, :285-386) used by envmap_utils.sample_env1 / sample_brdf1.  NOTE it
   is a DIFFERENT formula from MatDiffBSDF (Lambert diffuse, a 2.0x factor, +1e-4) — kept as the reference has it.
 
-Out of scope: MatBSDF, RefractBaseBRDF, MatrefractBSDF, TransBSDF, BRDF4scratch (editing features).
+* `TransBSDF` (mi_plugin.py:1477-1770): the transparency-editing plugin of trans_edit.py — MatDiffBSDF outside the edit
+  mask, a diffuse + metal + glass (reflection / transmission with the background looked up at the twice-refracted
+  screen position) BSDF inside; lane-level eval_pdf / sample / calculate_refracted_screen_coor, forward only.
+
+Out of scope: MatBSDF, RefractBaseBRDF, MatrefractBSDF, BRDF4scratch (other editing features).
 """
 import ctypes as C
 import math
@@ -247,6 +251,71 @@ class MatDiffBSDF:
 
     def to_string(self):
         return "MatDiffBSDF"
+
+
+class TransBSDF(MatDiffBSDF):
+    """props: MatDiffBSDF's plus 'ior' (default 1.3) and 'keep_albedo_color' (its PRESENCE sets refract_distance = 100,
+    mi_plugin.py:1484-1489).  Attributes specTrans / bg / mask / ior are what TransBSDF.traverse exposes (:1763-1770)."""
+
+    def __init__(self, props=None):
+        super().__init__(props)
+        props = props or {}
+        self.ior = float(props.get("ior", 1.3))
+        if "keep_albedo_color" in props:
+            self.keep_albedo_color = bool(props["keep_albedo_color"]); self.refract_distance = 1.0 * 100
+        else:
+            self.keep_albedo_color = False; self.refract_distance = 1.0
+        self.specTrans = 0.8
+        dev = self.a.device
+        self.bg = torch.full((self.height, self.width, 3), 0.5, device=dev)
+        self.mask = torch.zeros(self.height, self.width, dtype=torch.bool, device=dev)
+
+    def _trans(self):
+        self._keep = (self.bg.detach().contiguous().float(), (self.mask != 0).to(torch.uint8).contiguous())
+        return _abi.Trans(float(self.ior), float(self.specTrans), float(self.refract_distance), 0, self._keep[0].data_ptr(), self._keep[1].data_ptr())
+
+    def calculate_refracted_screen_coor(self, wi, normal, ior_ratio, position, screen_coor=None):
+        """(L,2) screen position of the background texel seen through the edited surface (:1503-1519); `ior_ratio` is accepted
+        for signature compatibility — the reference always passes 1/self.ior (:1528, :1757) and so does the kernel."""
+        L = wi.shape[0]
+        sc = torch.empty(L, 2, device=wi.device); flat = torch.empty(L, dtype=torch.int64, device=wi.device)
+        cfg = self._cfg(); t = self._trans()
+        _abi.check(_abi.lib.mb200_trans_refracted_texel(C.byref(cfg), C.byref(t), L, _abi.ptr(position.contiguous()), _abi.ptr(normal.contiguous()),
+                                                        _abi.ptr(wi.contiguous()), _abi.ptr(sc), _abi.ptr(flat), _abi.stream_ptr()),
+                   "mb200_trans_refracted_texel")
+        return sc
+
+    def eval_pdf(self, ctx, si, wo, active=True):
+        wo_w = si.to_world(wo).contiguous(); wi_w = si.to_world(si.wi).contiguous()
+        L = wo_w.shape[0]
+        f = torch.empty(L, 3, device=wo_w.device); pdf = torch.empty(L, device=wo_w.device)
+        a, r, m, n = self._maps()
+        cfg = self._cfg(); t = self._trans()
+        _abi.check(_abi.lib.mb200_trans_eval_pdf(C.byref(cfg), C.byref(t), L, _abi.ptr(si.p), _abi.ptr(si.n), _abi.ptr(wi_w), _abi.ptr(wo_w),
+                                                 _abi.ptr(a), _abi.ptr(r), _abi.ptr(m), _abi.ptr(n), _abi.ptr(f), _abi.ptr(pdf),
+                                                 _abi.stream_ptr()), "mb200_trans_eval_pdf")
+        return f, pdf
+
+    def sample(self, ctx, si, sample1, sample2, active=True):
+        wi_w = si.to_world(si.wi).contiguous()
+        L = wi_w.shape[0]
+        wo = torch.empty(L, 3, device=wi_w.device); pdf = torch.empty(L, device=wi_w.device); w = torch.empty(L, 3, device=wi_w.device)
+        a, r, m, n = self._maps()
+        cfg = self._cfg(); t = self._trans()
+        _abi.check(_abi.lib.mb200_trans_sample(C.byref(cfg), C.byref(t), L, _abi.ptr(si.p), _abi.ptr(si.n), _abi.ptr(wi_w),
+                                               _abi.ptr(sample1.contiguous().float()), _abi.ptr(sample2.contiguous().float()),
+                                               _abi.ptr(a), _abi.ptr(r), _abi.ptr(m), _abi.ptr(n), _abi.ptr(wo), _abi.ptr(pdf), _abi.ptr(w),
+                                               _abi.stream_ptr()), "mb200_trans_sample")
+        bs = BSDFSample3f(wo, pdf, self.m_flags)
+        bs.eta = self.ior                                   # :1542
+        return bs, w
+
+    def traverse(self, callback):
+        for k in ("a", "r", "m", "bg", "mask", "specTrans", "ior"):
+            callback.put_parameter(k, getattr(self, k), "Differentiable")
+
+    def to_string(self):
+        return "TransBSDF"
 
 
 _REGISTRY = {}

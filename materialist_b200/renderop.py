@@ -73,7 +73,19 @@ def _forward(scene, spp, seed, a, r, m, n, env_pack, extra_flags=0):
     partials = torch.empty(prows, scene.W, stride, device=scene.device)
     st = _abi.stream_ptr()
     nmap = None if scene.use_mesh_normal else n
-    if scene.mesh is not None:
+    if scene.trans is not None:                 # TransBSDF plugin (trans_edit.py): forward only
+        td = scene.trans.desc()
+        if scene.mesh is not None:
+            with _ktime("mesh_fwd_trans"):
+                _abi.check(_abi.lib.mb200_trans_mesh_shade_fwd(C.byref(cfg), C.byref(td), C.byref(scene.mesh.desc), _abi.ptr(scene.mesh.buf),
+                                                               _abi.ptr(a), _abi.ptr(r), _abi.ptr(m), _abi.ptr(nmap), _abi.ptr(env4), _abi.ptr(hier),
+                                                               C.byref(desc), _abi.ptr(partials), st), "mb200_trans_mesh_shade_fwd")
+        else:
+            with _ktime("shade_fwd_trans"):
+                _abi.check(_abi.lib.mb200_trans_shade_fwd(C.byref(cfg), C.byref(td), _abi.ptr(scene.gpos), _abi.ptr(scene.gnrm), _abi.ptr(a),
+                                                          _abi.ptr(r), _abi.ptr(m), _abi.ptr(nmap), _abi.ptr(env4), _abi.ptr(hier), C.byref(desc),
+                                                          _abi.ptr(partials), st), "mb200_trans_shade_fwd")
+    elif scene.mesh is not None:
         with _ktime("mesh_fwd"):
             _abi.check(_abi.lib.mb200_mesh_shade_fwd(C.byref(cfg), C.byref(scene.mesh.desc), _abi.ptr(scene.mesh.buf), _abi.ptr(a), _abi.ptr(r),
                                                      _abi.ptr(m), _abi.ptr(nmap), _abi.ptr(env4), _abi.ptr(hier), C.byref(desc),
@@ -172,6 +184,8 @@ class _RenderOp(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_img):
         scene = ctx.scene
+        if scene.trans is not None:
+            raise RuntimeError("TransBSDF is a forward-only editing plugin (the reference never differentiates it); render under torch.no_grad()")
         need = ctx.needs_input_grad[5:]
         want = [h and nd for h, nd in zip(ctx.has, need)]
         grad_img = grad_img.contiguous()

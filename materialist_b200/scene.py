@@ -70,6 +70,23 @@ class Camera:
         return l @ self.to_world[:3, :3].T
 
 
+class TransSettings:
+    """State of the `TransBSDF` plugin (myutils/mi_plugin.py:1477-1492): ior (default 1.3), specTrans (0.8), the background
+    image `bg` (0.5) and the edit `mask` (empty), and refract_distance = 100 when the plugin was created with a
+    keep_albedo_color property ("scale factor for real scene"), else 1."""
+
+    def __init__(self, H, W, device, ior=1.3, keep_albedo_color=None):
+        self.ior = float(ior)
+        self.keep_albedo_color = bool(keep_albedo_color) if keep_albedo_color is not None else False
+        self.refract_distance = 100.0 if keep_albedo_color is not None else 1.0
+        self.spec_trans = 0.8
+        self.bg = torch.full((H, W, 3), 0.5, device=device)
+        self.mask = torch.zeros(H, W, dtype=torch.uint8, device=device)
+
+    def desc(self):
+        return _abi.Trans(self.ior, self.spec_trans, self.refract_distance, 0, self.bg.data_ptr(), self.mask.data_ptr())
+
+
 class Scene:
     """G-buffer scene handle. Tensors live on one CUDA device; everything is fp32 and contiguous."""
 
@@ -109,6 +126,7 @@ class Scene:
             flags = _abi.FLAG_WO_WORLD_QUIRK | _abi.FLAG_ENV_HALF_TEXEL | (_abi.FLAG_ROW_STRIDE_H if H == W else 0)
         self.flags = int(flags)
         self.row0, self.rows = 0, H            # pixel shard (whole image by default)
+        self.trans = None                      # TransSettings when the shape's BSDF is the TransBSDF plugin (set_bsdf)
         self._env = None
         if envmap is None:
             envmap = torch.ones(16, 32, 3)
@@ -131,6 +149,19 @@ class Scene:
         # ~7 % of them slip between the triangles in float
         gpos, gnrm, _, _ = mesh.primary(c, 0.47, 0.53)
         return cls(gpos[..., :3], gnrm[..., :3], gpos[..., 3:], camera=camera, device=device, mesh=mesh if trace else None, **kw)
+
+    # ---------------------------------------------------------------- BSDF plugin
+    def set_bsdf(self, bsdf=None):
+        """The `bsdf=` argument of render_final.load_estimated_mesh_w_env (render_final.py:19-97): {'name': 'matDiffBSDF'} (default)
+        or {'name': 'TransBSDF', 'ior': ..., 'keep_albedo_color': ...} as trans_edit.py:18 passes it.  TransBSDF is forward only."""
+        name = (bsdf or {}).get("name", "matDiffBSDF")
+        if name in ("matDiffBSDF", "matbsdf"):
+            self.trans = None
+        elif name == "TransBSDF":
+            self.trans = TransSettings(self.H, self.W, self.device, ior=bsdf.get("ior", 1.3), keep_albedo_color=bsdf.get("keep_albedo_color"))
+        else:
+            raise ValueError(f"unsupported bsdf {name!r}: this operator implements matDiffBSDF and TransBSDF")
+        return self
 
     # ---------------------------------------------------------------- shard
     def set_shard(self, row0, rows):
@@ -193,6 +224,7 @@ class SceneParameters(dict):
     :216-220, :334-342; render_final.py:182-192).  Assign, then call update()."""
     KEYS = ("shape.bsdf.a", "shape.bsdf.r", "shape.bsdf.m", "shape.bsdf.n", "shape.bsdf.use_mesh_normal",
             "emitter.data", "integrator.max_depth")
+    TRANS_KEYS = ("shape.bsdf.bg", "shape.bsdf.mask", "shape.bsdf.specTrans", "shape.bsdf.ior")   # TransBSDF.traverse, mi_plugin.py:1763-1770
 
     def __init__(self, scene):
         super().__init__()
@@ -205,10 +237,17 @@ class SceneParameters(dict):
         dict.__setitem__(self, "shape.bsdf.use_mesh_normal", scene.use_mesh_normal)
         dict.__setitem__(self, "emitter.data", scene.env_user)
         dict.__setitem__(self, "integrator.max_depth", scene.max_depth)
+        if scene.trans is not None:
+            dict.__setitem__(self, "shape.bsdf.bg", scene.trans.bg)
+            dict.__setitem__(self, "shape.bsdf.mask", scene.trans.mask)
+            dict.__setitem__(self, "shape.bsdf.specTrans", scene.trans.spec_trans)
+            dict.__setitem__(self, "shape.bsdf.ior", scene.trans.ior)
 
     def __setitem__(self, key, value):
-        if key not in self.KEYS:
-            raise KeyError(f"unknown scene parameter {key!r}; known: {self.KEYS}")
+        if key in self.TRANS_KEYS and self._scene.trans is None:
+            raise KeyError(f"{key!r} exists only when the shape's BSDF is TransBSDF (Scene.set_bsdf)")
+        if key not in self.KEYS + self.TRANS_KEYS:
+            raise KeyError(f"unknown scene parameter {key!r}; known: {self.KEYS + self.TRANS_KEYS}")
         dict.__setitem__(self, key, value)
         self._dirty.add(key)
 
@@ -237,6 +276,18 @@ class SceneParameters(dict):
                 s.set_envmap(v, _abi.ENV_ASSIGNED)
             elif key == "integrator.max_depth":
                 s.max_depth = int(v)
+            elif key == "shape.bsdf.bg":
+                if not isinstance(v, torch.Tensor) or tuple(v.shape) != (H, W, 3) or v.dtype != torch.float32 or not v.is_cuda:
+                    raise ValueError(f"shape.bsdf.bg must be a float32 CUDA tensor of shape {(H, W, 3)}")
+                s.trans.bg = v.detach().contiguous()
+            elif key == "shape.bsdf.mask":
+                if not isinstance(v, torch.Tensor) or tuple(v.shape) != (H, W) or not v.is_cuda:
+                    raise ValueError(f"shape.bsdf.mask must be a CUDA tensor of shape {(H, W)}")
+                s.trans.mask = (v != 0).to(torch.uint8).contiguous()
+            elif key == "shape.bsdf.specTrans":
+                s.trans.spec_trans = float(v)
+            elif key == "shape.bsdf.ior":
+                s.trans.ior = float(v)
         self._dirty.clear()
 
 

@@ -422,7 +422,12 @@ static inline int64_t texel_index(const mb200_cfg* c, v3 p) {
     return flat < 0 ? 0 : (flat > last ? last : flat);
 }
 
-typedef struct { real a[3], r, m; v3 n; } material;
+typedef struct { real a[3], r, m; v3 n; real bg[3]; int edit; } material;   /* bg / edit: TransBSDF only */
+
+/* TransBSDF mode (mi_plugin.py:1477-1770): when set, eval_brdf / sample_brdf / fetch_material below follow the
+ * TransBSDF overrides in EVERY path of this oracle (lanes, G-buffer render, mesh render).  Forward only. */
+static mb200_trans g_trans; static int g_trans_on = 0;
+void mbo_set_trans(const mb200_trans* t) { if (t) { g_trans = *t; g_trans_on = 1; } else g_trans_on = 0; }
 typedef struct { real f[3], pdf; } bsdf_val;
 typedef struct { real ga[3], gr, gm; v3 gn; } bsdf_grad;
 
@@ -440,7 +445,9 @@ static inline real G1_GGX_Schlick(real NoV, real eta) {
     return R(1.0) / denom;
 }
 /* MatDiffBSDF.eval_brdf mi_plugin.py:1372-1427 (disney_brdf branch); wi = light, wo = view */
+static inline bsdf_val trans_eval_brdf(v3 wi, v3 wo, const material* mt);
 static inline bsdf_val eval_brdf(v3 wi, v3 wo, const material* mt) {
+    if (g_trans_on) return trans_eval_brdf(wi, wo, mt);
     v3 n = mt->n; bsdf_val o;
     v3 h = vnormalize(vadd(wi, wo));
     real NoL = FMAX(vdot(n, wi), R(0.0)), NoV = FMAX(vdot(n, wo), R(0.0));
@@ -514,6 +521,88 @@ static inline void eval_brdf_grad(v3 wi, v3 wo, const material* mt, const real w
     g->gn = gn;
 }
 /* mi_diffuse_sampler mi_plugin.py:255-281 */
+/* TransBSDF.calculate_refraction mi_plugin.py:1494-1501 */
+static inline v3 trans_refraction(v3 wi, v3 normal, real ior_ratio) {
+    real cos_theta_i = vdot(wi, normal);
+    real sin2_theta_i = FMAX(R(0.0), R(1.0) - cos_theta_i * cos_theta_i);
+    real sin2_theta_t = ior_ratio * ior_ratio * sin2_theta_i;
+    real cos_theta_t = safe_sqrt(R(1.0) - sin2_theta_t);
+    v3 d = vsub(vmul(vsub(vmul(normal, cos_theta_i), wi), ior_ratio), vmul(normal, cos_theta_t));
+    return vnormalize(d);
+}
+/* TransBSDF.calculate_refracted_screen_coor mi_plugin.py:1503-1519, called with ior_ratio = 1/ior (:1528) and inverted
+ * again on entry (:1504), so the first refraction uses `ior` and the second 1/ior.  Both screen coordinates are clamped
+ * to [0, width-1] (the WIDTH for both axes, as written). */
+static inline void trans_refracted_screen(const mb200_cfg* c, v3 wi, v3 normal, v3 position, real* sx, real* sy) {
+    real ior_ratio = R(1.0) / (R(1.0) / (real)g_trans.ior);
+    real dist = (real)g_trans.refract_distance;
+    v3 d1 = trans_refraction(wi, normal, ior_ratio);
+    v3 p1 = vadd(position, vmul(d1, R(0.3) * dist));
+    v3 d2 = trans_refraction(vmul(d1, R(-1.0)), normal, R(1.0) / ior_ratio);
+    v3 p2 = vadd(p1, vmul(d2, dist));
+    real x, y; world_to_screen(c, p2, &x, &y);
+    real hi = (real)(c->W - 1);
+    x = FMIN(FMAX(x, R(0.0)), hi); y = FMIN(FMAX(y, R(0.0)), hi);        /* NaN -> propagates in Dr.Jit's clamp ... */
+    *sx = x > R(0.0) ? x : R(0.0); *sy = y > R(0.0) ? y : R(0.0);        /* ... and select(x > 0, x, 0) sends it to 0 */
+}
+static inline int64_t trans_refracted_index(const mb200_cfg* c, v3 wi, v3 normal, v3 position) {
+    real sx, sy; trans_refracted_screen(c, wi, normal, position, &sx, &sy);
+    if (sx != sx) sx = R(0.0); if (sy != sy) sy = R(0.0);
+    int64_t stride = (c->flags & MB200_FLAG_ROW_STRIDE_H) ? c->H : c->W;
+    int64_t flat = (int64_t)FLOOR(sx) + (int64_t)FLOOR(sy) * stride, last = (int64_t)c->H * c->W - 1;
+    return flat < 0 ? 0 : (flat > last ? last : flat);
+}
+/* TransBSDF.eval_brdf mi_plugin.py:1618-1724; wi = light, wo = view */
+static inline bsdf_val trans_eval_brdf(v3 wi, v3 wo, const material* mt) {
+    v3 n = mt->n; bsdf_val o;
+    const real ior = (real)g_trans.ior, st = (real)g_trans.spec_trans;
+    v3 h = vnormalize(vadd(wi, wo));
+    real dNL = vdot(n, wi), dNV = vdot(n, wo);
+    real NoL = FMAX(dNL, R(0.0)), NoV = FMAX(dNV, R(0.0));
+    real VoH = FMAX(vdot(wo, h), R(0.0)), NoH = FMAX(vdot(n, h), R(0.0));
+    real D = D_GGX(NoH, mt->r);
+    real pdf_spec = D / (R(4.0) * FMAX(VoH, R(1e-4))) * NoH;
+    real pdf_diff = NoL / PI_R;
+    o.pdf = R(0.5) * pdf_spec + R(0.5) * pdf_diff;
+    real G = G1_GGX_Schlick(NoL, mt->r) * G1_GGX_Schlick(NoV, mt->r);
+    real X = pow5(R(1.0) - VoH);
+    if (!mt->edit) {                      /* brdf_ori: the MatDiffBSDF (disney) value */
+        real F_D90 = R(0.5) + R(2.0) * (VoH * VoH) * mt->r;
+        real F_D_w_out = R(1.0) + (F_D90 - R(1.0)) * pow5(R(1.0) - NoV);
+        real F_D_w_in = R(1.0) + (F_D90 - R(1.0)) * pow5(R(1.0) - NoL);
+        for (int c = 0; c < 3; ++c) {
+            real baseColor_d = mt->a[c] * (R(1.0) - mt->m);
+            real brdf_diff = baseColor_d / PI_R * F_D_w_out * F_D_w_in * NoL;
+            real C_0 = (R(1.0) - mt->m) * R(0.04) + mt->m * mt->a[c];
+            real F_m = C_0 + (R(1.0) - C_0) * X;
+            o.f[c] = brdf_diff + D * G * F_m / R(4.0) * NoL;
+        }
+    } else {                              /* bsdf_edit */
+        real LoH = FMAX(vdot(wi, h), R(0.0));
+        real hw_in = R(1.0) / (LoH + R(1e-6)), hw_out = R(1.0) / (VoH + R(1e-6));
+        real nw_in = R(1.0) / (NoL + R(1e-6)), nw_out = R(1.0) / (NoV + R(1e-6));
+        real R_s = (hw_in - ior * hw_out) / (hw_in + ior * hw_out);
+        real R_p = (ior * hw_in - hw_out) / (ior * hw_in + hw_out);
+        real F_glass = R(0.5) * (R_s * R_s + R_p * R_p);
+        real D_hacking = D_GGX(NoH, mt->r * R(0.0) + R(1.0));
+        real den = ior * hw_in + hw_out;
+        int reflect = NoL * NoV > R(0.0);              /* glass_mask */
+        for (int c = 0; c < 3; ++c) {
+            real kd = mt->a[c] * (R(1.0) - mt->m) * (R(1.0) - st);
+            real glass = (R(1.0) - mt->m) * (mt->bg[c] * st);          /* baseColor_glass */
+            real C_0 = (R(1.0) - mt->m) * R(0.04) + mt->m * mt->a[c];
+            real F_m = C_0 + (R(1.0) - C_0) * X;
+            real brdf_diff = kd / PI_R * NoL;
+            real brdf_metal = D * G * F_m / R(4.0) * NoL;
+            real btdf = SQRT(glass) * G * D_hacking * (R(1.0) - F_glass) * (ior * ior * hw_in * hw_out) / (nw_in * nw_out * (den * den));
+            real spec_edit = glass * D * G / (R(4.0) * nw_in);
+            o.f[c] = brdf_diff + brdf_metal + (reflect ? spec_edit : btdf);
+        }
+    }
+    for (int c = 0; c < 3; ++c) o.f[c] = o.f[c] > R(0.0) ? o.f[c] : R(0.0);   /* dr.select(bsdf > 0, bsdf, 0): also NaN -> 0 */
+    o.pdf = o.pdf > R(0.0) ? o.pdf : R(0.0);
+    return o;
+}
 static inline v3 nan_to_zero(v3 v) { return V3(v.x != v.x ? 0 : v.x, v.y != v.y ? 0 : v.y, v.z != v.z ? 0 : v.z); }
 static inline v3 diffuse_sampler(real u0, real u1, v3 normal) {
     real theta = ASIN(safe_sqrt(u0)), phi = R(2.0) * PI_R * u1;
@@ -543,16 +632,27 @@ static inline bsdf_smp sample_brdf(real s1, real s2x, real s2y, v3 wo, const mat
     o.wi = diffuse ? wd : ws; o.lobe = diffuse;
     bsdf_val bv = eval_brdf(o.wi, wo, mt);
     for (int c = 0; c < 3; ++c) {
-        real w = bv.f[c] / (bv.pdf + R(1e-6));
-        o.weight[c] = bv.pdf > R(1e-6) ? w : R(0.0);
+        if (g_trans_on) {                 /* TransBSDF.sample_brdf :1609-1613 */
+            real w = bv.f[c] / (bv.pdf + R(1e-4));
+            o.weight[c] = bv.pdf > R(0.0) ? w : R(0.0);
+        } else {
+            real w = bv.f[c] / (bv.pdf + R(1e-6));
+            o.weight[c] = bv.pdf > R(1e-6) ? w : R(0.0);
+        }
     }
     o.pdf = bv.pdf > R(0.0) ? bv.pdf : R(0.0);
     return o;
 }
 /* exported lane-array units (MatDiffBSDF.eval_pdf / .sample) */
-static inline void fetch_material(const mb200_cfg* c, v3 p, v3 n_geo, const float* a, const float* r, const float* m,
+static inline void fetch_material(const mb200_cfg* c, v3 p, v3 n_geo, v3 view, const float* a, const float* r, const float* m,
                                   const float* n_opt, material* mt, int64_t* flat_out) {
     int64_t flat = texel_index(c, p);
+    mt->edit = 0; mt->bg[0] = mt->bg[1] = mt->bg[2] = R(0.0);
+    if (g_trans_on) {                     /* :1624-1640: mask at the texel, bg at the refracted texel (own texel when unmasked) */
+        mt->edit = g_trans.mask[flat] != 0;
+        int64_t fr = mt->edit ? trans_refracted_index(c, view, n_geo, p) : flat;
+        mt->bg[0] = g_trans.bg[3 * fr]; mt->bg[1] = g_trans.bg[3 * fr + 1]; mt->bg[2] = g_trans.bg[3 * fr + 2];
+    }
     mt->a[0] = a[3 * flat]; mt->a[1] = a[3 * flat + 1]; mt->a[2] = a[3 * flat + 2];
     mt->r = r[flat]; mt->m = m[flat];
     mt->n = (c->use_mesh_normal || !n_opt) ? n_geo : V3(n_opt[3 * flat], n_opt[3 * flat + 1], n_opt[3 * flat + 2]);
@@ -561,7 +661,8 @@ static inline void fetch_material(const mb200_cfg* c, v3 p, v3 n_geo, const floa
 void mbo_bsdf_eval_pdf(const mb200_cfg* c, int64_t L, const float* p, const float* n_geo, const float* wi_w, const float* wo_w,
                        const float* a, const float* r, const float* m, const float* n_opt, float* out_f, float* out_pdf) {
     for (int64_t i = 0; i < L; ++i) {
-        material mt; fetch_material(c, V3(p[3 * i], p[3 * i + 1], p[3 * i + 2]), V3(n_geo[3 * i], n_geo[3 * i + 1], n_geo[3 * i + 2]), a, r, m, n_opt, &mt, 0);
+        material mt; fetch_material(c, V3(p[3 * i], p[3 * i + 1], p[3 * i + 2]), V3(n_geo[3 * i], n_geo[3 * i + 1], n_geo[3 * i + 2]),
+                                    V3(wi_w[3 * i], wi_w[3 * i + 1], wi_w[3 * i + 2]), a, r, m, n_opt, &mt, 0);
         /* eval_pdf: eval_brdf(wi:=wo (light), wo:=wi (view))  mi_plugin.py:1458 */
         bsdf_val bv = eval_brdf(V3(wo_w[3 * i], wo_w[3 * i + 1], wo_w[3 * i + 2]), V3(wi_w[3 * i], wi_w[3 * i + 1], wi_w[3 * i + 2]), &mt);
         out_f[3 * i] = (float)bv.f[0]; out_f[3 * i + 1] = (float)bv.f[1]; out_f[3 * i + 2] = (float)bv.f[2]; out_pdf[i] = (float)bv.pdf;
@@ -571,11 +672,19 @@ void mbo_bsdf_sample(const mb200_cfg* c, int64_t L, const float* p, const float*
                      const float* s1, const float* s2, const float* a, const float* r, const float* m, const float* n_opt,
                      float* out_wo, float* out_pdf, float* out_w) {
     for (int64_t i = 0; i < L; ++i) {
-        material mt; fetch_material(c, V3(p[3 * i], p[3 * i + 1], p[3 * i + 2]), V3(n_geo[3 * i], n_geo[3 * i + 1], n_geo[3 * i + 2]), a, r, m, n_opt, &mt, 0);
+        material mt; fetch_material(c, V3(p[3 * i], p[3 * i + 1], p[3 * i + 2]), V3(n_geo[3 * i], n_geo[3 * i + 1], n_geo[3 * i + 2]),
+                                    V3(wi_w[3 * i], wi_w[3 * i + 1], wi_w[3 * i + 2]), a, r, m, n_opt, &mt, 0);
         bsdf_smp bs = sample_brdf((real)s1[i], (real)s2[2 * i], (real)s2[2 * i + 1], V3(wi_w[3 * i], wi_w[3 * i + 1], wi_w[3 * i + 2]), &mt);
         out_wo[3 * i] = (float)bs.wi.x; out_wo[3 * i + 1] = (float)bs.wi.y; out_wo[3 * i + 2] = (float)bs.wi.z;
         out_pdf[i] = (float)bs.pdf;
         for (int k = 0; k < 3; ++k) out_w[3 * i + k] = (float)bs.weight[k];
+    }
+}
+void mbo_trans_refracted_texel(const mb200_cfg* c, int64_t L, const float* p, const float* n_geo, const float* wi_w, float* out_screen, int64_t* out_flat) {
+    for (int64_t i = 0; i < L; ++i) {
+        v3 P = V3(p[3 * i], p[3 * i + 1], p[3 * i + 2]), N = V3(n_geo[3 * i], n_geo[3 * i + 1], n_geo[3 * i + 2]), Wv = V3(wi_w[3 * i], wi_w[3 * i + 1], wi_w[3 * i + 2]);
+        real sx, sy; trans_refracted_screen(c, Wv, N, P, &sx, &sy);
+        out_screen[2 * i] = (float)sx; out_screen[2 * i + 1] = (float)sy; out_flat[i] = trans_refracted_index(c, Wv, N, P);
     }
 }
 /* sub-term unit exports (pinned against the reference's torch D_GGX / G_Smith / fresnelSchlick) */
@@ -663,8 +772,8 @@ static void trace_path(const scene_t* S, int px, int py, int s, int ad_weights, 
     real s2x = (real)pcg_next_float(&rng), s2y = (real)pcg_next_float(&rng);
     (void)pcg_next_float(&rng);   /* russian-roulette draw: consumed, never applied (rr_depth 5 > max_depth) */
     v3 p = V3(gp[0], gp[1], gp[2]), n_geo = V3(gn[0], gn[1], gn[2]);
-    fetch_material(c, p, n_geo, S->a, S->r, S->m, S->n_opt, &o->mt, &o->flat);
     o->view = vnormalize(vsub(cam_origin(c), p));
+    fetch_material(c, p, n_geo, o->view, S->a, S->r, S->m, S->n_opt, &o->mt, &o->flat);
     /* ---- emitter sampling */
     o->em = env_sample_direction(S->hier, S->d, u_shift, uex, uey);
     o->active_em = o->em.pdf != R(0.0);

@@ -290,7 +290,7 @@ static void trace_path_mesh(const mscene* S, int px, int py, int s, int ad_weigh
         V->tri = h.tri;
         hit_point(S->M, &h, &V->p, &V->n_geo, &V->sh);
         V->view = vmul(rd, R(-1.0));                     /* si.to_world(si.wi), si.wi = to_local(-ray.d) */
-        fetch_material(c, V->p, V->n_geo, S->a, S->r, S->m, S->n_opt, &V->mt, &V->flat);
+        fetch_material(c, V->p, V->n_geo, V->view, S->a, S->r, S->m, S->n_opt, &V->mt, &V->flat);
         /* ---- emitter sampling */
         real uex = (real)pcg_next_float(&rng), uey = (real)pcg_next_float(&rng);
         V->em = env_sample_direction(S->hier, S->d, u_shift, uex, uey);

@@ -34,6 +34,12 @@ class HierDesc(C.Structure):
                 ("total_floats", C.c_int32)]
 
 
+class Trans(C.Structure):
+    """mb200_trans (include/materialist_b200.h): TransBSDF parameters; bg / mask are HOST pointers for the oracle."""
+    _fields_ = [("ior", C.c_float), ("spec_trans", C.c_float), ("refract_distance", C.c_float), ("reserved", C.c_int32),
+                ("bg", C.c_void_p), ("mask", C.c_void_p)]
+
+
 def build(force=False):
     """Compile the oracle with gcc (Makefile in this directory)."""
     so = os.path.join(_HERE, "libmb_oracle.so")
@@ -152,6 +158,25 @@ class Oracle:
         wo = np.zeros((L, 3), np.float32); pdf = np.zeros(L, np.float32); w = np.zeros((L, 3), np.float32)
         self.lib.mbo_bsdf_sample(C.byref(cfg), C.c_int64(L), _p(p), _p(n_geo), _p(wi_w), _p(s1), _p(s2), _p(a), _p(r), _p(m), _p(n_opt), _p(wo), _p(pdf), _p(w))
         return wo, pdf, w
+
+    # ------------------------------------------------------------------ TransBSDF mode (mi_plugin.py:1477-1770)
+    def set_trans(self, ior=1.3, spec_trans=0.8, refract_distance=1.0, bg=None, mask=None):
+        """Switches EVERY BSDF evaluation of this oracle instance's library to TransBSDF (bg (H,W,3) fp32, mask (H,W) bool);
+        set_trans(bg=None) switches back to MatDiffBSDF."""
+        if bg is None:
+            self._trans_keep = None
+            self.lib.mbo_set_trans(None)
+            return
+        bg = _f32(bg); mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        t = Trans(float(ior), float(spec_trans), float(refract_distance), 0, bg.ctypes.data, mask.ctypes.data)
+        self._trans_keep = (bg, mask, t)
+        self.lib.mbo_set_trans(C.byref(t))
+
+    def trans_refracted_texel(self, cfg, p, n_geo, wi_w):
+        p, n_geo, wi_w = map(_f32, (p, n_geo, wi_w)); L = p.shape[0]
+        sc = np.zeros((L, 2), np.float32); flat = np.zeros(L, np.int64)
+        self.lib.mbo_trans_refracted_texel(C.byref(cfg), C.c_int64(L), _p(p), _p(n_geo), _p(wi_w), _p(sc), _p(flat, C.c_int64))
+        return sc, flat
 
     def terms(self, cos_h, NoV, NoL, VoH, rough, F0):
         arrs = list(map(_f32, (cos_h, NoV, NoL, VoH, rough, F0))); n = arrs[0].shape[0]
