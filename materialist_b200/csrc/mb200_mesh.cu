@@ -207,108 +207,289 @@ __device__ __forceinline__ Material fetch_material(const RenderParams& P, float3
     return mt;
 }
 
-// ---------------------------------------------------------------- forward: PathIntegrator::sample for one lane
-template <bool AD_W, bool TRANS = false>
-__device__ __forceinline__ float3 trace_path_fwd(const RenderParams& P, const MeshView& M, int px, int py, uint32_t lane_id, float& jx, float& jy) {
-    Pcg32 rng; rng.seed(P.seed, lane_id);
-    jx = rng.next_float(); jy = rng.next_float();
-    float3 ro = f3(P.cam.c2w[3], P.cam.c2w[7], P.cam.c2w[11]);
-    float3 rd = primary_dir_exact(P.cam, XADD((float)px, jx), XADD((float)py, jy));
-    float3 beta = f3(1.f, 1.f, 1.f), L = f3(0.f, 0.f, 0.f);
-    float prev_pdf = 1.f; bool prev_delta = true;
-    const int max_verts = min(P.max_depth - 1, kMaxVerts);
-    for (int nv = 0;; ++nv) {
-        Hit h;
-        if (!mesh_intersect<false>(M, ro, rd, kInf, h)) {          // direct emission: the environment
-            float u, v; dir_to_uv(rd, u, v);
-            const float em_pdf = prev_delta ? 0.f : env_pdf_direction(P.hier, P.env, rd, u, v);
-            if (prev_pdf > 0.f) L = L + beta * env_value(P.env, env_lookup<false>(P.env, u, v)) * mis_weight(prev_pdf, em_pdf);
-            break;
+// ---------------------------------------------------------------- resumable traversal (one node / leaf per step)
+// The same traversal as mesh_intersect, cut into steps so that a warp can stop it when too few of its lanes still hold
+// a ray, let the finished lanes shade and fetch new rays, and resume — the "persistent lanes" scheme of the kernels below.
+struct Trav {
+    float3 o, d, inv, oi; float best; uint32_t cur; int sp; bool active, any, found; Hit h;
+};
+__device__ __forceinline__ void trav_begin(const MeshView& M, Trav& T, float3 o, float3 d, float maxt, bool any) {
+    T.o = o; T.d = d;
+    T.inv = f3(__fdiv_rn(1.f, d.x), __fdiv_rn(1.f, d.y), __fdiv_rn(1.f, d.z));
+    T.oi = f3(o.x * T.inv.x, o.y * T.inv.y, o.z * T.inv.z);
+    T.best = maxt; T.found = false; T.any = any; T.sp = 0; T.active = true;
+    T.h.slot = -1; T.h.tri = -1; T.h.t = maxt; T.h.u = T.h.v = 0.f;
+    T.cur = (uint32_t)M.n_levels << 27;
+}
+__device__ __forceinline__ void trav_step(const MeshView& M, Trav& T, uint2* stack) {
+    const uint32_t level = T.cur >> 27, idx = T.cur & 0x7ffffffu;
+    // the loads of BOTH kinds of step are issued before the warp splits into its leaf lanes and its node lanes, so a mixed
+    // warp pays one memory round trip per step instead of two (the kernel is latency bound: profiles/r1u)
+    const bool leaf = level == 0;
+    const float4* src = leaf ? M.tv + 3 * (size_t)idx * kLeaf : M.nodes + (size_t)(M.lvl_off[leaf ? 0 : level - 1] + (int)idx) * 6;
+    const float4 d0 = __ldg(src), d1 = __ldg(src + 1), d2 = __ldg(src + 2);
+    float4 d3 = d0, d4 = d0, d5 = d0;
+    if (!leaf) { d3 = __ldg(src + 3); d4 = __ldg(src + 4); d5 = __ldg(src + 5); }
+    if (leaf) {
+#pragma unroll
+        for (int k = 0; k < kLeaf; ++k) {
+            const int slot = (int)idx * kLeaf + k;
+            const float4 q0 = k == 0 ? d0 : __ldg(M.tv + 3 * (size_t)slot);
+            const int tri = __float_as_int(q0.w);
+            if (tri < 0) continue;
+            const float4 q1 = k == 0 ? d1 : __ldg(M.tv + 3 * (size_t)slot + 1), q2 = k == 0 ? d2 : __ldg(M.tv + 3 * (size_t)slot + 2);
+            float tt, uu, vv;
+            if (!tri_intersect(f3(q0.x, q0.y, q0.z), f3(q1.x, q1.y, q1.z), f3(q2.x, q2.y, q2.z), T.o, T.d, T.best, tt, uu, vv)) continue;
+            if (T.any) { T.found = true; T.active = false; return; }
+            if (!T.found || tt < T.h.t || (tt == T.h.t && tri < T.h.tri)) { T.h.slot = slot; T.h.tri = tri; T.h.t = tt; T.h.u = uu; T.h.v = vv; T.best = tt; T.found = true; }
         }
-        if (nv >= max_verts) break;                                 // depth + 1 >= max_depth
-        const SurfacePoint sp = hit_point(M, h);
-        const float3 view = f3(-rd.x, -rd.y, -rd.z);
-        long long flat; const Material mt = fetch_material(P, sp.p, sp.ng, flat);
-        TransMat tm; if (TRANS) tm = trans_fetch(P.cam, P.trans, flat, view, sp.ng, sp.p);
-        // ---- emitter sampling
-        const float uex = rng.next_float(), uey = rng.next_float();
-        const EmSample em = env_sample_direction(P.hier, P.env, uex, uey);
-        const bool visible = em.pdf != 0.f && shadow_visible(M, sp.p, sp.ng, em.d);
-        const float s1 = rng.next_float();
-        const float s2x = rng.next_float(), s2y = rng.next_float();
-        if (visible) {
-            const BsdfVal fv = TRANS ? trans_eval_brdf(em.d, view, mt, tm, P.trans) : eval_brdf(em.d, view, mt);
-            L = L + beta * fv.f * env_value(P.env, em.b) * (mis_weight(em.pdf, fv.pdf) / em.pdf);
+    } else {
+        const float lox[4] = {d0.x, d0.y, d0.z, d0.w}, loy[4] = {d1.x, d1.y, d1.z, d1.w}, loz[4] = {d2.x, d2.y, d2.z, d2.w};
+        const float hix[4] = {d3.x, d3.y, d3.z, d3.w}, hiy[4] = {d4.x, d4.y, d4.z, d4.w}, hiz[4] = {d5.x, d5.y, d5.z, d5.w};
+        float ct[4]; uint32_t cc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float ax = fmaf(lox[k], T.inv.x, -T.oi.x), bx = fmaf(hix[k], T.inv.x, -T.oi.x);
+            const float ay = fmaf(loy[k], T.inv.y, -T.oi.y), by = fmaf(hiy[k], T.inv.y, -T.oi.y);
+            const float az = fmaf(loz[k], T.inv.z, -T.oi.z), bz = fmaf(hiz[k], T.inv.z, -T.oi.z);
+            const float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
+            const float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.0000004f;
+            const bool hit = t0 <= fminf(t1, T.best) && lox[k] <= hix[k];
+            ct[k] = hit ? t0 : kInf;
+            cc[k] = ((level - 1) << 27) | (idx * 4u + (uint32_t)k);
         }
-        // ---- BSDF sampling
-        const BsdfSample bs = TRANS ? trans_sample_brdf(s1, s2x, s2y, view, mt, tm, P.trans, make_frame(mt.n)) : sample_brdf(s1, s2x, s2y, view, mt, make_frame(mt.n));
-        const float3 d_bs = (P.flags & MB200_FLAG_WO_WORLD_QUIRK) ? to_world(sp.sh, bs.wi) : bs.wi;     // mi_plugin.py:1444
-        float3 w = bs.weight;
-        if (AD_W) {
-            const BsdfVal b2 = eval_brdf(d_bs, view, mt);
-            if (b2.pdf > 0.f) w = b2.f * (1.f / b2.pdf);
+        MB_CSWAP(0, 1) MB_CSWAP(2, 3) MB_CSWAP(0, 2) MB_CSWAP(1, 3) MB_CSWAP(1, 2)
+        if (ct[0] < kInf) {
+            if (ct[1] < kInf) {
+                if (ct[2] < kInf) {
+                    if (ct[3] < kInf) stack[T.sp++] = make_uint2(cc[3], __float_as_uint(ct[3]));
+                    stack[T.sp++] = make_uint2(cc[2], __float_as_uint(ct[2]));
+                }
+                stack[T.sp++] = make_uint2(cc[1], __float_as_uint(ct[1]));
+            }
+            T.cur = cc[0];
+            return;
         }
-        ro = offset_p(sp.p, sp.ng, d_bs); rd = d_bs;
-        beta = beta * w; prev_pdf = bs.pdf; prev_delta = false;
-        rng.next_float();                                           // russian-roulette draw (rr_depth 5: never applied)
-        if (fmax3(beta.x, beta.y, beta.z) == 0.f) break;
     }
-    return L;
+    while (T.sp > 0) {
+        const uint2 e = stack[--T.sp];
+        if (__uint_as_float(e.y) <= T.best) { T.cur = e.x; return; }
+    }
+    T.active = false;
+}
+// Scene::sample_emitter_direction's visibility ray (see shadow_visible) as a resumable any-hit query
+__device__ __forceinline__ void trav_begin_shadow(const MeshView& M, Trav& T, float3 p, float3 n, float3 d) {
+    const float3 c = f3(__ldg(M.header), __ldg(M.header + 1), __ldg(M.header + 2));
+    const float3 pc = p - c;
+    const float rad = fmaxf(__ldg(M.header + 3), sqrtf(dot(pc, pc)));
+    const float3 target = p + d * (2.f * rad);
+    const float3 o = offset_p(p, n, target - p);
+    float3 dd = target - o;
+    const float dist = sqrtf(dot(dd, dd));
+    dd = dd * (1.f / dist);
+    trav_begin(M, T, o, dd, dist * (1.f - kShadowEps), true);
 }
 
+// ---------------------------------------------------------------- forward: PathIntegrator::sample, persistent lanes
+// A warp owns a POOL of up to kPool paths (whole pixels: kPool / spp of them, or one kPool-sample chunk of a pixel when
+// spp > kPool).  Each lane runs a small state machine — closest-hit ray in flight / shadow ray in flight / idle — and
+// fetches the next path of the pool when its own ends; all rays of the warp advance together one BVH step at a time, and
+// the traversal loop is left for a shading pass only when fewer than kMinActive lanes still hold a ray.  (One pixel's 32
+// samples per warp pass, every lane waiting for the slowest ray of every bounce, ran at 6.2 of 32 threads per
+// instruction: profiles/r1q.)  Radiance of finished paths is parked in shared memory and the film taps are reduced per
+// pixel afterwards in sample order, so the image is bitwise independent of the order in which lanes finished.
+// resident CTAs per SM the path kernels are compiled for (register cap 65536 / (256 N)).  The kernels are latency bound
+// (long-scoreboard stalls on BVH / triangle loads, 3.6 warps per scheduler at 128 registers: profiles/r1u), so trading a few
+// spills for occupancy pays: C2m forward 175 / 154 / 157 ms and adjoint 182 / 173 / 165 ms at 2 / 3 / 4 CTAs (profiles/r1v).
+#ifndef MB200_MESH_MIN_BLOCKS_FWD
+#define MB200_MESH_MIN_BLOCKS_FWD 3
+#endif
+#ifndef MB200_MESH_MIN_BLOCKS_BWD
+#define MB200_MESH_MIN_BLOCKS_BWD 4
+#endif
+#ifndef MB200_MESH_POOL
+#define MB200_MESH_POOL 256
+#endif
+#ifndef MB200_MESH_MIN_ACTIVE
+#define MB200_MESH_MIN_ACTIVE 24
+#endif
+constexpr int kPool = MB200_MESH_POOL;
+constexpr int kMinActive = MB200_MESH_MIN_ACTIVE;
+enum { ST_IDLE = 0, ST_CLOSEST = 1, ST_SHADOW = 2, ST_DONE = 3 };
+
 template <int FILTER, bool AD_W, bool TRANS = false>
-__global__ void __launch_bounds__(kThreads, 2) mesh_fwd_kernel(const __grid_constant__ RenderParams P, const __grid_constant__ MeshView M) {
-    __shared__ __align__(16) float s_rec[FILTER == MB200_FILTER_GAUSSIAN ? kWarpsPerBlock * 32 * kRecStride : 4];
+__global__ void __launch_bounds__(kThreads, MB200_MESH_MIN_BLOCKS_FWD) mesh_fwd_kernel(const __grid_constant__ RenderParams P, const __grid_constant__ MeshView M) {
+    extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* rec = s_rec + (FILTER == MB200_FILTER_GAUSSIAN ? warp * 32 * kRecStride : 0);
+    float4* pool = reinterpret_cast<float4*>(smem) + warp * kPool;
+    float* rec = smem + kWarpsPerBlock * kPool * 4 + warp * 32 * kRecStride;        // gaussian film only
+    uint2 stack[kStack];
     const int npix = P.prows * P.W;
+    const int chunks = (P.spp + kPool - 1) / kPool;              // kPool-sample chunks per pixel (1 unless spp > kPool)
+    const int ppp = chunks > 1 ? 1 : kPool / P.spp;              // whole pixels per pool
+    const int npools = (npix + ppp - 1) / ppp;
     const int ti = lane % 5, tj = lane / 5;
-    for (int pix = blockIdx.x * kWarpsPerBlock + warp; pix < npix; pix += gridDim.x * kWarpsPerBlock) {
-        const int py = P.prow0 + pix / P.W, px = pix % P.W;
-        const int gpix = py * P.W + px;
+    const int max_verts = min(P.max_depth - 1, kMaxVerts);
+    const float3 cam_o = f3(P.cam.c2w[3], P.cam.c2w[7], P.cam.c2w[11]);
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int pool_id = blockIdx.x * kWarpsPerBlock + warp; pool_id < npools; pool_id += gridDim.x * kWarpsPerBlock) {
+        const int pix0 = pool_id * ppp, pixn = min(ppp, npix - pix0);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s0 = 0; s0 < P.spp; s0 += 32) {
-            const int s = s0 + lane;
-            float3 L = f3(0.f, 0.f, 0.f); float jx = 0.f, jy = 0.f;
-            const bool act = s < P.spp;
-            if (act) L = trace_path_fwd<AD_W, TRANS>(P, M, px, py, (uint32_t)gpix * (uint32_t)P.spp + (uint32_t)s, jx, jy);
+        for (int c = 0; c < chunks; ++c) {
+            const int s_lo = c * kPool, s_n = min(P.spp - s_lo, kPool);
+            const int pool_n = pixn * s_n;
+            // ================================================= trace the pool
+            int next_q = 0, stage = ST_IDLE, q = 0, nv = 0;
+            Trav T; T.active = false;
+            Pcg32 rng;
+            float3 beta = f3(1.f, 1.f, 1.f), L = f3(0.f, 0.f, 0.f), cem = f3(0.f, 0.f, 0.f), nro = f3(0.f, 0.f, 0.f), nrd = f3(0.f, 0.f, 1.f);
+            float prev_pdf = 1.f; bool prev_delta = true, dead = false;
+            for (;;) {
+                // ---- shading pass: lanes whose ray has finished
+                if (!T.active && stage != ST_DONE) {
+                    bool path_end = false, start_next = false;
+                    if (stage == ST_CLOSEST) {
+                        if (!T.found) {                                              // direct emission: the environment
+                            float u, v; dir_to_uv(T.d, u, v);
+                            const float em_pdf = prev_delta ? 0.f : env_pdf_direction(P.hier, P.env, T.d, u, v);
+                            if (prev_pdf > 0.f) L = L + beta * env_value(P.env, env_lookup<false>(P.env, u, v)) * mis_weight(prev_pdf, em_pdf);
+                            path_end = true;
+                        } else if (nv >= max_verts) {                                // depth + 1 >= max_depth
+                            path_end = true;
+                        } else {
+                            const SurfacePoint sp = hit_point(M, T.h);
+                            const float3 view = f3(-T.d.x, -T.d.y, -T.d.z);
+                            long long flat; const Material mt = fetch_material(P, sp.p, sp.ng, flat);
+                            TransMat tm; if (TRANS) tm = trans_fetch(P.cam, P.trans, flat, view, sp.ng, sp.p);
+                            const float uex = rng.next_float(), uey = rng.next_float();
+                            const EmSample em = env_sample_direction(P.hier, P.env, uex, uey);
+                            const float s1 = rng.next_float();
+                            const float s2x = rng.next_float(), s2y = rng.next_float();
+                            cem = f3(0.f, 0.f, 0.f);
+                            if (em.pdf != 0.f) {                                     // added when the shadow ray comes back unoccluded
+                                const BsdfVal fv = TRANS ? trans_eval_brdf(em.d, view, mt, tm, P.trans) : eval_brdf(em.d, view, mt);
+                                cem = beta * fv.f * env_value(P.env, em.b) * (mis_weight(em.pdf, fv.pdf) / em.pdf);
+                            }
+                            const BsdfSample bs = TRANS ? trans_sample_brdf(s1, s2x, s2y, view, mt, tm, P.trans, make_frame(mt.n))
+                                                        : sample_brdf(s1, s2x, s2y, view, mt, make_frame(mt.n));
+                            const float3 d_bs = (P.flags & MB200_FLAG_WO_WORLD_QUIRK) ? to_world(sp.sh, bs.wi) : bs.wi;     // mi_plugin.py:1444
+                            float3 w = bs.weight;
+                            if (AD_W) {
+                                const BsdfVal b2 = eval_brdf(d_bs, view, mt);
+                                if (b2.pdf > 0.f) w = b2.f * (1.f / b2.pdf);
+                            }
+                            nro = offset_p(sp.p, sp.ng, d_bs); nrd = d_bs;
+                            beta = beta * w; prev_pdf = bs.pdf; prev_delta = false; nv += 1;
+                            rng.next_float();                                        // russian-roulette draw (rr_depth 5: never applied)
+                            dead = fmax3(beta.x, beta.y, beta.z) == 0.f;
+                            if (em.pdf != 0.f) { trav_begin_shadow(M, T, sp.p, sp.ng, em.d); stage = ST_SHADOW; }
+                            else if (dead) path_end = true;
+                            else start_next = true;
+                        }
+                    } else if (stage == ST_SHADOW) {
+                        if (!T.found) L = L + cem;
+                        if (dead) path_end = true; else start_next = true;
+                    }
+                    if (start_next) { trav_begin(M, T, nro, nrd, kInf, false); stage = ST_CLOSEST; }
+                    if (path_end) { pool[q] = make_float4(L.x, L.y, L.z, 0.f); stage = ST_IDLE; }
+                }
+                // ---- fetch: idle lanes take the next paths of the pool
+                {
+                    const bool want = stage == ST_IDLE;
+                    const unsigned wm = __ballot_sync(0xffffffffu, want);
+                    if (want) {
+                        q = next_q + __popc(wm & lt_mask);
+                        if (q < pool_n) {
+                            const int pix = pix0 + q / s_n, s = s_lo + q % s_n;
+                            const int py = P.prow0 + pix / P.W, px = pix % P.W;
+                            rng.seed(P.seed, (uint32_t)(py * P.W + px) * (uint32_t)P.spp + (uint32_t)s);
+                            const float jx = rng.next_float(), jy = rng.next_float();
+                            beta = f3(1.f, 1.f, 1.f); L = f3(0.f, 0.f, 0.f); prev_pdf = 1.f; prev_delta = true; nv = 0;
+                            trav_begin(M, T, cam_o, primary_dir_exact(P.cam, XADD((float)px, jx), XADD((float)py, jy)), kInf, false);
+                            stage = ST_CLOSEST;
+                        } else stage = ST_DONE;
+                    }
+                    next_q += __popc(wm);
+                }
+                // ---- traversal: all rays of the warp, one BVH step at a time
+                if (!__ballot_sync(0xffffffffu, T.active)) break;                    // every lane is ST_DONE
+                for (;;) {
+                    if (T.active) trav_step(M, T, stack);
+                    const int na = __popc(__ballot_sync(0xffffffffu, T.active));
+                    if (na == 0) break;
+                    if (na < kMinActive && na < __popc(__ballot_sync(0xffffffffu, stage != ST_DONE))) break;
+                }
+            }
             __syncwarp();
-            if (FILTER == MB200_FILTER_GAUSSIAN) {
-                float wx[5], wy[5]; film_taps(jx, wx); film_taps(jy, wy);
-                if (!act) { wx[0] = wx[1] = wx[2] = wx[3] = wx[4] = 0.f; }
-                float4* r4 = reinterpret_cast<float4*>(rec + lane * kRecStride);
-                r4[0] = make_float4(wx[0], wx[1], wx[2], wx[3]);
-                r4[1] = make_float4(wx[4], wy[0], wy[1], wy[2]);
-                r4[2] = make_float4(wy[3], wy[4], 0.f, 0.f);
-                r4[3] = make_float4(L.x, L.y, L.z, 1.f);
-                __syncwarp();
-                if (lane < MB200_FILM_TAPS) {
-                    const float* rt = rec + ti; const float* ru = rec + 5 + tj;
+            // ================================================= film: the pool's pixels, samples in order
+            for (int pi = 0; pi < pixn; ++pi) {
+                const int pix = pix0 + pi;
+                const int py = P.prow0 + pix / P.W, px = pix % P.W;
+                const int gpix = py * P.W + px;
+                if (chunks == 1) acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int b0 = 0; b0 < s_n; b0 += 32) {
+                    const int sl = b0 + lane;                                        // sample index inside the chunk
+                    const bool act = sl < s_n;
+                    float3 Ls = f3(0.f, 0.f, 0.f);
+                    if (act) { const float4 r4 = pool[pi * s_n + sl]; Ls = f3(r4.x, r4.y, r4.z); }
+                    if (FILTER == MB200_FILTER_GAUSSIAN) {
+                        float wx[5], wy[5];
+                        if (act) {
+                            Pcg32 r2; r2.seed(P.seed, (uint32_t)gpix * (uint32_t)P.spp + (uint32_t)(s_lo + sl));
+                            const float jx = r2.next_float(), jy = r2.next_float();
+                            film_taps(jx, wx); film_taps(jy, wy);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 5; ++i) { wx[i] = 0.f; wy[i] = 0.f; }
+                        }
+                        float4* r4 = reinterpret_cast<float4*>(rec + lane * kRecStride);
+                        r4[0] = make_float4(wx[0], wx[1], wx[2], wx[3]);
+                        r4[1] = make_float4(wx[4], wy[0], wy[1], wy[2]);
+                        r4[2] = make_float4(wy[3], wy[4], 0.f, 0.f);
+                        r4[3] = make_float4(Ls.x, Ls.y, Ls.z, 1.f);
+                        __syncwarp();
+                        if (lane < MB200_FILM_TAPS) {
+                            const float* rt = rec + ti; const float* ru = rec + 5 + tj;
 #pragma unroll 8
-                    for (int k = 0; k < 32; ++k) {
-                        const float w = rt[k * kRecStride] * ru[k * kRecStride];
-                        const float4 l4 = *reinterpret_cast<const float4*>(rec + k * kRecStride + 12);
-                        acc.x = fmaf(w, l4.x, acc.x); acc.y = fmaf(w, l4.y, acc.y); acc.z = fmaf(w, l4.z, acc.z); acc.w += w;
+                            for (int k = 0; k < 32; ++k) {
+                                const float w = rt[k * kRecStride] * ru[k * kRecStride];
+                                const float4 l4 = *reinterpret_cast<const float4*>(rec + k * kRecStride + 12);
+                                acc.x = fmaf(w, l4.x, acc.x); acc.y = fmaf(w, l4.y, acc.y); acc.z = fmaf(w, l4.z, acc.z); acc.w += w;
+                            }
+                        }
+                        __syncwarp();
+                    } else {
+                        acc.x += Ls.x; acc.y += Ls.y; acc.z += Ls.z;
                     }
                 }
-                __syncwarp();
-            } else {
-                acc.x += L.x; acc.y += L.y; acc.z += L.z;
-            }
-        }
-        if (FILTER == MB200_FILTER_GAUSSIAN) {
-            if (lane < MB200_FILM_TAPS)
-                reinterpret_cast<float4*>(P.partials)[(size_t)pix * MB200_FILM_TAPS + lane] = acc;
-        } else {
+                if (c == chunks - 1) {
+                    if (FILTER == MB200_FILTER_GAUSSIAN) {
+                        if (lane < MB200_FILM_TAPS)
+                            reinterpret_cast<float4*>(P.partials)[(size_t)pix * MB200_FILM_TAPS + lane] = acc;
+                    } else {
+                        float4 t = acc;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-                acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+                        for (int o = 16; o > 0; o >>= 1) {
+                            t.x += __shfl_xor_sync(0xffffffffu, t.x, o);
+                            t.y += __shfl_xor_sync(0xffffffffu, t.y, o);
+                            t.z += __shfl_xor_sync(0xffffffffu, t.z, o);
+                        }
+                        if (lane == 0) reinterpret_cast<float4*>(P.partials)[pix] = make_float4(t.x, t.y, t.z, (float)P.spp);
+                    }
+                }
             }
-            if (lane == 0) reinterpret_cast<float4*>(P.partials)[pix] = make_float4(acc.x, acc.y, acc.z, (float)P.spp);
+            __syncwarp();
         }
     }
+}
+inline size_t mesh_fwd_smem(int filter) {
+    return (size_t)kWarpsPerBlock * ((size_t)kPool * 16 + (filter == MB200_FILTER_GAUSSIAN ? 32 * kRecStride * 4 : 0));
+}
+template <typename K>
+inline void launch_mesh_fwd(K kernel, int filter, int grid, cudaStream_t st, const RenderParams& P, const MeshView& M) {
+    const size_t bytes = mesh_fwd_smem(filter);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    kernel<<<grid, kThreads, bytes, st>>>(P, M);
 }
 
 // ---------------------------------------------------------------- adjoint
@@ -336,110 +517,99 @@ __device__ __forceinline__ void reduce_peers(unsigned peers, float (&x)[N]) {
     }
 }
 
+// Persistent lanes as in mesh_fwd_kernel: the forward walk of each path is cut at its rays; a lane whose path has ended
+// keeps its vertex records until the warp-synchronous backward walk that follows the shading pass (lanes that did not end
+// a path in this pass take part with zero vertices), then fetches the next path of the pool.
 template <int FILTER, bool WANT_MAT, bool WANT_N, bool WANT_ENV>
-__global__ void __launch_bounds__(kThreads, 2) mesh_bwd_kernel(const __grid_constant__ RenderParams P, const __grid_constant__ MeshView M) {
-    __shared__ float4 s_g[FILTER == MB200_FILTER_GAUSSIAN ? kWarpsPerBlock * MB200_FILM_TAPS : 1];
+__global__ void __launch_bounds__(kThreads, MB200_MESH_MIN_BLOCKS_BWD) mesh_bwd_kernel(const __grid_constant__ RenderParams P, const __grid_constant__ MeshView M) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float4* gt = s_g + (FILTER == MB200_FILTER_GAUSSIAN ? warp * MB200_FILM_TAPS : 0);
     const int npix = P.prows * P.W;
     float4* const genv = WANT_ENV ? P.g_env4 + (long long)(blockIdx.x % P.env_slabs) * P.env_slab_stride : nullptr;
     const int max_verts = min(P.max_depth - 1, kMaxVerts);
     const float3 cam_o = f3(P.cam.c2w[3], P.cam.c2w[7], P.cam.c2w[11]);
+    const unsigned lt_mask = (1u << lane) - 1u;
     VRec recs[WANT_MAT ? kMaxVerts : 1];
-    for (int pix = blockIdx.x * kWarpsPerBlock + warp; pix < npix; pix += gridDim.x * kWarpsPerBlock) {
-        const int py = P.prow0 + pix / P.W, px = pix % P.W;
-        const int gpix = py * P.W + px;
-        float3 gbox = f3(0, 0, 0);
-        if (FILTER == MB200_FILTER_GAUSSIAN) {
-            __syncwarp();
-            if (lane < MB200_FILM_TAPS) {
-                const int qy = py + (lane / 5 - 2), qx = px + (lane % 5 - 2);
-                float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (qx >= 0 && qx < P.W && qy >= P.grow0 && qy < P.grow0 + P.grows && qy >= 0 && qy < P.H)
-                    g = __ldg(P.gadj + (size_t)(qy - P.grow0) * P.W + qx);
-                gt[lane] = g;
-            }
-            __syncwarp();
-        } else {
-            const float4 g = __ldg(P.gadj + (size_t)(py - P.grow0) * P.W + px);
-            gbox = f3(g.x, g.y, g.z);
-        }
-        for (int s0 = 0; s0 < P.spp; s0 += 32) {
-            const int s = s0 + lane;
-            bool alive = s < P.spp;
-            Pcg32 rng; rng.seed(P.seed, (uint32_t)gpix * (uint32_t)P.spp + (uint32_t)s);
-            const float jx = rng.next_float(), jy = rng.next_float();
-            float3 dl = gbox;
-            if (FILTER == MB200_FILTER_GAUSSIAN) {
-                float wx[5], wy[5]; film_taps(jx, wx); film_taps(jy, wy);
-                dl = f3(0, 0, 0);
-#pragma unroll
-                for (int j = 0; j < 5; ++j) {
-                    float3 row = f3(0, 0, 0);
-#pragma unroll
-                    for (int i = 0; i < 5; ++i) {
-                        const float4 g = gt[j * 5 + i];
-                        row.x = fmaf(wx[i], g.x, row.x); row.y = fmaf(wx[i], g.y, row.y); row.z = fmaf(wx[i], g.z, row.z);
+    uint2 stack[kStack];
+    const int ppp = P.spp >= kPool ? 1 : kPool / P.spp;          // whole pixels per pool (no film reduction here: a pool may hold any number of samples)
+    const int npools = (npix + ppp - 1) / ppp;
+    for (int pool_id = blockIdx.x * kWarpsPerBlock + warp; pool_id < npools; pool_id += gridDim.x * kWarpsPerBlock) {
+        const int pix0 = pool_id * ppp, pixn = min(ppp, npix - pix0);
+        const int pool_n = pixn * P.spp;
+        int next_q = 0, stage = ST_IDLE, nv = 0;
+        Trav T; T.active = false;
+        Pcg32 rng;
+        float3 beta = f3(1.f, 1.f, 1.f), dl = f3(0.f, 0.f, 0.f), R = f3(0.f, 0.f, 0.f), nro = f3(0.f, 0.f, 0.f), nrd = f3(0.f, 0.f, 1.f);
+        float3 scat = f3(0.f, 0.f, 0.f), pE = f3(0.f, 0.f, 0.f), pcem = f3(0.f, 0.f, 0.f); Bilerp pb; pb.i00 = 0; pb.w0x = pb.w1x = pb.w0y = pb.w1y = 0.f;
+        float prev_pdf = 1.f; bool prev_delta = true, dead = false;
+        for (;;) {
+            bool path_end = false;
+            // ---- shading pass
+            if (!T.active && stage != ST_DONE) {
+                bool start_next = false;
+                if (stage == ST_CLOSEST) {
+                    if (!T.found) {
+                        if (prev_pdf > 0.f) {
+                            float u, v; dir_to_uv(T.d, u, v);
+                            const float mis = mis_weight(prev_pdf, prev_delta ? 0.f : env_pdf_direction(P.hier, P.env, T.d, u, v));
+                            const Bilerp bb = env_lookup<false>(P.env, u, v);
+                            if (WANT_MAT) R = env_value(P.env, bb) * mis;
+                            if (WANT_ENV) env_scatter(genv, P.env.Wi, bb, dl * beta * mis);
+                        }
+                        path_end = true;
+                    } else if (nv >= max_verts) {
+                        path_end = true;
+                    } else {
+                        const SurfacePoint sp = hit_point(M, T.h);
+                        const float3 view = f3(-T.d.x, -T.d.y, -T.d.z);
+                        long long flat; const Material mt = fetch_material(P, sp.p, sp.ng, flat);
+                        const float uex = rng.next_float(), uey = rng.next_float();
+                        const EmSample em = env_sample_direction(P.hier, P.env, uex, uey);
+                        const float s1 = rng.next_float();
+                        const float s2x = rng.next_float(), s2y = rng.next_float();
+                        pE = f3(0.f, 0.f, 0.f); pcem = f3(0.f, 0.f, 0.f); scat = f3(0.f, 0.f, 0.f);
+                        if (em.pdf != 0.f) {                        // applied when the shadow ray comes back unoccluded
+                            const BsdfVal fv = eval_brdf(em.d, view, mt);
+                            const float k = mis_weight(em.pdf, fv.pdf) / em.pdf;
+                            if (WANT_MAT) { const float3 lek = env_value(P.env, em.b) * k; pE = fv.f * lek; pcem = dl * beta * lek; }
+                            if (WANT_ENV) { scat = dl * beta * fv.f * k; pb = em.b; }
+                        }
+                        const BsdfSample bs = sample_brdf(s1, s2x, s2y, view, mt, make_frame(mt.n));
+                        const float3 d_bs = (P.flags & MB200_FLAG_WO_WORLD_QUIRK) ? to_world(sp.sh, bs.wi) : bs.wi;
+                        const BsdfVal b2 = eval_brdf(d_bs, view, mt);
+                        const float3 w = b2.pdf > 0.f ? b2.f * (1.f / b2.pdf) : bs.weight;
+                        if (WANT_MAT) {
+                            VRec& V = recs[nv];
+                            V.mt = mt; V.view = view; V.em_d = em.d; V.cem = f3(0.f, 0.f, 0.f); V.d_bs = d_bs; V.w = w; V.E = f3(0.f, 0.f, 0.f); V.flat = (int)flat;
+                            V.cpre = b2.pdf > 0.f ? dl * beta * (1.f / b2.pdf) : f3(0.f, 0.f, 0.f);
+                        }
+                        nro = offset_p(sp.p, sp.ng, d_bs); nrd = d_bs;
+                        beta = beta * w; prev_pdf = bs.pdf; prev_delta = false; nv += 1;
+                        rng.next_float();
+                        dead = fmax3(beta.x, beta.y, beta.z) == 0.f;
+                        if (em.pdf != 0.f) { trav_begin_shadow(M, T, sp.p, sp.ng, em.d); stage = ST_SHADOW; }
+                        else if (dead) path_end = true;
+                        else start_next = true;
                     }
-                    dl.x = fmaf(wy[j], row.x, dl.x); dl.y = fmaf(wy[j], row.y, dl.y); dl.z = fmaf(wy[j], row.z, dl.z);
-                }
-            }
-            // ---- forward walk (per lane; no warp-level operation inside)
-            float3 ro = cam_o, rd = primary_dir_exact(P.cam, XADD((float)px, jx), XADD((float)py, jy));
-            float3 beta = f3(1.f, 1.f, 1.f), R = f3(0.f, 0.f, 0.f);
-            float prev_pdf = 1.f; bool prev_delta = true; int nv = 0;
-            while (alive) {
-                Hit h;
-                if (!mesh_intersect<false>(M, ro, rd, kInf, h)) {
-                    if (prev_pdf > 0.f) {
-                        float u, v; dir_to_uv(rd, u, v);
-                        const float mis = mis_weight(prev_pdf, prev_delta ? 0.f : env_pdf_direction(P.hier, P.env, rd, u, v));
-                        const Bilerp bb = env_lookup<false>(P.env, u, v);
-                        if (WANT_MAT) R = env_value(P.env, bb) * mis;
-                        if (WANT_ENV) env_scatter(genv, P.env.Wi, bb, dl * beta * mis);
+                } else if (stage == ST_SHADOW) {
+                    if (!T.found) {                                 // visible
+                        if (WANT_MAT) { recs[nv - 1].E = pE; recs[nv - 1].cem = pcem; }
+                        if (WANT_ENV) env_scatter(genv, P.env.Wi, pb, scat);
                     }
-                    break;
+                    if (dead) path_end = true; else start_next = true;
                 }
-                if (nv >= max_verts) break;
-                const SurfacePoint sp = hit_point(M, h);
-                const float3 view = f3(-rd.x, -rd.y, -rd.z);
-                long long flat; const Material mt = fetch_material(P, sp.p, sp.ng, flat);
-                const float uex = rng.next_float(), uey = rng.next_float();
-                const EmSample em = env_sample_direction(P.hier, P.env, uex, uey);
-                const bool visible = em.pdf != 0.f && shadow_visible(M, sp.p, sp.ng, em.d);
-                const float s1 = rng.next_float();
-                const float s2x = rng.next_float(), s2y = rng.next_float();
-                float3 E = f3(0.f, 0.f, 0.f), cem = f3(0.f, 0.f, 0.f);
-                if (visible) {
-                    const BsdfVal fv = eval_brdf(em.d, view, mt);
-                    const float k = mis_weight(em.pdf, fv.pdf) / em.pdf;
-                    if (WANT_MAT) { const float3 lek = env_value(P.env, em.b) * k; E = fv.f * lek; cem = dl * beta * lek; }
-                    if (WANT_ENV) env_scatter(genv, P.env.Wi, em.b, dl * beta * fv.f * k);
-                }
-                const BsdfSample bs = sample_brdf(s1, s2x, s2y, view, mt, make_frame(mt.n));
-                const float3 d_bs = (P.flags & MB200_FLAG_WO_WORLD_QUIRK) ? to_world(sp.sh, bs.wi) : bs.wi;
-                const BsdfVal b2 = eval_brdf(d_bs, view, mt);
-                const float3 w = b2.pdf > 0.f ? b2.f * (1.f / b2.pdf) : bs.weight;
-                if (WANT_MAT) {
-                    VRec& V = recs[nv];
-                    V.mt = mt; V.view = view; V.em_d = em.d; V.cem = cem; V.d_bs = d_bs; V.w = w; V.E = E; V.flat = (int)flat;
-                    V.cpre = b2.pdf > 0.f ? dl * beta * (1.f / b2.pdf) : f3(0.f, 0.f, 0.f);
-                }
-                ro = offset_p(sp.p, sp.ng, d_bs); rd = d_bs;
-                beta = beta * w; prev_pdf = bs.pdf; prev_delta = false; nv += 1;
-                rng.next_float();
-                if (fmax3(beta.x, beta.y, beta.z) == 0.f) break;
+                if (start_next) { trav_begin(M, T, nro, nrd, kInf, false); stage = ST_CLOSEST; }
+                if (path_end) stage = ST_IDLE;
             }
-            // ---- backward walk, warp-synchronous: R = radiance leaving vertex k+1 towards vertex k
+            // ---- backward walk of the paths that ended in this pass, warp-synchronous: R = radiance leaving vertex k+1 towards vertex k
             if (WANT_MAT) {
-                __syncwarp();
-                const int max_nv = __reduce_max_sync(0xffffffffu, nv);
+                const int wnv = path_end ? nv : 0;
+                const int max_nv = __reduce_max_sync(0xffffffffu, wnv);
                 for (int k = max_nv - 1; k >= 0; --k) {
                     float g[WANT_N ? 8 : 5];
 #pragma unroll
                     for (int i = 0; i < (WANT_N ? 8 : 5); ++i) g[i] = 0.f;
                     int flat = -1 - lane;                       // unique: lanes without vertex k form singleton groups
-                    if (k < nv) {
+                    if (k < wnv) {
                         const VRec& V = recs[k];
                         flat = V.flat;
                         if (V.cem.x != 0.f || V.cem.y != 0.f || V.cem.z != 0.f) {
@@ -464,6 +634,53 @@ __global__ void __launch_bounds__(kThreads, 2) mesh_bwd_kernel(const __grid_cons
                         if (WANT_N && P.g_n) { atomicAdd(P.g_n + 3 * (size_t)flat, g[5]); atomicAdd(P.g_n + 3 * (size_t)flat + 1, g[6]); atomicAdd(P.g_n + 3 * (size_t)flat + 2, g[7]); }
                     }
                 }
+            }
+            // ---- fetch
+            {
+                const bool want = stage == ST_IDLE;
+                const unsigned wm = __ballot_sync(0xffffffffu, want);
+                if (want) {
+                    const int q = next_q + __popc(wm & lt_mask);
+                    if (q < pool_n) {
+                        const int pix = pix0 + q / P.spp, s = q % P.spp;
+                        const int py = P.prow0 + pix / P.W, px = pix % P.W;
+                        rng.seed(P.seed, (uint32_t)(py * P.W + px) * (uint32_t)P.spp + (uint32_t)s);
+                        const float jx = rng.next_float(), jy = rng.next_float();
+                        if (FILTER == MB200_FILTER_GAUSSIAN) {      // film adjoint: 5x5 gather of G = grad / W around the pixel
+                            float wx[5], wy[5]; film_taps(jx, wx); film_taps(jy, wy);
+                            dl = f3(0.f, 0.f, 0.f);
+#pragma unroll
+                            for (int j = 0; j < 5; ++j) {
+                                float3 row = f3(0.f, 0.f, 0.f);
+                                const int qy = py + (j - 2);
+                                const bool rowok = qy >= P.grow0 && qy < P.grow0 + P.grows && qy >= 0 && qy < P.H;
+#pragma unroll
+                                for (int i = 0; i < 5; ++i) {
+                                    const int qx = px + (i - 2);
+                                    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                                    if (rowok && qx >= 0 && qx < P.W) g = __ldg(P.gadj + (size_t)(qy - P.grow0) * P.W + qx);
+                                    row.x = fmaf(wx[i], g.x, row.x); row.y = fmaf(wx[i], g.y, row.y); row.z = fmaf(wx[i], g.z, row.z);
+                                }
+                                dl.x = fmaf(wy[j], row.x, dl.x); dl.y = fmaf(wy[j], row.y, dl.y); dl.z = fmaf(wy[j], row.z, dl.z);
+                            }
+                        } else {
+                            const float4 g = __ldg(P.gadj + (size_t)(py - P.grow0) * P.W + px);
+                            dl = f3(g.x, g.y, g.z);
+                        }
+                        beta = f3(1.f, 1.f, 1.f); R = f3(0.f, 0.f, 0.f); prev_pdf = 1.f; prev_delta = true; nv = 0;
+                        trav_begin(M, T, cam_o, primary_dir_exact(P.cam, XADD((float)px, jx), XADD((float)py, jy)), kInf, false);
+                        stage = ST_CLOSEST;
+                    } else stage = ST_DONE;
+                }
+                next_q += __popc(wm);
+            }
+            // ---- traversal
+            if (!__ballot_sync(0xffffffffu, T.active)) break;
+            for (;;) {
+                if (T.active) trav_step(M, T, stack);
+                const int na = __popc(__ballot_sync(0xffffffffu, T.active));
+                if (na == 0) break;
+                if (na < kMinActive && na < __popc(__ballot_sync(0xffffffffu, stage != ST_DONE))) break;
             }
         }
     }
@@ -806,11 +1023,11 @@ int mb200_mesh_shade_fwd(const mb200_cfg* c, const mb200_mesh_desc* md, const vo
     cudaStream_t st = (cudaStream_t)stream;
     const bool ad = (c->flags & MB200_FLAG_AD_WEIGHTS) != 0;
     if (c->filter == MB200_FILTER_GAUSSIAN) {
-        if (ad) mesh_fwd_kernel<MB200_FILTER_GAUSSIAN, true><<<grid, kThreads, 0, st>>>(P, M);
-        else    mesh_fwd_kernel<MB200_FILTER_GAUSSIAN, false><<<grid, kThreads, 0, st>>>(P, M);
+        if (ad) launch_mesh_fwd(mesh_fwd_kernel<MB200_FILTER_GAUSSIAN, true, false>, c->filter, grid, st, P, M);
+        else    launch_mesh_fwd(mesh_fwd_kernel<MB200_FILTER_GAUSSIAN, false, false>, c->filter, grid, st, P, M);
     } else {
-        if (ad) mesh_fwd_kernel<MB200_FILTER_BOX, true><<<grid, kThreads, 0, st>>>(P, M);
-        else    mesh_fwd_kernel<MB200_FILTER_BOX, false><<<grid, kThreads, 0, st>>>(P, M);
+        if (ad) launch_mesh_fwd(mesh_fwd_kernel<MB200_FILTER_BOX, true, false>, c->filter, grid, st, P, M);
+        else    launch_mesh_fwd(mesh_fwd_kernel<MB200_FILTER_BOX, false, false>, c->filter, grid, st, P, M);
     }
     return mb200_check_launch();
 }
@@ -828,8 +1045,8 @@ int mb200_trans_mesh_shade_fwd(const mb200_cfg* c, const mb200_trans* t, const m
     P.prows = mb200_fwd_partial_rows(c, &P.prow0); P.partials = partials;
     const int grid = grid_for(P.prows * P.W);
     cudaStream_t st = (cudaStream_t)stream;
-    if (c->filter == MB200_FILTER_GAUSSIAN) mesh_fwd_kernel<MB200_FILTER_GAUSSIAN, false, true><<<grid, kThreads, 0, st>>>(P, M);
-    else                                    mesh_fwd_kernel<MB200_FILTER_BOX, false, true><<<grid, kThreads, 0, st>>>(P, M);
+    if (c->filter == MB200_FILTER_GAUSSIAN) launch_mesh_fwd(mesh_fwd_kernel<MB200_FILTER_GAUSSIAN, false, true>, c->filter, grid, st, P, M);
+    else                                    launch_mesh_fwd(mesh_fwd_kernel<MB200_FILTER_BOX, false, true>, c->filter, grid, st, P, M);
     return mb200_check_launch();
 }
 

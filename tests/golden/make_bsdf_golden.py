@@ -73,8 +73,12 @@ def lanes(L, H, W, seed, cam_json):
     n = wi + 0.6 * rng.randn(L, 3); n /= np.linalg.norm(n, axis=-1, keepdims=True)
     wo = n + 0.9 * rng.randn(L, 3); wo /= np.linalg.norm(wo, axis=-1, keepdims=True)
     g = torch.Generator(device="cpu").manual_seed(seed)
-    maps = dict(a=torch.rand(H, W, 3, generator=g).numpy(), r=(torch.rand(H, W, 1, generator=g) * 0.93 + 0.07).numpy(),
-                m=torch.rand(H, W, 1, generator=g).numpy(), bg=torch.rand(H, W, 3, generator=g).numpy())
+    # 64 x 64 random blocks tiled over the image: the fixture stores the blocks only (tests rebuild the maps with np.tile)
+    B = 64
+    blocks = dict(a=torch.rand(B, B, 3, generator=g).numpy(), r=(torch.rand(B, B, 1, generator=g) * 0.93 + 0.07).numpy(),
+                  m=torch.rand(B, B, 1, generator=g).numpy(), bg=torch.rand(B, B, 3, generator=g).numpy())
+    maps = {k: np.ascontiguousarray(np.tile(v, (H // B, W // B, 1))) for k, v in blocks.items()}
+    maps["blocks"] = blocks
     yy, xx = np.mgrid[0:H, 0:W]
     maps["mask"] = (((xx // 16) + (yy // 16)) % 2 == 0)
     return dict(p=p.astype(np.float32), n=n.astype(np.float32), wi=wi.astype(np.float32), wo=wo.astype(np.float32),
@@ -96,14 +100,14 @@ def main():
     sc = mp.mi_world_to_screen(si.p, b.view_matrix, b.persp_proj_matx, b.width, b.height)
     f, pdf = b.eval_pdf(None, si, wo_local)
     bs, w = b.sample(None, si, mi.Float(ln["s1"]), mi.Vector2f(ln["s2"]), True)
-    np.savez_compressed(os.path.join(HERE, "matdiff_bsdf.npz"), H=H, W=W, **ln, a=maps["a"], r=maps["r"], m=maps["m"],
+    blk = {k + "_block": v for k, v in maps["blocks"].items()}
+    np.savez_compressed(os.path.join(HERE, "matdiff_bsdf.npz"), H=H, W=W, **ln, a_block=blk["a_block"], r_block=blk["r_block"], m_block=blk["m_block"],
                         view=b.view_matrix.m, proj=b.persp_proj_matx.m, screen=sc.numpy(),
                         wo_world_used=si.to_world(wo_local).numpy(), wi_world_used=si.to_world(si.wi).numpy(),
                         eval_f=f.numpy(), eval_pdf=pdf.numpy(), sample_wo=bs.wo.numpy(), sample_pdf=bs.pdf.numpy(), sample_weight=w.numpy())
 
     # ---------------------------------------------------------------- TransBSDF (both refract_distance settings)
-    out = dict(H=H, W=W, **ln, a=maps["a"], r=maps["r"], m=maps["m"], bg=maps["bg"], mask=maps["mask"], view=b.view_matrix.m,
-               proj=b.persp_proj_matx.m)
+    out = dict(H=H, W=W, **ln, **blk, mask_cell=16, view=b.view_matrix.m, proj=b.persp_proj_matx.m)   # mask = 16-px checkerboard
     for tag, props, ior, st in (("k", dict(ior=1.2, keep_albedo_color=True), 1.2, 0.4), ("d", dict(), 1.3, 0.8)):
         t = mp.TransBSDF(mi.Properties(cam_meta=cam_json, **props))
         t.a = mi.TensorXf(maps["a"]); t.r = mi.TensorXf(maps["r"]); t.m = mi.TensorXf(maps["m"])
