@@ -6,7 +6,7 @@ The reference's mesh has vertex k = row*W + col sitting exactly on pixel (col,ro
 [PROBE]: reprojection error 1e-13 px), followed by extra 'curtain' vertices; so the first H*W vertices ARE the
 position buffer.  Normals are the normalised cross product of the central differences of neighbouring vertices,
 flipped towards the camera (the reference shades flat triangle normals; per-triangle primary hits are the §8f
-'next' row).  Small readers for the file formats involved (binary PLY, Radiance .hdr / OpenEXR via OpenCV) live here
+'next' row).  Small readers for the file formats involved live here (binary PLY; Radiance .hdr / OpenEXR via imageio)
 too so that the shipped scenes (output_imgs/*) can be relit without Mitsuba's mi.Bitmap.
 """
 import os
@@ -67,8 +67,13 @@ def gbuffer_from_ply(path, H=512, W=512, camera=None):
 
 
 def read_image(path):
-    """Radiance .hdr / OpenEXR / PNG -> float32 RGB(A) array in linear file values (OpenCV, BGR -> RGB)."""
-    os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
+    """Radiance .hdr / OpenEXR -> float32 RGB(A) array in linear file values through the library's own readers
+    (imageio.read_bitmap, csrc/mb200_io.cu); PNG (bg.png / mask.png of the editing scripts) through OpenCV."""
+    if not os.path.exists(path):
+        raise FileNotFoundError(path)
+    if path.lower().endswith((".hdr", ".exr")):
+        from .imageio import read_bitmap
+        return read_bitmap(path)
     import cv2
     img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
     if img is None:
