@@ -207,6 +207,24 @@ __device__ __forceinline__ Material fetch_material(const RenderParams& P, float3
     return mt;
 }
 
+// ---------------------------------------------------------------- out-of-line copies of the big shading functions
+// The path kernels inline a BVH traversal loop AND a full shading pass; with every BSDF evaluation inlined (3 per vertex
+// forward, 5 in the adjoint) they were 64-130 KB of SASS and 27 % of the issue stalls were instruction fetches
+// (stall_no_instruction 3.7 per issue, profiles/r1x).  One shared body per function keeps the kernels inside the
+// instruction cache; the calls sit in the shading pass, not in the traversal loop.
+__device__ __noinline__ BsdfVal eval_brdf_ool(float3 wi, float3 wo, const Material& mt) { return eval_brdf(wi, wo, mt); }
+__device__ __noinline__ BsdfSample sample_brdf_ool(float s1, float s2x, float s2y, float3 wo, const Material& mt) { return sample_brdf(s1, s2x, s2y, wo, mt, make_frame(mt.n)); }
+template <bool WANT_N>
+__device__ __noinline__ BsdfGrad eval_brdf_grad_ool(float3 wi, float3 wo, const Material& mt, float3 w) { return eval_brdf_grad<WANT_N>(wi, wo, mt, w); }
+__device__ __noinline__ EmSample env_sample_direction_ool(const HierView& h, const EnvView& e, float u0, float u1) { return env_sample_direction(h, e, u0, u1); }
+// Le(d) * MIS weight of an escaped ray (and its bilinear footprint for the adjoint)
+__device__ __noinline__ float3 env_miss_ool(const HierView& h, const EnvView& e, float3 d, float prev_pdf, bool prev_delta, Bilerp& bb, float& mis) {
+    float u, v; dir_to_uv(d, u, v);
+    mis = mis_weight(prev_pdf, prev_delta ? 0.f : env_pdf_direction(h, e, d, u, v));
+    bb = env_lookup<false>(e, u, v);
+    return env_value(e, bb);
+}
+
 // ---------------------------------------------------------------- resumable traversal (one node / leaf per step)
 // The same traversal as mesh_intersect, cut into steps so that a warp can stop it when too few of its lanes still hold
 // a ray, let the finished lanes shade and fetch new rays, and resume — the "persistent lanes" scheme of the kernels below.
@@ -350,9 +368,10 @@ __global__ void __launch_bounds__(kThreads, MB200_MESH_MIN_BLOCKS_FWD) mesh_fwd_
                     bool path_end = false, start_next = false;
                     if (stage == ST_CLOSEST) {
                         if (!T.found) {                                              // direct emission: the environment
-                            float u, v; dir_to_uv(T.d, u, v);
-                            const float em_pdf = prev_delta ? 0.f : env_pdf_direction(P.hier, P.env, T.d, u, v);
-                            if (prev_pdf > 0.f) L = L + beta * env_value(P.env, env_lookup<false>(P.env, u, v)) * mis_weight(prev_pdf, em_pdf);
+                            if (prev_pdf > 0.f) {
+                                Bilerp bb; float mis; const float3 le = env_miss_ool(P.hier, P.env, T.d, prev_pdf, prev_delta, bb, mis);
+                                L = L + beta * le * mis;
+                            }
                             path_end = true;
                         } else if (nv >= max_verts) {                                // depth + 1 >= max_depth
                             path_end = true;
@@ -362,27 +381,29 @@ __global__ void __launch_bounds__(kThreads, MB200_MESH_MIN_BLOCKS_FWD) mesh_fwd_
                             long long flat; const Material mt = fetch_material(P, sp.p, sp.ng, flat);
                             TransMat tm; if (TRANS) tm = trans_fetch(P.cam, P.trans, flat, view, sp.ng, sp.p);
                             const float uex = rng.next_float(), uey = rng.next_float();
-                            const EmSample em = env_sample_direction(P.hier, P.env, uex, uey);
+                            const EmSample em = env_sample_direction_ool(P.hier, P.env, uex, uey);
                             const float s1 = rng.next_float();
                             const float s2x = rng.next_float(), s2y = rng.next_float();
                             cem = f3(0.f, 0.f, 0.f);
-                            if (em.pdf != 0.f) {                                     // added when the shadow ray comes back unoccluded
-                                const BsdfVal fv = TRANS ? trans_eval_brdf(em.d, view, mt, tm, P.trans) : eval_brdf(em.d, view, mt);
+                            bool need_shadow = false;                                // an emitter sample below the horizon has f = 0 exactly:
+                            if (em.pdf != 0.f) {                                     // its visibility cannot change the result, the ray is not traced
+                                const BsdfVal fv = TRANS ? trans_eval_brdf(em.d, view, mt, tm, P.trans) : eval_brdf_ool(em.d, view, mt);
                                 cem = beta * fv.f * env_value(P.env, em.b) * (mis_weight(em.pdf, fv.pdf) / em.pdf);
+                                need_shadow = fmax3(fv.f.x, fv.f.y, fv.f.z) > 0.f;
                             }
                             const BsdfSample bs = TRANS ? trans_sample_brdf(s1, s2x, s2y, view, mt, tm, P.trans, make_frame(mt.n))
-                                                        : sample_brdf(s1, s2x, s2y, view, mt, make_frame(mt.n));
+                                                        : sample_brdf_ool(s1, s2x, s2y, view, mt);
                             const float3 d_bs = (P.flags & MB200_FLAG_WO_WORLD_QUIRK) ? to_world(sp.sh, bs.wi) : bs.wi;     // mi_plugin.py:1444
                             float3 w = bs.weight;
                             if (AD_W) {
-                                const BsdfVal b2 = eval_brdf(d_bs, view, mt);
+                                const BsdfVal b2 = eval_brdf_ool(d_bs, view, mt);
                                 if (b2.pdf > 0.f) w = b2.f * (1.f / b2.pdf);
                             }
                             nro = offset_p(sp.p, sp.ng, d_bs); nrd = d_bs;
                             beta = beta * w; prev_pdf = bs.pdf; prev_delta = false; nv += 1;
                             rng.next_float();                                        // russian-roulette draw (rr_depth 5: never applied)
                             dead = fmax3(beta.x, beta.y, beta.z) == 0.f;
-                            if (em.pdf != 0.f) { trav_begin_shadow(M, T, sp.p, sp.ng, em.d); stage = ST_SHADOW; }
+                            if (need_shadow) { trav_begin_shadow(M, T, sp.p, sp.ng, em.d); stage = ST_SHADOW; }
                             else if (dead) path_end = true;
                             else start_next = true;
                         }
@@ -549,10 +570,8 @@ __global__ void __launch_bounds__(kThreads, MB200_MESH_MIN_BLOCKS_BWD) mesh_bwd_
                 if (stage == ST_CLOSEST) {
                     if (!T.found) {
                         if (prev_pdf > 0.f) {
-                            float u, v; dir_to_uv(T.d, u, v);
-                            const float mis = mis_weight(prev_pdf, prev_delta ? 0.f : env_pdf_direction(P.hier, P.env, T.d, u, v));
-                            const Bilerp bb = env_lookup<false>(P.env, u, v);
-                            if (WANT_MAT) R = env_value(P.env, bb) * mis;
+                            Bilerp bb; float mis; const float3 le = env_miss_ool(P.hier, P.env, T.d, prev_pdf, prev_delta, bb, mis);
+                            if (WANT_MAT) R = le * mis;
                             if (WANT_ENV) env_scatter(genv, P.env.Wi, bb, dl * beta * mis);
                         }
                         path_end = true;
@@ -563,19 +582,21 @@ __global__ void __launch_bounds__(kThreads, MB200_MESH_MIN_BLOCKS_BWD) mesh_bwd_
                         const float3 view = f3(-T.d.x, -T.d.y, -T.d.z);
                         long long flat; const Material mt = fetch_material(P, sp.p, sp.ng, flat);
                         const float uex = rng.next_float(), uey = rng.next_float();
-                        const EmSample em = env_sample_direction(P.hier, P.env, uex, uey);
+                        const EmSample em = env_sample_direction_ool(P.hier, P.env, uex, uey);
                         const float s1 = rng.next_float();
                         const float s2x = rng.next_float(), s2y = rng.next_float();
                         pE = f3(0.f, 0.f, 0.f); pcem = f3(0.f, 0.f, 0.f); scat = f3(0.f, 0.f, 0.f);
-                        if (em.pdf != 0.f) {                        // applied when the shadow ray comes back unoccluded
-                            const BsdfVal fv = eval_brdf(em.d, view, mt);
+                        bool need_shadow = false;                   // f = 0 exactly (emitter sample below the horizon): value and every gradient
+                        if (em.pdf != 0.f) {                        // of this term are 0 whatever the visibility -> the shadow ray is not traced
+                            const BsdfVal fv = eval_brdf_ool(em.d, view, mt);
+                            need_shadow = dot(mt.n, em.d) > 0.f;       // NoL = 0 multiplies the value and every term of eval_brdf_grad
                             const float k = mis_weight(em.pdf, fv.pdf) / em.pdf;
                             if (WANT_MAT) { const float3 lek = env_value(P.env, em.b) * k; pE = fv.f * lek; pcem = dl * beta * lek; }
                             if (WANT_ENV) { scat = dl * beta * fv.f * k; pb = em.b; }
                         }
-                        const BsdfSample bs = sample_brdf(s1, s2x, s2y, view, mt, make_frame(mt.n));
+                        const BsdfSample bs = sample_brdf_ool(s1, s2x, s2y, view, mt);
                         const float3 d_bs = (P.flags & MB200_FLAG_WO_WORLD_QUIRK) ? to_world(sp.sh, bs.wi) : bs.wi;
-                        const BsdfVal b2 = eval_brdf(d_bs, view, mt);
+                        const BsdfVal b2 = eval_brdf_ool(d_bs, view, mt);
                         const float3 w = b2.pdf > 0.f ? b2.f * (1.f / b2.pdf) : bs.weight;
                         if (WANT_MAT) {
                             VRec& V = recs[nv];
@@ -586,7 +607,7 @@ __global__ void __launch_bounds__(kThreads, MB200_MESH_MIN_BLOCKS_BWD) mesh_bwd_
                         beta = beta * w; prev_pdf = bs.pdf; prev_delta = false; nv += 1;
                         rng.next_float();
                         dead = fmax3(beta.x, beta.y, beta.z) == 0.f;
-                        if (em.pdf != 0.f) { trav_begin_shadow(M, T, sp.p, sp.ng, em.d); stage = ST_SHADOW; }
+                        if (need_shadow) { trav_begin_shadow(M, T, sp.p, sp.ng, em.d); stage = ST_SHADOW; }
                         else if (dead) path_end = true;
                         else start_next = true;
                     }
@@ -613,13 +634,13 @@ __global__ void __launch_bounds__(kThreads, MB200_MESH_MIN_BLOCKS_BWD) mesh_bwd_
                         const VRec& V = recs[k];
                         flat = V.flat;
                         if (V.cem.x != 0.f || V.cem.y != 0.f || V.cem.z != 0.f) {
-                            const BsdfGrad bg = eval_brdf_grad<WANT_N>(V.em_d, V.view, V.mt, V.cem);
+                            const BsdfGrad bg = eval_brdf_grad_ool<WANT_N>(V.em_d, V.view, V.mt, V.cem);
                             g[0] += bg.ga.x; g[1] += bg.ga.y; g[2] += bg.ga.z; g[3] += bg.gr; g[4] += bg.gm;
                             if (WANT_N) { g[5] += bg.gn.x; g[6] += bg.gn.y; g[7] += bg.gn.z; }
                         }
                         const float3 cw = V.cpre * R;
                         if (cw.x != 0.f || cw.y != 0.f || cw.z != 0.f) {
-                            const BsdfGrad bg = eval_brdf_grad<WANT_N>(V.d_bs, V.view, V.mt, cw);
+                            const BsdfGrad bg = eval_brdf_grad_ool<WANT_N>(V.d_bs, V.view, V.mt, cw);
                             g[0] += bg.ga.x; g[1] += bg.ga.y; g[2] += bg.ga.z; g[3] += bg.gr; g[4] += bg.gm;
                             if (WANT_N) { g[5] += bg.gn.x; g[6] += bg.gn.y; g[7] += bg.gn.z; }
                         }
