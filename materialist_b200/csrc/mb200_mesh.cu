@@ -309,10 +309,10 @@ __device__ __forceinline__ void trav_begin_shadow(const MeshView& M, Trav& T, fl
 }
 
 // ---------------------------------------------------------------- forward: PathIntegrator::sample, persistent lanes
-// A warp owns a POOL of up to kPool paths (whole pixels: kPool / spp of them, or one kPool-sample chunk of a pixel when
+// A warp owns a POOL of up to kPool (128) paths (whole pixels: kPool / spp of them, or one kPool-sample chunk of a pixel when
 // spp > kPool).  Each lane runs a small state machine — closest-hit ray in flight / shadow ray in flight / idle — and
 // fetches the next path of the pool when its own ends; all rays of the warp advance together one BVH step at a time, and
-// the traversal loop is left for a shading pass only when fewer than kMinActive lanes still hold a ray.  (One pixel's 32
+// the traversal loop is left for a shading pass only when fewer than kMinActive (8) lanes still hold a ray.  (One pixel's 32
 // samples per warp pass, every lane waiting for the slowest ray of every bounce, ran at 6.2 of 32 threads per
 // instruction: profiles/r1q.)  Radiance of finished paths is parked in shared memory and the film taps are reduced per
 // pixel afterwards in sample order, so the image is bitwise independent of the order in which lanes finished.
@@ -320,19 +320,27 @@ __device__ __forceinline__ void trav_begin_shadow(const MeshView& M, Trav& T, fl
 // (long-scoreboard stalls on BVH / triangle loads, 3.6 warps per scheduler at 128 registers: profiles/r1u), so trading a few
 // spills for occupancy pays: C2m forward 175 / 154 / 157 ms and adjoint 182 / 173 / 165 ms at 2 / 3 / 4 CTAs (profiles/r1v).
 #ifndef MB200_MESH_MIN_BLOCKS_FWD
-#define MB200_MESH_MIN_BLOCKS_FWD 3
+#define MB200_MESH_MIN_BLOCKS_FWD 4
 #endif
 #ifndef MB200_MESH_MIN_BLOCKS_BWD
 #define MB200_MESH_MIN_BLOCKS_BWD 4
 #endif
-#ifndef MB200_MESH_POOL
-#define MB200_MESH_POOL 256
+#ifndef MB200_MESH_POOL_FWD
+#define MB200_MESH_POOL_FWD 128          // paths per warp pool, forward (16 B of shared memory each: the pool competes with L1)
 #endif
-#ifndef MB200_MESH_MIN_ACTIVE
-#define MB200_MESH_MIN_ACTIVE 24
+#ifndef MB200_MESH_POOL_BWD
+#define MB200_MESH_POOL_BWD 1024         // adjoint: the pool is only an index range (no film reduction, no shared memory)
 #endif
-constexpr int kPool = MB200_MESH_POOL;
-constexpr int kMinActive = MB200_MESH_MIN_ACTIVE;
+#ifndef MB200_MESH_MIN_ACTIVE_FWD
+#define MB200_MESH_MIN_ACTIVE_FWD 8      // leave the traversal loop for a shading pass when fewer lanes than this hold a ray
+#endif
+#ifndef MB200_MESH_MIN_ACTIVE_BWD
+#define MB200_MESH_MIN_ACTIVE_BWD 8
+#endif
+constexpr int kPool = MB200_MESH_POOL_FWD;
+constexpr int kPoolBwd = MB200_MESH_POOL_BWD;
+constexpr int kMinActive = MB200_MESH_MIN_ACTIVE_FWD;
+constexpr int kMinActiveBwd = MB200_MESH_MIN_ACTIVE_BWD;
 enum { ST_IDLE = 0, ST_CLOSEST = 1, ST_SHADOW = 2, ST_DONE = 3 };
 
 template <int FILTER, bool AD_W, bool TRANS = false>
@@ -551,7 +559,7 @@ __global__ void __launch_bounds__(kThreads, MB200_MESH_MIN_BLOCKS_BWD) mesh_bwd_
     const unsigned lt_mask = (1u << lane) - 1u;
     VRec recs[WANT_MAT ? kMaxVerts : 1];
     uint2 stack[kStack];
-    const int ppp = P.spp >= kPool ? 1 : kPool / P.spp;          // whole pixels per pool (no film reduction here: a pool may hold any number of samples)
+    const int ppp = P.spp >= kPoolBwd ? 1 : kPoolBwd / P.spp;          // whole pixels per pool (no film reduction here: a pool may hold any number of samples)
     const int npools = (npix + ppp - 1) / ppp;
     for (int pool_id = blockIdx.x * kWarpsPerBlock + warp; pool_id < npools; pool_id += gridDim.x * kWarpsPerBlock) {
         const int pix0 = pool_id * ppp, pixn = min(ppp, npix - pix0);
@@ -701,7 +709,7 @@ __global__ void __launch_bounds__(kThreads, MB200_MESH_MIN_BLOCKS_BWD) mesh_bwd_
                 if (T.active) trav_step(M, T, stack);
                 const int na = __popc(__ballot_sync(0xffffffffu, T.active));
                 if (na == 0) break;
-                if (na < kMinActive && na < __popc(__ballot_sync(0xffffffffu, stage != ST_DONE))) break;
+                if (na < kMinActiveBwd && na < __popc(__ballot_sync(0xffffffffu, stage != ST_DONE))) break;
             }
         }
     }

@@ -167,6 +167,42 @@ def test_mesh_adjoint_matches_oracle(oracle32, max_depth, gaussian, use_mesh_nor
     oracle32.mesh_destroy(om)
 
 
+@pytest.mark.parametrize("spp,gaussian", [(300, True), (7, True), (257, False), (1, False)])
+def test_mesh_ragged_sample_counts_vs_oracle(oracle32, spp, gaussian):
+    """The path pools of the persistent-lane kernels: spp > 256 (a pixel spans several 256-sample chunks, film taps carried
+    across them), spp that does not divide 256 (ragged pools, ragged 32-sample film batches), spp = 1 (256 pixels per pool);
+    forward and adjoint."""
+    import materialist_b200 as mb
+    H = W = 12
+    cam, verts, tris, a, r, m, env = _scene(H, W)
+    om = oracle32.mesh_create(verts, tris)
+    env_int, hier, d = oracle32.env_prepare(env, orc.ENV_ASSIGNED)
+    seed = 4; sg = mb.default_seed_grad(seed)
+    cfg = pin_cfg(d, seed, 0, H, spp=spp, H=H, W=W, max_depth=4)
+    cfg.filter = orc.FILTER_GAUSSIAN if gaussian else orc.FILTER_BOX
+    ref = oracle32.mesh_render_fwd(cfg, om, a, r, m, None, env_int, hier, d)
+    G = np.random.RandomState(3).randn(H, W, 3).astype(np.float32)
+    cfg.seed = sg
+    gref = oracle32.mesh_render_bwd(cfg, om, a, r, m, None, env_int, hier, d, G, want=("a", "r", "m", "env"))
+    gref["env"] = oracle32.env_grad_finish(gref.pop("env_int"), env.shape[1], orc.ENV_ASSIGNED)
+    oracle32.mesh_destroy(om)
+    s = _cuda_scene(cam, verts, tris, env, REF_FLAGS, 4, gaussian)
+    ta, tr, tm = (torch.from_numpy(x).cuda().requires_grad_(True) for x in (a, r, m))
+    te = torch.from_numpy(env).cuda().requires_grad_(True)
+    img = mb.render(s, spp=spp, seed=seed, albedo=ta, roughness=tr, metallic=tm, envmap=te)
+    if spp >= 32:
+        assert_radiance_parity(img.detach().cpu().numpy(), ref, spp, shape=(H, W) if gaussian else None)
+    else:                                                   # a flipped secondary decision is a large share of so few samples: bulk only
+        e = np.abs(img.detach().cpu().numpy() - ref).sum(-1).reshape(-1); keep = np.argsort(e)[:int(0.97 * e.size)]
+        assert rel_l2(img.detach().cpu().numpy().reshape(-1, 3)[keep], ref.reshape(-1, 3)[keep]) <= 1e-4
+    img.backward(torch.from_numpy(G).cuda())
+    for k, v in {"a": ta.grad, "r": tr.grad, "m": tm.grad, "env": te.grad}.items():
+        e = rel_l2(v.cpu().numpy(), gref[k])
+        assert e <= (1e-3 if spp >= 32 else 5e-2), (k, e)
+    again = mb.render(s, spp=spp, seed=seed, albedo=ta.detach(), roughness=tr.detach(), metallic=tm.detach())
+    assert torch.equal(again, img.detach())                 # bitwise deterministic whatever order the lanes finished in
+
+
 def test_mesh_shard_rows_bitwise_equal_full_image():
     import materialist_b200 as mb
     H = W = 32
