@@ -239,29 +239,23 @@ __device__ __forceinline__ void trav_begin(const MeshView& M, Trav& T, float3 o,
     T.h.slot = -1; T.h.tri = -1; T.h.t = maxt; T.h.u = T.h.v = 0.f;
     T.cur = (uint32_t)M.n_levels << 27;
 }
+// Called by ALL lanes of the warp (lanes without a ray do nothing): the three phases — box tests, triangle test, stack pop —
+// each start converged, so e.g. the pop loop runs once per step for every lane that needs it instead of once per divergent
+// path that reaches it (it ran at 3.6 of 32 lanes: profiles/r1x).
 __device__ __forceinline__ void trav_step(const MeshView& M, Trav& T, uint2* stack) {
+    const bool act = T.active;
     const uint32_t level = T.cur >> 27, idx = T.cur & 0x7ffffffu;
+    const bool leaf = act && level == 0, node = act && level != 0;
     // the loads of BOTH kinds of step are issued before the warp splits into its leaf lanes and its node lanes, so a mixed
     // warp pays one memory round trip per step instead of two (the kernel is latency bound: profiles/r1u)
-    const bool leaf = level == 0;
-    const float4* src = leaf ? M.tv + 3 * (size_t)idx * kLeaf : M.nodes + (size_t)(M.lvl_off[leaf ? 0 : level - 1] + (int)idx) * 6;
-    const float4 d0 = __ldg(src), d1 = __ldg(src + 1), d2 = __ldg(src + 2);
-    float4 d3 = d0, d4 = d0, d5 = d0;
-    if (!leaf) { d3 = __ldg(src + 3); d4 = __ldg(src + 4); d5 = __ldg(src + 5); }
-    if (leaf) {
-#pragma unroll
-        for (int k = 0; k < kLeaf; ++k) {
-            const int slot = (int)idx * kLeaf + k;
-            const float4 q0 = k == 0 ? d0 : __ldg(M.tv + 3 * (size_t)slot);
-            const int tri = __float_as_int(q0.w);
-            if (tri < 0) continue;
-            const float4 q1 = k == 0 ? d1 : __ldg(M.tv + 3 * (size_t)slot + 1), q2 = k == 0 ? d2 : __ldg(M.tv + 3 * (size_t)slot + 2);
-            float tt, uu, vv;
-            if (!tri_intersect(f3(q0.x, q0.y, q0.z), f3(q1.x, q1.y, q1.z), f3(q2.x, q2.y, q2.z), T.o, T.d, T.best, tt, uu, vv)) continue;
-            if (T.any) { T.found = true; T.active = false; return; }
-            if (!T.found || tt < T.h.t || (tt == T.h.t && tri < T.h.tri)) { T.h.slot = slot; T.h.tri = tri; T.h.t = tt; T.h.u = uu; T.h.v = vv; T.best = tt; T.found = true; }
-        }
-    } else {
+    float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = d0, d2 = d0, d3 = d0, d4 = d0, d5 = d0;
+    if (act) {
+        const float4* src = leaf ? M.tv + 3 * (size_t)idx * kLeaf : M.nodes + (size_t)(M.lvl_off[leaf ? 0 : level - 1] + (int)idx) * 6;
+        d0 = __ldg(src); d1 = __ldg(src + 1); d2 = __ldg(src + 2);
+        if (!leaf) { d3 = __ldg(src + 3); d4 = __ldg(src + 4); d5 = __ldg(src + 5); }
+    }
+    bool need_pop = false;
+    if (node) {
         const float lox[4] = {d0.x, d0.y, d0.z, d0.w}, loy[4] = {d1.x, d1.y, d1.z, d1.w}, loz[4] = {d2.x, d2.y, d2.z, d2.w};
         const float hix[4] = {d3.x, d3.y, d3.z, d3.w}, hiy[4] = {d4.x, d4.y, d4.z, d4.w}, hiz[4] = {d5.x, d5.y, d5.z, d5.w};
         float ct[4]; uint32_t cc[4];
@@ -286,14 +280,33 @@ __device__ __forceinline__ void trav_step(const MeshView& M, Trav& T, uint2* sta
                 stack[T.sp++] = make_uint2(cc[1], __float_as_uint(ct[1]));
             }
             T.cur = cc[0];
-            return;
+        } else need_pop = true;
+    }
+    __syncwarp();
+    if (leaf) {
+        need_pop = true;
+#pragma unroll
+        for (int k = 0; k < kLeaf; ++k) {
+            const int slot = (int)idx * kLeaf + k;
+            const float4 q0 = k == 0 ? d0 : __ldg(M.tv + 3 * (size_t)slot);
+            const int tri = __float_as_int(q0.w);
+            if (tri < 0) continue;
+            const float4 q1 = k == 0 ? d1 : __ldg(M.tv + 3 * (size_t)slot + 1), q2 = k == 0 ? d2 : __ldg(M.tv + 3 * (size_t)slot + 2);
+            float tt, uu, vv;
+            if (!tri_intersect(f3(q0.x, q0.y, q0.z), f3(q1.x, q1.y, q1.z), f3(q2.x, q2.y, q2.z), T.o, T.d, T.best, tt, uu, vv)) continue;
+            if (T.any) { T.found = true; T.active = false; need_pop = false; break; }
+            if (!T.found || tt < T.h.t || (tt == T.h.t && tri < T.h.tri)) { T.h.slot = slot; T.h.tri = tri; T.h.t = tt; T.h.u = uu; T.h.v = vv; T.best = tt; T.found = true; }
         }
     }
-    while (T.sp > 0) {
-        const uint2 e = stack[--T.sp];
-        if (__uint_as_float(e.y) <= T.best) { T.cur = e.x; return; }
+    __syncwarp();
+    if (need_pop) {
+        bool got = false;
+        while (T.sp > 0) {
+            const uint2 e = stack[--T.sp];
+            if (__uint_as_float(e.y) <= T.best) { T.cur = e.x; got = true; break; }
+        }
+        if (!got) T.active = false;
     }
-    T.active = false;
 }
 // Scene::sample_emitter_direction's visibility ray (see shadow_visible) as a resumable any-hit query
 __device__ __forceinline__ void trav_begin_shadow(const MeshView& M, Trav& T, float3 p, float3 n, float3 d) {
@@ -443,7 +456,7 @@ __global__ void __launch_bounds__(kThreads, MB200_MESH_MIN_BLOCKS_FWD) mesh_fwd_
                 // ---- traversal: all rays of the warp, one BVH step at a time
                 if (!__ballot_sync(0xffffffffu, T.active)) break;                    // every lane is ST_DONE
                 for (;;) {
-                    if (T.active) trav_step(M, T, stack);
+                    trav_step(M, T, stack);
                     const int na = __popc(__ballot_sync(0xffffffffu, T.active));
                     if (na == 0) break;
                     if (na < kMinActive && na < __popc(__ballot_sync(0xffffffffu, stage != ST_DONE))) break;
@@ -706,7 +719,7 @@ __global__ void __launch_bounds__(kThreads, MB200_MESH_MIN_BLOCKS_BWD) mesh_bwd_
             // ---- traversal
             if (!__ballot_sync(0xffffffffu, T.active)) break;
             for (;;) {
-                if (T.active) trav_step(M, T, stack);
+                trav_step(M, T, stack);
                 const int na = __popc(__ballot_sync(0xffffffffu, T.active));
                 if (na == 0) break;
                 if (na < kMinActiveBwd && na < __popc(__ballot_sync(0xffffffffu, stage != ST_DONE))) break;
