@@ -139,13 +139,16 @@ class FusedBRDFOptimizer:
         self.pred_srgb = torch.empty(sh.rows, W, 3, device=dev)
         self.k, self._lr, self._epoch = 0, lr, 0
         self.last = {}
-        # Adam segments over this rank's rows (contiguous in the row-major maps)
+        # Adam segments over this rank's rows (contiguous in the row-major maps).  Mesh mode under sharding: a path that starts in
+        # this rank's rows scatters material gradients to whatever texels its secondary vertices hit, and reads the maps there —
+        # so the map gradients are summed over the ranks and every rank steps the WHOLE image (replicated state, 5 floats / pixel).
+        self.replicated = scene.mesh is not None and sh.world_size > 1
         segs = (_abi.AdamSeg * len(self.names))()
         npx = float(H * W)
         for i, k in enumerate(self.names):
             c = ch[k]
-            off = sh.row0 * W * c * 4
-            n = sh.rows * W * c
+            off = 0 if self.replicated else sh.row0 * W * c * 4
+            n = (H if self.replicated else sh.rows) * W * c
             segs[i].p = self.params[k].data_ptr() + off; segs[i].mat = self.mat[k].data_ptr() + off
             segs[i].g = self.grads[k].data_ptr() + off; segs[i].ori = self.ori[k].data_ptr() + off
             segs[i].m = self.exp_avg[k].data_ptr() + off; segs[i].v = self.exp_avg_sq[k].data_ptr() + off
@@ -173,6 +176,8 @@ class FusedBRDFOptimizer:
         _rop._backward(sc, self.spp, _rop.default_seed_grad(int(seed)), a, r, m, None, env_pack, grad,
                        "albedo" in self.names, "roughness" in self.names, "metallic" in self.names, False, False,
                        out=(self.grads["albedo"], self.grads["roughness"], self.grads["metallic"]))
+        if self.replicated:
+            sh.all_reduce_sum(self.gflat)
         self.k += 1
         lr = self._lr
         if self._lr > 1.5e-4:                                  # StepLR(100, 0.8), advanced only above the floor (:431-432)
