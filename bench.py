@@ -390,10 +390,8 @@ def run_b200(args, wl):
     if wl.get("rolling"):
         return run_rolling(args, wl, case, scene, dev, world, rank, local)
     if wl.get("pos_mlp"):
-        if world > 1:
-            raise SystemExit("the pos_mlp workload is single-GPU (brdf_net sees every pixel)")
-        torch.manual_seed(0)
-        opt = PosMLPBRDFOptimizer(scene, mat, gt, "arm", spp=spp)
+        torch.manual_seed(0)                           # same initial weights on every rank
+        opt = PosMLPBRDFOptimizer(scene, mat, gt, "arm", spp=spp, shard=shard)
         with torch.no_grad():                          # lin4 is zero-initialised (mlps.py:174-176): perturb so the timed steps do real work
             opt.net.lin4.weight.normal_(0, 0.02)
         args.optimizer = "autograd+posmlp"

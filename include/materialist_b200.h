@@ -309,6 +309,8 @@ typedef struct mb200_posmlp_desc {
     int32_t output_type;  /* 0 = 'envmap' (softplus), 1 = 'arm' (1.3*tanh + img, STE clamp)    */
     int32_t H, W;         /* pixel grid the N rows enumerate (row-major)                       */
     int32_t impl;         /* MB200_POSMLP_*                                                    */
+    int32_t row0;         /* first image row of the N pixels (row shard of an (H, W) image): pixel n has row = row0 + n / W,
+                             col = n % W; 0 for the whole image                                */
 } mb200_posmlp_desc;
 /* parameter packing: [W0 (h0 x d0) | b0 | W1 | b1 | W2 | b2 | W3 | b3 | W4 | b4], nn.Linear row-major (out,in) */
 int64_t mb200_posmlp_param_count(const mb200_posmlp_desc* d_host);

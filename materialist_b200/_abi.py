@@ -55,7 +55,7 @@ class Trans(C.Structure):
 
 class PosMLPDesc(C.Structure):
     _fields_ = [("n_color", C.c_int32), ("n_out", C.c_int32), ("hidden", C.c_int32), ("n_freq", C.c_int32),
-                ("output_type", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("impl", C.c_int32)]
+                ("output_type", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("impl", C.c_int32), ("row0", C.c_int32)]
 
 
 class AdamSeg(C.Structure):

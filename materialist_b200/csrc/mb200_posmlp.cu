@@ -35,7 +35,7 @@ __device__ __forceinline__ void load_points(const Dims& D, const float* __restri
 #pragma unroll
         for (int k = 0; k < 16; ++k) f[k] = 0.f;
         if (n < N) {
-            const float row = (float)(n / D.W), col = (float)(n % D.W);
+            const float row = (float)(n / D.W + D.row0), col = (float)(n % D.W);
             f[0] = row; f[1] = col;
             f[2] = sinf(row); f[3] = sinf(col); f[4] = cosf(row); f[5] = cosf(col);
             f[6] = sinf(row * 2.f); f[7] = sinf(col * 2.f); f[8] = cosf(row * 2.f); f[9] = cosf(col * 2.f);
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(NT) posmlp_wgrad_kernel(const Dims D, const fl
                 if (k < h_in) x = sinf(zc[n * ZSTRIDE + (l - 1) * HID + k]);
                 else {
                     const int f = k - h_in;                              // point feature
-                    const float row = (float)(n / D.W), col = (float)(n % D.W);
+                    const float row = (float)(n / D.W + D.row0), col = (float)(n % D.W);
                     x = f == 0 ? row : f == 1 ? col : f == 2 ? sinf(row) : f == 3 ? sinf(col) : f == 4 ? cosf(row) : f == 5 ? cosf(col)
                       : f == 6 ? sinf(row * 2.f) : f == 7 ? sinf(col * 2.f) : f == 8 ? cosf(row * 2.f) : f == 9 ? cosf(col * 2.f)
                       : img[n * D.n_color + (f - 10)];

@@ -215,7 +215,7 @@ __device__ __forceinline__ void embed_pixel(const Dims& D, const float* __restri
 #pragma unroll
     for (int k = 0; k < 16; ++k) e[k] = 0.f;
     if (n < N) {
-        const float row = (float)(n / D.W), col = (float)(n % D.W);
+        const float row = (float)(n / D.W + D.row0), col = (float)(n % D.W);
         e[0] = row; e[1] = col;
         e[2] = sinf(row); e[3] = sinf(col); e[4] = cosf(row); e[5] = cosf(col);
         e[6] = sinf(row * 2.f); e[7] = sinf(col * 2.f); e[8] = cosf(row * 2.f); e[9] = cosf(col * 2.f);

@@ -193,49 +193,83 @@ class FusedBRDFOptimizer:
 class PosMLPBRDFOptimizer:
     """BRDF phase with `model_name == 'pos_mlp'` (inverse_img_w_mi.py:471-552): the maps are the output of `brdf_net`
     (PosMLP on the tensor cores, mymodels/mlps.py) applied to the initial estimate `start_arm`; the network weights are
-    optimised with AdamW(lr=3e-4) + the guarded StepLR(100, 0.8).  Single-GPU (the network sees every pixel)."""
+    optimised with AdamW(lr=3e-4) + the guarded StepLR(100, 0.8).
 
-    def __init__(self, scene, mat, gt_image, optimize_part="arm", spp=64, lr=3e-4, scale_delta=0.1, net=None):
+    Row sharding (`shard`): each rank evaluates the network only on the rows it renders — its own rows plus the 2-row film halo
+    (the whole image in mesh mode, where paths read the maps anywhere) — through PosMLP's `row0`; the three image sums of the
+    loss are all-reduced as in FusedBRDFOptimizer, and the 198 662 weight gradients are summed over the ranks before the
+    (replicated) AdamW step."""
+
+    def __init__(self, scene, mat, gt_image, optimize_part="arm", spp=64, lr=3e-4, scale_delta=0.1, net=None, shard=None):
         from .mymodels.mlps import PosMLP
         self.scene, self.spp, self.scale_delta, self.part = scene, spp, scale_delta, optimize_part
-        scene.set_shard(0, scene.H)
-        dev = scene.device
+        self.shard = sh = shard or ShardContext(scene.H, scene.W)
+        scene.set_shard(sh.row0, sh.rows)
+        dev, H, W = scene.device, scene.H, scene.W
         self.net = net if net is not None else PosMLP(in_dims=7, out_dims=5, dims=[256] * 4, skip_connection=[1, 3], weight_norm=False,
                                                       multires_view=2, output_type="arm", color_ch=5).to(dev)   # :163
         self.mat = {k: v.detach().clone() for k, v in mat.items()}
         self.ori = {k: v.detach().clone() for k, v in mat.items()}
         self.start_arm = torch.cat([mat["albedo"].reshape(-1, 3), mat["roughness"].reshape(-1, 1), mat["metallic"].reshape(-1, 1)],
                                    dim=-1).clamp(0, 1).contiguous()                                               # :205
+        if scene.mesh is not None or sh.world_size == 1:
+            self.er0, self.er1 = 0, H
+        else:
+            self.er0, self.er1 = max(0, sh.row0 - sh.halo), min(H, sh.row0 + sh.rows + sh.halo)
         self.opt = torch.optim.AdamW(self.net.parameters(), lr=lr)
         self.sched = torch.optim.lr_scheduler.StepLR(self.opt, step_size=100, gamma=0.8)
-        self.gt_srgb = linear_to_srgb(gt_image)
-        self.gt_mean = gt_image.mean()
+        self.rows = slice(sh.row0, sh.row0 + sh.rows)
+        self.gt_srgb = linear_to_srgb(gt_image[self.rows])
+        self.gt_mean = gt_image.mean()                       # gt is replicated: the global mean needs no exchange
+        self.n_total = H * W * 3
         self.last = {}
 
-    def step(self, seed):
+    def _maps(self):
         H, W = self.scene.H, self.scene.W
-        arm = self.net(self.start_arm, hw=(H, W))                                                                # :493
+        e0, e1 = self.er0, self.er1
+        arm = self.net(self.start_arm[e0 * W:e1 * W], hw=(H, W), row0=e0)                                        # :493
         albedo, roughness, metallic = arm[..., 0:3].clamp(0, 1), (arm[..., 3:4] * 0.93 + 0.07).clamp(0, 1), arm[..., 4:5].clamp(0, 1)
         mat = dict(self.mat)
-        if "a" in self.part: mat["albedo"] = albedo.reshape(H, W, 3)
-        if "r" in self.part: mat["roughness"] = roughness.reshape(H, W, 1)
-        if "m" in self.part: mat["metallic"] = metallic.reshape(H, W, 1)
-        pred = render(self.scene, spp=self.spp, seed=seed, albedo=mat["albedo"], roughness=mat["roughness"], metallic=mat["metallic"])
-        pred = pred * (self.gt_mean / pred.detach().mean())
+        for key, k, val, c in (("albedo", "a", albedo, 3), ("roughness", "r", roughness, 1), ("metallic", "m", metallic, 1)):
+            if k in self.part:
+                if (e0, e1) == (0, H):
+                    mat[key] = val.reshape(H, W, c)
+                else:                                         # rows outside [e0, e1) are never read by this rank's kernels
+                    mat[key] = torch.cat([self.mat[key][:e0], val.reshape(e1 - e0, W, c), self.mat[key][e1:]], 0)
+        return mat
+
+    def step(self, seed):
+        sh = self.shard
+        mat = self._maps()
+        pred = render(self.scene, spp=self.spp, seed=seed, albedo=mat["albedo"], roughness=mat["roughness"], metallic=mat["metallic"],
+                      halo_exchange=sh.halo_exchange if sh.world_size > 1 else None)
+        s_pred = sh.all_reduce_sum(pred.detach().sum().reshape(1).clone())
+        pred = pred * (self.gt_mean / (s_pred / self.n_total))
         pred_srgb = linear_to_srgb(pred)
-        loss_mse, loss_l1 = NF.mse_loss(pred_srgb, self.gt_srgb), NF.l1_loss(pred_srgb, self.gt_srgb)
+        diff = pred_srgb - self.gt_srgb
+        mse_local, l1_local = (diff * diff).sum() / self.n_total, diff.abs().sum() / self.n_total
+        g = sh.all_reduce_sum(torch.stack([mse_local.detach(), l1_local.detach()]))
+        loss_mse, loss_l1 = g[0], g[1]
         aux = 0.0
-        if "a" in self.part: aux = aux + NF.l1_loss(mat["albedo"], self.ori["albedo"])
-        if "r" in self.part: aux = aux + NF.l1_loss(mat["roughness"], self.ori["roughness"])
-        if "m" in self.part: aux = aux + NF.l1_loss(mat["metallic"], self.ori["metallic"])
-        loss = 3 * (loss_l1.detach() / loss_mse.detach()) * loss_mse + loss_l1 + aux * self.scale_delta
+        npx = self.scene.H * self.scene.W
+        for key, k, c in (("albedo", "a", 3), ("roughness", "r", 1), ("metallic", "m", 1)):
+            if k in self.part:
+                aux = aux + (mat[key][self.rows] - self.ori[key][self.rows]).abs().sum() / (npx * c)
+        loss = 3 * (loss_l1 / loss_mse) * mse_local + l1_local + aux * self.scale_delta      # summed over the ranks = the reference's loss
         loss.backward()
+        if sh.world_size > 1:
+            params = [p for p in self.net.parameters() if p.grad is not None]
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            sh.all_reduce_sum(flat)
+            off = 0
+            for p in params:
+                p.grad.copy_(flat[off:off + p.numel()].view_as(p)); off += p.numel()
         self.opt.step()
         self.opt.zero_grad(set_to_none=True)
         if self.opt.param_groups[0]["lr"] > 1.5e-4:
             self.sched.step()
         self.last = {"loss_mse": loss_mse.detach(), "loss_l1": loss_l1.detach(), "pred": pred_srgb.detach()}
-        return loss.detach()
+        return loss_mse.detach()
 
 
 class _SumGradOverRanks(torch.autograd.Function):

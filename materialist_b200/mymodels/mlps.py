@@ -114,7 +114,9 @@ class PosMLP(nn.Module):
             parts += [lin.weight.reshape(-1), lin.bias.reshape(-1)]
         return torch.cat(parts)
 
-    def _desc(self, N, hw):
+    def _desc(self, N, hw, row0=0):
+        if hw is None and row0:
+            raise ValueError("row0 needs an explicit hw=(H, W)")
         if hw is None:                              # img2points, mlps.py:190-198
             if N > 512:
                 h = int(round(N ** 0.5))
@@ -126,22 +128,25 @@ class PosMLP(nn.Module):
                 if not float(h).is_integer():
                     raise ValueError("width should be double of height")
                 hw = (int(h), 2 * int(h))
-        if hw[0] * hw[1] != N:
-            raise ValueError("hw does not match the number of rows of img")
+        if N % hw[1] != 0 or row0 < 0 or row0 + N // hw[1] > hw[0]:
+            raise ValueError("img must hold whole rows [row0, row0 + N / W) of the (H, W) image")
         d = _abi.PosMLPDesc()
         d.n_color, d.n_out, d.hidden, d.n_freq = self.color_ch, self.out_dims, 256, 2
         d.output_type = 0 if self.output_type == "envmap" else 1
         d.H, d.W = hw
         d.impl = self.impl
+        d.row0 = int(row0)
         return d
 
-    def forward(self, img, hw=None):
+    def forward(self, img, hw=None, row0=0):
+        """img: (N, color_ch) = the pixels of rows [row0, row0 + N / W) of an (H, W) image, row-major (`hw`, `row0` default to the
+        whole image as the reference's img2points lays it out).  Row shards give bitwise the rows of the full evaluation."""
         if img.ndim != 2 or img.shape[1] != self.color_ch:
             raise ValueError(f"img must be (N, {self.color_ch})")
         if not img.is_cuda:
             raise ValueError("PosMLP runs on CUDA tensors only (no CPU fallback)")
         img = img.contiguous().float()
-        desc = self._desc(img.shape[0], hw)
+        desc = self._desc(img.shape[0], hw, row0)
         flat = self.flat_params()
         if flat.numel() != _abi.lib.mb200_posmlp_param_count(C.byref(desc)):
             raise RuntimeError("parameter packing mismatch")

@@ -81,6 +81,36 @@ def test_posmlp_ragged_size_vs_oracle(H, W, impl):
             assert rel_l2(lin.bias.grad.cpu().numpy(), gb[l]) < 1e-4, (l, want_gx)
 
 
+@pytest.mark.parametrize("impl", ["tcgen05", "ffma"])
+def test_posmlp_row_shards_equal_full_evaluation(impl):
+    """PosMLP(img[rows], hw, row0) gives BITWISE the rows of the full evaluation (pixels are independent; the coordinates come
+    from row0), and the weight gradients of the shards sum to the full gradient — what PosMLPBRDFOptimizer relies on under
+    row sharding."""
+    from materialist_b200 import _abi
+    from materialist_b200.mymodels.mlps import PosMLP
+    H, W = 37, 53
+    torch.manual_seed(3)
+    net = PosMLP(in_dims=7, out_dims=5, dims=[256] * 4, skip_connection=[1, 3], weight_norm=False, multires_view=2, output_type="arm", color_ch=5).cuda()
+    net.impl = _abi.POSMLP_TCGEN05 if impl == "tcgen05" else _abi.POSMLP_FFMA
+    with torch.no_grad():
+        net.lin4.weight.normal_(0, 0.05); net.lin4.bias.normal_(0, 0.05)
+    x = torch.rand(H * W, 5, device="cuda")
+    gy = torch.randn(H * W, 5, device="cuda")
+    y = net(x, hw=(H, W)); y.backward(gy)
+    g_full = torch.cat([p.grad.reshape(-1) for p in net.parameters()]); net.zero_grad()
+    g_sum = torch.zeros_like(g_full)
+    for r0, r1 in ((0, 11), (11, 30), (30, 37)):
+        ys = net(x[r0 * W:r1 * W], hw=(H, W), row0=r0)
+        assert torch.equal(ys, y[r0 * W:r1 * W]), (impl, r0)
+        ys.backward(gy[r0 * W:r1 * W])
+        g_sum += torch.cat([p.grad.reshape(-1) for p in net.parameters()]); net.zero_grad()
+    assert float((g_sum - g_full).norm() / g_full.norm()) < 1e-5
+    with pytest.raises(ValueError):
+        net(x[:W * 3], hw=(H, W), row0=36)                   # rows past the end of the image
+    with pytest.raises(ValueError):
+        net(x[:W * 3 + 1], hw=(H, W), row0=0)                # not whole rows
+
+
 def test_posmlp_gradient_scale_invariance():
     """The tensor-core backward carries gradients scaled by a power of two chosen from max|g_out|: results must not depend on
     the magnitude of the incoming gradient (1e-12 .. 1e+6 here)."""
