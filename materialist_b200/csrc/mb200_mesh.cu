@@ -231,6 +231,21 @@ __device__ __noinline__ float3 env_miss_ool(const HierView& h, const EnvView& e,
 struct Trav {
     float3 o, d, inv, oi; float best; uint32_t cur; int sp; bool active, any, found; Hit h;
 };
+// Traversal stack: the first kSmStack entries of a thread live in shared memory (entry e of thread t at sh[e * kThreads], bank
+// conflict free), deeper ones in local memory.  Local stores are written through to L2: with the whole stack in local memory
+// half of the L2 traffic of the adjoint kernel was stack + spill traffic and its L2 hit rate 68 % (profiles/r1x).
+#ifndef MB200_MESH_SM_STACK_BWD
+#define MB200_MESH_SM_STACK_BWD 16
+#endif
+#ifndef MB200_MESH_SM_STACK_FWD
+#define MB200_MESH_SM_STACK_FWD 0
+#endif
+template <int SM>
+struct TStack {
+    uint2* loc; uint2* sh;
+    __device__ __forceinline__ void push(int& sp, uint2 e) { if (SM > 0 && sp < SM) sh[sp * kThreads] = e; else loc[sp] = e; ++sp; }
+    __device__ __forceinline__ uint2 pop(int& sp) { --sp; return (SM > 0 && sp < SM) ? sh[sp * kThreads] : loc[sp]; }
+};
 __device__ __forceinline__ void trav_begin(const MeshView& M, Trav& T, float3 o, float3 d, float maxt, bool any) {
     T.o = o; T.d = d;
     T.inv = f3(__fdiv_rn(1.f, d.x), __fdiv_rn(1.f, d.y), __fdiv_rn(1.f, d.z));
@@ -242,7 +257,8 @@ __device__ __forceinline__ void trav_begin(const MeshView& M, Trav& T, float3 o,
 // Called by ALL lanes of the warp (lanes without a ray do nothing): the three phases — box tests, triangle test, stack pop —
 // each start converged, so e.g. the pop loop runs once per step for every lane that needs it instead of once per divergent
 // path that reaches it (it ran at 3.6 of 32 lanes: profiles/r1x).
-__device__ __forceinline__ void trav_step(const MeshView& M, Trav& T, uint2* stack) {
+template <int SM>
+__device__ __forceinline__ void trav_step(const MeshView& M, Trav& T, TStack<SM> stack) {
     const bool act = T.active;
     const uint32_t level = T.cur >> 27, idx = T.cur & 0x7ffffffu;
     const bool leaf = act && level == 0, node = act && level != 0;
@@ -274,10 +290,10 @@ __device__ __forceinline__ void trav_step(const MeshView& M, Trav& T, uint2* sta
         if (ct[0] < kInf) {
             if (ct[1] < kInf) {
                 if (ct[2] < kInf) {
-                    if (ct[3] < kInf) stack[T.sp++] = make_uint2(cc[3], __float_as_uint(ct[3]));
-                    stack[T.sp++] = make_uint2(cc[2], __float_as_uint(ct[2]));
+                    if (ct[3] < kInf) stack.push(T.sp, make_uint2(cc[3], __float_as_uint(ct[3])));
+                    stack.push(T.sp, make_uint2(cc[2], __float_as_uint(ct[2])));
                 }
-                stack[T.sp++] = make_uint2(cc[1], __float_as_uint(ct[1]));
+                stack.push(T.sp, make_uint2(cc[1], __float_as_uint(ct[1])));
             }
             T.cur = cc[0];
         } else need_pop = true;
@@ -302,7 +318,7 @@ __device__ __forceinline__ void trav_step(const MeshView& M, Trav& T, uint2* sta
     if (need_pop) {
         bool got = false;
         while (T.sp > 0) {
-            const uint2 e = stack[--T.sp];
+            const uint2 e = stack.pop(T.sp);
             if (__uint_as_float(e.y) <= T.best) { T.cur = e.x; got = true; break; }
         }
         if (!got) T.active = false;
@@ -362,7 +378,10 @@ __global__ void __launch_bounds__(kThreads, MB200_MESH_MIN_BLOCKS_FWD) mesh_fwd_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float4* pool = reinterpret_cast<float4*>(smem) + warp * kPool;
     float* rec = smem + kWarpsPerBlock * kPool * 4 + warp * 32 * kRecStride;        // gaussian film only
-    uint2 stack[kStack];
+    uint2 stack_loc[kStack];
+    TStack<MB200_MESH_SM_STACK_FWD> stack;
+    stack.loc = stack_loc;
+    stack.sh = reinterpret_cast<uint2*>(smem + kWarpsPerBlock * kPool * 4 + (FILTER == MB200_FILTER_GAUSSIAN ? kWarpsPerBlock * 32 * kRecStride : 0)) + threadIdx.x;
     const int npix = P.prows * P.W;
     const int chunks = (P.spp + kPool - 1) / kPool;              // kPool-sample chunks per pixel (1 unless spp > kPool)
     const int ppp = chunks > 1 ? 1 : kPool / P.spp;              // whole pixels per pool
@@ -525,7 +544,8 @@ __global__ void __launch_bounds__(kThreads, MB200_MESH_MIN_BLOCKS_FWD) mesh_fwd_
     }
 }
 inline size_t mesh_fwd_smem(int filter) {
-    return (size_t)kWarpsPerBlock * ((size_t)kPool * 16 + (filter == MB200_FILTER_GAUSSIAN ? 32 * kRecStride * 4 : 0));
+    return (size_t)kWarpsPerBlock * ((size_t)kPool * 16 + (filter == MB200_FILTER_GAUSSIAN ? 32 * kRecStride * 4 : 0)) +
+           (size_t)MB200_MESH_SM_STACK_FWD * kThreads * 8;
 }
 template <typename K>
 inline void launch_mesh_fwd(K kernel, int filter, int grid, cudaStream_t st, const RenderParams& P, const MeshView& M) {
@@ -571,7 +591,10 @@ __global__ void __launch_bounds__(kThreads, MB200_MESH_MIN_BLOCKS_BWD) mesh_bwd_
     const float3 cam_o = f3(P.cam.c2w[3], P.cam.c2w[7], P.cam.c2w[11]);
     const unsigned lt_mask = (1u << lane) - 1u;
     VRec recs[WANT_MAT ? kMaxVerts : 1];
-    uint2 stack[kStack];
+    __shared__ uint2 s_stack[MB200_MESH_SM_STACK_BWD > 0 ? MB200_MESH_SM_STACK_BWD * kThreads : 1];
+    uint2 stack_loc[kStack];
+    TStack<MB200_MESH_SM_STACK_BWD> stack;
+    stack.loc = stack_loc; stack.sh = s_stack + threadIdx.x;
     const int ppp = P.spp >= kPoolBwd ? 1 : kPoolBwd / P.spp;          // whole pixels per pool (no film reduction here: a pool may hold any number of samples)
     const int npools = (npix + ppp - 1) / ppp;
     for (int pool_id = blockIdx.x * kWarpsPerBlock + warp; pool_id < npools; pool_id += gridDim.x * kWarpsPerBlock) {
