@@ -100,6 +100,33 @@ def test_shards_equal_full_image(oracle32):
     assert np.array_equal(np.concatenate(parts, 0), full)
 
 
+def test_host_pipelined_front_end_equals_direct_calls():
+    """materialist_b200.hostpipe: copies on side streams, double-buffered inputs — same images and gradients as direct calls."""
+    import materialist_b200 as mb
+    from materialist_b200.hostpipe import HostPipelinedRenderWBRDF
+    c = Case(H=40, W=40, spp=32, He=16, We=32, gaussian=True)
+    s = c.scene()
+    sets = []
+    for k in range(3):                                                        # three different input sets through two buffer sets
+        a, r, m = (t.numpy() for t in __import__("materialist_b200").synthetic.materials(c.H, c.W, seed_base=20 + k))
+        g = np.random.RandomState(k).randn(c.H, c.W, 3).astype(np.float32)
+        sets.append(tuple(torch.from_numpy(x).pin_memory() for x in (a, r, m, g)))
+    outs = [tuple(torch.empty(*sh).pin_memory() for sh in ((c.H, c.W, 3), (c.H, c.W, 3), (c.H, c.W, 1), (c.H, c.W, 1))) for _ in range(3)]
+    pipe = HostPipelinedRenderWBRDF(s, c.spp)
+    pipe.stage(0, *sets[0])
+    for k in range(3):
+        pipe.step(50 + k, k % 2, *outs[k], next_inputs=sets[k + 1] if k < 2 else None)
+    pipe.synchronize()
+    for k in range(3):
+        a, r, m, g = (t.cuda() for t in sets[k])
+        a.requires_grad_(True); r.requires_grad_(True); m.requires_grad_(True)
+        img = mb.render(s, spp=c.spp, seed=50 + k, albedo=a, roughness=r, metallic=m)
+        img.backward(g)
+        assert torch.equal(outs[k][0], img.detach().cpu())
+        for got, ref in zip(outs[k][1:], (a.grad, r.grad, m.grad)):
+            assert rel_l2(got.numpy(), ref.cpu().numpy()) < 1e-5          # float atomics: order-dependent in the last bits
+
+
 def test_no_cpu_fallback():
     import materialist_b200 as mb
     c = Case(H=8, W=8, spp=4, He=8, We=16)
