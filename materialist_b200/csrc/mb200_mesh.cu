@@ -274,7 +274,10 @@ __device__ __forceinline__ void trav_step(const MeshView& M, Trav& T, TStack<SM>
     if (node) {
         const float lox[4] = {d0.x, d0.y, d0.z, d0.w}, loy[4] = {d1.x, d1.y, d1.z, d1.w}, loz[4] = {d2.x, d2.y, d2.z, d2.w};
         const float hix[4] = {d3.x, d3.y, d3.z, d3.w}, hiy[4] = {d4.x, d4.y, d4.z, d4.w}, hiz[4] = {d5.x, d5.y, d5.z, d5.w};
-        float ct[4]; uint32_t cc[4];
+        // one 32-bit key per child: entry distance with its two low mantissa bits replaced by the child number (t0 >= 0, so
+        // the keys order like the distances; clearing mantissa bits only lowers t0 -> culling stays conservative); a miss is
+        // +inf.  The 5-comparator network then costs two integer min/max per comparator instead of a compare and four selects.
+        uint32_t key[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const float ax = fmaf(lox[k], T.inv.x, -T.oi.x), bx = fmaf(hix[k], T.inv.x, -T.oi.x);
@@ -283,19 +286,21 @@ __device__ __forceinline__ void trav_step(const MeshView& M, Trav& T, TStack<SM>
             const float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
             const float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.0000004f;
             const bool hit = t0 <= fminf(t1, T.best) && lox[k] <= hix[k];
-            ct[k] = hit ? t0 : kInf;
-            cc[k] = ((level - 1) << 27) | (idx * 4u + (uint32_t)k);
+            key[k] = ((hit ? __float_as_uint(t0) : 0x7f800000u) & ~3u) | (uint32_t)k;
         }
-        MB_CSWAP(0, 1) MB_CSWAP(2, 3) MB_CSWAP(0, 2) MB_CSWAP(1, 3) MB_CSWAP(1, 2)
-        if (ct[0] < kInf) {
-            if (ct[1] < kInf) {
-                if (ct[2] < kInf) {
-                    if (ct[3] < kInf) stack.push(T.sp, make_uint2(cc[3], __float_as_uint(ct[3])));
-                    stack.push(T.sp, make_uint2(cc[2], __float_as_uint(ct[2])));
+#define MB_KSWAP(i, j) { const uint32_t lo_ = min(key[i], key[j]), hi_ = max(key[i], key[j]); key[i] = lo_; key[j] = hi_; }
+        MB_KSWAP(0, 1) MB_KSWAP(2, 3) MB_KSWAP(0, 2) MB_KSWAP(1, 3) MB_KSWAP(1, 2)
+#undef MB_KSWAP
+        const uint32_t cbase = ((level - 1) << 27) | (idx * 4u);
+        if (key[0] < 0x7f800000u) {
+            if (key[1] < 0x7f800000u) {
+                if (key[2] < 0x7f800000u) {
+                    if (key[3] < 0x7f800000u) stack.push(T.sp, make_uint2(cbase | (key[3] & 3u), key[3] & ~3u));
+                    stack.push(T.sp, make_uint2(cbase | (key[2] & 3u), key[2] & ~3u));
                 }
-                stack.push(T.sp, make_uint2(cc[1], __float_as_uint(ct[1])));
+                stack.push(T.sp, make_uint2(cbase | (key[1] & 3u), key[1] & ~3u));
             }
-            T.cur = cc[0];
+            T.cur = cbase | (key[0] & 3u);
         } else need_pop = true;
     }
     __syncwarp();
