@@ -238,13 +238,13 @@ struct Trav {
 #define MB200_MESH_SM_STACK_BWD 16
 #endif
 #ifndef MB200_MESH_SM_STACK_FWD
-#define MB200_MESH_SM_STACK_FWD 0
+#define MB200_MESH_SM_STACK_FWD 0          // forward: measured slower with a shared stack, even one that aliases the idle film staging slice (119 vs 116 ms)
 #endif
-template <int SM>
+template <int SM, int STRIDE = kThreads>      // STRIDE: threads that interleave in the shared area (the CTA, or one warp)
 struct TStack {
     uint2* loc; uint2* sh;
-    __device__ __forceinline__ void push(int& sp, uint2 e) { if (SM > 0 && sp < SM) sh[sp * kThreads] = e; else loc[sp] = e; ++sp; }
-    __device__ __forceinline__ uint2 pop(int& sp) { --sp; return (SM > 0 && sp < SM) ? sh[sp * kThreads] : loc[sp]; }
+    __device__ __forceinline__ void push(int& sp, uint2 e) { if (SM > 0 && sp < SM) sh[sp * STRIDE] = e; else loc[sp] = e; ++sp; }
+    __device__ __forceinline__ uint2 pop(int& sp) { --sp; return (SM > 0 && sp < SM) ? sh[sp * STRIDE] : loc[sp]; }
 };
 __device__ __forceinline__ void trav_begin(const MeshView& M, Trav& T, float3 o, float3 d, float maxt, bool any) {
     T.o = o; T.d = d;
@@ -257,8 +257,8 @@ __device__ __forceinline__ void trav_begin(const MeshView& M, Trav& T, float3 o,
 // Called by ALL lanes of the warp (lanes without a ray do nothing): the three phases — box tests, triangle test, stack pop —
 // each start converged, so e.g. the pop loop runs once per step for every lane that needs it instead of once per divergent
 // path that reaches it (it ran at 3.6 of 32 lanes: profiles/r1x).
-template <int SM>
-__device__ __forceinline__ void trav_step(const MeshView& M, Trav& T, TStack<SM> stack) {
+template <int SM, int STRIDE>
+__device__ __forceinline__ void trav_step(const MeshView& M, Trav& T, TStack<SM, STRIDE> stack) {
     const bool act = T.active;
     const uint32_t level = T.cur >> 27, idx = T.cur & 0x7ffffffu;
     const bool leaf = act && level == 0, node = act && level != 0;
@@ -384,9 +384,11 @@ __global__ void __launch_bounds__(kThreads, MB200_MESH_MIN_BLOCKS_FWD) mesh_fwd_
     float4* pool = reinterpret_cast<float4*>(smem) + warp * kPool;
     float* rec = smem + kWarpsPerBlock * kPool * 4 + warp * 32 * kRecStride;        // gaussian film only
     uint2 stack_loc[kStack];
-    TStack<MB200_MESH_SM_STACK_FWD> stack;
+    TStack<MB200_MESH_SM_STACK_FWD, 32> stack;
     stack.loc = stack_loc;
-    stack.sh = reinterpret_cast<uint2*>(smem + kWarpsPerBlock * kPool * 4 + (FILTER == MB200_FILTER_GAUSSIAN ? kWarpsPerBlock * 32 * kRecStride : 0)) + threadIdx.x;
+    // the first entries of the traversal stack share THIS WARP's film staging slice: a warp's stack is empty whenever it reduces its film
+    static_assert(MB200_MESH_SM_STACK_FWD * 8 * 32 <= 32 * kRecStride * 4, "shared stack must fit the warp's staging slice");
+    stack.sh = reinterpret_cast<uint2*>(rec) + lane;
     const int npix = P.prows * P.W;
     const int chunks = (P.spp + kPool - 1) / kPool;              // kPool-sample chunks per pixel (1 unless spp > kPool)
     const int ppp = chunks > 1 ? 1 : kPool / P.spp;              // whole pixels per pool
@@ -549,8 +551,8 @@ __global__ void __launch_bounds__(kThreads, MB200_MESH_MIN_BLOCKS_FWD) mesh_fwd_
     }
 }
 inline size_t mesh_fwd_smem(int filter) {
-    return (size_t)kWarpsPerBlock * ((size_t)kPool * 16 + (filter == MB200_FILTER_GAUSSIAN ? 32 * kRecStride * 4 : 0)) +
-           (size_t)MB200_MESH_SM_STACK_FWD * kThreads * 8;
+    // pool records + the film staging area (gaussian film, or whenever the shared stack aliases it)
+    return (size_t)kWarpsPerBlock * ((size_t)kPool * 16 + ((filter == MB200_FILTER_GAUSSIAN || MB200_MESH_SM_STACK_FWD > 0) ? 32 * kRecStride * 4 : 0));
 }
 template <typename K>
 inline void launch_mesh_fwd(K kernel, int filter, int grid, cudaStream_t st, const RenderParams& P, const MeshView& M) {
