@@ -145,9 +145,33 @@ def run_reference(args, wl):
     cores = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     O = orc.Oracle()
+    if wl.get("real"):                                             # C1: forward render of the shipped scene, traced (as run_real)
+        from test_reference_render_pin import pin_cfg
+        g = np.load(os.path.join(ROOT, "tests", "golden", "indoor_pin.npz"))
+        om = O.mesh_create(g["verts"], g["tris"])
+        env_int, hier, d = O.env_prepare(g["env"], orc.ENV_ASSIGNED)
+        rows, row0, W, spp = 16, 248, 512, wl["spp"]
+        for i in range(args.warmup):
+            O.mesh_render_fwd(pin_cfg(d, i, row0, rows), om, g["a"], g["r"], g["m"], None, env_int, hier, d)
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            O.mesh_render_fwd(pin_cfg(d, 100 + i, row0, rows), om, g["a"], g["r"], g["m"], None, env_int, hier, d)
+        dt = (time.perf_counter() - t0) / args.steps
+        val = rows * W * spp / dt / 1e9
+        sample = f"rows [{row0},{row0 + rows}) of the 512x512 image, {spp} spp, forward render"
+        print(json.dumps({"impl": "reference", "metric": "forward shaded samples/s (relight of the shipped scene, traced)", "value": val, "unit": UNIT,
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+                          "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32", "data": "shipped scene fixture (tests/golden/indoor_pin.npz)",
+                          "config": {"workload": wl["desc"], "sample": sample},
+                          "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                                           "note": "restated Mitsuba path (oracle/, C + OpenMP), not Mitsuba itself: mitsuba==3.5.2 is not installable here"},
+                          "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
     case = build_case(wl, 1)
     H, W, spp = case["H"], case["W"], wl["spp"]
     rows = max(4, min(H, int(2.0e6 // (W * spp)) or 1))           # ~2 M samples per step
+    if case["mesh"] is not None:
+        rows = max(4, rows // 8)                                   # traced paths are ~10x the work per sample
     row0 = (H - rows) // 2
     env_int, hier, d = O.env_prepare(case["env"].numpy(), orc.ENV_FILE)
     gpos = np.ascontiguousarray(np.concatenate([case["pos"], case["valid"][..., None].astype(np.float32)], -1))
