@@ -42,6 +42,9 @@ WORKLOADS = {
                desc="render_final.py --save_name=indoor --mode=real: the shipped output_imgs/indoor scene (522 220-face PLY, optimised maps, "
                     "16x32 envmap; tests/golden/indoor_pin.npz) TRACED as the reference does (path max_depth 4), 64 spp per mi.render call, forward only; "
                     "seeds sharded over the GPUs (replicas, no collective)"),
+    "c1t": dict(H=512, W=512, spp=64, He=16, We=32, scaling="weak", real=True, trans=True,
+                desc="trans_edit.py --save_name=indoor --ior 1.2 --specTrans 0.4: the shipped indoor scene TRACED with the TransBSDF editing plugin "
+                     "(a disc of radius 150 px as edit mask, background = the scene's albedo map), 64 spp per mi.render call, forward only"),
     "tinym": dict(H=64, W=64, spp=32, He=16, We=32, scaling="weak", mesh=True, desc="tiny self-test workload, mesh mode"),
     "tiny": dict(H=64, W=64, spp=32, He=16, We=32, scaling="weak", desc="tiny self-test workload"),
 }
@@ -300,8 +303,15 @@ def run_real(args, wl, dev, world, rank, local):
     cam = mb.Camera(width=W, height=H)
     scene = mb.Scene.from_mesh(g["verts"], g["tris"], cam, device=dev, envmap=torch.from_numpy(g["env"]), use_mesh_normal=True, max_depth=4)
     scene.set_envmap(torch.from_numpy(g["env"]), mb._abi.ENV_ASSIGNED)
+    if wl.get("trans"):
+        scene.set_bsdf({"name": "TransBSDF", "ior": 1.2, "keep_albedo_color": False})
     p = mb.traverse(scene)
     p["shape.bsdf.a"], p["shape.bsdf.r"], p["shape.bsdf.m"] = (torch.from_numpy(g[k]).to(dev) for k in ("a", "r", "m"))
+    if wl.get("trans"):
+        yy, xx = np.mgrid[0:H, 0:W]
+        p["shape.bsdf.mask"] = torch.from_numpy(((xx - 256) ** 2 + (yy - 256) ** 2) < 150 ** 2).to(dev)
+        p["shape.bsdf.bg"] = torch.from_numpy(np.ascontiguousarray(g["a"])).to(dev)
+        p["shape.bsdf.specTrans"] = 0.4
     p.update()
 
     def sync():
@@ -343,7 +353,7 @@ def run_real(args, wl, dev, world, rank, local):
     if rank == 0:
         samples = H * W * spp * world
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and not wl.get("trans"):
             from oracle import oracle as orc
             from test_reference_render_pin import pin_cfg
             O = orc.Oracle(); om = O.mesh_create(g["verts"], g["tris"])
@@ -369,7 +379,7 @@ def run_real(args, wl, dev, world, rank, local):
                           "e2e": {"value": samples / t_e / 1e9, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": himg.numel() * 4,
                                   "ms_per_step": t_e * 1e3, "bytes_are": "per rank", "what": "mi.render(scene, spp, seed) + download of the image; inputs are scene state, as in render_final.py"},
                           "gpu_launches": 2 * args.steps, "gpu_launches_note": "per render: mesh_fwd, film_develop",
-                          "kernel_ms": {"mesh_fwd": t_kernel},
+                          "kernel_ms": {("mesh_fwd_trans" if wl.get("trans") else "mesh_fwd"): t_kernel},
                           "roofline": {"bound": "hbm", "kernel": "mesh_fwd", "achieved": alg / (t_kernel * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                        "frac": alg / (t_kernel * 1e-3) / 1e9 / peak, "traffic": None, "alg_bytes_per_launch": alg,
                                        "note": "traced paths are bound by L2/L1 latency on dependent BVH loads (profiles/r1u), not by HBM; reported for the contract"},
