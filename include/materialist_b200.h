@@ -298,6 +298,17 @@ int mb200_trans_refracted_texel(const mb200_cfg* cfg_host, const mb200_trans* tr
                                 const float* p, const float* n_geo, const float* wi_world,
                                 float* out_screen, int64_t* out_flat, void* stream);
 
+/* Wavefront formulation of mb200_mesh_shade_fwd / mb200_trans_mesh_shade_fwd (trans_host may be NULL = MatDiffBSDF): the path
+ * loop is cut into kernels at its rays (traversal-only kernels at high occupancy, coherent shading kernels); path state lives
+ * in `scratch` (device, 256-byte aligned, mb200_mesh_fwd_wf_scratch_bytes(cfg) bytes: 156 bytes per path, <= 4 Mi paths at a
+ * time).  Same film partials as the one-kernel formulation. */
+size_t mb200_mesh_fwd_wf_scratch_bytes(const mb200_cfg* cfg_host);
+int mb200_mesh_shade_fwd_wf(const mb200_cfg* cfg_host, const mb200_trans* trans_host,
+                            const mb200_mesh_desc* desc_host, const void* mesh_buf,
+                            const float* a, const float* r, const float* m, const float* n_opt,
+                            const float* env4, const float* hier, const mb200_hier_desc* hdesc_host,
+                            float* partials, void* scratch, size_t scratch_bytes, void* stream);
+
 /* ---------------------------------------------------------------- PosMLP */
 #define MB200_POSMLP_TCGEN05 0   /* 256-wide layers on tcgen05 tensor cores, FP16x2-split operands, FP32 TMEM accumulators */
 #define MB200_POSMLP_FFMA    1   /* all layers in FP32 FFMA (first-generation kernels; kept for A/B measurement)           */

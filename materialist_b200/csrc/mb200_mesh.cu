@@ -561,6 +561,233 @@ inline void launch_mesh_fwd(K kernel, int filter, int grid, cudaStream_t st, con
     kernel<<<grid, kThreads, bytes, st>>>(P, M);
 }
 
+// ---------------------------------------------------------------- forward, wavefront formulation
+// The same PathIntegrator::sample, cut into kernels at its rays (Laine, Karras, Aila 2013): per batch of <= kWfBatch paths
+//   wf_gen      primary rays + path state
+//   wf_trace    closest hits of the queued rays      (traversal only: ~48 registers, no spills, every lane always holds a ray —
+//   wf_shade    one thread per live path: miss / vertex; queues the shadow ray and the continuation ray      lanes refill from a global counter)
+//   wf_trace    any-hit of the shadow rays; adds the parked emitter term of the unoccluded ones
+//   ... repeated max_depth-1 times ...     wf_film: per pixel, samples in order -> the same film partials as mesh_fwd_kernel.
+// Path state lives in a caller-provided scratch buffer (mb200_mesh_fwd_wf_scratch_bytes), SoA in float4s: 156 bytes per path.
+// Measured against the one-kernel persistent-lane formulation above (profiles/r3f): C2m forward 116 -> 79 ms, C1 60 -> 44 ms;
+// in the launch list the two traversal kernels are 93 % of the time and all shading 7 %.
+#ifndef MB200_WF_BATCH_LOG2
+#define MB200_WF_BATCH_LOG2 24          // paths per batch (156 B of scratch each): 2^20 / 2^22 / 2^24 -> 120 / 94 / 87 ms C2m forward (fewer, fuller launches)
+#endif
+#ifndef MB200_WF_TRACE_BLOCKS
+#define MB200_WF_TRACE_BLOCKS 4          // CTAs per SM of the traversal kernels: 64 registers, no spills (5: 94 ms, 4: 84 ms, 3: 87 ms, 6: 122 ms)
+#endif
+constexpr int kWfBatch = 1 << MB200_WF_BATCH_LOG2;
+struct WfBuf {
+    float4 *ray_o, *ray_d, *hit, *sray_o, *sray_d, *beta, *L, *cem; uint4* rng;
+    uint32_t *qa, *qb, *qs; uint32_t* counters;          // counters: [0] n(qa) [1] n(qb) [2] n(qs) [3] fetch cursor
+};
+inline size_t wf_scratch_bytes(long long nb) { return (size_t)nb * (9 * 16 + 3 * 4) + 256; }
+inline WfBuf wf_carve(void* scratch, long long nb) {
+    WfBuf B; char* p = (char*)scratch;
+    B.counters = (uint32_t*)p; p += 256;
+    B.ray_o = (float4*)p; p += nb * 16; B.ray_d = (float4*)p; p += nb * 16; B.hit = (float4*)p; p += nb * 16;
+    B.sray_o = (float4*)p; p += nb * 16; B.sray_d = (float4*)p; p += nb * 16; B.beta = (float4*)p; p += nb * 16;
+    B.L = (float4*)p; p += nb * 16; B.cem = (float4*)p; p += nb * 16; B.rng = (uint4*)p; p += nb * 16;
+    B.qa = (uint32_t*)p; p += nb * 4; B.qb = (uint32_t*)p; p += nb * 4; B.qs = (uint32_t*)p;
+    return B;
+}
+__device__ __forceinline__ uint32_t wf_append(uint32_t* counter, bool want) {      // warp-aggregated queue append (returns the slot)
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    uint32_t base = 0;
+    const int lane = threadIdx.x & 31;
+    if (lane == 0 && m) base = atomicAdd(counter, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    return base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+}
+__global__ void wf_gen_kernel(const __grid_constant__ RenderParams P, WfBuf B, long long pix0, int nb) {
+    const float3 cam_o = f3(P.cam.c2w[3], P.cam.c2w[7], P.cam.c2w[11]);
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nb; p += gridDim.x * blockDim.x) {
+        const long long pix = pix0 + p / P.spp; const int s = p % P.spp;
+        const int py = P.prow0 + (int)(pix / P.W), px = (int)(pix % P.W);
+        Pcg32 rng; rng.seed(P.seed, (uint32_t)(py * P.W + px) * (uint32_t)P.spp + (uint32_t)s);
+        const float jx = rng.next_float(), jy = rng.next_float();
+        const float3 d = primary_dir_exact(P.cam, XADD((float)px, jx), XADD((float)py, jy));
+        B.ray_o[p] = make_float4(cam_o.x, cam_o.y, cam_o.z, 0.f); B.ray_d[p] = make_float4(d.x, d.y, d.z, 0.f);
+        B.beta[p] = make_float4(1.f, 1.f, 1.f, 1.f);                               // w = prev_pdf
+        B.L[p] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x100));               // w = nv | prev_delta << 8
+        B.rng[p] = make_uint4((uint32_t)rng.state, (uint32_t)(rng.state >> 32), (uint32_t)rng.inc, (uint32_t)(rng.inc >> 32));
+        B.qa[p] = (uint32_t)p;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { B.counters[0] = (uint32_t)nb; B.counters[1] = 0; B.counters[2] = 0; B.counters[3] = 0; }
+}
+// rays of queue q[0 .. *count): ANY = false -> hit record; ANY = true -> L += cem when unoccluded
+template <bool ANY>
+__global__ void __launch_bounds__(kThreads, MB200_WF_TRACE_BLOCKS) wf_trace_kernel(const __grid_constant__ MeshView M, WfBuf B, const uint32_t* __restrict__ q,
+                                                                const uint32_t* __restrict__ count, uint32_t* cursor) {
+    uint2 stack_loc[kStack];
+    TStack<0> stack; stack.loc = stack_loc; stack.sh = nullptr;
+    const uint32_t n = *count;
+    Trav T; T.active = false; uint32_t pid = 0; bool done = false;
+    for (;;) {
+        // lanes without a ray take the next ones of the queue
+        const bool want = !T.active && !done;
+        const unsigned wm = __ballot_sync(0xffffffffu, want);
+        if (wm) {
+            uint32_t base = 0; const int lane = threadIdx.x & 31;
+            if (lane == 0) base = atomicAdd(cursor, (uint32_t)__popc(wm));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (want) {
+                const uint32_t i = base + (uint32_t)__popc(wm & ((1u << lane) - 1u));
+                if (i < n) {
+                    pid = q[i];
+                    const float4 o = ANY ? B.sray_o[pid] : B.ray_o[pid], d = ANY ? B.sray_d[pid] : B.ray_d[pid];
+                    trav_begin(M, T, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), ANY ? d.w : kInf, ANY);
+                } else done = true;
+            }
+        }
+        if (!__ballot_sync(0xffffffffu, T.active)) break;
+        const bool was = T.active;
+        trav_step(M, T, stack);
+        if (was && !T.active) {                                                    // this lane's ray has finished
+            if (ANY) {
+                if (!T.found) { float4 L = B.L[pid]; const float4 c = B.cem[pid]; L.x += c.x; L.y += c.y; L.z += c.z; B.L[pid] = L; }
+            } else {
+                B.hit[pid] = make_float4(__int_as_float(T.found ? T.h.slot : -1), T.h.t, T.h.u, T.h.v);
+            }
+        }
+    }
+}
+template <bool AD_W, bool TRANS>
+__global__ void __launch_bounds__(kThreads, 2) wf_shade_kernel(const __grid_constant__ RenderParams P, const __grid_constant__ MeshView M, WfBuf B,
+                                                                const uint32_t* __restrict__ qin, uint32_t* __restrict__ qout, int cin, int cout) {
+    const uint32_t n = B.counters[cin];
+    const int max_verts = min(P.max_depth - 1, kMaxVerts);
+    const uint32_t nthreads = gridDim.x * blockDim.x;
+    for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += nthreads) {           // warp-uniform trip count (queue appends are warp-wide)
+        const uint32_t i = i0 + threadIdx.x;
+        const bool have = i < n;
+        bool cont = false, shadow = false; uint32_t pid = 0;
+        if (have) {
+            pid = qin[i];
+            const float4 hr = B.hit[pid], rd4 = B.ray_d[pid];
+            const float3 rd = f3(rd4.x, rd4.y, rd4.z);
+            float4 b4 = B.beta[pid], L4 = B.L[pid];
+            float3 beta = f3(b4.x, b4.y, b4.z), L = f3(L4.x, L4.y, L4.z);
+            const float prev_pdf = b4.w; const int fl = __float_as_int(L4.w); int nv = fl & 0xff; const bool prev_delta = (fl >> 8) & 1;
+            const int slot = __float_as_int(hr.x);
+            if (slot < 0) {
+                if (prev_pdf > 0.f) { Bilerp bb; float mis; const float3 le = env_miss_ool(P.hier, P.env, rd, prev_pdf, prev_delta, bb, mis); L = L + beta * le * mis; }
+                B.L[pid] = make_float4(L.x, L.y, L.z, L4.w);
+            } else if (nv < max_verts) {
+                Hit h; h.slot = slot; h.tri = 0; h.t = hr.y; h.u = hr.z; h.v = hr.w;
+                const SurfacePoint sp = hit_point(M, h);
+                const float3 view = f3(-rd.x, -rd.y, -rd.z);
+                long long flat; const Material mt = fetch_material(P, sp.p, sp.ng, flat);
+                TransMat tm; if (TRANS) tm = trans_fetch(P.cam, P.trans, flat, view, sp.ng, sp.p);
+                const uint4 r4 = B.rng[pid];
+                Pcg32 rng; rng.state = (uint64_t)r4.x | ((uint64_t)r4.y << 32); rng.inc = (uint64_t)r4.z | ((uint64_t)r4.w << 32);
+                const float uex = rng.next_float(), uey = rng.next_float();
+                const EmSample em = env_sample_direction_ool(P.hier, P.env, uex, uey);
+                const float s1 = rng.next_float();
+                const float s2x = rng.next_float(), s2y = rng.next_float();
+                if (em.pdf != 0.f) {
+                    const BsdfVal fv = TRANS ? trans_eval_brdf(em.d, view, mt, tm, P.trans) : eval_brdf_ool(em.d, view, mt);
+                    if (fmax3(fv.f.x, fv.f.y, fv.f.z) > 0.f) {
+                        const float3 cem = beta * fv.f * env_value(P.env, em.b) * (mis_weight(em.pdf, fv.pdf) / em.pdf);
+                        B.cem[pid] = make_float4(cem.x, cem.y, cem.z, 0.f);
+                        // Scene::sample_emitter_direction's visibility ray (trav_begin_shadow)
+                        const float3 c = f3(__ldg(M.header), __ldg(M.header + 1), __ldg(M.header + 2));
+                        const float3 pc = sp.p - c;
+                        const float rad = fmaxf(__ldg(M.header + 3), sqrtf(dot(pc, pc)));
+                        const float3 target = sp.p + em.d * (2.f * rad);
+                        const float3 o = offset_p(sp.p, sp.ng, target - sp.p);
+                        float3 dd = target - o;
+                        const float dist = sqrtf(dot(dd, dd));
+                        dd = dd * (1.f / dist);
+                        B.sray_o[pid] = make_float4(o.x, o.y, o.z, 0.f); B.sray_d[pid] = make_float4(dd.x, dd.y, dd.z, dist * (1.f - kShadowEps));
+                        shadow = true;
+                    }
+                }
+                const BsdfSample bs = TRANS ? trans_sample_brdf(s1, s2x, s2y, view, mt, tm, P.trans, make_frame(mt.n)) : sample_brdf_ool(s1, s2x, s2y, view, mt);
+                const float3 d_bs = (P.flags & MB200_FLAG_WO_WORLD_QUIRK) ? to_world(sp.sh, bs.wi) : bs.wi;
+                float3 w = bs.weight;
+                if (AD_W) { const BsdfVal b2 = eval_brdf_ool(d_bs, view, mt); if (b2.pdf > 0.f) w = b2.f * (1.f / b2.pdf); }
+                const float3 no = offset_p(sp.p, sp.ng, d_bs);
+                beta = beta * w; nv += 1;
+                rng.next_float();
+                B.rng[pid] = make_uint4((uint32_t)rng.state, (uint32_t)(rng.state >> 32), (uint32_t)rng.inc, (uint32_t)(rng.inc >> 32));
+                B.beta[pid] = make_float4(beta.x, beta.y, beta.z, bs.pdf);
+                B.L[pid] = make_float4(L.x, L.y, L.z, __int_as_float(nv));            // prev_delta = false from now on
+                cont = fmax3(beta.x, beta.y, beta.z) != 0.f;
+                if (cont) { B.ray_o[pid] = make_float4(no.x, no.y, no.z, 0.f); B.ray_d[pid] = make_float4(d_bs.x, d_bs.y, d_bs.z, 0.f); }
+            }
+        }
+        const uint32_t sa = wf_append(B.counters + cout, cont);
+        if (cont) qout[sa] = pid;
+        const uint32_t sb = wf_append(B.counters + 2, shadow);
+        if (shadow) B.qs[sb] = pid;
+    }
+}
+// film: the pixels of the batch, samples in order (same arithmetic as mesh_fwd_kernel's reduction)
+template <int FILTER>
+__global__ void wf_film_kernel(const __grid_constant__ RenderParams P, WfBuf B, long long pix0, int npix_batch, int s_lo, int s_n, int first, int last) {
+    __shared__ __align__(16) float s_rec[FILTER == MB200_FILTER_GAUSSIAN ? kWarpsPerBlock * 32 * kRecStride : 4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* rec = s_rec + (FILTER == MB200_FILTER_GAUSSIAN ? warp * 32 * kRecStride : 0);
+    const int ti = lane % 5, tj = lane / 5;
+    for (int pi = blockIdx.x * kWarpsPerBlock + warp; pi < npix_batch; pi += gridDim.x * kWarpsPerBlock) {
+        const long long pix = pix0 + pi;
+        const int py = P.prow0 + (int)(pix / P.W), px = (int)(pix % P.W);
+        const int gpix = py * P.W + px;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!first) {                                                                // a pixel spanning several batches (spp > kWfBatch)
+            if (FILTER == MB200_FILTER_GAUSSIAN) { if (lane < MB200_FILM_TAPS) acc = reinterpret_cast<float4*>(P.partials)[(size_t)pix * MB200_FILM_TAPS + lane]; }
+            else if (lane == 0) acc = reinterpret_cast<float4*>(P.partials)[pix];
+        }
+        for (int b0 = 0; b0 < s_n; b0 += 32) {
+            const int sl = b0 + lane; const bool act = sl < s_n;
+            float3 Ls = f3(0.f, 0.f, 0.f);
+            if (act) { const float4 r4 = B.L[(size_t)pi * s_n + sl]; Ls = f3(r4.x, r4.y, r4.z); }
+            if (FILTER == MB200_FILTER_GAUSSIAN) {
+                float wx[5], wy[5];
+                if (act) {
+                    Pcg32 r2; r2.seed(P.seed, (uint32_t)gpix * (uint32_t)P.spp + (uint32_t)(s_lo + sl));
+                    const float jx = r2.next_float(), jy = r2.next_float();
+                    film_taps(jx, wx); film_taps(jy, wy);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) { wx[i] = 0.f; wy[i] = 0.f; }
+                }
+                float4* r4 = reinterpret_cast<float4*>(rec + lane * kRecStride);
+                r4[0] = make_float4(wx[0], wx[1], wx[2], wx[3]);
+                r4[1] = make_float4(wx[4], wy[0], wy[1], wy[2]);
+                r4[2] = make_float4(wy[3], wy[4], 0.f, 0.f);
+                r4[3] = make_float4(Ls.x, Ls.y, Ls.z, 1.f);
+                __syncwarp();
+                if (lane < MB200_FILM_TAPS) {
+                    const float* rt = rec + ti; const float* ru = rec + 5 + tj;
+#pragma unroll 8
+                    for (int k = 0; k < 32; ++k) {
+                        const float w = rt[k * kRecStride] * ru[k * kRecStride];
+                        const float4 l4 = *reinterpret_cast<const float4*>(rec + k * kRecStride + 12);
+                        acc.x = fmaf(w, l4.x, acc.x); acc.y = fmaf(w, l4.y, acc.y); acc.z = fmaf(w, l4.z, acc.z); acc.w += w;
+                    }
+                }
+                __syncwarp();
+            } else {
+                acc.x += Ls.x; acc.y += Ls.y; acc.z += Ls.z;
+            }
+        }
+        if (FILTER == MB200_FILTER_GAUSSIAN) {
+            if (lane < MB200_FILM_TAPS) reinterpret_cast<float4*>(P.partials)[(size_t)pix * MB200_FILM_TAPS + lane] = acc;
+        } else {
+            float4 t = acc;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                t.x += __shfl_xor_sync(0xffffffffu, t.x, o); t.y += __shfl_xor_sync(0xffffffffu, t.y, o); t.z += __shfl_xor_sync(0xffffffffu, t.z, o);
+            }
+            (void)last;
+            if (lane == 0) reinterpret_cast<float4*>(P.partials)[pix] = make_float4(t.x, t.y, t.z, (float)P.spp);
+        }
+    }
+}
+
 // ---------------------------------------------------------------- adjoint
 struct VRec {                       // what the backward walk needs of one scattering vertex (30 words, local memory)
     Material mt; float3 view, em_d, cem, d_bs, cpre, w, E; int flat;
@@ -1100,6 +1327,58 @@ int mb200_mesh_shade_fwd(const mb200_cfg* c, const mb200_mesh_desc* md, const vo
     } else {
         if (ad) launch_mesh_fwd(mesh_fwd_kernel<MB200_FILTER_BOX, true, false>, c->filter, grid, st, P, M);
         else    launch_mesh_fwd(mesh_fwd_kernel<MB200_FILTER_BOX, false, false>, c->filter, grid, st, P, M);
+    }
+    return mb200_check_launch();
+}
+
+size_t mb200_mesh_fwd_wf_scratch_bytes(const mb200_cfg* c) {
+    if (!c || c->spp <= 0 || c->spp > kWfBatch) return 0;
+    int r0; const int prows = mb200_fwd_partial_rows(c, &r0);
+    const long long npix = (long long)prows * c->W, bp = kWfBatch / c->spp;
+    const long long nb = (npix < bp ? npix : bp) * c->spp;
+    return wf_scratch_bytes(nb);
+}
+
+int mb200_mesh_shade_fwd_wf(const mb200_cfg* c, const mb200_trans* t, const mb200_mesh_desc* md, const void* mesh_buf,
+                            const float* a, const float* r, const float* m, const float* n_opt,
+                            const float* env4, const float* hier, const mb200_hier_desc* d, float* partials,
+                            void* scratch, size_t scratch_bytes, void* stream) {
+    RenderParams P; int rc = mesh_render_params(c, a, r, m, n_opt, env4, hier, d, P);
+    if (rc) return rc;
+    if (t && (rc = fill_trans(t, P)) != MB200_OK) return rc;
+    MeshView M; rc = make_view(md, mesh_buf, M);
+    if (rc) return rc;
+    if (!partials || !scratch) return MB200_EINVAL;
+    if (c->spp > kWfBatch) return MB200_EUNSUPPORTED;
+    const bool ad = (c->flags & MB200_FLAG_AD_WEIGHTS) != 0;
+    if (t && ad) return MB200_EUNSUPPORTED;
+    P.prows = mb200_fwd_partial_rows(c, &P.prow0); P.partials = partials;
+    const long long npix = (long long)P.prows * P.W, bp = kWfBatch / c->spp;
+    const long long nb_max = (npix < bp ? npix : bp) * c->spp;
+    if (scratch_bytes < wf_scratch_bytes(nb_max)) return MB200_EINVAL;
+    WfBuf B = wf_carve(scratch, nb_max);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int sms = mb200_sm_count();
+    const int max_verts = (c->max_depth - 1 < kMaxVerts ? c->max_depth - 1 : kMaxVerts);
+    for (long long pix0 = 0; pix0 < npix; pix0 += bp) {
+        const int npb = (int)((npix - pix0) < bp ? (npix - pix0) : bp);
+        const int nb = npb * c->spp;
+        wf_gen_kernel<<<sms * 8, 256, 0, st>>>(P, B, pix0, nb);
+        uint32_t* qin = B.qa; uint32_t* qout = B.qb; int cin = 0, cout = 1;
+        for (int it = 0; it <= (max_verts < 0 ? 0 : max_verts); ++it) {
+            cudaMemsetAsync(B.counters + 3, 0, 4, st);
+            wf_trace_kernel<false><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, st>>>(M, B, qin, B.counters + cin, B.counters + 3);
+            cudaMemsetAsync(B.counters + cout, 0, 4, st);
+            cudaMemsetAsync(B.counters + 2, 0, 4, st);
+            if (t)       wf_shade_kernel<false, true><<<sms * 4, kThreads, 0, st>>>(P, M, B, qin, qout, cin, cout);
+            else if (ad) wf_shade_kernel<true, false><<<sms * 4, kThreads, 0, st>>>(P, M, B, qin, qout, cin, cout);
+            else         wf_shade_kernel<false, false><<<sms * 4, kThreads, 0, st>>>(P, M, B, qin, qout, cin, cout);
+            cudaMemsetAsync(B.counters + 3, 0, 4, st);
+            wf_trace_kernel<true><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, st>>>(M, B, B.qs, B.counters + 2, B.counters + 3);
+            uint32_t* tq = qin; qin = qout; qout = tq; const int tc = cin; cin = cout; cout = tc;
+        }
+        if (c->filter == MB200_FILTER_GAUSSIAN) wf_film_kernel<MB200_FILTER_GAUSSIAN><<<sms * 8, kThreads, 0, st>>>(P, B, pix0, npb, 0, c->spp, 1, 1);
+        else                                    wf_film_kernel<MB200_FILTER_BOX><<<sms * 8, kThreads, 0, st>>>(P, B, pix0, npb, 0, c->spp, 1, 1);
     }
     return mb200_check_launch();
 }

@@ -73,7 +73,19 @@ def _forward(scene, spp, seed, a, r, m, n, env_pack, extra_flags=0):
     partials = torch.empty(prows, scene.W, stride, device=scene.device)
     st = _abi.stream_ptr()
     nmap = None if scene.use_mesh_normal else n
-    if scene.trans is not None:                 # TransBSDF plugin (trans_edit.py): forward only
+    if scene.mesh is not None and scene.mesh_forward == "wavefront":
+        td = scene.trans.desc() if scene.trans is not None else None
+        nbytes = _abi.lib.mb200_mesh_fwd_wf_scratch_bytes(C.byref(cfg))
+        if nbytes == 0:
+            raise ValueError("wavefront forward: unsupported configuration (spp too large)")
+        if scene._wf_scratch is None or scene._wf_scratch.numel() * 8 < nbytes:
+            scene._wf_scratch = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=scene.device)
+        with _ktime("mesh_fwd_wf"):
+            _abi.check(_abi.lib.mb200_mesh_shade_fwd_wf(C.byref(cfg), C.byref(td) if td is not None else None, C.byref(scene.mesh.desc),
+                                                        _abi.ptr(scene.mesh.buf), _abi.ptr(a), _abi.ptr(r), _abi.ptr(m), _abi.ptr(nmap),
+                                                        _abi.ptr(env4), _abi.ptr(hier), C.byref(desc), _abi.ptr(partials),
+                                                        _abi.ptr(scene._wf_scratch), scene._wf_scratch.numel() * 8, st), "mb200_mesh_shade_fwd_wf")
+    elif scene.trans is not None:               # TransBSDF plugin (trans_edit.py): forward only
         td = scene.trans.desc()
         if scene.mesh is not None:
             with _ktime("mesh_fwd_trans"):

@@ -127,6 +127,10 @@ class Scene:
         self.flags = int(flags)
         self.row0, self.rows = 0, H            # pixel shard (whole image by default)
         self.trans = None                      # TransSettings when the shape's BSDF is the TransBSDF plugin (set_bsdf)
+        # forward formulation of mesh mode: "wavefront" (mb200_mesh_shade_fwd_wf: traversal and shading in separate kernels, path
+        # state in a scratch buffer; the faster one) or "persistent" (mb200_mesh_shade_fwd: one kernel, no scratch memory)
+        self.mesh_forward = os.environ.get("MB200_MESH_FORWARD", "wavefront")
+        self._wf_scratch = None
         self._env = None
         if envmap is None:
             envmap = torch.ones(16, 32, 3)

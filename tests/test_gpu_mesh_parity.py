@@ -203,6 +203,21 @@ def test_mesh_ragged_sample_counts_vs_oracle(oracle32, spp, gaussian):
     assert torch.equal(again, img.detach())                 # bitwise deterministic whatever order the lanes finished in
 
 
+def test_wavefront_and_persistent_forward_agree():
+    """The two forward formulations of mesh mode trace the same paths: images equal up to FMA-contraction differences."""
+    import materialist_b200 as mb
+    H = W = 40
+    cam, verts, tris, a, r, m, env = _scene(H, W)
+    s = _cuda_scene(cam, verts, tris, env, REF_FLAGS)
+    ta, tr, tm = (torch.from_numpy(x).cuda() for x in (a, r, m))
+    imgs = {}
+    for impl in ("wavefront", "persistent"):
+        s.mesh_forward = impl
+        with torch.no_grad():
+            imgs[impl] = mb.render(s, spp=48, seed=3, albedo=ta, roughness=tr, metallic=tm)
+    assert rel_l2(imgs["wavefront"].cpu().numpy(), imgs["persistent"].cpu().numpy()) < 1e-5
+
+
 def test_mesh_shard_rows_bitwise_equal_full_image():
     import materialist_b200 as mb
     H = W = 32
