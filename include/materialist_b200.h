@@ -309,6 +309,16 @@ int mb200_mesh_shade_fwd_wf(const mb200_cfg* cfg_host, const mb200_trans* trans_
                             const float* env4, const float* hier, const mb200_hier_desc* hdesc_host,
                             float* partials, void* scratch, size_t scratch_bytes, void* stream);
 
+/* Wavefront formulation of mb200_mesh_shade_bwd (same arguments + scratch: mb200_mesh_bwd_wf_scratch_bytes(cfg) bytes, device,
+ * 256-byte aligned; 224 + 128 * (max_depth - 1) bytes per path, <= 8 Mi paths at a time). */
+size_t mb200_mesh_bwd_wf_scratch_bytes(const mb200_cfg* cfg_host);
+int mb200_mesh_shade_bwd_wf(const mb200_cfg* cfg_host, const mb200_mesh_desc* desc_host, const void* mesh_buf,
+                            const float* a, const float* r, const float* m, const float* n_opt,
+                            const float* env4, const float* hier, const mb200_hier_desc* hdesc_host,
+                            const float* gadj,
+                            float* g_a, float* g_r, float* g_m, float* g_n, float* g_env4, int n_env_slabs,
+                            void* scratch, size_t scratch_bytes, void* stream);
+
 /* ---------------------------------------------------------------- PosMLP */
 #define MB200_POSMLP_TCGEN05 0   /* 256-wide layers on tcgen05 tensor cores, FP16x2-split operands, FP32 TMEM accumulators */
 #define MB200_POSMLP_FFMA    1   /* all layers in FP32 FFMA (first-generation kernels; kept for A/B measurement)           */

@@ -581,6 +581,8 @@ constexpr int kWfBatch = 1 << MB200_WF_BATCH_LOG2;
 struct WfBuf {
     float4 *ray_o, *ray_d, *hit, *sray_o, *sray_d, *beta, *L, *cem; uint4* rng;
     uint32_t *qa, *qb, *qs; uint32_t* counters;          // counters: [0] n(qa) [1] n(qb) [2] n(qs) [3] fetch cursor
+    // adjoint only: film cotangent, pending envmap scatter (cotangent + bilinear footprint), visibility, vertex records
+    float4 *dl, *scat, *pbw, *vrec; uint32_t* vis; long long nb; int max_verts;
 };
 inline size_t wf_scratch_bytes(long long nb) { return (size_t)nb * (9 * 16 + 3 * 4) + 256; }
 inline WfBuf wf_carve(void* scratch, long long nb) {
@@ -589,9 +591,24 @@ inline WfBuf wf_carve(void* scratch, long long nb) {
     B.ray_o = (float4*)p; p += nb * 16; B.ray_d = (float4*)p; p += nb * 16; B.hit = (float4*)p; p += nb * 16;
     B.sray_o = (float4*)p; p += nb * 16; B.sray_d = (float4*)p; p += nb * 16; B.beta = (float4*)p; p += nb * 16;
     B.L = (float4*)p; p += nb * 16; B.cem = (float4*)p; p += nb * 16; B.rng = (uint4*)p; p += nb * 16;
-    B.qa = (uint32_t*)p; p += nb * 4; B.qb = (uint32_t*)p; p += nb * 4; B.qs = (uint32_t*)p;
+    B.qa = (uint32_t*)p; p += nb * 4; B.qb = (uint32_t*)p; p += nb * 4; B.qs = (uint32_t*)p; p += nb * 4;
+    B.dl = B.scat = B.pbw = B.vrec = nullptr; B.vis = nullptr; B.nb = nb; B.max_verts = 0;
     return B;
 }
+constexpr int kVRecF4 = 8;                               // float4s per vertex record
+inline size_t wf_bwd_scratch_bytes(long long nb, int max_verts) {
+    return wf_scratch_bytes(nb) + (size_t)nb * (3 * 16 + 4 + (size_t)max_verts * kVRecF4 * 16) + 256;
+}
+inline WfBuf wf_carve_bwd(void* scratch, long long nb, int max_verts) {
+    WfBuf B = wf_carve(scratch, nb);
+    char* p = (char*)scratch + ((wf_scratch_bytes(nb) + 255) & ~(size_t)255);
+    B.dl = (float4*)p; p += nb * 16; B.scat = (float4*)p; p += nb * 16; B.pbw = (float4*)p; p += nb * 16;
+    B.vrec = (float4*)p; p += (size_t)nb * max_verts * kVRecF4 * 16; B.vis = (uint32_t*)p;
+    B.max_verts = max_verts;
+    return B;
+}
+// vertex record k of path pid: 8 float4s, each array coalesced over pid
+__device__ __forceinline__ float4* vrec_at(const WfBuf& B, int k, int j, uint32_t pid) { return B.vrec + ((size_t)(k * kVRecF4 + j) * B.nb + pid); }
 __device__ __forceinline__ uint32_t wf_append(uint32_t* counter, bool want) {      // warp-aggregated queue append (returns the slot)
     const unsigned m = __ballot_sync(0xffffffffu, want);
     uint32_t base = 0;
@@ -616,10 +633,12 @@ __global__ void wf_gen_kernel(const __grid_constant__ RenderParams P, WfBuf B, l
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { B.counters[0] = (uint32_t)nb; B.counters[1] = 0; B.counters[2] = 0; B.counters[3] = 0; }
 }
-// rays of queue q[0 .. *count): ANY = false -> hit record; ANY = true -> L += cem when unoccluded
-template <bool ANY>
+// rays of queue q[0 .. *count): MODE 0 = closest hit -> hit record; 1 = any hit, L += cem when unoccluded (forward);
+// 2 = any hit, visibility flag (adjoint)
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, MB200_WF_TRACE_BLOCKS) wf_trace_kernel(const __grid_constant__ MeshView M, WfBuf B, const uint32_t* __restrict__ q,
                                                                 const uint32_t* __restrict__ count, uint32_t* cursor) {
+    constexpr bool ANY = MODE != 0;
     uint2 stack_loc[kStack];
     TStack<0> stack; stack.loc = stack_loc; stack.sh = nullptr;
     const uint32_t n = *count;
@@ -645,8 +664,10 @@ __global__ void __launch_bounds__(kThreads, MB200_WF_TRACE_BLOCKS) wf_trace_kern
         const bool was = T.active;
         trav_step(M, T, stack);
         if (was && !T.active) {                                                    // this lane's ray has finished
-            if (ANY) {
+            if (MODE == 1) {
                 if (!T.found) { float4 L = B.L[pid]; const float4 c = B.cem[pid]; L.x += c.x; L.y += c.y; L.z += c.z; B.L[pid] = L; }
+            } else if (MODE == 2) {
+                B.vis[pid] = T.found ? 0u : 1u;
             } else {
                 B.hit[pid] = make_float4(__int_as_float(T.found ? T.h.slot : -1), T.h.t, T.h.u, T.h.v);
             }
@@ -986,6 +1007,205 @@ __global__ void __launch_bounds__(kThreads, MB200_MESH_MIN_BLOCKS_BWD) mesh_bwd_
 }
 
 // ---------------------------------------------------------------- debug / G-buffer extraction kernels
+// ---------------------------------------------------------------- adjoint, wavefront formulation
+// As the forward: wf_gen_bwd (primary rays + the film cotangent dl of every path) -> per bounce wf_trace<closest> ->
+// wf_shade_bwd (miss term; vertex: record for the backward walk, parked emitter term, shadow + continuation rays) ->
+// wf_trace<visibility> -> wf_apply_bwd (unoccluded: scatter the emitter term's envmap gradient; occluded: drop the term from the
+// record) -> finally wf_walk: one thread per path, the backward walk over its records with the same per-texel peer reduction.
+template <int FILTER>
+__global__ void wf_gen_bwd_kernel(const __grid_constant__ RenderParams P, WfBuf B, long long pix0, int nb) {
+    const float3 cam_o = f3(P.cam.c2w[3], P.cam.c2w[7], P.cam.c2w[11]);
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nb; p += gridDim.x * blockDim.x) {
+        const long long pix = pix0 + p / P.spp; const int s = p % P.spp;
+        const int py = P.prow0 + (int)(pix / P.W), px = (int)(pix % P.W);
+        Pcg32 rng; rng.seed(P.seed, (uint32_t)(py * P.W + px) * (uint32_t)P.spp + (uint32_t)s);
+        const float jx = rng.next_float(), jy = rng.next_float();
+        float3 dl;
+        if (FILTER == MB200_FILTER_GAUSSIAN) {          // film adjoint: 5x5 gather of G = grad / W around the pixel
+            float wx[5], wy[5]; film_taps(jx, wx); film_taps(jy, wy);
+            dl = f3(0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                float3 row = f3(0.f, 0.f, 0.f);
+                const int qy = py + (j - 2);
+                const bool rowok = qy >= P.grow0 && qy < P.grow0 + P.grows && qy >= 0 && qy < P.H;
+#pragma unroll
+                for (int i = 0; i < 5; ++i) {
+                    const int qx = px + (i - 2);
+                    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rowok && qx >= 0 && qx < P.W) g = __ldg(P.gadj + (size_t)(qy - P.grow0) * P.W + qx);
+                    row.x = fmaf(wx[i], g.x, row.x); row.y = fmaf(wx[i], g.y, row.y); row.z = fmaf(wx[i], g.z, row.z);
+                }
+                dl.x = fmaf(wy[j], row.x, dl.x); dl.y = fmaf(wy[j], row.y, dl.y); dl.z = fmaf(wy[j], row.z, dl.z);
+            }
+        } else {
+            const float4 g = __ldg(P.gadj + (size_t)(py - P.grow0) * P.W + px);
+            dl = f3(g.x, g.y, g.z);
+        }
+        const float3 d = primary_dir_exact(P.cam, XADD((float)px, jx), XADD((float)py, jy));
+        B.ray_o[p] = make_float4(cam_o.x, cam_o.y, cam_o.z, 0.f); B.ray_d[p] = make_float4(d.x, d.y, d.z, 0.f);
+        B.beta[p] = make_float4(1.f, 1.f, 1.f, 1.f);
+        B.L[p] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x100));               // (R.xyz, nv | prev_delta << 8)
+        B.dl[p] = make_float4(dl.x, dl.y, dl.z, 0.f);
+        B.rng[p] = make_uint4((uint32_t)rng.state, (uint32_t)(rng.state >> 32), (uint32_t)rng.inc, (uint32_t)(rng.inc >> 32));
+        B.qa[p] = (uint32_t)p;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { B.counters[0] = (uint32_t)nb; B.counters[1] = 0; B.counters[2] = 0; B.counters[3] = 0; }
+}
+template <bool WANT_MAT, bool WANT_ENV>
+__global__ void __launch_bounds__(kThreads, 2) wf_shade_bwd_kernel(const __grid_constant__ RenderParams P, const __grid_constant__ MeshView M, WfBuf B,
+                                                                    const uint32_t* __restrict__ qin, uint32_t* __restrict__ qout, int cin, int cout) {
+    const uint32_t n = B.counters[cin];
+    const int max_verts = min(P.max_depth - 1, kMaxVerts);
+    float4* const genv = WANT_ENV ? P.g_env4 + (long long)(blockIdx.x % P.env_slabs) * P.env_slab_stride : nullptr;
+    const uint32_t nthreads = gridDim.x * blockDim.x;
+    for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += nthreads) {
+        const uint32_t i = i0 + threadIdx.x;
+        const bool have = i < n;
+        bool cont = false, shadow = false; uint32_t pid = 0;
+        if (have) {
+            pid = qin[i];
+            const float4 hr = B.hit[pid], rd4 = B.ray_d[pid], b4 = B.beta[pid], L4 = B.L[pid], dl4 = B.dl[pid];
+            const float3 rd = f3(rd4.x, rd4.y, rd4.z), dl = f3(dl4.x, dl4.y, dl4.z);
+            float3 beta = f3(b4.x, b4.y, b4.z);
+            const float prev_pdf = b4.w; const int fl = __float_as_int(L4.w); int nv = fl & 0xff; const bool prev_delta = (fl >> 8) & 1;
+            const int slot = __float_as_int(hr.x);
+            if (slot < 0) {
+                if (prev_pdf > 0.f) {
+                    Bilerp bb; float mis; const float3 le = env_miss_ool(P.hier, P.env, rd, prev_pdf, prev_delta, bb, mis);
+                    if (WANT_MAT) B.L[pid] = make_float4(le.x * mis, le.y * mis, le.z * mis, L4.w);
+                    if (WANT_ENV) env_scatter(genv, P.env.Wi, bb, dl * beta * mis);
+                }
+            } else if (nv < max_verts) {
+                Hit h; h.slot = slot; h.tri = 0; h.t = hr.y; h.u = hr.z; h.v = hr.w;
+                const SurfacePoint sp = hit_point(M, h);
+                const float3 view = f3(-rd.x, -rd.y, -rd.z);
+                long long flat; const Material mt = fetch_material(P, sp.p, sp.ng, flat);
+                const uint4 r4 = B.rng[pid];
+                Pcg32 rng; rng.state = (uint64_t)r4.x | ((uint64_t)r4.y << 32); rng.inc = (uint64_t)r4.z | ((uint64_t)r4.w << 32);
+                const float uex = rng.next_float(), uey = rng.next_float();
+                const EmSample em = env_sample_direction_ool(P.hier, P.env, uex, uey);
+                const float s1 = rng.next_float();
+                const float s2x = rng.next_float(), s2y = rng.next_float();
+                float3 E = f3(0.f, 0.f, 0.f), cem = f3(0.f, 0.f, 0.f);
+                if (em.pdf != 0.f && dot(mt.n, em.d) > 0.f) {      // NoL = 0 multiplies the value and every gradient term: no shadow ray
+                    const BsdfVal fv = eval_brdf_ool(em.d, view, mt);
+                    const float k = mis_weight(em.pdf, fv.pdf) / em.pdf;
+                    if (WANT_MAT) { const float3 lek = env_value(P.env, em.b) * k; E = fv.f * lek; cem = dl * beta * lek; }
+                    if (WANT_ENV) {
+                        const float3 sc = dl * beta * fv.f * k;
+                        B.scat[pid] = make_float4(sc.x, sc.y, sc.z, __uint_as_float(em.b.i00));
+                        B.pbw[pid] = make_float4(em.b.w0x, em.b.w1x, em.b.w0y, em.b.w1y);
+                    }
+                    const float3 c = f3(__ldg(M.header), __ldg(M.header + 1), __ldg(M.header + 2));
+                    const float3 pc = sp.p - c;
+                    const float rad = fmaxf(__ldg(M.header + 3), sqrtf(dot(pc, pc)));
+                    const float3 target = sp.p + em.d * (2.f * rad);
+                    const float3 o = offset_p(sp.p, sp.ng, target - sp.p);
+                    float3 dd = target - o;
+                    const float dist = sqrtf(dot(dd, dd));
+                    dd = dd * (1.f / dist);
+                    B.sray_o[pid] = make_float4(o.x, o.y, o.z, 0.f); B.sray_d[pid] = make_float4(dd.x, dd.y, dd.z, dist * (1.f - kShadowEps));
+                    shadow = true;
+                }
+                const BsdfSample bs = sample_brdf_ool(s1, s2x, s2y, view, mt);
+                const float3 d_bs = (P.flags & MB200_FLAG_WO_WORLD_QUIRK) ? to_world(sp.sh, bs.wi) : bs.wi;
+                const BsdfVal b2 = eval_brdf_ool(d_bs, view, mt);
+                const float3 w = b2.pdf > 0.f ? b2.f * (1.f / b2.pdf) : bs.weight;
+                if (WANT_MAT) {
+                    const float3 cpre = b2.pdf > 0.f ? dl * beta * (1.f / b2.pdf) : f3(0.f, 0.f, 0.f);
+                    *vrec_at(B, nv, 0, pid) = make_float4(mt.a.x, mt.a.y, mt.a.z, mt.r);
+                    *vrec_at(B, nv, 1, pid) = make_float4(mt.m, mt.n.x, mt.n.y, mt.n.z);
+                    *vrec_at(B, nv, 2, pid) = make_float4(view.x, view.y, view.z, __int_as_float((int)flat));
+                    *vrec_at(B, nv, 3, pid) = make_float4(em.d.x, em.d.y, em.d.z, cem.x);
+                    *vrec_at(B, nv, 4, pid) = make_float4(cem.y, cem.z, d_bs.x, d_bs.y);
+                    *vrec_at(B, nv, 5, pid) = make_float4(d_bs.z, cpre.x, cpre.y, cpre.z);
+                    *vrec_at(B, nv, 6, pid) = make_float4(w.x, w.y, w.z, E.x);
+                    *vrec_at(B, nv, 7, pid) = make_float4(E.y, E.z, 0.f, 0.f);
+                }
+                const float3 no = offset_p(sp.p, sp.ng, d_bs);
+                beta = beta * w; nv += 1;
+                rng.next_float();
+                B.rng[pid] = make_uint4((uint32_t)rng.state, (uint32_t)(rng.state >> 32), (uint32_t)rng.inc, (uint32_t)(rng.inc >> 32));
+                B.beta[pid] = make_float4(beta.x, beta.y, beta.z, bs.pdf);
+                B.L[pid] = make_float4(0.f, 0.f, 0.f, __int_as_float(nv));
+                cont = fmax3(beta.x, beta.y, beta.z) != 0.f;
+                if (cont) { B.ray_o[pid] = make_float4(no.x, no.y, no.z, 0.f); B.ray_d[pid] = make_float4(d_bs.x, d_bs.y, d_bs.z, 0.f); }
+            }
+        }
+        const uint32_t sa = wf_append(B.counters + cout, cont);
+        if (cont) qout[sa] = pid;
+        const uint32_t sb = wf_append(B.counters + 2, shadow);
+        if (shadow) B.qs[sb] = pid;
+    }
+}
+template <bool WANT_MAT, bool WANT_ENV>
+__global__ void wf_apply_bwd_kernel(const __grid_constant__ RenderParams P, WfBuf B) {
+    const uint32_t n = B.counters[2];
+    float4* const genv = WANT_ENV ? P.g_env4 + (long long)(blockIdx.x % P.env_slabs) * P.env_slab_stride : nullptr;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t pid = B.qs[i];
+        if (B.vis[pid]) {
+            if (WANT_ENV) {
+                const float4 sc = B.scat[pid], w = B.pbw[pid];
+                Bilerp b; b.i00 = __float_as_uint(sc.w); b.w0x = w.x; b.w1x = w.y; b.w0y = w.z; b.w1y = w.w;
+                env_scatter(genv, P.env.Wi, b, f3(sc.x, sc.y, sc.z));
+            }
+        } else if (WANT_MAT) {                                                     // occluded: the emitter term of this vertex vanishes
+            const int k = (__float_as_int(B.L[pid].w) & 0xff) - 1;
+            float4* r3 = vrec_at(B, k, 3, pid); float4* r4 = vrec_at(B, k, 4, pid); float4* r6 = vrec_at(B, k, 6, pid); float4* r7 = vrec_at(B, k, 7, pid);
+            float4 v3 = *r3, v4 = *r4, v6 = *r6, v7 = *r7;
+            v3.w = 0.f; v4.x = 0.f; v4.y = 0.f; v6.w = 0.f; v7.x = 0.f; v7.y = 0.f;
+            *r3 = v3; *r4 = v4; *r6 = v6; *r7 = v7;
+        }
+    }
+}
+template <bool WANT_N>
+__global__ void __launch_bounds__(kThreads, 3) wf_walk_kernel(const __grid_constant__ RenderParams P, WfBuf B, int nb) {
+    const int lane = threadIdx.x & 31;
+    const int nb_pad = (nb + 31) & ~31;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nb_pad; p += gridDim.x * blockDim.x) {     // warp-uniform trip count
+        const bool have = p < nb;
+        float3 R = f3(0.f, 0.f, 0.f); int nv = 0;
+        if (have) { const float4 L4 = B.L[p]; R = f3(L4.x, L4.y, L4.z); nv = __float_as_int(L4.w) & 0xff; }
+        const int max_nv = __reduce_max_sync(0xffffffffu, nv);
+        for (int k = max_nv - 1; k >= 0; --k) {
+            float g[WANT_N ? 8 : 5];
+#pragma unroll
+            for (int i = 0; i < (WANT_N ? 8 : 5); ++i) g[i] = 0.f;
+            int flat = -1 - lane;
+            if (k < nv) {
+                const float4 v0 = *vrec_at(B, k, 0, p), v1 = *vrec_at(B, k, 1, p), v2 = *vrec_at(B, k, 2, p), v3 = *vrec_at(B, k, 3, p);
+                const float4 v4 = *vrec_at(B, k, 4, p), v5 = *vrec_at(B, k, 5, p), v6 = *vrec_at(B, k, 6, p), v7 = *vrec_at(B, k, 7, p);
+                Material mt; mt.a = f3(v0.x, v0.y, v0.z); mt.r = v0.w; mt.m = v1.x; mt.n = f3(v1.y, v1.z, v1.w);
+                const float3 view = f3(v2.x, v2.y, v2.z), em_d = f3(v3.x, v3.y, v3.z), cem = f3(v3.w, v4.x, v4.y), d_bs = f3(v4.z, v4.w, v5.x);
+                const float3 cpre = f3(v5.y, v5.z, v5.w), w = f3(v6.x, v6.y, v6.z), E = f3(v6.w, v7.x, v7.y);
+                flat = __float_as_int(v2.w);
+                if (cem.x != 0.f || cem.y != 0.f || cem.z != 0.f) {
+                    const BsdfGrad bg = eval_brdf_grad_ool<WANT_N>(em_d, view, mt, cem);
+                    g[0] += bg.ga.x; g[1] += bg.ga.y; g[2] += bg.ga.z; g[3] += bg.gr; g[4] += bg.gm;
+                    if (WANT_N) { g[5] += bg.gn.x; g[6] += bg.gn.y; g[7] += bg.gn.z; }
+                }
+                const float3 cw = cpre * R;
+                if (cw.x != 0.f || cw.y != 0.f || cw.z != 0.f) {
+                    const BsdfGrad bg = eval_brdf_grad_ool<WANT_N>(d_bs, view, mt, cw);
+                    g[0] += bg.ga.x; g[1] += bg.ga.y; g[2] += bg.ga.z; g[3] += bg.gr; g[4] += bg.gm;
+                    if (WANT_N) { g[5] += bg.gn.x; g[6] += bg.gn.y; g[7] += bg.gn.z; }
+                }
+                R = E + w * R;
+            }
+            const unsigned peers = __match_any_sync(0xffffffffu, flat);
+            reduce_peers(peers, g);
+            if (flat >= 0 && lane == __ffs(peers) - 1) {
+                if (P.g_a) { atomicAdd(P.g_a + 3 * (size_t)flat, g[0]); atomicAdd(P.g_a + 3 * (size_t)flat + 1, g[1]); atomicAdd(P.g_a + 3 * (size_t)flat + 2, g[2]); }
+                if (P.g_r) atomicAdd(P.g_r + flat, g[3]);
+                if (P.g_m) atomicAdd(P.g_m + flat, g[4]);
+                if (WANT_N && P.g_n) { atomicAdd(P.g_n + 3 * (size_t)flat, g[5]); atomicAdd(P.g_n + 3 * (size_t)flat + 1, g[6]); atomicAdd(P.g_n + 3 * (size_t)flat + 2, g[7]); }
+            }
+        }
+    }
+}
+
 __global__ void mesh_intersect_kernel(const __grid_constant__ MeshView M, const float* __restrict__ o, const float* __restrict__ d,
                                       const float* __restrict__ maxt, int n, int any_hit, int32_t* __restrict__ out_tri, float* __restrict__ out_tuv) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1367,14 +1587,14 @@ int mb200_mesh_shade_fwd_wf(const mb200_cfg* c, const mb200_trans* t, const mb20
         uint32_t* qin = B.qa; uint32_t* qout = B.qb; int cin = 0, cout = 1;
         for (int it = 0; it <= (max_verts < 0 ? 0 : max_verts); ++it) {
             cudaMemsetAsync(B.counters + 3, 0, 4, st);
-            wf_trace_kernel<false><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, st>>>(M, B, qin, B.counters + cin, B.counters + 3);
+            wf_trace_kernel<0><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, st>>>(M, B, qin, B.counters + cin, B.counters + 3);
             cudaMemsetAsync(B.counters + cout, 0, 4, st);
             cudaMemsetAsync(B.counters + 2, 0, 4, st);
             if (t)       wf_shade_kernel<false, true><<<sms * 4, kThreads, 0, st>>>(P, M, B, qin, qout, cin, cout);
             else if (ad) wf_shade_kernel<true, false><<<sms * 4, kThreads, 0, st>>>(P, M, B, qin, qout, cin, cout);
             else         wf_shade_kernel<false, false><<<sms * 4, kThreads, 0, st>>>(P, M, B, qin, qout, cin, cout);
             cudaMemsetAsync(B.counters + 3, 0, 4, st);
-            wf_trace_kernel<true><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, st>>>(M, B, B.qs, B.counters + 2, B.counters + 3);
+            wf_trace_kernel<1><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, st>>>(M, B, B.qs, B.counters + 2, B.counters + 3);
             uint32_t* tq = qin; qin = qout; qout = tq; const int tc = cin; cin = cout; cout = tc;
         }
         if (c->filter == MB200_FILTER_GAUSSIAN) wf_film_kernel<MB200_FILTER_GAUSSIAN><<<sms * 8, kThreads, 0, st>>>(P, B, pix0, npb, 0, c->spp, 1, 1);
@@ -1421,6 +1641,72 @@ int mb200_mesh_shade_bwd(const mb200_cfg* c, const mb200_mesh_desc* md, const vo
     cudaStream_t st = (cudaStream_t)stream;
     return c->filter == MB200_FILTER_GAUSSIAN ? launch_mesh_bwd<MB200_FILTER_GAUSSIAN>(P, M, want_mat, want_n, want_env, st)
                                               : launch_mesh_bwd<MB200_FILTER_BOX>(P, M, want_mat, want_n, want_env, st);
+}
+
+#ifndef MB200_WF_BWD_BATCH_LOG2
+#define MB200_WF_BWD_BATCH_LOG2 23
+#endif
+static long long wf_bwd_batch_pixels(const mb200_cfg* c) { const long long bp = (1ll << MB200_WF_BWD_BATCH_LOG2) / c->spp; return bp < 1 ? 1 : bp; }
+size_t mb200_mesh_bwd_wf_scratch_bytes(const mb200_cfg* c) {
+    if (!c || c->spp <= 0 || c->spp > (1 << MB200_WF_BWD_BATCH_LOG2)) return 0;
+    const long long npix = (long long)c->rows * c->W, bp = wf_bwd_batch_pixels(c);
+    const int mv = (c->max_depth - 1 < kMaxVerts ? c->max_depth - 1 : kMaxVerts);
+    return wf_bwd_scratch_bytes((npix < bp ? npix : bp) * c->spp, mv < 1 ? 1 : mv);
+}
+
+int mb200_mesh_shade_bwd_wf(const mb200_cfg* c, const mb200_mesh_desc* md, const void* mesh_buf,
+                            const float* a, const float* r, const float* m, const float* n_opt,
+                            const float* env4, const float* hier, const mb200_hier_desc* d, const float* gadj,
+                            float* g_a, float* g_r, float* g_m, float* g_n, float* g_env4, int n_env_slabs,
+                            void* scratch, size_t scratch_bytes, void* stream) {
+    RenderParams P; int rc = mesh_render_params(c, a, r, m, n_opt, env4, hier, d, P);
+    if (rc) return rc;
+    MeshView M; rc = make_view(md, mesh_buf, M);
+    if (rc) return rc;
+    if (!gadj || !scratch || (g_env4 && n_env_slabs < 1)) return MB200_EINVAL;
+    if (c->spp > (1 << MB200_WF_BWD_BATCH_LOG2)) return MB200_EUNSUPPORTED;
+    P.env_slabs = g_env4 ? n_env_slabs : 1; P.env_slab_stride = (long long)d->res_x * d->res_y;
+    P.prow0 = c->row0; P.prows = c->rows;
+    P.gadj = reinterpret_cast<const float4*>(gadj); P.grows = mb200_bwd_gadj_rows(c, &P.grow0);
+    P.g_a = g_a; P.g_r = g_r; P.g_m = g_m; P.g_n = g_n; P.g_env4 = reinterpret_cast<float4*>(g_env4);
+    const bool want_n = g_n != nullptr && !c->use_mesh_normal && n_opt != nullptr;
+    const bool want_mat = g_a || g_r || g_m || want_n;
+    const bool want_env = g_env4 != nullptr;
+    if (!want_mat && !want_env) return MB200_OK;
+    const long long npix = (long long)P.prows * P.W, bp = wf_bwd_batch_pixels(c);
+    int max_verts = (c->max_depth - 1 < kMaxVerts ? c->max_depth - 1 : kMaxVerts); if (max_verts < 0) max_verts = 0;
+    const long long nb_max = (npix < bp ? npix : bp) * c->spp;
+    if (scratch_bytes < wf_bwd_scratch_bytes(nb_max, max_verts < 1 ? 1 : max_verts)) return MB200_EINVAL;
+    WfBuf B = wf_carve_bwd(scratch, nb_max, max_verts < 1 ? 1 : max_verts);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int sms = mb200_sm_count();
+    for (long long pix0 = 0; pix0 < npix; pix0 += bp) {
+        const int npb = (int)((npix - pix0) < bp ? (npix - pix0) : bp);
+        const int nb = npb * c->spp;
+        if (c->filter == MB200_FILTER_GAUSSIAN) wf_gen_bwd_kernel<MB200_FILTER_GAUSSIAN><<<sms * 8, 256, 0, st>>>(P, B, pix0, nb);
+        else                                    wf_gen_bwd_kernel<MB200_FILTER_BOX><<<sms * 8, 256, 0, st>>>(P, B, pix0, nb);
+        uint32_t* qin = B.qa; uint32_t* qout = B.qb; int cin = 0, cout = 1;
+        for (int it = 0; it <= max_verts; ++it) {
+            cudaMemsetAsync(B.counters + 3, 0, 4, st);
+            wf_trace_kernel<0><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, st>>>(M, B, qin, B.counters + cin, B.counters + 3);
+            cudaMemsetAsync(B.counters + cout, 0, 4, st);
+            cudaMemsetAsync(B.counters + 2, 0, 4, st);
+            if (want_mat && want_env)  wf_shade_bwd_kernel<true, true><<<sms * 4, kThreads, 0, st>>>(P, M, B, qin, qout, cin, cout);
+            else if (want_mat)         wf_shade_bwd_kernel<true, false><<<sms * 4, kThreads, 0, st>>>(P, M, B, qin, qout, cin, cout);
+            else                       wf_shade_bwd_kernel<false, true><<<sms * 4, kThreads, 0, st>>>(P, M, B, qin, qout, cin, cout);
+            cudaMemsetAsync(B.counters + 3, 0, 4, st);
+            wf_trace_kernel<2><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, st>>>(M, B, B.qs, B.counters + 2, B.counters + 3);
+            if (want_mat && want_env)  wf_apply_bwd_kernel<true, true><<<sms * 4, 256, 0, st>>>(P, B);
+            else if (want_mat)         wf_apply_bwd_kernel<true, false><<<sms * 4, 256, 0, st>>>(P, B);
+            else                       wf_apply_bwd_kernel<false, true><<<sms * 4, 256, 0, st>>>(P, B);
+            uint32_t* tq = qin; qin = qout; qout = tq; const int tc = cin; cin = cout; cout = tc;
+        }
+        if (want_mat) {
+            if (want_n) wf_walk_kernel<true><<<sms * 6, kThreads, 0, st>>>(P, B, nb);
+            else        wf_walk_kernel<false><<<sms * 6, kThreads, 0, st>>>(P, B, nb);
+        }
+    }
+    return mb200_check_launch();
 }
 
 int mb200_mesh_intersect(const mb200_mesh_desc* md, const void* mesh_buf, const float* o, const float* d, const float* maxt,

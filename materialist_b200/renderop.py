@@ -142,7 +142,19 @@ def _backward(scene, spp, seed_grad, a, r, m, n, env_pack, grad_img_halo, want_a
     n_slabs = _abi.lib.mb200_env_grad_slabs(He, We, mode) if want_env else 1
     g_env4 = torch.zeros((n_slabs,) + tuple(env4.shape), device=dev) if want_env else None
     nmap = None if scene.use_mesh_normal else n
-    if scene.mesh is not None:
+    if scene.mesh is not None and scene.mesh_backward == "wavefront":
+        nbytes = _abi.lib.mb200_mesh_bwd_wf_scratch_bytes(C.byref(cfg))
+        if nbytes == 0:
+            raise ValueError("wavefront adjoint: unsupported configuration (spp too large)")
+        if scene._wf_scratch is None or scene._wf_scratch.numel() * 8 < nbytes:
+            scene._wf_scratch = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=scene.device)
+        with _ktime("mesh_bwd_wf"):
+            _abi.check(_abi.lib.mb200_mesh_shade_bwd_wf(C.byref(cfg), C.byref(scene.mesh.desc), _abi.ptr(scene.mesh.buf), _abi.ptr(a), _abi.ptr(r),
+                                                        _abi.ptr(m), _abi.ptr(nmap), _abi.ptr(env4), _abi.ptr(hier), C.byref(desc),
+                                                        _abi.ptr(gadj), _abi.ptr(g_a), _abi.ptr(g_r), _abi.ptr(g_m), _abi.ptr(g_n),
+                                                        _abi.ptr(g_env4), n_slabs, _abi.ptr(scene._wf_scratch), scene._wf_scratch.numel() * 8, st),
+                       "mb200_mesh_shade_bwd_wf")
+    elif scene.mesh is not None:
         with _ktime("mesh_bwd"):
             _abi.check(_abi.lib.mb200_mesh_shade_bwd(C.byref(cfg), C.byref(scene.mesh.desc), _abi.ptr(scene.mesh.buf), _abi.ptr(a), _abi.ptr(r),
                                                      _abi.ptr(m), _abi.ptr(nmap), _abi.ptr(env4), _abi.ptr(hier), C.byref(desc),

@@ -130,6 +130,7 @@ class Scene:
         # forward formulation of mesh mode: "wavefront" (mb200_mesh_shade_fwd_wf: traversal and shading in separate kernels, path
         # state in a scratch buffer; the faster one) or "persistent" (mb200_mesh_shade_fwd: one kernel, no scratch memory)
         self.mesh_forward = os.environ.get("MB200_MESH_FORWARD", "wavefront")
+        self.mesh_backward = os.environ.get("MB200_MESH_BACKWARD", "wavefront")    # mb200_mesh_shade_bwd_wf / "persistent": mb200_mesh_shade_bwd
         self._wf_scratch = None
         self._env = None
         if envmap is None:
