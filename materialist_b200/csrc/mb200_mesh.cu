@@ -257,7 +257,7 @@ __device__ __forceinline__ void trav_begin(const MeshView& M, Trav& T, float3 o,
 // Called by ALL lanes of the warp (lanes without a ray do nothing): the three phases — box tests, triangle test, stack pop —
 // each start converged, so e.g. the pop loop runs once per step for every lane that needs it instead of once per divergent
 // path that reaches it (it ran at 3.6 of 32 lanes: profiles/r1x).
-template <int SM, int STRIDE>
+template <int LEAF_MIN = 1, int SM, int STRIDE>
 __device__ __forceinline__ void trav_step(const MeshView& M, Trav& T, TStack<SM, STRIDE> stack) {
     const bool act = T.active;
     const uint32_t level = T.cur >> 27, idx = T.cur & 0x7ffffffu;
@@ -303,8 +303,15 @@ __device__ __forceinline__ void trav_step(const MeshView& M, Trav& T, TStack<SM,
             T.cur = cbase | (key[0] & 3u);
         } else need_pop = true;
     }
-    __syncwarp();
-    if (leaf) {
+    // LEAF_MIN > 1: leaf lanes wait until at least that many of them hold a triangle (or no lane has box work left), so that the
+    // ~170-instruction exact triangle test runs at more than its usual 2-4 of 32 lanes.  Measured on the traversal-only kernels
+    // (profiles/r3l): 1 / 4 / 8 / 12 / 16 -> C2m 158 / 161 / 169 / 180 / 195 ms — waiting costs more than the divergence; default 1.
+    bool run_leaf = true;
+    if (LEAF_MIN > 1) {
+        const unsigned leaf_mask = __ballot_sync(0xffffffffu, leaf), node_mask = __ballot_sync(0xffffffffu, node);
+        run_leaf = __popc(leaf_mask) >= LEAF_MIN || node_mask == 0u;
+    }
+    if (leaf && run_leaf) {
         need_pop = true;
 #pragma unroll
         for (int k = 0; k < kLeaf; ++k) {
@@ -574,6 +581,9 @@ inline void launch_mesh_fwd(K kernel, int filter, int grid, cudaStream_t st, con
 #ifndef MB200_WF_BATCH_LOG2
 #define MB200_WF_BATCH_LOG2 24          // paths per batch (156 B of scratch each): 2^20 / 2^22 / 2^24 -> 120 / 94 / 87 ms C2m forward (fewer, fuller launches)
 #endif
+#ifndef MB200_WF_LEAF_MIN
+#define MB200_WF_LEAF_MIN 1
+#endif
 #ifndef MB200_WF_TRACE_BLOCKS
 #define MB200_WF_TRACE_BLOCKS 4          // CTAs per SM of the traversal kernels: 64 registers, no spills (5: 94 ms, 4: 84 ms, 3: 87 ms, 6: 122 ms)
 #endif
@@ -662,7 +672,7 @@ __global__ void __launch_bounds__(kThreads, MB200_WF_TRACE_BLOCKS) wf_trace_kern
         }
         if (!__ballot_sync(0xffffffffu, T.active)) break;
         const bool was = T.active;
-        trav_step(M, T, stack);
+        trav_step<MB200_WF_LEAF_MIN>(M, T, stack);
         if (was && !T.active) {                                                    // this lane's ray has finished
             if (MODE == 1) {
                 if (!T.found) { float4 L = B.L[pid]; const float4 c = B.cem[pid]; L.x += c.x; L.y += c.y; L.z += c.z; B.L[pid] = L; }
