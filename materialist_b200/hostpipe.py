@@ -23,11 +23,11 @@ class HostPipelinedRenderWBRDF:
         H, W = scene.H, scene.W
         mk = lambda *shape: [torch.empty(*shape, device=dev) for _ in range(2)]
         self.a, self.r, self.m, self.g = mk(H, W, 3), mk(H, W, 1), mk(H, W, 1), mk(scene.rows, W, 3)
-        self.ev_in = [torch.cuda.Event(), torch.cuda.Event()]
-        self.ev_free = [torch.cuda.Event(), torch.cuda.Event()]       # buffer set no longer read by the main stream
-        self.ev_out = torch.cuda.Event()                              # previous step's downloads have left their source tensors
-        self._staged = None
-        self._keep = []
+        # device-side staging of the outputs, owned by the pipe: the copy-out stream never touches a tensor the caching allocator
+        # may recycle (no record_stream, no deferred frees)
+        self.o_img, self.o_ga, self.o_gr, self.o_gm = mk(scene.rows, W, 3), mk(H, W, 3), mk(H, W, 1), mk(H, W, 1)
+        ev = lambda: [torch.cuda.Event(), torch.cuda.Event()]
+        self.ev_in, self.ev_free, self.ev_img, self.ev_bwd, self.ev_out = ev(), ev(), ev(), ev(), ev()
 
     def stage(self, slot, ha, hr, hm, hgrad):
         """Upload one step's inputs (pinned host tensors) into buffer set `slot` on the copy-in stream."""
@@ -36,31 +36,31 @@ class HostPipelinedRenderWBRDF:
             self.a[slot].copy_(ha, non_blocking=True); self.r[slot].copy_(hr, non_blocking=True)
             self.m[slot].copy_(hm, non_blocking=True); self.g[slot].copy_(hgrad, non_blocking=True)
             self.ev_in[slot].record(self.s_in)
-        self._staged = slot
 
     def step(self, seed, slot, himg, hga, hgr, hgm, next_inputs=None):
         """Render forward + adjoint with buffer set `slot` (already staged); downloads go to the pinned tensors himg / hga /
         hgr / hgm.  `next_inputs` = (ha, hr, hm, hgrad) of the following step is uploaded into the other set meanwhile."""
-        main = self.main
+        main, s_out = self.main, self.s_out
         main.wait_event(self.ev_in[slot])
+        main.wait_event(self.ev_out[slot])                      # the downloads of two steps ago have left this slot's staging
         if next_inputs is not None:
             self.stage(1 - slot, *next_inputs)
         a = self.a[slot].detach().requires_grad_(True); r = self.r[slot].detach().requires_grad_(True); m = self.m[slot].detach().requires_grad_(True)
         img = render(self.scene, spp=self.spp, seed=seed, albedo=a, roughness=r, metallic=m, halo_exchange=self.halo_exchange)
-        ev_img = torch.cuda.Event(); ev_img.record(main)
-        with torch.cuda.stream(self.s_out):
-            self.s_out.wait_event(ev_img)
-            himg.copy_(img.detach(), non_blocking=True)
-        img.detach().record_stream(self.s_out)
+        self.o_img[slot].copy_(img.detach())
+        self.ev_img[slot].record(main)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(self.ev_img[slot])
+            himg.copy_(self.o_img[slot], non_blocking=True)
         img.backward(self.g[slot])
-        ev_bwd = torch.cuda.Event(); ev_bwd.record(main)
+        self.o_ga[slot].copy_(a.grad); self.o_gr[slot].copy_(r.grad); self.o_gm[slot].copy_(m.grad)
+        self.ev_bwd[slot].record(main)
         self.ev_free[slot].record(main)
-        with torch.cuda.stream(self.s_out):
-            self.s_out.wait_event(ev_bwd)
-            hga.copy_(a.grad, non_blocking=True); hgr.copy_(r.grad, non_blocking=True); hgm.copy_(m.grad, non_blocking=True)
-            self.ev_out.record(self.s_out)
-        for t in (a.grad, r.grad, m.grad):
-            t.record_stream(self.s_out)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(self.ev_bwd[slot])
+            hga.copy_(self.o_ga[slot], non_blocking=True); hgr.copy_(self.o_gr[slot], non_blocking=True); hgm.copy_(self.o_gm[slot], non_blocking=True)
+            self.ev_out[slot].record(s_out)
+        self.last_out = self.ev_out[slot]
 
     def synchronize(self):
         self.s_in.synchronize(); self.s_out.synchronize(); self.main.synchronize()
