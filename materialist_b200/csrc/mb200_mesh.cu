@@ -1561,6 +1561,20 @@ int mb200_mesh_shade_fwd(const mb200_cfg* c, const mb200_mesh_desc* md, const vo
     return mb200_check_launch();
 }
 
+// The shadow-ray traversal of bounce k and the closest-hit traversal of bounce k+1 are independent: the former runs on a side
+// stream (one per device, created on first use) so that the nearly empty grids of the late bounces overlap.
+struct WfSide { cudaStream_t s = nullptr; cudaEvent_t shaded = nullptr, any_done = nullptr; };
+static WfSide* wf_side() {
+    static WfSide side[64];
+    int dev = 0; if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    WfSide& w = side[dev];
+    if (!w.s) {
+        if (cudaStreamCreateWithFlags(&w.s, cudaStreamNonBlocking) != cudaSuccess) { w.s = nullptr; return nullptr; }
+        cudaEventCreateWithFlags(&w.shaded, cudaEventDisableTiming); cudaEventCreateWithFlags(&w.any_done, cudaEventDisableTiming);
+    }
+    return &w;
+}
+
 size_t mb200_mesh_fwd_wf_scratch_bytes(const mb200_cfg* c) {
     if (!c || c->spp <= 0 || c->spp > kWfBatch) return 0;
     int r0; const int prows = mb200_fwd_partial_rows(c, &r0);
@@ -1590,23 +1604,30 @@ int mb200_mesh_shade_fwd_wf(const mb200_cfg* c, const mb200_trans* t, const mb20
     cudaStream_t st = (cudaStream_t)stream;
     const int sms = mb200_sm_count();
     const int max_verts = (c->max_depth - 1 < kMaxVerts ? c->max_depth - 1 : kMaxVerts);
+    WfSide* side = wf_side();
     for (long long pix0 = 0; pix0 < npix; pix0 += bp) {
         const int npb = (int)((npix - pix0) < bp ? (npix - pix0) : bp);
         const int nb = npb * c->spp;
         wf_gen_kernel<<<sms * 8, 256, 0, st>>>(P, B, pix0, nb);
         uint32_t* qin = B.qa; uint32_t* qout = B.qb; int cin = 0, cout = 1;
+        bool any_pending = false;
         for (int it = 0; it <= (max_verts < 0 ? 0 : max_verts); ++it) {
             cudaMemsetAsync(B.counters + 3, 0, 4, st);
             wf_trace_kernel<0><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, st>>>(M, B, qin, B.counters + cin, B.counters + 3);
+            if (any_pending) { cudaStreamWaitEvent(st, side->any_done, 0); any_pending = false; }   // the shadow rays of the previous bounce
             cudaMemsetAsync(B.counters + cout, 0, 4, st);
             cudaMemsetAsync(B.counters + 2, 0, 4, st);
             if (t)       wf_shade_kernel<false, true><<<sms * 4, kThreads, 0, st>>>(P, M, B, qin, qout, cin, cout);
             else if (ad) wf_shade_kernel<true, false><<<sms * 4, kThreads, 0, st>>>(P, M, B, qin, qout, cin, cout);
             else         wf_shade_kernel<false, false><<<sms * 4, kThreads, 0, st>>>(P, M, B, qin, qout, cin, cout);
-            cudaMemsetAsync(B.counters + 3, 0, 4, st);
-            wf_trace_kernel<1><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, st>>>(M, B, B.qs, B.counters + 2, B.counters + 3);
+            cudaStream_t sa = side ? side->s : st;
+            if (side) { cudaEventRecord(side->shaded, st); cudaStreamWaitEvent(sa, side->shaded, 0); }
+            cudaMemsetAsync(B.counters + 4, 0, 4, sa);
+            wf_trace_kernel<1><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, sa>>>(M, B, B.qs, B.counters + 2, B.counters + 4);
+            if (side) { cudaEventRecord(side->any_done, sa); any_pending = true; }
             uint32_t* tq = qin; qin = qout; qout = tq; const int tc = cin; cin = cout; cout = tc;
         }
+        if (any_pending) cudaStreamWaitEvent(st, side->any_done, 0);
         if (c->filter == MB200_FILTER_GAUSSIAN) wf_film_kernel<MB200_FILTER_GAUSSIAN><<<sms * 8, kThreads, 0, st>>>(P, B, pix0, npb, 0, c->spp, 1, 1);
         else                                    wf_film_kernel<MB200_FILTER_BOX><<<sms * 8, kThreads, 0, st>>>(P, B, pix0, npb, 0, c->spp, 1, 1);
     }
@@ -1690,27 +1711,34 @@ int mb200_mesh_shade_bwd_wf(const mb200_cfg* c, const mb200_mesh_desc* md, const
     WfBuf B = wf_carve_bwd(scratch, nb_max, max_verts < 1 ? 1 : max_verts);
     cudaStream_t st = (cudaStream_t)stream;
     const int sms = mb200_sm_count();
+    WfSide* side = wf_side();
     for (long long pix0 = 0; pix0 < npix; pix0 += bp) {
         const int npb = (int)((npix - pix0) < bp ? (npix - pix0) : bp);
         const int nb = npb * c->spp;
         if (c->filter == MB200_FILTER_GAUSSIAN) wf_gen_bwd_kernel<MB200_FILTER_GAUSSIAN><<<sms * 8, 256, 0, st>>>(P, B, pix0, nb);
         else                                    wf_gen_bwd_kernel<MB200_FILTER_BOX><<<sms * 8, 256, 0, st>>>(P, B, pix0, nb);
         uint32_t* qin = B.qa; uint32_t* qout = B.qb; int cin = 0, cout = 1;
+        bool any_pending = false;
         for (int it = 0; it <= max_verts; ++it) {
             cudaMemsetAsync(B.counters + 3, 0, 4, st);
             wf_trace_kernel<0><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, st>>>(M, B, qin, B.counters + cin, B.counters + 3);
+            if (any_pending) { cudaStreamWaitEvent(st, side->any_done, 0); any_pending = false; }
             cudaMemsetAsync(B.counters + cout, 0, 4, st);
             cudaMemsetAsync(B.counters + 2, 0, 4, st);
             if (want_mat && want_env)  wf_shade_bwd_kernel<true, true><<<sms * 4, kThreads, 0, st>>>(P, M, B, qin, qout, cin, cout);
             else if (want_mat)         wf_shade_bwd_kernel<true, false><<<sms * 4, kThreads, 0, st>>>(P, M, B, qin, qout, cin, cout);
             else                       wf_shade_bwd_kernel<false, true><<<sms * 4, kThreads, 0, st>>>(P, M, B, qin, qout, cin, cout);
-            cudaMemsetAsync(B.counters + 3, 0, 4, st);
-            wf_trace_kernel<2><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, st>>>(M, B, B.qs, B.counters + 2, B.counters + 3);
-            if (want_mat && want_env)  wf_apply_bwd_kernel<true, true><<<sms * 4, 256, 0, st>>>(P, B);
-            else if (want_mat)         wf_apply_bwd_kernel<true, false><<<sms * 4, 256, 0, st>>>(P, B);
-            else                       wf_apply_bwd_kernel<false, true><<<sms * 4, 256, 0, st>>>(P, B);
+            cudaStream_t sa = side ? side->s : st;
+            if (side) { cudaEventRecord(side->shaded, st); cudaStreamWaitEvent(sa, side->shaded, 0); }
+            cudaMemsetAsync(B.counters + 4, 0, 4, sa);
+            wf_trace_kernel<2><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, sa>>>(M, B, B.qs, B.counters + 2, B.counters + 4);
+            if (want_mat && want_env)  wf_apply_bwd_kernel<true, true><<<sms * 4, 256, 0, sa>>>(P, B);
+            else if (want_mat)         wf_apply_bwd_kernel<true, false><<<sms * 4, 256, 0, sa>>>(P, B);
+            else                       wf_apply_bwd_kernel<false, true><<<sms * 4, 256, 0, sa>>>(P, B);
+            if (side) { cudaEventRecord(side->any_done, sa); any_pending = true; }
             uint32_t* tq = qin; qin = qout; qout = tq; const int tc = cin; cin = cout; cout = tc;
         }
+        if (any_pending) cudaStreamWaitEvent(st, side->any_done, 0);
         if (want_mat) {
             if (want_n) wf_walk_kernel<true><<<sms * 6, kThreads, 0, st>>>(P, B, nb);
             else        wf_walk_kernel<false><<<sms * 6, kThreads, 0, st>>>(P, B, nb);
