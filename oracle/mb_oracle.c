@@ -8,17 +8,25 @@
  * PARITY STATUS
  *   - BSDF (B-rows): restated line by line from the reference's own source
  *       myutils/mi_plugin.py:60-97 (G1/G_Smith/D_GGX), :217-281 (samplers), :585-595, :645-671
- *       (projection), :1296-1341 (sample_brdf), :1372-1427 (eval_brdf), :1429-1460 (sample/eval_pdf).
- *     Pinned on the shared sub-terms against the reference's torch functions, imported from
- *     /root/reference under stub modules (tests/golden/make_golden.py -> tests/golden/bsdf_terms.npz).
+ *       (projection), :1296-1341 (sample_brdf), :1372-1427 (eval_brdf), :1429-1460 (sample/eval_pdf),
+ *       :1477-1770 (TransBSDF: refraction, refracted screen coordinate, eval_brdf, sample_brdf).
+ *     PINNED: tests/golden/make_bsdf_golden.py EXECUTES that Dr.Jit-typed source (imported from /root/reference) on numpy
+ *     stand-ins for the drjit / mitsuba array types (drjit_np_shim.py) -> matdiff_bsdf.npz, trans_bsdf.npz; this file matches
+ *     them with median error 0 / 99 % <= 4e-6 and identical texel indices (tests/test_bsdf_plugin_golden.py).  The shared
+ *     sub-terms are also pinned against the reference's torch functions (make_golden.py -> bsdf_terms.npz).
  *   - Render operator (P-rows): the arithmetic lives in the un-vendored dependency
  *     mitsuba==3.5.2 / drjit==0.4.6 (requirements.txt:7,:1), absent from /root/reference and from this
  *     image.  Restated from its published algorithm: src/integrators/path.cpp, src/emitters/envmap.cpp,
  *     include/mitsuba/core/distr_2d.h (Hierarchical2D), core/warp.h (square_to_bilinear),
  *     src/samplers/independent.cpp, render/sampler.h, core/random.h (sample_tea_32), drjit random.h
  *     (PCG32), src/render/imageblock.cpp, src/films/hdrfilm.cpp, src/rfilters/gaussian.cpp,
- *     src/python/python/util.py (render / seed_grad).  Only pin available: the official PCG32
- *     known-answer vector.  ==> "parity unpinned" for the P-rows.
+ *     src/python/python/util.py (render / seed_grad); mesh mode (mb_oracle_mesh.c): render/mesh.h, render/interaction.h,
+ *     render/scene.cpp.  PINNED on the forward render by the reference's OWN saved output: with the recovered sampler seed
+ *     (993) the mesh-mode oracle reproduces output_imgs/indoor/best_results/rendered_img.exr down to its Monte-Carlo noise
+ *     pattern (0.5 % / 1.2 % rel-L2 on absolute radiance vs 6-7 % for any other seed; tests/test_reference_render_pin.py),
+ *     plus the official PCG32 and Mitsuba TEA known answers.  The ADJOINT has no reference output to pin against (Mitsuba is
+ *     not installable here): it is checked against an independent float64 autograd mirror (tests/torch_mirror.py) ==>
+ *     "parity unpinned" for the adjoint pass only.
  *
  * Build: see oracle/Makefile.  -ffp-contract=off is REQUIRED (integer decisions must not depend on
  * FMA contraction); fmaf() is used only where upstream writes fmadd.
