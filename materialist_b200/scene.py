@@ -16,7 +16,9 @@ import torch
 
 from . import _abi
 
-_DEFAULT_CAM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "myutils", "default_cam.json")
+# The camera of the reference's myutils/default_cam.json (the `cam_meta` every script passes): perspective, x_fov 35 deg,
+# clip [0.01f, 1e4], 512 x 512 film, sensor at the origin looking down -z (to_world = diag(-1, 1, -1, 1)).  These are the
+# defaults of Camera() below; a caller with another camera passes its own JSON path.
 
 
 class Camera:
@@ -38,7 +40,9 @@ class Camera:
 
     @classmethod
     def from_json(cls, path=None, width=None, height=None):
-        meta = json.load(open(path or _DEFAULT_CAM))
+        if path is None:                            # the reference's default camera
+            return cls(width=width or 512, height=height or 512)
+        meta = json.load(open(path))
         w, h = meta["film.size"]
         return cls(np.array(meta["to_world"])[0], meta["x_fov"][0], meta["near_clip"], meta["far_clip"],
                    width or w, height or h)
