@@ -357,11 +357,12 @@ int mb200_sh_reconstruct(const double* coef, int nrows, int ncols, int clip, dou
 /* ---------------------------------------------------------------- on-disk image formats (HOST functions, host pointers) */
 /* What mi.Bitmap(path) / mi.util.write_bitmap(path, img) do in the reference (myutils/misc.py:99-111,
  * myutils/mi_plugin.py:701-739, render_final.py:182-202, inverse_img_w_mi.py:54).  Radiance RGBE .hdr (read flat + RLE,
- * write RLE) and OpenEXR scanline files (read NONE / ZIPS / ZIP / PIZ, HALF / FLOAT / UINT; write ZIP FLOAT).
+ * write RLE), OpenEXR scanline files (read NONE / ZIPS / ZIP / PIZ, HALF / FLOAT / UINT; write ZIP FLOAT) and PNG (8 / 16 bit,
+ * non-interlaced; values / 255 or / 65535 as plt.imread returns them for bg.png / mask.png; write 8 bit).
  * Images are (H, W, C) fp32 row-major in R,G,B(,A) order; single-channel files are C = 1. */
 int mb200_image_info(const char* path, int* H, int* W, int* C);
 int mb200_image_read(const char* path, float* out_host, int H, int W, int C);
-int mb200_image_write(const char* path, const float* img_host, int H, int W, int C);   /* by extension: .hdr (C = 3) or .exr */
+int mb200_image_write(const char* path, const float* img_host, int H, int W, int C);   /* by extension: .hdr (C = 3), .exr, .png */
 
 /* ---------------------------------------------------------------- fused loss + optimiser step (BRDF phase) */
 /* What sits between the forward and the adjoint render of one iteration of `optimize_envmap_ARMN`

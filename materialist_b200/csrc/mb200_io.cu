@@ -453,6 +453,93 @@ int exr_write(const char* path, const float* img, int H, int W, int C) {
     return MB200_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------ PNG (bg.png / mask.png / previews)
+// read: 8 / 16-bit gray, gray+alpha, RGB, RGBA and 8-bit palette, non-interlaced -> float in [0,1] (value / 255 or / 65535, what
+// plt.imread returns for the reference's mi_plugin.py:717-731); write: 8-bit gray / RGB / RGBA from floats clamped to [0,1].
+inline uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+struct PngInfo { int W = 0, H = 0, depth = 0, ctype = 0, interlace = 0; int channels() const { return ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 3 : ctype == 4 ? 2 : 4; } };
+bool png_header(const std::vector<uint8_t>& b, PngInfo& pi) {
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    if (b.size() < 33 || memcmp(b.data(), sig, 8) != 0 || memcmp(b.data() + 12, "IHDR", 4) != 0) return false;
+    pi.W = (int)be32(b.data() + 16); pi.H = (int)be32(b.data() + 20); pi.depth = b[24]; pi.ctype = b[25]; pi.interlace = b[28];
+    if (pi.W <= 0 || pi.H <= 0 || pi.interlace != 0) return false;
+    if (!((pi.depth == 8) || (pi.depth == 16 && pi.ctype != 3))) return false;
+    return pi.ctype == 0 || pi.ctype == 2 || pi.ctype == 3 || pi.ctype == 4 || pi.ctype == 6;
+}
+int png_read(const std::vector<uint8_t>& b, const PngInfo& pi, float* out) {
+    std::vector<uint8_t> idat, plte;
+    size_t p = 8;
+    while (p + 12 <= b.size()) {
+        const uint32_t len = be32(b.data() + p);
+        if (p + 12 + len > b.size()) return MB200_EINVAL;
+        if (!memcmp(b.data() + p + 4, "IDAT", 4)) idat.insert(idat.end(), b.data() + p + 8, b.data() + p + 8 + len);
+        else if (!memcmp(b.data() + p + 4, "PLTE", 4)) plte.assign(b.data() + p + 8, b.data() + p + 8 + len);
+        else if (!memcmp(b.data() + p + 4, "IEND", 4)) break;
+        p += 12 + len;
+    }
+    const int spp = pi.ctype == 3 ? 1 : pi.channels(), bps = pi.depth / 8, bpp = spp * bps;
+    const size_t stride = (size_t)pi.W * bpp;
+    std::vector<uint8_t> raw((stride + 1) * pi.H);
+    uLongf got = (uLongf)raw.size();
+    if (uncompress(raw.data(), &got, idat.data(), (uLong)idat.size()) != Z_OK || got != raw.size()) return MB200_EINVAL;
+    std::vector<uint8_t> prev(stride, 0), cur(stride);
+    const int C = pi.channels();
+    for (int y = 0; y < pi.H; ++y) {
+        const uint8_t* src = raw.data() + (stride + 1) * y; const int ft = src[0]; ++src;
+        for (size_t i = 0; i < stride; ++i) {
+            const int a = i >= (size_t)bpp ? cur[i - bpp] : 0, bb = prev[i], c = i >= (size_t)bpp ? prev[i - bpp] : 0;
+            int v = src[i];
+            if (ft == 1) v += a; else if (ft == 2) v += bb; else if (ft == 3) v += (a + bb) >> 1;
+            else if (ft == 4) { const int pp = a + bb - c, pa = abs(pp - a), pb = abs(pp - bb), pc = abs(pp - c); v += (pa <= pb && pa <= pc) ? a : (pb <= pc ? bb : c); }
+            else if (ft != 0) return MB200_EINVAL;
+            cur[i] = (uint8_t)v;
+        }
+        float* o = out + (size_t)y * pi.W * C;
+        for (int x = 0; x < pi.W; ++x) {
+            if (pi.ctype == 3) {
+                const size_t k = (size_t)cur[x] * 3;
+                for (int c = 0; c < 3; ++c) o[x * 3 + c] = (k + c < plte.size() ? plte[k + c] : 0) / 255.0f;
+            } else
+                for (int c = 0; c < C; ++c) {
+                    const uint8_t* q = &cur[(size_t)(x * spp + c) * bps];
+                    o[x * C + c] = bps == 1 ? q[0] / 255.0f : (float)((q[0] << 8) | q[1]) / 65535.0f;
+                }
+        }
+        prev.swap(cur);
+    }
+    return MB200_OK;
+}
+void png_chunk(FILE* f, const char* type, const uint8_t* data, uint32_t len) {
+    uint8_t hdr[8] = {(uint8_t)(len >> 24), (uint8_t)(len >> 16), (uint8_t)(len >> 8), (uint8_t)len, (uint8_t)type[0], (uint8_t)type[1], (uint8_t)type[2], (uint8_t)type[3]};
+    fwrite(hdr, 1, 8, f); if (len) fwrite(data, 1, len, f);
+    uLong crc = crc32(0L, hdr + 4, 4); if (len) crc = crc32(crc, data, len);
+    const uint8_t c4[4] = {(uint8_t)(crc >> 24), (uint8_t)(crc >> 16), (uint8_t)(crc >> 8), (uint8_t)crc};
+    fwrite(c4, 1, 4, f);
+}
+int png_write(const char* path, const float* img, int H, int W, int C) {
+    if (C != 1 && C != 3 && C != 4) return MB200_EINVAL;
+    std::vector<uint8_t> raw((size_t)H * ((size_t)W * C + 1));
+    for (int y = 0; y < H; ++y) {
+        uint8_t* row = raw.data() + (size_t)y * ((size_t)W * C + 1); row[0] = 0;
+        for (size_t i = 0; i < (size_t)W * C; ++i) {
+            float v = img[(size_t)y * W * C + i]; v = v != v ? 0.f : (v < 0.f ? 0.f : (v > 1.f ? 1.f : v));
+            row[1 + i] = (uint8_t)(v * 255.0f + 0.5f);
+        }
+    }
+    uLongf cap = compressBound((uLong)raw.size()); std::vector<uint8_t> z(cap);
+    if (compress2(z.data(), &cap, raw.data(), (uLong)raw.size(), Z_DEFAULT_COMPRESSION) != Z_OK) return MB200_EINVAL;
+    FILE* f = fopen(path, "wb");
+    if (!f) return MB200_EINVAL;
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    fwrite(sig, 1, 8, f);
+    const uint8_t ihdr[13] = {(uint8_t)(W >> 24), (uint8_t)(W >> 16), (uint8_t)(W >> 8), (uint8_t)W, (uint8_t)(H >> 24), (uint8_t)(H >> 16), (uint8_t)(H >> 8), (uint8_t)H,
+                              8, (uint8_t)(C == 1 ? 0 : C == 3 ? 2 : 6), 0, 0, 0};
+    png_chunk(f, "IHDR", ihdr, 13); png_chunk(f, "IDAT", z.data(), (uint32_t)cap); png_chunk(f, "IEND", nullptr, 0);
+    fclose(f);
+    return MB200_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -461,7 +548,8 @@ int mb200_image_info(const char* path, int* H, int* W, int* C) {
     if (!path || !H || !W || !C) return MB200_EINVAL;
     std::vector<uint8_t> b;
     if (!read_file(path, b)) return MB200_EINVAL;
-    HdrInfo hi; ExrInfo ei;
+    HdrInfo hi; ExrInfo ei; PngInfo pi;
+    if (png_header(b, pi)) { *H = pi.H; *W = pi.W; *C = pi.channels(); return MB200_OK; }
     if (hdr_header(b, hi)) { *H = hi.H; *W = hi.W; *C = 3; return MB200_OK; }
     if (exr_header(b, ei)) { int map[4]; const int nc = exr_out_channels(ei, map); if (!nc) return MB200_EUNSUPPORTED; *H = ei.H(); *W = ei.W(); *C = nc; return MB200_OK; }
     return MB200_EUNSUPPORTED;
@@ -471,7 +559,8 @@ int mb200_image_read(const char* path, float* out, int H, int W, int C) {
     if (!path || !out) return MB200_EINVAL;
     std::vector<uint8_t> b;
     if (!read_file(path, b)) return MB200_EINVAL;
-    HdrInfo hi; ExrInfo ei;
+    HdrInfo hi; ExrInfo ei; PngInfo pi;
+    if (png_header(b, pi)) { if (pi.H != H || pi.W != W || pi.channels() != C) return MB200_EINVAL; return png_read(b, pi, out); }
     if (hdr_header(b, hi)) { if (hi.H != H || hi.W != W || C != 3) return MB200_EINVAL; return hdr_read(b, hi, out); }
     if (exr_header(b, ei)) { if (ei.H() != H || ei.W() != W) return MB200_EINVAL; return exr_read(b, ei, out, C); }
     return MB200_EUNSUPPORTED;
@@ -481,6 +570,7 @@ int mb200_image_write(const char* path, const float* img, int H, int W, int C) {
     if (!path || !img || H <= 0 || W <= 0) return MB200_EINVAL;
     if (ends_with(path, ".hdr")) return C == 3 ? hdr_write(path, img, H, W) : MB200_EINVAL;
     if (ends_with(path, ".exr")) return exr_write(path, img, H, W, C);
+    if (ends_with(path, ".png")) return png_write(path, img, H, W, C);
     return MB200_EUNSUPPORTED;
 }
 

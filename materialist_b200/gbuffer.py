@@ -68,10 +68,11 @@ def gbuffer_from_ply(path, H=512, W=512, camera=None):
 
 def read_image(path):
     """Radiance .hdr / OpenEXR -> float32 RGB(A) array in linear file values through the library's own readers
-    (imageio.read_bitmap, csrc/mb200_io.cu); PNG (bg.png / mask.png of the editing scripts) through OpenCV."""
+    (imageio.read_bitmap, csrc/mb200_io.cu), PNG (bg.png / mask.png of the editing scripts) -> [0, 1] floats the same way;
+    anything else through OpenCV."""
     if not os.path.exists(path):
         raise FileNotFoundError(path)
-    if path.lower().endswith((".hdr", ".exr")):
+    if path.lower().endswith((".hdr", ".exr", ".png")):
         from .imageio import read_bitmap
         return read_bitmap(path)
     import cv2

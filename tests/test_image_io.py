@@ -108,11 +108,35 @@ def test_hdr_reader_and_writer_match_opencv(tmp_path):
         assert np.all(np.abs(a - img)[ok] <= img.max(-1, keepdims=True).repeat(3, -1)[ok] / 128 + 1e-30)   # 8-bit shared-exponent mantissa
 
 
+def test_png_reader_and_writer_match_opencv(tmp_path):
+    """bg.png / mask.png of the editing scripts (mi_plugin.py:717-731, plt.imread -> floats in [0, 1])."""
+    rs = np.random.RandomState(4)
+    cases = [("gray8", rs.randint(0, 256, (21, 34)).astype(np.uint8)), ("rgb8", rs.randint(0, 256, (33, 17, 3)).astype(np.uint8)),
+             ("rgba8", rs.randint(0, 256, (9, 40, 4)).astype(np.uint8)), ("gray16", rs.randint(0, 65536, (12, 13)).astype(np.uint16)),
+             ("rgb16", rs.randint(0, 65536, (14, 15, 3)).astype(np.uint16)), ("smooth", (np.add.outer(np.arange(64), np.arange(48)) % 256).astype(np.uint8))]
+    for tag, img in cases:
+        p = str(tmp_path / f"{tag}.png")
+        a = img if img.ndim == 2 else img[..., [2, 1, 0] + ([3] if img.shape[2] == 4 else [])]
+        assert cv2.imwrite(p, np.ascontiguousarray(a))                           # OpenCV picks its own row filters
+        got = io.read_bitmap(p)
+        ref = img.astype(np.float32) / (255.0 if img.dtype == np.uint8 else 65535.0)
+        assert got.shape == ref.shape and np.array_equal(got, ref), tag
+    for C in (1, 3, 4):
+        img = rs.rand(19, 23, C).astype(np.float32) if C > 1 else rs.rand(19, 23).astype(np.float32)
+        p = str(tmp_path / f"w{C}.png")
+        io.write_bitmap(p, img)
+        back = cv2.imread(p, cv2.IMREAD_UNCHANGED)
+        if back.ndim == 3:
+            back = back[..., [2, 1, 0] + ([3] if back.shape[2] == 4 else [])]
+        assert np.array_equal(back, np.floor(np.clip(img, 0, 1) * 255.0 + 0.5).astype(np.uint8))
+        assert np.array_equal(io.read_bitmap(p), back.astype(np.float32) / 255.0)
+
+
 def test_errors():
     with pytest.raises(ValueError):
         io.read_bitmap("/nonexistent/file.exr")
     with pytest.raises(Exception):
-        io.write_bitmap("/tmp/x.png", np.zeros((2, 2, 3), np.float32))            # only .hdr / .exr
+        io.write_bitmap("/tmp/x.jpg", np.zeros((2, 2, 3), np.float32))            # only .hdr / .exr / .png
     with pytest.raises(ValueError):
         io.write_bitmap("/tmp/x.hdr", np.zeros((2, 2), np.float32))               # RGBE needs 3 channels
 
