@@ -98,4 +98,22 @@ def load_estimated_brdf(mat_dir):
     npath = os.path.join(mat_dir, "normal.exr")
     if os.path.exists(npath):
         out["normal"] = read_image(npath)[..., :3]
-    return {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in out.items()}
+    out = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in out.items()}
+    # the editing inputs (mi_plugin.py:717-735): background image (resized to the maps, bilinear / align_corners like the
+    # reference), edit mask (first channel as bool), optimised envmap
+    bpath, mpath, epath = (os.path.join(mat_dir, n) for n in ("bg.png", "mask.png", "envmap.hdr"))
+    if os.path.exists(bpath):
+        bg = read_image(bpath)[..., :3]
+        H, W = out["albedo"].shape[:2]
+        if bg.shape[0] != H:
+            import torch
+            import torch.nn.functional as NF
+            bg = NF.interpolate(torch.from_numpy(np.ascontiguousarray(bg))[None].permute(0, 3, 1, 2), size=(H, W), mode="bilinear",
+                                align_corners=True)[0].permute(1, 2, 0).numpy()
+        out["bg"] = np.ascontiguousarray(bg, dtype=np.float32)
+    if os.path.exists(mpath):
+        mk = read_image(mpath)
+        out["mask"] = np.ascontiguousarray((mk[..., 0] if mk.ndim == 3 else mk) != 0)
+    if os.path.exists(epath):
+        out["envmap"] = np.ascontiguousarray(read_image(epath)[..., :3], dtype=np.float32)
+    return out

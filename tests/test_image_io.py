@@ -148,6 +148,10 @@ def test_load_estimated_brdf_goes_through_the_native_readers(tmp_path):
     a, r, m, n = rs.rand(12, 12, 3).astype(np.float32), rs.rand(12, 12).astype(np.float32), rs.rand(12, 12).astype(np.float32), rs.rand(12, 12, 3).astype(np.float32)
     for name, img in (("albedo", a), ("roughness", r), ("metallic", m), ("normal", n)):
         io.write_bitmap(str(tmp_path / f"{name}.exr"), img)
+    bg = rs.rand(7, 9, 4).astype(np.float32); mk = (rs.rand(12, 12, 4) > 0.5).astype(np.float32); env = (rs.rand(4, 8, 3) + 0.5).astype(np.float32)
+    io.write_bitmap(str(tmp_path / "bg.png"), bg); io.write_bitmap(str(tmp_path / "mask.png"), mk); io.write_bitmap(str(tmp_path / "envmap.hdr"), env)
     mat = gbuffer.load_estimated_brdf(str(tmp_path))
+    assert mat["bg"].shape == (12, 12, 3) and mat["mask"].dtype == np.bool_ and np.array_equal(mat["mask"], mk[..., 0] > 0.5)
+    assert mat["envmap"].shape == (4, 8, 3) and np.allclose(mat["envmap"], env, rtol=1 / 64)
     assert np.array_equal(mat["albedo"], a) and np.allclose(mat["roughness"][..., 0], r * 0.95 + 0.05) and np.array_equal(mat["metallic"][..., 0], m)
     assert np.array_equal(mat["normal"], n)
