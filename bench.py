@@ -44,7 +44,7 @@ WORKLOADS = {
                     "seeds sharded over the GPUs (replicas, no collective)"),
     "c1t": dict(H=512, W=512, spp=64, He=16, We=32, scaling="weak", real=True, trans=True,
                 desc="trans_edit.py --save_name=indoor --ior 1.2 --specTrans 0.4: the shipped indoor scene TRACED with the TransBSDF editing plugin "
-                     "(a disc of radius 150 px as edit mask, background = the scene's albedo map), 64 spp per mi.render call, forward only"),
+                     "(the scene's shipped edit mask and background image, trans_edit.py's material overrides), 64 spp per mi.render call, forward only"),
     "tinym": dict(H=64, W=64, spp=32, He=16, We=32, scaling="weak", mesh=True, desc="tiny self-test workload, mesh mode"),
     "tiny": dict(H=64, W=64, spp=32, He=16, We=32, scaling="weak", desc="tiny self-test workload"),
 }
@@ -308,9 +308,19 @@ def run_real(args, wl, dev, world, rank, local):
     p = mb.traverse(scene)
     p["shape.bsdf.a"], p["shape.bsdf.r"], p["shape.bsdf.m"] = (torch.from_numpy(g[k]).to(dev) for k in ("a", "r", "m"))
     if wl.get("trans"):
-        yy, xx = np.mgrid[0:H, 0:W]
-        p["shape.bsdf.mask"] = torch.from_numpy(((xx - 256) ** 2 + (yy - 256) ** 2) < 150 ** 2).to(dev)
-        p["shape.bsdf.bg"] = torch.from_numpy(np.ascontiguousarray(g["a"])).to(dev)
+        # the scene's own edit mask and background image (output_imgs/indoor/best_results/{mask,bg}.png, shipped by the reference)
+        from materialist_b200.imageio import read_bitmap
+        import torch.nn.functional as NF
+        gold = os.path.join(ROOT, "tests", "golden")
+        mk = read_bitmap(os.path.join(gold, "indoor_mask.png"))[..., 0] != 0
+        bg = torch.from_numpy(np.ascontiguousarray(read_bitmap(os.path.join(gold, "indoor_bg.png"))[..., :3]))
+        bg = NF.interpolate(bg[None].permute(0, 3, 1, 2), size=(H, W), mode="bilinear", align_corners=True)[0].permute(1, 2, 0).contiguous()
+        from materialist_b200.trans_edit import edit_materials
+        ea, er, em = edit_materials({"albedo": p["shape.bsdf.a"], "roughness": p["shape.bsdf.r"], "metallic": p["shape.bsdf.m"],
+                                     "mask": torch.from_numpy(mk).to(dev)}, False)
+        p["shape.bsdf.a"], p["shape.bsdf.r"], p["shape.bsdf.m"] = ea, er, em
+        p["shape.bsdf.mask"] = torch.from_numpy(mk).to(dev)
+        p["shape.bsdf.bg"] = bg.to(dev)
         p["shape.bsdf.specTrans"] = 0.4
     p.update()
 
