@@ -581,6 +581,9 @@ inline void launch_mesh_fwd(K kernel, int filter, int grid, cudaStream_t st, con
 #ifndef MB200_WF_BATCH_LOG2
 #define MB200_WF_BATCH_LOG2 24          // paths per batch (156 B of scratch each): 2^20 / 2^22 / 2^24 -> 120 / 94 / 87 ms C2m forward (fewer, fuller launches)
 #endif
+#ifndef MB200_WF_BINS
+#define MB200_WF_BINS 1
+#endif
 #ifndef MB200_WF_LEAF_MIN
 #define MB200_WF_LEAF_MIN 1
 #endif
@@ -588,20 +591,26 @@ inline void launch_mesh_fwd(K kernel, int filter, int grid, cudaStream_t st, con
 #define MB200_WF_TRACE_BLOCKS 4          // CTAs per SM of the traversal kernels: 64 registers, no spills (5: 94 ms, 4: 84 ms, 3: 87 ms, 6: 122 ms)
 #endif
 constexpr int kWfBatch = 1 << MB200_WF_BATCH_LOG2;
+// Ray queues can be binned by direction octant (MB200_WF_BINS = 8: bin b of queue q at q + b * nb, counts in
+// counters[8 * (1 + queue) + b]; the traversal kernel drains bin after bin, so the lanes of a warp hold rays of one octant).
+// Measured (profiles/r3p): C2m 155 -> 167 ms, C1 42.9 -> 46.9 ms — queue order = pixel order keeps the ORIGINS of a warp's rays
+// together, which is worth more than like directions; default 1 bin.
+constexpr int kBins = MB200_WF_BINS;
+enum { CNT_A = 8, CNT_B = 16, CNT_S = 24 };
 struct WfBuf {
     float4 *ray_o, *ray_d, *hit, *sray_o, *sray_d, *beta, *L, *cem; uint4* rng;
     uint32_t *qa, *qb, *qs; uint32_t* counters;          // counters: [0] n(qa) [1] n(qb) [2] n(qs) [3] fetch cursor
     // adjoint only: film cotangent, pending envmap scatter (cotangent + bilinear footprint), visibility, vertex records
     float4 *dl, *scat, *pbw, *vrec; uint32_t* vis; long long nb; int max_verts;
 };
-inline size_t wf_scratch_bytes(long long nb) { return (size_t)nb * (9 * 16 + 3 * 4) + 256; }
+inline size_t wf_scratch_bytes(long long nb) { return (size_t)nb * (9 * 16 + 3 * 4 * kBins) + 256; }
 inline WfBuf wf_carve(void* scratch, long long nb) {
     WfBuf B; char* p = (char*)scratch;
     B.counters = (uint32_t*)p; p += 256;
     B.ray_o = (float4*)p; p += nb * 16; B.ray_d = (float4*)p; p += nb * 16; B.hit = (float4*)p; p += nb * 16;
     B.sray_o = (float4*)p; p += nb * 16; B.sray_d = (float4*)p; p += nb * 16; B.beta = (float4*)p; p += nb * 16;
     B.L = (float4*)p; p += nb * 16; B.cem = (float4*)p; p += nb * 16; B.rng = (uint4*)p; p += nb * 16;
-    B.qa = (uint32_t*)p; p += nb * 4; B.qb = (uint32_t*)p; p += nb * 4; B.qs = (uint32_t*)p; p += nb * 4;
+    B.qa = (uint32_t*)p; p += nb * 4 * kBins; B.qb = (uint32_t*)p; p += nb * 4 * kBins; B.qs = (uint32_t*)p; p += nb * 4 * kBins;
     B.dl = B.scat = B.pbw = B.vrec = nullptr; B.vis = nullptr; B.nb = nb; B.max_verts = 0;
     return B;
 }
@@ -627,6 +636,30 @@ __device__ __forceinline__ uint32_t wf_append(uint32_t* counter, bool want) {   
     base = __shfl_sync(0xffffffffu, base, 0);
     return base + (uint32_t)__popc(m & ((1u << lane) - 1u));
 }
+struct QView { uint32_t pre[kBins + 1]; };
+__device__ __forceinline__ QView wf_qview(const uint32_t* counts) {
+    QView v; v.pre[0] = 0;
+#pragma unroll
+    for (int b = 0; b < kBins; ++b) v.pre[b + 1] = v.pre[b] + counts[b];
+    return v;
+}
+__device__ __forceinline__ uint32_t wf_qget(const uint32_t* q, const QView& v, uint32_t i, long long nb) {
+    int b = 0;
+#pragma unroll
+    for (int k = 1; k < kBins; ++k) b += i >= v.pre[k] ? 1 : 0;
+    return q[(size_t)b * nb + (i - v.pre[b])];
+}
+__device__ __forceinline__ int wf_octant(float dx, float dy, float dz) {
+    return kBins == 8 ? ((dx < 0.f ? 1 : 0) | (dy < 0.f ? 2 : 0) | (dz < 0.f ? 4 : 0)) : 0;
+}
+__device__ __forceinline__ void wf_append_bin(uint32_t* counts, uint32_t* q, long long nb, bool want, int bin, uint32_t pid) {
+#pragma unroll
+    for (int b = 0; b < kBins; ++b) {
+        const bool w = want && bin == b;
+        const uint32_t slot = wf_append(counts + b, w);
+        if (w) q[(size_t)b * nb + slot] = pid;
+    }
+}
 __global__ void wf_gen_kernel(const __grid_constant__ RenderParams P, WfBuf B, long long pix0, int nb) {
     const float3 cam_o = f3(P.cam.c2w[3], P.cam.c2w[7], P.cam.c2w[11]);
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nb; p += gridDim.x * blockDim.x) {
@@ -641,7 +674,10 @@ __global__ void wf_gen_kernel(const __grid_constant__ RenderParams P, WfBuf B, l
         B.rng[p] = make_uint4((uint32_t)rng.state, (uint32_t)(rng.state >> 32), (uint32_t)rng.inc, (uint32_t)(rng.inc >> 32));
         B.qa[p] = (uint32_t)p;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { B.counters[0] = (uint32_t)nb; B.counters[1] = 0; B.counters[2] = 0; B.counters[3] = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int i = 0; i < 64; ++i) B.counters[i] = 0;
+        B.counters[CNT_A] = (uint32_t)nb;                                          // primary rays: one bin (they are coherent anyway)
+    }
 }
 // rays of queue q[0 .. *count): MODE 0 = closest hit -> hit record; 1 = any hit, L += cem when unoccluded (forward);
 // 2 = any hit, visibility flag (adjoint)
@@ -651,7 +687,8 @@ __global__ void __launch_bounds__(kThreads, MB200_WF_TRACE_BLOCKS) wf_trace_kern
     constexpr bool ANY = MODE != 0;
     uint2 stack_loc[kStack];
     TStack<0> stack; stack.loc = stack_loc; stack.sh = nullptr;
-    const uint32_t n = *count;
+    const QView qv = wf_qview(count);
+    const uint32_t n = qv.pre[kBins];
     Trav T; T.active = false; uint32_t pid = 0; bool done = false;
     for (;;) {
         // lanes without a ray take the next ones of the queue
@@ -664,7 +701,7 @@ __global__ void __launch_bounds__(kThreads, MB200_WF_TRACE_BLOCKS) wf_trace_kern
             if (want) {
                 const uint32_t i = base + (uint32_t)__popc(wm & ((1u << lane) - 1u));
                 if (i < n) {
-                    pid = q[i];
+                    pid = wf_qget(q, qv, i, B.nb);
                     const float4 o = ANY ? B.sray_o[pid] : B.ray_o[pid], d = ANY ? B.sray_d[pid] : B.ray_d[pid];
                     trav_begin(M, T, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), ANY ? d.w : kInf, ANY);
                 } else done = true;
@@ -687,15 +724,16 @@ __global__ void __launch_bounds__(kThreads, MB200_WF_TRACE_BLOCKS) wf_trace_kern
 template <bool AD_W, bool TRANS>
 __global__ void __launch_bounds__(kThreads, 2) wf_shade_kernel(const __grid_constant__ RenderParams P, const __grid_constant__ MeshView M, WfBuf B,
                                                                 const uint32_t* __restrict__ qin, uint32_t* __restrict__ qout, int cin, int cout) {
-    const uint32_t n = B.counters[cin];
+    const QView qv = wf_qview(B.counters + cin);
+    const uint32_t n = qv.pre[kBins];
     const int max_verts = min(P.max_depth - 1, kMaxVerts);
     const uint32_t nthreads = gridDim.x * blockDim.x;
     for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += nthreads) {           // warp-uniform trip count (queue appends are warp-wide)
         const uint32_t i = i0 + threadIdx.x;
         const bool have = i < n;
-        bool cont = false, shadow = false; uint32_t pid = 0;
+        bool cont = false, shadow = false; uint32_t pid = 0; int obin = 0, sbin = 0;
         if (have) {
-            pid = qin[i];
+            pid = wf_qget(qin, qv, i, B.nb);
             const float4 hr = B.hit[pid], rd4 = B.ray_d[pid];
             const float3 rd = f3(rd4.x, rd4.y, rd4.z);
             float4 b4 = B.beta[pid], L4 = B.L[pid];
@@ -732,7 +770,7 @@ __global__ void __launch_bounds__(kThreads, 2) wf_shade_kernel(const __grid_cons
                         const float dist = sqrtf(dot(dd, dd));
                         dd = dd * (1.f / dist);
                         B.sray_o[pid] = make_float4(o.x, o.y, o.z, 0.f); B.sray_d[pid] = make_float4(dd.x, dd.y, dd.z, dist * (1.f - kShadowEps));
-                        shadow = true;
+                        shadow = true; sbin = wf_octant(dd.x, dd.y, dd.z);
                     }
                 }
                 const BsdfSample bs = TRANS ? trans_sample_brdf(s1, s2x, s2y, view, mt, tm, P.trans, make_frame(mt.n)) : sample_brdf_ool(s1, s2x, s2y, view, mt);
@@ -746,13 +784,11 @@ __global__ void __launch_bounds__(kThreads, 2) wf_shade_kernel(const __grid_cons
                 B.beta[pid] = make_float4(beta.x, beta.y, beta.z, bs.pdf);
                 B.L[pid] = make_float4(L.x, L.y, L.z, __int_as_float(nv));            // prev_delta = false from now on
                 cont = fmax3(beta.x, beta.y, beta.z) != 0.f;
-                if (cont) { B.ray_o[pid] = make_float4(no.x, no.y, no.z, 0.f); B.ray_d[pid] = make_float4(d_bs.x, d_bs.y, d_bs.z, 0.f); }
+                if (cont) { B.ray_o[pid] = make_float4(no.x, no.y, no.z, 0.f); B.ray_d[pid] = make_float4(d_bs.x, d_bs.y, d_bs.z, 0.f); obin = wf_octant(d_bs.x, d_bs.y, d_bs.z); }
             }
         }
-        const uint32_t sa = wf_append(B.counters + cout, cont);
-        if (cont) qout[sa] = pid;
-        const uint32_t sb = wf_append(B.counters + 2, shadow);
-        if (shadow) B.qs[sb] = pid;
+        wf_append_bin(B.counters + cout, qout, B.nb, cont, obin, pid);
+        wf_append_bin(B.counters + CNT_S, B.qs, B.nb, shadow, sbin, pid);
     }
 }
 // film: the pixels of the batch, samples in order (same arithmetic as mesh_fwd_kernel's reduction)
@@ -1060,21 +1096,25 @@ __global__ void wf_gen_bwd_kernel(const __grid_constant__ RenderParams P, WfBuf 
         B.rng[p] = make_uint4((uint32_t)rng.state, (uint32_t)(rng.state >> 32), (uint32_t)rng.inc, (uint32_t)(rng.inc >> 32));
         B.qa[p] = (uint32_t)p;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { B.counters[0] = (uint32_t)nb; B.counters[1] = 0; B.counters[2] = 0; B.counters[3] = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int i = 0; i < 64; ++i) B.counters[i] = 0;
+        B.counters[CNT_A] = (uint32_t)nb;                                          // primary rays: one bin (they are coherent anyway)
+    }
 }
 template <bool WANT_MAT, bool WANT_ENV>
 __global__ void __launch_bounds__(kThreads, 2) wf_shade_bwd_kernel(const __grid_constant__ RenderParams P, const __grid_constant__ MeshView M, WfBuf B,
                                                                     const uint32_t* __restrict__ qin, uint32_t* __restrict__ qout, int cin, int cout) {
-    const uint32_t n = B.counters[cin];
+    const QView qv = wf_qview(B.counters + cin);
+    const uint32_t n = qv.pre[kBins];
     const int max_verts = min(P.max_depth - 1, kMaxVerts);
     float4* const genv = WANT_ENV ? P.g_env4 + (long long)(blockIdx.x % P.env_slabs) * P.env_slab_stride : nullptr;
     const uint32_t nthreads = gridDim.x * blockDim.x;
     for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += nthreads) {
         const uint32_t i = i0 + threadIdx.x;
         const bool have = i < n;
-        bool cont = false, shadow = false; uint32_t pid = 0;
+        bool cont = false, shadow = false; uint32_t pid = 0; int obin = 0, sbin = 0;
         if (have) {
-            pid = qin[i];
+            pid = wf_qget(qin, qv, i, B.nb);
             const float4 hr = B.hit[pid], rd4 = B.ray_d[pid], b4 = B.beta[pid], L4 = B.L[pid], dl4 = B.dl[pid];
             const float3 rd = f3(rd4.x, rd4.y, rd4.z), dl = f3(dl4.x, dl4.y, dl4.z);
             float3 beta = f3(b4.x, b4.y, b4.z);
@@ -1116,7 +1156,7 @@ __global__ void __launch_bounds__(kThreads, 2) wf_shade_bwd_kernel(const __grid_
                     const float dist = sqrtf(dot(dd, dd));
                     dd = dd * (1.f / dist);
                     B.sray_o[pid] = make_float4(o.x, o.y, o.z, 0.f); B.sray_d[pid] = make_float4(dd.x, dd.y, dd.z, dist * (1.f - kShadowEps));
-                    shadow = true;
+                    shadow = true; sbin = wf_octant(dd.x, dd.y, dd.z);
                 }
                 const BsdfSample bs = sample_brdf_ool(s1, s2x, s2y, view, mt);
                 const float3 d_bs = (P.flags & MB200_FLAG_WO_WORLD_QUIRK) ? to_world(sp.sh, bs.wi) : bs.wi;
@@ -1140,21 +1180,20 @@ __global__ void __launch_bounds__(kThreads, 2) wf_shade_bwd_kernel(const __grid_
                 B.beta[pid] = make_float4(beta.x, beta.y, beta.z, bs.pdf);
                 B.L[pid] = make_float4(0.f, 0.f, 0.f, __int_as_float(nv));
                 cont = fmax3(beta.x, beta.y, beta.z) != 0.f;
-                if (cont) { B.ray_o[pid] = make_float4(no.x, no.y, no.z, 0.f); B.ray_d[pid] = make_float4(d_bs.x, d_bs.y, d_bs.z, 0.f); }
+                if (cont) { B.ray_o[pid] = make_float4(no.x, no.y, no.z, 0.f); B.ray_d[pid] = make_float4(d_bs.x, d_bs.y, d_bs.z, 0.f); obin = wf_octant(d_bs.x, d_bs.y, d_bs.z); }
             }
         }
-        const uint32_t sa = wf_append(B.counters + cout, cont);
-        if (cont) qout[sa] = pid;
-        const uint32_t sb = wf_append(B.counters + 2, shadow);
-        if (shadow) B.qs[sb] = pid;
+        wf_append_bin(B.counters + cout, qout, B.nb, cont, obin, pid);
+        wf_append_bin(B.counters + CNT_S, B.qs, B.nb, shadow, sbin, pid);
     }
 }
 template <bool WANT_MAT, bool WANT_ENV>
 __global__ void wf_apply_bwd_kernel(const __grid_constant__ RenderParams P, WfBuf B) {
-    const uint32_t n = B.counters[2];
+    const QView qv = wf_qview(B.counters + CNT_S);
+    const uint32_t n = qv.pre[kBins];
     float4* const genv = WANT_ENV ? P.g_env4 + (long long)(blockIdx.x % P.env_slabs) * P.env_slab_stride : nullptr;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t pid = B.qs[i];
+        const uint32_t pid = wf_qget(B.qs, qv, i, B.nb);
         if (B.vis[pid]) {
             if (WANT_ENV) {
                 const float4 sc = B.scat[pid], w = B.pbw[pid];
@@ -1609,21 +1648,21 @@ int mb200_mesh_shade_fwd_wf(const mb200_cfg* c, const mb200_trans* t, const mb20
         const int npb = (int)((npix - pix0) < bp ? (npix - pix0) : bp);
         const int nb = npb * c->spp;
         wf_gen_kernel<<<sms * 8, 256, 0, st>>>(P, B, pix0, nb);
-        uint32_t* qin = B.qa; uint32_t* qout = B.qb; int cin = 0, cout = 1;
+        uint32_t* qin = B.qa; uint32_t* qout = B.qb; int cin = CNT_A, cout = CNT_B;
         bool any_pending = false;
         for (int it = 0; it <= (max_verts < 0 ? 0 : max_verts); ++it) {
             cudaMemsetAsync(B.counters + 3, 0, 4, st);
             wf_trace_kernel<0><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, st>>>(M, B, qin, B.counters + cin, B.counters + 3);
             if (any_pending) { cudaStreamWaitEvent(st, side->any_done, 0); any_pending = false; }   // the shadow rays of the previous bounce
-            cudaMemsetAsync(B.counters + cout, 0, 4, st);
-            cudaMemsetAsync(B.counters + 2, 0, 4, st);
+            cudaMemsetAsync(B.counters + cout, 0, 4 * kBins, st);
+            cudaMemsetAsync(B.counters + CNT_S, 0, 4 * kBins, st);
             if (t)       wf_shade_kernel<false, true><<<sms * 4, kThreads, 0, st>>>(P, M, B, qin, qout, cin, cout);
             else if (ad) wf_shade_kernel<true, false><<<sms * 4, kThreads, 0, st>>>(P, M, B, qin, qout, cin, cout);
             else         wf_shade_kernel<false, false><<<sms * 4, kThreads, 0, st>>>(P, M, B, qin, qout, cin, cout);
             cudaStream_t sa = side ? side->s : st;
             if (side) { cudaEventRecord(side->shaded, st); cudaStreamWaitEvent(sa, side->shaded, 0); }
             cudaMemsetAsync(B.counters + 4, 0, 4, sa);
-            wf_trace_kernel<1><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, sa>>>(M, B, B.qs, B.counters + 2, B.counters + 4);
+            wf_trace_kernel<1><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, sa>>>(M, B, B.qs, B.counters + CNT_S, B.counters + 4);
             if (side) { cudaEventRecord(side->any_done, sa); any_pending = true; }
             uint32_t* tq = qin; qin = qout; qout = tq; const int tc = cin; cin = cout; cout = tc;
         }
@@ -1717,21 +1756,21 @@ int mb200_mesh_shade_bwd_wf(const mb200_cfg* c, const mb200_mesh_desc* md, const
         const int nb = npb * c->spp;
         if (c->filter == MB200_FILTER_GAUSSIAN) wf_gen_bwd_kernel<MB200_FILTER_GAUSSIAN><<<sms * 8, 256, 0, st>>>(P, B, pix0, nb);
         else                                    wf_gen_bwd_kernel<MB200_FILTER_BOX><<<sms * 8, 256, 0, st>>>(P, B, pix0, nb);
-        uint32_t* qin = B.qa; uint32_t* qout = B.qb; int cin = 0, cout = 1;
+        uint32_t* qin = B.qa; uint32_t* qout = B.qb; int cin = CNT_A, cout = CNT_B;
         bool any_pending = false;
         for (int it = 0; it <= max_verts; ++it) {
             cudaMemsetAsync(B.counters + 3, 0, 4, st);
             wf_trace_kernel<0><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, st>>>(M, B, qin, B.counters + cin, B.counters + 3);
             if (any_pending) { cudaStreamWaitEvent(st, side->any_done, 0); any_pending = false; }
-            cudaMemsetAsync(B.counters + cout, 0, 4, st);
-            cudaMemsetAsync(B.counters + 2, 0, 4, st);
+            cudaMemsetAsync(B.counters + cout, 0, 4 * kBins, st);
+            cudaMemsetAsync(B.counters + CNT_S, 0, 4 * kBins, st);
             if (want_mat && want_env)  wf_shade_bwd_kernel<true, true><<<sms * 4, kThreads, 0, st>>>(P, M, B, qin, qout, cin, cout);
             else if (want_mat)         wf_shade_bwd_kernel<true, false><<<sms * 4, kThreads, 0, st>>>(P, M, B, qin, qout, cin, cout);
             else                       wf_shade_bwd_kernel<false, true><<<sms * 4, kThreads, 0, st>>>(P, M, B, qin, qout, cin, cout);
             cudaStream_t sa = side ? side->s : st;
             if (side) { cudaEventRecord(side->shaded, st); cudaStreamWaitEvent(sa, side->shaded, 0); }
             cudaMemsetAsync(B.counters + 4, 0, 4, sa);
-            wf_trace_kernel<2><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, sa>>>(M, B, B.qs, B.counters + 2, B.counters + 4);
+            wf_trace_kernel<2><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, sa>>>(M, B, B.qs, B.counters + CNT_S, B.counters + 4);
             if (want_mat && want_env)  wf_apply_bwd_kernel<true, true><<<sms * 4, 256, 0, sa>>>(P, B);
             else if (want_mat)         wf_apply_bwd_kernel<true, false><<<sms * 4, 256, 0, sa>>>(P, B);
             else                       wf_apply_bwd_kernel<false, true><<<sms * 4, 256, 0, sa>>>(P, B);
