@@ -197,6 +197,17 @@ int mb200_debug_sample_indices(const mb200_cfg* cfg_host, const float* gpos, con
                                const float* hier, const mb200_hier_desc* desc_host,
                                int32_t* out, void* stream);
 
+/* Per-lane decision record of the PRODUCTION forward sample function (the kernels' own shade_sample, instrumented):
+ * (S,12) int32 per lane = hier off.x, off.y, texel flat index (-1: no surface), lobe, envmap cell (flat index of the
+ * upper-left texel) of the emitter sample, envmap cell of the BSDF-sampled direction (of the primary ray for pixels
+ * without a surface), IEEE bits of the emitter direction (3) and of the BSDF-sampled direction (3).  out_radiance
+ * (S,3) float or NULL: the lane's radiance.  cfg.flags & MB200_FLAG_AD_WEIGHTS selects the AD-pass weights.
+ * north_star "CDF/sample indices bit-exact": every word is compared for equality with the oracle's. */
+int mb200_debug_sample_record(const mb200_cfg* cfg_host, const float* gpos, const float* gnrm,
+                              const float* a, const float* r, const float* m, const float* n_opt,
+                              const float* env4, const float* hier, const mb200_hier_desc* desc_host,
+                              int32_t* out, float* out_radiance, void* stream);
+
 /* ---------------------------------------------------------------- mesh mode (triangle mesh instead of a G-buffer) */
 #ifndef MB200_MESH_LEAF
 #define MB200_MESH_LEAF        1    /* triangles per BVH leaf (compile-time; mb200_mesh_describe reports the layout) */

@@ -95,6 +95,7 @@ def _load():
         "mb200_bwd_gadj_rows": (i32, [pc, C.POINTER(C.c_int)]),
         "mb200_shade_bwd": (i32, [pc] + [vp] * 8 + [ph] + [vp] * 6 + [i32, vp]),
         "mb200_debug_sample_indices": (i32, [pc, vp, vp, vp, ph, vp, vp]),
+        "mb200_debug_sample_record": (i32, [pc, vp, vp, vp, vp, vp, vp, vp, vp, ph, vp, vp, vp]),
         "mb200_mesh_describe": (i32, [i32, i32, i32, pd]),
         "mb200_mesh_scratch_bytes": (sz, [i32, i32, i32]),
         "mb200_mesh_build": (i32, [vp, vp, pd, vp, vp, vp]),

@@ -49,27 +49,8 @@ struct MeshView {
 
 struct Hit { int slot, tri; float t, u, v; };
 
-// ---------------------------------------------------------------- exact (non-contracted) vector helpers
-__device__ __forceinline__ float3 xsub3(float3 a, float3 b) { return f3(XSUB(a.x, b.x), XSUB(a.y, b.y), XSUB(a.z, b.z)); }
-__device__ __forceinline__ float xdot3(float3 a, float3 b) { return XADD(XADD(XMUL(a.x, b.x), XMUL(a.y, b.y)), XMUL(a.z, b.z)); }
-__device__ __forceinline__ float3 xcross3(float3 a, float3 b) {
-    return f3(XSUB(XMUL(a.y, b.z), XMUL(a.z, b.y)), XSUB(XMUL(a.z, b.x), XMUL(a.x, b.z)), XSUB(XMUL(a.x, b.y), XMUL(a.y, b.x)));
-}
-__device__ __forceinline__ float3 xnormalize3(float3 a) {
-    const float inv = XDIV(1.f, XSQRT(xdot3(a, a)));
-    return f3(XMUL(a.x, inv), XMUL(a.y, inv), XMUL(a.z, inv));
-}
+// exact (non-contracted) vector helpers and the exact sensor ray: mb200_device.cuh (xsub3, xdot3, xcross3, xnormalize3, primary_dir)
 __device__ __forceinline__ float3 cross3(float3 a, float3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
-
-// perspective sensor ray, bit-identical to the oracle's primary_dir (oracle/mb_oracle.c)
-__device__ __forceinline__ float3 primary_dir_exact(const CamView& c, float sx, float sy) {
-    const float t = c.tan_half_fov_x, aspect = XDIV((float)c.W, (float)c.H);
-    float3 l = f3(XMUL(XSUB(1.f, XDIV(XMUL(2.f, sx), (float)c.W)), t), XDIV(XMUL(XSUB(1.f, XDIV(XMUL(2.f, sy), (float)c.H)), t), aspect), 1.f);
-    l = xnormalize3(l);
-    return f3(XADD(XADD(XMUL(c.c2w[0], l.x), XMUL(c.c2w[1], l.y)), XMUL(c.c2w[2], l.z)),
-              XADD(XADD(XMUL(c.c2w[4], l.x), XMUL(c.c2w[5], l.y)), XMUL(c.c2w[6], l.z)),
-              XADD(XADD(XMUL(c.c2w[8], l.x), XMUL(c.c2w[9], l.y)), XMUL(c.c2w[10], l.z)));
-}
 
 // Mesh::ray_intersect_triangle (Moeller-Trumbore), operation order of the oracle's tri_intersect
 __device__ __forceinline__ bool tri_intersect(float3 p0, float3 p1, float3 p2, float3 o, float3 d, float maxt, float& tt, float& uu, float& vv) {
@@ -480,7 +461,7 @@ __global__ void __launch_bounds__(kThreads, MB200_MESH_MIN_BLOCKS_FWD) mesh_fwd_
                             rng.seed(P.seed, (uint32_t)(py * P.W + px) * (uint32_t)P.spp + (uint32_t)s);
                             const float jx = rng.next_float(), jy = rng.next_float();
                             beta = f3(1.f, 1.f, 1.f); L = f3(0.f, 0.f, 0.f); prev_pdf = 1.f; prev_delta = true; nv = 0;
-                            trav_begin(M, T, cam_o, primary_dir_exact(P.cam, XADD((float)px, jx), XADD((float)py, jy)), kInf, false);
+                            trav_begin(M, T, cam_o, primary_dir(P.cam, XADD((float)px, jx), XADD((float)py, jy)), kInf, false);
                             stage = ST_CLOSEST;
                         } else stage = ST_DONE;
                     }
@@ -667,7 +648,7 @@ __global__ void wf_gen_kernel(const __grid_constant__ RenderParams P, WfBuf B, l
         const int py = P.prow0 + (int)(pix / P.W), px = (int)(pix % P.W);
         Pcg32 rng; rng.seed(P.seed, (uint32_t)(py * P.W + px) * (uint32_t)P.spp + (uint32_t)s);
         const float jx = rng.next_float(), jy = rng.next_float();
-        const float3 d = primary_dir_exact(P.cam, XADD((float)px, jx), XADD((float)py, jy));
+        const float3 d = primary_dir(P.cam, XADD((float)px, jx), XADD((float)py, jy));
         B.ray_o[p] = make_float4(cam_o.x, cam_o.y, cam_o.z, 0.f); B.ray_d[p] = make_float4(d.x, d.y, d.z, 0.f);
         B.beta[p] = make_float4(1.f, 1.f, 1.f, 1.f);                               // w = prev_pdf
         B.L[p] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x100));               // w = nv | prev_delta << 8
@@ -1034,7 +1015,7 @@ __global__ void __launch_bounds__(kThreads, MB200_MESH_MIN_BLOCKS_BWD) mesh_bwd_
                             dl = f3(g.x, g.y, g.z);
                         }
                         beta = f3(1.f, 1.f, 1.f); R = f3(0.f, 0.f, 0.f); prev_pdf = 1.f; prev_delta = true; nv = 0;
-                        trav_begin(M, T, cam_o, primary_dir_exact(P.cam, XADD((float)px, jx), XADD((float)py, jy)), kInf, false);
+                        trav_begin(M, T, cam_o, primary_dir(P.cam, XADD((float)px, jx), XADD((float)py, jy)), kInf, false);
                         stage = ST_CLOSEST;
                     } else stage = ST_DONE;
                 }
@@ -1088,7 +1069,7 @@ __global__ void wf_gen_bwd_kernel(const __grid_constant__ RenderParams P, WfBuf 
             const float4 g = __ldg(P.gadj + (size_t)(py - P.grow0) * P.W + px);
             dl = f3(g.x, g.y, g.z);
         }
-        const float3 d = primary_dir_exact(P.cam, XADD((float)px, jx), XADD((float)py, jy));
+        const float3 d = primary_dir(P.cam, XADD((float)px, jx), XADD((float)py, jy));
         B.ray_o[p] = make_float4(cam_o.x, cam_o.y, cam_o.z, 0.f); B.ray_d[p] = make_float4(d.x, d.y, d.z, 0.f);
         B.beta[p] = make_float4(1.f, 1.f, 1.f, 1.f);
         B.L[p] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x100));               // (R.xyz, nv | prev_delta << 8)
@@ -1273,7 +1254,7 @@ __global__ void mesh_primary_kernel(const __grid_constant__ RenderParams P, cons
     if (i >= P.H * P.W) return;
     const int py = i / P.W, px = i % P.W;
     const float3 ro = f3(P.cam.c2w[3], P.cam.c2w[7], P.cam.c2w[11]);
-    const float3 rd = primary_dir_exact(P.cam, XADD((float)px, jx), XADD((float)py, jy));
+    const float3 rd = primary_dir(P.cam, XADD((float)px, jx), XADD((float)py, jy));
     Hit h;
     if (mesh_intersect<false>(M, ro, rd, kInf, h)) {
         const SurfacePoint sp = hit_point(M, h);

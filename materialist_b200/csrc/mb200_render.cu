@@ -15,75 +15,10 @@
 // with warp shuffles and leave as one RED per channel; envmap gradients leave as 16-byte vector
 // reductions (red.global.add.v4.f32) into a float4 texel grid.
 #include "mb200_render_common.cuh"
+#include "mb200_shade.cuh"
 
 namespace {
 
-
-struct PixelCtx {
-    bool valid; long long flat; Material mt; float3 view; Frame fgeo, fshade; TransMat tm;
-};
-
-template <bool TRANS = false>
-__device__ __forceinline__ PixelCtx load_pixel(const RenderParams& P, int gpix) {
-    PixelCtx c;
-    const float4 gp = __ldg(P.gpos + gpix), gn = __ldg(P.gnrm + gpix);
-    c.valid = gp.w != 0.f;
-    const float3 p = f3(gp.x, gp.y, gp.z), ng = f3(gn.x, gn.y, gn.z);
-    c.flat = 0; c.mt.a = f3(0, 0, 0); c.mt.r = 1.f; c.mt.m = 0.f; c.mt.n = ng; c.view = f3(0, 0, 1);
-    if (c.valid) {
-        c.flat = texel_index(P.cam, p);
-        c.mt.a = f3(__ldg(P.a + 3 * c.flat), __ldg(P.a + 3 * c.flat + 1), __ldg(P.a + 3 * c.flat + 2));
-        c.mt.r = __ldg(P.r + c.flat); c.mt.m = __ldg(P.m + c.flat);
-        if (!P.use_mesh_normal && P.n_opt)
-            c.mt.n = f3(__ldg(P.n_opt + 3 * c.flat), __ldg(P.n_opt + 3 * c.flat + 1), __ldg(P.n_opt + 3 * c.flat + 2));
-        c.view = normalize(f3(P.cam.c2w[3], P.cam.c2w[7], P.cam.c2w[11]) - p);
-        if (TRANS) c.tm = trans_fetch(P.cam, P.trans, c.flat, c.view, ng, p);
-    }
-    c.fgeo = make_frame(ng); c.fshade = make_frame(c.mt.n);
-    return c;
-}
-
-// ---------------------------------------------------------------- one forward sample
-template <bool AD_W, bool TRANS = false>
-__device__ __forceinline__ float3 shade_sample(const RenderParams& P, const PixelCtx& c, int px, int py, uint32_t lane_id,
-                                               float& jx, float& jy) {
-    Pcg32 rng; rng.seed(P.seed, lane_id);
-    jx = rng.next_float(); jy = rng.next_float();
-    if (!c.valid) {
-        const float3 d = primary_dir(P.cam, (float)px + jx, (float)py + jy);
-        float u, v; dir_to_uv(d, u, v);
-        return env_value(P.env, env_lookup<false>(P.env, u, v));
-    }
-    float3 L = f3(0.f, 0.f, 0.f);
-    if (P.max_depth < 2) return L;
-    const float uex = rng.next_float(), uey = rng.next_float();
-    const float s1 = rng.next_float();
-    const float s2x = rng.next_float(), s2y = rng.next_float();
-    // (the russian-roulette draw that follows is never consumed: rr_depth 5 > max_depth)
-    // ---- emitter sampling
-    const EmSample em = env_sample_direction(P.hier, P.env, uex, uey);
-    if (em.pdf != 0.f) {
-        const float3 le = env_value(P.env, em.b);
-        const BsdfVal fv = TRANS ? trans_eval_brdf(em.d, c.view, c.mt, c.tm, P.trans) : eval_brdf(em.d, c.view, c.mt);
-        const float k = mis_weight(em.pdf, fv.pdf) / em.pdf;
-        L = fv.f * le * k;
-    }
-    // ---- BSDF sampling
-    const BsdfSample bs = TRANS ? trans_sample_brdf(s1, s2x, s2y, c.view, c.mt, c.tm, P.trans, c.fshade) : sample_brdf(s1, s2x, s2y, c.view, c.mt, c.fshade);
-    const float3 d_bs = (P.flags & MB200_FLAG_WO_WORLD_QUIRK) ? to_world(c.fgeo, bs.wi) : bs.wi;
-    float3 w_bs = bs.weight;
-    if (AD_W) {
-        const BsdfVal b2 = eval_brdf(d_bs, c.view, c.mt);
-        if (b2.pdf > 0.f) w_bs = b2.f * (1.f / b2.pdf);
-    }
-    if (fmax3(w_bs.x, w_bs.y, w_bs.z) != 0.f && bs.pdf > 0.f) {
-        float u, v; dir_to_uv(d_bs, u, v);
-        const float em_pdf = env_pdf_direction(P.hier, P.env, d_bs, u, v);
-        const float3 le = env_value(P.env, env_lookup<false>(P.env, u, v));
-        L = L + w_bs * le * mis_weight(bs.pdf, em_pdf);
-    }
-    return L;
-}
 
 // ---------------------------------------------------------------- forward kernel
 template <int FILTER, bool AD_W, bool TRANS = false>
@@ -264,9 +199,9 @@ __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_BWD) shade_bwd_kernel(
             }
             if (!c.valid) {
                 if (WANT_ENV) {
-                    const float3 d = primary_dir(P.cam, (float)px + jx, (float)py + jy);
+                    const float3 d = primary_dir(P.cam, XADD((float)px, jx), XADD((float)py, jy));
                     float u, v; dir_to_uv(d, u, v);
-                    env_scatter(genv, P.env.Wi, env_lookup<false>(P.env, u, v), dl);
+                    env_scatter(genv, P.env.Wi, env_lookup(P.env, u, v), dl);
                 }
                 continue;
             }
@@ -294,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_BWD) shade_bwd_kernel(
             if (fmax3(w_bs.x, w_bs.y, w_bs.z) != 0.f && bs.pdf > 0.f) {
                 float u, v; dir_to_uv(d_bs, u, v);
                 const float mis = mis_weight(bs.pdf, env_pdf_direction(P.hier, P.env, d_bs, u, v));
-                const Bilerp bb = env_lookup<false>(P.env, u, v);
+                const Bilerp bb = env_lookup(P.env, u, v);
                 if (WANT_MAT && b2.pdf > 0.f) {
                     const float3 le = env_value(P.env, bb);
                     const BsdfGrad bg = eval_brdf_grad<WANT_N>(d_bs, c.view, c.mt, dl * le * (mis / b2.pdf));
@@ -347,6 +282,28 @@ __global__ void sample_indices_kernel(const __grid_constant__ RenderParams P, in
     reinterpret_cast<int4*>(out)[i] = make_int4(o0, o1, o2, o3);
 }
 
+
+// per-sample decision record through the production shade_sample (DBG instantiation): 12 int32 words per lane =
+// hier off.x, off.y, texel index, lobe, envmap cell of the emitter sample, envmap cell of the BSDF-sampled direction,
+// float bits of the emitter direction (3), float bits of the BSDF-sampled direction (3)
+__global__ void sample_record_kernel(const __grid_constant__ RenderParams P, int32_t* __restrict__ out, float* __restrict__ out_L) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = (long long)P.prows * P.W * P.spp;
+    if (i >= n) return;
+    const int s = (int)(i % P.spp); const long long pix = i / P.spp;
+    const int py = P.prow0 + (int)(pix / P.W), px = (int)(pix % P.W);
+    const int gpix = py * P.W + px;
+    const PixelCtx c = load_pixel(P, gpix);
+    SampleDbg d; float jx, jy;
+    const float3 L = (P.flags & MB200_FLAG_AD_WEIGHTS)
+        ? shade_sample<true, false, true>(P, c, px, py, (uint32_t)gpix * (uint32_t)P.spp + (uint32_t)s, jx, jy, &d)
+        : shade_sample<false, false, true>(P, c, px, py, (uint32_t)gpix * (uint32_t)P.spp + (uint32_t)s, jx, jy, &d);
+    int32_t* o = out + 12 * i;
+    o[0] = (int32_t)d.ox; o[1] = (int32_t)d.oy; o[2] = (int32_t)d.flat; o[3] = d.lobe; o[4] = d.em_i00; o[5] = d.bs_i00;
+    o[6] = __float_as_int(d.d_em.x); o[7] = __float_as_int(d.d_em.y); o[8] = __float_as_int(d.d_em.z);
+    o[9] = __float_as_int(d.d_bs.x); o[10] = __float_as_int(d.d_bs.y); o[11] = __float_as_int(d.d_bs.z);
+    if (out_L) { out_L[3 * i] = L.x; out_L[3 * i + 1] = L.y; out_L[3 * i + 2] = L.z; }
+}
 
 template <int FILTER>
 int launch_bwd(const RenderParams& P, bool want_mat, bool want_n, bool want_env, cudaStream_t st) {
@@ -480,6 +437,18 @@ int mb200_debug_sample_indices(const mb200_cfg* c, const float* gpos, const floa
     P.prow0 = c->row0; P.prows = c->rows;
     const long long n = (long long)P.prows * P.W * P.spp; const int tb = 256;
     sample_indices_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, (cudaStream_t)stream>>>(P, out);
+    return mb200_check_launch();
+}
+
+int mb200_debug_sample_record(const mb200_cfg* c, const float* gpos, const float* gnrm, const float* a, const float* r, const float* m,
+                              const float* n_opt, const float* env4, const float* hier, const mb200_hier_desc* d,
+                              int32_t* out, float* out_radiance, void* stream) {
+    if (!out) return MB200_EINVAL;
+    RenderParams P; int rc = fill_params(c, gpos, gnrm, a, r, m, n_opt, env4, hier, d, P);
+    if (rc) return rc;
+    P.prow0 = c->row0; P.prows = c->rows;
+    const long long n = (long long)P.prows * P.W * P.spp; const int tb = 128;
+    sample_record_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, (cudaStream_t)stream>>>(P, out, out_radiance);
     return mb200_check_launch();
 }
 

@@ -264,3 +264,19 @@ def sample_indices(scene, spp, seed):
     _abi.check(_abi.lib.mb200_debug_sample_indices(C.byref(cfg), _abi.ptr(scene.gpos), _abi.ptr(scene.r), _abi.ptr(hier),
                                                    C.byref(desc), _abi.ptr(out), _abi.stream_ptr()), "mb200_debug_sample_indices")
     return out
+
+
+def sample_record(scene, spp, seed, ad_weights=False, want_radiance=False):
+    """Decision record of every lane of the shard through the kernels' own forward sample function: (S, 12) int32 =
+    (hier off.x, off.y, texel index, lobe, emitter-sample envmap cell, BSDF-direction envmap cell, bits of the emitter
+    direction x/y/z, bits of the BSDF-sampled direction x/y/z) [+ (S, 3) radiance per lane]."""
+    env4, hier, desc, He, We, mode = scene.prepared_env()
+    cfg = scene.make_cfg(spp, seed, desc.res_x, _abi.FLAG_AD_WEIGHTS if ad_weights else 0)
+    S = cfg.rows * scene.W * spp
+    out = torch.empty(S, 12, dtype=torch.int32, device=scene.device)
+    rad = torch.empty(S, 3, device=scene.device) if want_radiance else None
+    nmap = None if scene.use_mesh_normal else scene.n
+    _abi.check(_abi.lib.mb200_debug_sample_record(C.byref(cfg), _abi.ptr(scene.gpos), _abi.ptr(scene.gnrm), _abi.ptr(scene.a), _abi.ptr(scene.r),
+                                                  _abi.ptr(scene.m), _abi.ptr(nmap), _abi.ptr(env4), _abi.ptr(hier), C.byref(desc),
+                                                  _abi.ptr(out), _abi.ptr(rad), _abi.stream_ptr()), "mb200_debug_sample_record")
+    return (out, rad) if want_radiance else out

@@ -37,6 +37,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "../include/materialist_b200.h"   /* cfg / hier_desc struct definitions only */
+#include "../include/mb200_exact_math.h"   /* reproducible float32 sincospi / atan2 / acos shared with the kernels */
 
 #ifdef MBO_DOUBLE
 typedef double real;
@@ -54,6 +55,8 @@ typedef double real;
 #define FMAX fmax
 #define FMIN fmin
 #define COPYSIGN copysign
+/* float64 build (error measurement / finite differences): libm */
+static inline void SINCOSPI(double x, double* s, double* c) { *s = sin(x * 3.14159265358979323846); *c = cos(x * 3.14159265358979323846); }
 #else
 typedef float real;
 #define R(x) x##f
@@ -70,6 +73,13 @@ typedef float real;
 #define FMAX fmaxf
 #define FMIN fminf
 #define COPYSIGN copysignf
+/* float32 build: the transcendental functions that feed directions (and through them integer decisions and the GGX peak)
+ * are the shared reproducible implementations of include/mb200_exact_math.h, bit-identical to the kernels' */
+#undef ACOS
+#undef ATAN2
+#define ACOS mbx_acos
+#define ATAN2 mbx_atan2
+#define SINCOSPI mbx_sincospi
 #endif
 
 #define PI_R      ((real)3.14159265358979323846)
@@ -357,8 +367,8 @@ typedef struct { v3 d; real pdf; bilerp b; uint32_t offx, offy; } emsample;
 static inline emsample env_sample_direction(const float* hier, const mb200_hier_desc* d, real u_shift, real s0, real s1) {
     emsample e; hsample h = hier_sample(hier, d, s0, s1);
     real u = h.u + u_shift, v = h.v;
-    real theta = v * PI_R, phi = u * TWO_PI;
-    real st = SIN(theta), ct = COS(theta), sp = SIN(phi), cp = COS(phi);
+    /* theta = v pi, phi = u 2pi: sin / cos of (pi x) evaluated directly (exact range reduction) */
+    real st, ct, sp, cp; SINCOSPI(v, &st, &ct); SINCOSPI(R(2.0) * u, &sp, &cp);
     v3 d0 = V3(st * cp, st * sp, ct);
     e.d = V3(d0.y, d0.z, -d0.x);
     e.pdf = h.pdf * inv_sin_theta(e.d) * (R(1.0) / (R(2.0) * PI_R * PI_R));
@@ -613,8 +623,10 @@ static inline bsdf_val trans_eval_brdf(v3 wi, v3 wo, const material* mt) {
 }
 static inline v3 nan_to_zero(v3 v) { return V3(v.x != v.x ? 0 : v.x, v.y != v.y ? 0 : v.y, v.z != v.z ? 0 : v.z); }
 static inline v3 diffuse_sampler(real u0, real u1, v3 normal) {
-    real theta = ASIN(safe_sqrt(u0)), phi = R(2.0) * PI_R * u1;
-    v3 wi = V3(SIN(theta) * COS(phi), SIN(theta) * SIN(phi), COS(theta));
+    /* theta = asin(sqrt(u0)): sin(theta) = sqrt(u0), cos(theta) = sqrt(1 - u0) (<= 1 ulp from the literal asin -> sin / cos,
+     * and reproducible); phi = 2 pi u1 through sincospi */
+    real sin_theta = safe_sqrt(u0), cos_theta = safe_sqrt(R(1.0) - u0), sp, cp; SINCOSPI(R(2.0) * u1, &sp, &cp);
+    v3 wi = V3(sin_theta * cp, sin_theta * sp, cos_theta);
     frame f = make_frame(normal);
     return nan_to_zero(to_world(&f, wi));
 }
@@ -623,8 +635,8 @@ static inline v3 specular_sampler(real u0, real u1, real roughness, v3 wo, v3 no
     real alpha = roughness * roughness;
     real cos_theta = safe_sqrt((R(1.0) - u0) / (u0 * (alpha * alpha - R(1.0)) + R(1.0)));
     real sin_theta = safe_sqrt(FMAX(R(0.0), R(1.0) - cos_theta * cos_theta));
-    real phi = R(2.0) * PI_R * u1;
-    v3 wh = V3(sin_theta * COS(phi), sin_theta * SIN(phi), cos_theta);
+    real sp, cp; SINCOSPI(R(2.0) * u1, &sp, &cp);            /* phi = 2 pi u1 */
+    v3 wh = V3(sin_theta * cp, sin_theta * sp, cos_theta);
     frame f = make_frame(normal);
     wh = to_world(&f, wh);
     v3 wi = vsub(vmul(wh, R(2.0) * vdot(wo, wh)), wo);
@@ -871,6 +883,42 @@ int mbo_render_fwd(const mb200_cfg* c, const float* gpos, const float* gnrm, con
             o[0] = (float)(acc[0] / wsum); o[1] = (float)(acc[1] / wsum); o[2] = (float)(acc[2] / wsum);
         }
     free(part);
+    return MB200_OK;
+}
+
+/* Per-lane decision record (the oracle side of mb200_debug_sample_record): 12 int32 words per lane =
+ * hier off.x, off.y, texel index (-1: no surface), lobe, envmap cell of the emitter sample, envmap cell of the BSDF-sampled
+ * direction (of the primary ray where there is no surface; computed whether or not the sample carries weight), IEEE bits
+ * of the emitter direction and of the BSDF-sampled direction.  out_L (S,3) or NULL: the lane's radiance. */
+int mbo_sample_record(const mb200_cfg* c, const float* gpos, const float* gnrm, const float* a, const float* r, const float* m,
+                      const float* n_opt, const float* env_int, const float* hier, const mb200_hier_desc* d,
+                      int32_t* out, float* out_L) {
+    scene_t S = { c, gpos, gnrm, a, r, m, n_opt, env_int, hier, d };
+    const int W = c->W, spp = c->spp, ad = (c->flags & MB200_FLAG_AD_WEIGHTS) != 0;
+    const real u_shift = (real)c->env_u_shift;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int py = c->row0; py < c->row0 + c->rows; ++py)
+        for (int px = 0; px < W; ++px)
+            for (int s = 0; s < spp; ++s) {
+                path_rec o; memset(&o.d_bs, 0, sizeof(o.d_bs)); trace_path(&S, px, py, s, ad, &o);
+                const size_t i = ((size_t)(py - c->row0) * W + px) * spp + s;
+                int32_t* I = out + 12 * i;
+                union { float f; int32_t i; } cv;
+                I[0] = I[1] = 0; I[2] = -1; I[3] = -1; I[4] = I[5] = -1; for (int k = 6; k < 12; ++k) I[k] = 0;
+                if (!o.valid) {
+                    v3 dir = primary_dir(c, (real)px + o.jx, (real)py + o.jy);
+                    I[5] = (int32_t)o.b_miss.idx[0];
+                    cv.f = (float)dir.x; I[9] = cv.i; cv.f = (float)dir.y; I[10] = cv.i; cv.f = (float)dir.z; I[11] = cv.i;
+                } else if (c->max_depth >= 2) {
+                    I[0] = (int32_t)o.em.offx; I[1] = (int32_t)o.em.offy; I[2] = (int32_t)o.flat; I[3] = o.lobe; I[4] = (int32_t)o.em.b.idx[0];
+                    real u, v; dir_to_uv(o.d_bs, &u, &v);
+                    bilerp b = env_lookup(u, v, d->res_x, d->res_y, u_shift);
+                    I[5] = (int32_t)b.idx[0];
+                    cv.f = (float)o.em.d.x; I[6] = cv.i; cv.f = (float)o.em.d.y; I[7] = cv.i; cv.f = (float)o.em.d.z; I[8] = cv.i;
+                    cv.f = (float)o.d_bs.x; I[9] = cv.i; cv.f = (float)o.d_bs.y; I[10] = cv.i; cv.f = (float)o.d_bs.z; I[11] = cv.i;
+                }
+                if (out_L) { out_L[3 * i] = (float)o.L[0]; out_L[3 * i + 1] = (float)o.L[1]; out_L[3 * i + 2] = (float)o.L[2]; }
+            }
     return MB200_OK;
 }
 

@@ -43,7 +43,8 @@ class Trans(C.Structure):
 def build(force=False):
     """Compile the oracle with gcc (Makefile in this directory)."""
     so = os.path.join(_HERE, "libmb_oracle.so")
-    src_m = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("mb_oracle.c", "mb_oracle_mesh.c", "mb_oracle_aux.c", "Makefile"))
+    src_m = max(os.path.getmtime(f) for f in [os.path.join(_HERE, f) for f in ("mb_oracle.c", "mb_oracle_mesh.c", "mb_oracle_aux.c", "Makefile")]
+                + [os.path.join(_HERE, "..", "include", "mb200_exact_math.h")])
     if force or not os.path.exists(so) or os.path.getmtime(so) < src_m:
         subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
     return so
@@ -199,6 +200,17 @@ class Oracle:
         if rc != 0:
             raise RuntimeError(f"mbo_render_fwd rc={rc}")
         return (img, idx) if want_indices else img
+
+    def sample_record(self, cfg, gpos, gnrm, a, r, m, n_opt, env_int, hier, d, want_radiance=False):
+        """(S, 12) int32 decision record per lane (see mbo_sample_record) [+ (S, 3) radiance]."""
+        S = cfg.rows * cfg.W * cfg.spp
+        out = np.zeros((S, 12), np.int32)
+        rad = np.zeros((S, 3), np.float32) if want_radiance else None
+        rc = self.lib.mbo_sample_record(C.byref(cfg), _p(gpos), _p(gnrm), _p(a), _p(r), _p(m), _p(n_opt), _p(env_int), _p(hier), C.byref(d),
+                                        _p(out, C.c_int32), _p(rad))
+        if rc != 0:
+            raise RuntimeError(f"mbo_sample_record rc={rc}")
+        return (out, rad) if want_radiance else out
 
     def render_bwd(self, cfg, gpos, gnrm, a, r, m, n_opt, env_int, hier, d, grad_img, want=("a", "r", "m", "env")):
         H, W = cfg.H, cfg.W

@@ -84,7 +84,9 @@ def test_bsdf_pdf_and_sampler_angles_match_reference(oracle32):
     # polar angles of the two lobes (azimuth conventions differ between the torch frame and mi.Frame3f)
     n = len(p)
     wi_d, _, _ = O.bsdf_sample(cfg, p, g["normal"], g["wo"], np.full(n, 0.9, np.float32), g["s2"], c.a, c.r, c.m)
-    np.testing.assert_allclose((wi_d * g["normal"]).sum(-1), g["diffuse_cos"], rtol=0, atol=3e-6)
+    # (the oracle takes cos(asin(sqrt(u0))) as sqrt(1 - u0): exact where the reference's literal asin -> cos chain cancels, so a
+    # grazing lane with u0 -> 1 differs by up to ~6e-6 absolute)
+    np.testing.assert_allclose((wi_d * g["normal"]).sum(-1), g["diffuse_cos"], rtol=0, atol=1e-5)
     wi_s, _, _ = O.bsdf_sample(cfg, p, g["normal"], g["wo"], np.full(n, 0.1, np.float32), g["s2"], c.a, c.r, c.m)
     h = wi_s + g["wo"]; h /= np.linalg.norm(h, axis=-1, keepdims=True)
     # h = sign(wo.wh) wh, and the sign depends on the (convention-dependent) azimuth of wh: compare |cos theta_h|
