@@ -262,6 +262,12 @@ int mb200_bsdf_eval_pdf(const mb200_cfg* cfg_host, int64_t L,
                         const float* p, const float* n_geo, const float* wi_world, const float* wo_world,
                         const float* a, const float* r, const float* m, const float* n_opt,
                         float* out_f /*(L,3)*/, float* out_pdf /*(L)*/, void* stream);
+/* Adjoint of mb200_bsdf_eval_pdf's rgb value (what dr.backward through MatDiffBSDF.eval_pdf, mi_plugin.py:1449-1460, returns for
+ * a cotangent w on f; the pdf is detached by the path integrator): per lane, at the lane's texel. */
+int mb200_bsdf_eval_grad(const mb200_cfg* cfg_host, int64_t L,
+                         const float* p, const float* n_geo, const float* wi_world, const float* wo_world,
+                         const float* a, const float* r, const float* m, const float* n_opt, const float* w /*(L,3)*/,
+                         float* g_a /*(L,3)*/, float* g_r /*(L)*/, float* g_m /*(L)*/, float* g_n /*(L,3)*/, void* stream);
 int mb200_bsdf_sample(const mb200_cfg* cfg_host, int64_t L,
                       const float* p, const float* n_geo, const float* wi_world,
                       const float* sample1 /*(L)*/, const float* sample2 /*(L,2)*/,

@@ -105,6 +105,7 @@ def _load():
         "mb200_mesh_primary": (i32, [pc, pd, vp, C.c_float, C.c_float, vp, vp, vp, vp, vp]),
         "mb200_bsdf_eval_pdf": (i32, [pc, i64] + [vp] * 11),
         "mb200_bsdf_sample": (i32, [pc, i64] + [vp] * 13),
+        "mb200_bsdf_eval_grad": (i32, [pc, i64] + [vp] * 14),
         "mb200_trans_shade_fwd": (i32, [pc, pt] + [vp] * 8 + [ph, vp, vp]),
         "mb200_trans_mesh_shade_fwd": (i32, [pc, pt, pd] + [vp] * 7 + [ph, vp, vp]),
         "mb200_mesh_fwd_wf_scratch_bytes": (sz, [pc]),

@@ -29,6 +29,14 @@ __global__ void bsdf_eval_pdf_kernel(const __grid_constant__ LaneParams P) {
     const BsdfVal v = eval_brdf(ld3(P.wo, i), ld3(P.wi, i), mt);   // eval_brdf(wi := light (wo), wo := view (si.wi))
     st3(P.o3, i, v.f); P.o1[i] = v.pdf;
 }
+// adjoint of eval_pdf's rgb value: cotangent in P.s2 (L,3) -> g_a (o3), g_r (o1), g_m (ow, 1 per lane), g_n (og)
+__global__ void bsdf_eval_grad_kernel(const __grid_constant__ LaneParams P, float* __restrict__ og) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.L) return;
+    const Material mt = lane_material(P, i);
+    const BsdfGrad g = eval_brdf_grad<true>(ld3(P.wo, i), ld3(P.wi, i), mt, ld3(P.s2, i));
+    st3(P.o3, i, g.ga); P.o1[i] = g.gr; P.ow[i] = g.gm; st3(og, i, g.gn);
+}
 __global__ void bsdf_sample_kernel(const __grid_constant__ LaneParams P) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.L) return;
@@ -90,6 +98,18 @@ int mb200_bsdf_eval_pdf(const mb200_cfg* c, int64_t L, const float* p, const flo
     P.L = L; P.p = p; P.n_geo = n_geo; P.wi = wi_world; P.wo = wo_world; P.a = a; P.r = r; P.m = m; P.n_opt = n_opt;
     P.o3 = out_f; P.o1 = out_pdf;
     bsdf_eval_pdf_kernel<<<(unsigned)((L + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P);
+    return mb200_check_launch();
+}
+
+int mb200_bsdf_eval_grad(const mb200_cfg* c, int64_t L, const float* p, const float* n_geo, const float* wi_world,
+                         const float* wo_world, const float* a, const float* r, const float* m, const float* n_opt, const float* w,
+                         float* g_a, float* g_r, float* g_m, float* g_n, void* stream) {
+    LaneParams P; int rc = fill(c, P); if (rc) return rc;
+    if (L < 0 || !p || !n_geo || !wi_world || !wo_world || !a || !r || !m || !w || !g_a || !g_r || !g_m || !g_n) return MB200_EINVAL;
+    if (L == 0) return MB200_OK;
+    P.L = L; P.p = p; P.n_geo = n_geo; P.wi = wi_world; P.wo = wo_world; P.a = a; P.r = r; P.m = m; P.n_opt = n_opt; P.s2 = w;
+    P.o3 = g_a; P.o1 = g_r; P.ow = g_m;
+    bsdf_eval_grad_kernel<<<(unsigned)((L + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P, g_n);
     return mb200_check_launch();
 }
 

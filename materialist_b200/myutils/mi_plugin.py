@@ -218,6 +218,19 @@ class MatDiffBSDF:
                                                 _abi.stream_ptr()), "mb200_bsdf_eval_pdf")
         return f, pdf
 
+    def eval_pdf_backward(self, ctx, si, wo, grad_f):
+        """What `dr.backward` through `eval_pdf` delivers to the traversed parameters for a cotangent `grad_f` (L,3) on the rgb value
+        (the pdf is detached by the path integrator): per lane (g_a (L,3), g_r (L), g_m (L), g_n (L,3)) at the lane's texel."""
+        wo_w = si.to_world(wo).contiguous(); wi_w = si.to_world(si.wi).contiguous()
+        L, dev = wo_w.shape[0], wo_w.device
+        ga = torch.empty(L, 3, device=dev); gr = torch.empty(L, device=dev); gm = torch.empty(L, device=dev); gn = torch.empty(L, 3, device=dev)
+        a, r, m, n = self._maps()
+        cfg = self._cfg()
+        _abi.check(_abi.lib.mb200_bsdf_eval_grad(C.byref(cfg), L, _abi.ptr(si.p), _abi.ptr(si.n), _abi.ptr(wi_w), _abi.ptr(wo_w),
+                                                 _abi.ptr(a), _abi.ptr(r), _abi.ptr(m), _abi.ptr(n), _abi.ptr(grad_f.contiguous().float()),
+                                                 _abi.ptr(ga), _abi.ptr(gr), _abi.ptr(gm), _abi.ptr(gn), _abi.stream_ptr()), "mb200_bsdf_eval_grad")
+        return ga, gr, gm, gn
+
     def sample(self, ctx, si, sample1, sample2, active=True):
         """Returns (BSDFSample3f, weight (L,3)); bs.wo is in WORLD space like the reference (mi_plugin.py:1444)."""
         wi_w = si.to_world(si.wi).contiguous()

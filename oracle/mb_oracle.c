@@ -688,6 +688,21 @@ void mbo_bsdf_eval_pdf(const mb200_cfg* c, int64_t L, const float* p, const floa
         out_f[3 * i] = (float)bv.f[0]; out_f[3 * i + 1] = (float)bv.f[1]; out_f[3 * i + 2] = (float)bv.f[2]; out_pdf[i] = (float)bv.pdf;
     }
 }
+/* adjoint of MatDiffBSDF.eval_pdf's rgb value on lanes: cotangent w (L,3) -> d/d albedo (L,3), roughness (L), metallic (L), normal (L,3)
+ * at each lane's texel (pinned against finite differences of the reference's own source: tests/golden/make_bsdf_grad_golden.py) */
+void mbo_bsdf_eval_grad(const mb200_cfg* c, int64_t L, const float* p, const float* n_geo, const float* wi_w, const float* wo_w,
+                        const float* a, const float* r, const float* m, const float* n_opt, const float* w,
+                        float* g_a, float* g_r, float* g_m, float* g_n) {
+    for (int64_t i = 0; i < L; ++i) {
+        material mt; fetch_material(c, V3(p[3 * i], p[3 * i + 1], p[3 * i + 2]), V3(n_geo[3 * i], n_geo[3 * i + 1], n_geo[3 * i + 2]),
+                                    V3(wi_w[3 * i], wi_w[3 * i + 1], wi_w[3 * i + 2]), a, r, m, n_opt, &mt, 0);
+        real ww[3] = { (real)w[3 * i], (real)w[3 * i + 1], (real)w[3 * i + 2] };
+        bsdf_grad bg; eval_brdf_grad(V3(wo_w[3 * i], wo_w[3 * i + 1], wo_w[3 * i + 2]), V3(wi_w[3 * i], wi_w[3 * i + 1], wi_w[3 * i + 2]), &mt, ww, &bg);
+        for (int k = 0; k < 3; ++k) g_a[3 * i + k] = (float)bg.ga[k];
+        g_r[i] = (float)bg.gr; g_m[i] = (float)bg.gm;
+        g_n[3 * i] = (float)bg.gn.x; g_n[3 * i + 1] = (float)bg.gn.y; g_n[3 * i + 2] = (float)bg.gn.z;
+    }
+}
 void mbo_bsdf_sample(const mb200_cfg* c, int64_t L, const float* p, const float* n_geo, const float* wi_w,
                      const float* s1, const float* s2, const float* a, const float* r, const float* m, const float* n_opt,
                      float* out_wo, float* out_pdf, float* out_w) {

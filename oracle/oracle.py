@@ -154,6 +154,14 @@ class Oracle:
         self.lib.mbo_bsdf_eval_pdf(C.byref(cfg), C.c_int64(L), _p(p), _p(n_geo), _p(wi_w), _p(wo_w), _p(a), _p(r), _p(m), _p(n_opt), _p(f), _p(pdf))
         return f, pdf
 
+    def bsdf_eval_grad(self, cfg, p, n_geo, wi_world, wo_world, a, r, m, w, n_opt=None):
+        """Adjoint of eval_pdf's rgb value for cotangent w (L,3): (g_a (L,3), g_r (L), g_m (L), g_n (L,3)) at each lane's texel."""
+        p, n_geo, wi_world, wo_world, w = map(_f32, (p, n_geo, wi_world, wo_world, w)); L = p.shape[0]
+        ga = np.zeros((L, 3), np.float32); gr = np.zeros(L, np.float32); gm = np.zeros(L, np.float32); gn = np.zeros((L, 3), np.float32)
+        self.lib.mbo_bsdf_eval_grad(C.byref(cfg), C.c_int64(L), _p(p), _p(n_geo), _p(wi_world), _p(wo_world), _p(_f32(a)), _p(_f32(r)), _p(_f32(m)),
+                                    _p(None if n_opt is None else _f32(n_opt)), _p(w), _p(ga), _p(gr), _p(gm), _p(gn))
+        return ga, gr, gm, gn
+
     def bsdf_sample(self, cfg, p, n_geo, wi_w, s1, s2, a, r, m, n_opt=None):
         p, n_geo, wi_w, s1, s2 = map(_f32, (p, n_geo, wi_w, s1, s2)); L = p.shape[0]
         wo = np.zeros((L, 3), np.float32); pdf = np.zeros(L, np.float32); w = np.zeros((L, 3), np.float32)

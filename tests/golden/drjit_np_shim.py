@@ -16,12 +16,15 @@ run to produce golden vectors.  With these stand-ins the REFERENCE'S OWN SOURCE 
 Test infrastructure only: nothing in the product imports this file.
 """
 import math
+import os
 import sys
 import types
 
 import numpy as np
 
-F32 = np.float32
+# MB_SHIM_F64=1: every "float32" below becomes float64 — used by make_bsdf_grad_golden.py to take finite differences of the
+# reference's BSDF source in double precision (the adjoint pin); the default is Dr.Jit's float32.
+F32 = np.float64 if os.environ.get("MB_SHIM_F64") == "1" else np.float32
 
 
 def _raw(x):

@@ -239,6 +239,28 @@ def test_matdiffbsdf_lanes_vs_oracle(oracle32):
         assert np.median(e) < 5e-6 and np.percentile(e, 99) < 2e-3 and e.max() < 5e-2, (name, np.median(e), np.percentile(e, 99), e.max())
 
 
+@pytest.mark.parametrize("tag", ["mesh", "nmap"])
+def test_cuda_bsdf_grad_matches_reference_source(tag):
+    """Adjoint pin on the device: mb200_bsdf_eval_grad (the same eval_brdf_grad device function the adjoint kernels call) against
+    J^T w with J = float64 finite differences of the REFERENCE'S OWN MatDiffBSDF.eval_pdf source (matdiff_bsdf_grad.npz)."""
+    from materialist_b200.myutils.mi_plugin import MatDiffBSDF, SurfaceInteraction
+    from test_bsdf_plugin_golden import load_golden
+    from test_bsdf_grad_pin import check_grad, grad_case
+    g = load_golden("matdiff_bsdf_grad.npz")
+    lanes, w, ref, J, n_map = grad_case(g, tag)
+    bsdf = MatDiffBSDF({"use_mesh_normal": tag == "mesh"})
+    bsdf.a, bsdf.r, bsdf.m = (torch.from_numpy(g[k]).cuda() for k in ("a", "r", "m"))
+    if n_map is not None:
+        bsdf.n = torch.from_numpy(n_map).cuda()
+    cu = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    si = SurfaceInteraction(cu(lanes["p"]), cu(lanes["n"]), torch.zeros(len(w), 3, device="cuda"))
+    # world directions in, world directions used: go through the frame's exact inverse-free path by giving the LOCAL directions
+    si.wi = si.to_local(cu(lanes["wi_world_used"]))
+    ga, gr, gm, gn = bsdf.eval_pdf_backward(None, si, si.to_local(cu(lanes["wo_world_used"])), cu(w))
+    got = torch.cat([ga, gr[:, None], gm[:, None]] + ([gn] if tag == "nmap" else []), -1).cpu().numpy()
+    check_grad(got, ref, J, w, "cuda " + tag)
+
+
 # ---------------------------------------------------------------- relighting a shipped scene (C1, statistical)
 def test_relight_shipped_scene_statistical():
     """C1: output_imgs/indoor (shipped, 4x box-downsampled fixture) relit with its own optimised envmap reproduces the
