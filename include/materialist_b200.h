@@ -152,9 +152,9 @@ int mb200_env_prepare(const float* env_in, int He, int We, int mode,
  * adjoint kernel spread over them (slab = blockIdx % n) so that hot texels (a sun) are n L2 addresses instead of one.
  * Sized to keep n * He * Wi * 16 bytes <= 64 MB (L2-resident). */
 int mb200_env_grad_slabs(int He, int We, int mode);
-/* g_env4 (n_slabs, He, Wi, 4) -> g_env (He, We, 3): sums the slabs in a fixed order, then the adjoint of the ingest map;
- * g_env is OVERWRITTEN */
-int mb200_env_grad_finish(const float* g_env4, int n_slabs, int He, int We, int mode, float* g_env, void* stream);
+/* g_env4 (n_slabs, He, Wi, 4) -> g_env (He, We, 3): sums the slabs in a fixed order (in place: slab 0 of g_env4 receives the sum,
+ * g_env4 is scratch the caller re-zeroes before the next adjoint), then the adjoint of the ingest map; g_env is OVERWRITTEN */
+int mb200_env_grad_finish(float* g_env4, int n_slabs, int He, int We, int mode, float* g_env, void* stream);
 
 /* ---------------------------------------------------------------- render */
 /* G-buffer: gpos (H,W,4) = (x,y,z,valid?1:0), gnrm (H,W,4) = (nx,ny,nz,0)  — full image, fp32.

@@ -841,26 +841,6 @@ struct VRec {                       // what the backward walk needs of one scatt
     Material mt; float3 view, em_d, cem, d_bs, cpre, w, E; int flat;
 };
 
-// sums x over the lanes of `peers` (all lanes of the warp must call); result valid in the lowest lane of each group
-template <int N>
-__device__ __forceinline__ void reduce_peers(unsigned peers, float (&x)[N]) {
-    const int lane = threadIdx.x & 31;
-    int rel_pos = __popc(peers << (32 - lane)) ;
-    if (lane == 0) rel_pos = 0;
-    peers &= (0xfffffffeu << lane);
-    while (__any_sync(0xffffffffu, peers)) {
-        const int next = __ffs(peers);
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            const float t = __shfl_sync(0xffffffffu, x[i], (next - 1) & 31);
-            if (next) x[i] += t;
-        }
-        const unsigned done = rel_pos & 1;
-        peers &= ~__ballot_sync(0xffffffffu, done);
-        rel_pos >>= 1;
-    }
-}
-
 // Persistent lanes as in mesh_fwd_kernel: the forward walk of each path is cut at its rays; a lane whose path has ended
 // keeps its vertex records until the warp-synchronous backward walk that follows the shading pass (lanes that did not end
 // a path in this pass take part with zero vertices), then fetches the next path of the pool.

@@ -19,11 +19,17 @@
 
 namespace {
 
+// dynamic shared memory the env staging may use per CTA: static + dynamic stays under the 48 KB that needs no opt-in
+// (forward: 20 KB of tap records; adjoint: 3.2 KB of film cotangents)
+constexpr size_t kStageBudgetFwd = 27 * 1024, kStageBudgetBwd = 44 * 1024;
+
 
 // ---------------------------------------------------------------- forward kernel
 template <int FILTER, bool AD_W, bool TRANS = false>
 __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_FWD) shade_fwd_kernel(const __grid_constant__ RenderParams P) {
     __shared__ __align__(16) float s_rec[FILTER == MB200_FILTER_GAUSSIAN ? kWarpsPerBlock * 32 * kRecStride : 4];
+    extern __shared__ float4 s_dyn[];
+    const StagedEnv S = stage_env(P, s_dyn);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* rec = s_rec + (FILTER == MB200_FILTER_GAUSSIAN ? warp * 32 * kRecStride : 0);
     const int npix = P.prows * P.W;
@@ -37,7 +43,7 @@ __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_FWD) shade_fwd_kernel(
             const int s = s0 + lane;
             float3 L = f3(0.f, 0.f, 0.f); float jx = 0.f, jy = 0.f;
             const bool act = s < P.spp;
-            if (act) L = shade_sample<AD_W, TRANS>(P, c, px, py, (uint32_t)gpix * (uint32_t)P.spp + (uint32_t)s, jx, jy);
+            if (act) L = shade_sample<AD_W, TRANS>(P, c, px, py, (uint32_t)gpix * (uint32_t)P.spp + (uint32_t)s, jx, jy, nullptr, S);
             if (FILTER == MB200_FILTER_GAUSSIAN) {
                 float wx[5], wy[5]; film_taps(jx, wx); film_taps(jy, wy);
                 if (!act) { wx[0] = wx[1] = wx[2] = wx[3] = wx[4] = 0.f; }
@@ -116,15 +122,21 @@ __global__ void __launch_bounds__(kThreads) film_weights_kernel(int W, int spp, 
 #pragma unroll
             for (int t = 0; t < MB200_FILM_TAPS; ++t) acc[t] = fmaf(wx[t % 5], wy[t / 5], acc[t]);
         }
+        // reduce-scatter butterfly over the warp (the 25 tap sums padded to 32): at the step with partner distance h a lane keeps the
+        // half of its values whose index bit equals its own lane bit and hands the other half to its partner, so after 5 steps
+        // lane t holds the warp total of tap t: 31 shuffles instead of 25 x 5, and the store is coalesced
+        float v[32];
 #pragma unroll
-        for (int t = 0; t < MB200_FILM_TAPS; ++t) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int t = 0; t < MB200_FILM_TAPS; ++t) wpart[(size_t)pix * MB200_FILM_TAPS + t] = acc[t];
-        }
+        for (int t = 0; t < 32; ++t) v[t] = t < MB200_FILM_TAPS ? acc[t] : 0.f;
+#define MB_RS_STEP(HALF)                                                                              \
+        {   const bool up = (lane & HALF) != 0;                                                       \
+            _Pragma("unroll") for (int i = 0; i < HALF; ++i) {                                         \
+                const float send = up ? v[i] : v[i + HALF], keep = up ? v[i + HALF] : v[i];            \
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, HALF);                                \
+            } }
+        MB_RS_STEP(16) MB_RS_STEP(8) MB_RS_STEP(4) MB_RS_STEP(2) MB_RS_STEP(1)
+#undef MB_RS_STEP
+        if (lane < MB200_FILM_TAPS) wpart[(size_t)pix * MB200_FILM_TAPS + lane] = v[0];
     }
 }
 // G[q] = grad[q] / W_q
@@ -150,14 +162,26 @@ __global__ void film_adjoint_kernel(const float* __restrict__ wpart, int H, int 
 
 // ---------------------------------------------------------------- adjoint kernel
 
-template <int FILTER, bool WANT_MAT, bool WANT_N, bool WANT_ENV>
+// ENVAGG (envmap-gradient scatter): false = every lane issues its four 16-byte reductions into the CTA's L2-resident slab as it goes
+// (the default: the kernel is instruction-issue bound and the L2 atomic units absorb the updates, profiles/r4b_envphase*.log);
+// true = warp-aggregated (match.any + register peer reduction) and, for small maps, block-privatised in shared memory — what
+// north_star prescribes; measured SLOWER on B200 (16x32 + sun: 1.55 / 1.64 ms against 1.40 ms) and kept selectable (MB200_ENV_SCATTER=agg).
+template <int FILTER, bool WANT_MAT, bool WANT_N, bool WANT_ENV, bool ENVAGG = false>
 __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_BWD) shade_bwd_kernel(const __grid_constant__ RenderParams P) {
     __shared__ float4 s_g[FILTER == MB200_FILTER_GAUSSIAN ? kWarpsPerBlock * MB200_FILM_TAPS : 1];
+    extern __shared__ float4 s_dyn[];
+    const StagedEnv S = stage_env(P, s_dyn);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float4* gt = s_g + (FILTER == MB200_FILTER_GAUSSIAN ? warp * MB200_FILM_TAPS : 0);
     const int npix = P.prows * P.W;
-    // this CTA's privatised copy of the envmap-gradient grid (mb200_env_grad_slabs)
+    // this CTA's privatised copy of the envmap-gradient grid (mb200_env_grad_slabs) and, for small maps, its shared-memory accumulator
     float4* const genv = WANT_ENV ? P.g_env4 + (long long)(blockIdx.x % P.env_slabs) * P.env_slab_stride : nullptr;
+    float* senv = nullptr;
+    if (WANT_ENV && ENVAGG && P.env_grad_smem) {
+        senv = reinterpret_cast<float*>(s_dyn + ((P.hier.smem_floats + 3) >> 2) + P.env_smem_texels);
+        for (int i = threadIdx.x; i < 3 * (int)P.env_slab_stride; i += blockDim.x) senv[i] = 0.f;
+        __syncthreads();
+    }
     for (int pix = blockIdx.x * kWarpsPerBlock + warp; pix < npix; pix += gridDim.x * kWarpsPerBlock) {
         const int py = P.prow0 + pix / P.W, px = pix % P.W;
         const int gpix = py * P.W + px;
@@ -178,7 +202,12 @@ __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_BWD) shade_bwd_kernel(
             gbox = f3(g.x, g.y, g.z);
         }
         float3 ga = f3(0, 0, 0), gn = f3(0, 0, 0); float gr = 0.f, gm = 0.f;
-        for (int s = lane; s < P.spp; s += 32) {
+        for (int s0 = 0; s0 < P.spp; s0 += 32) {          // uniform trip count: the aggregated envmap scatter below is warp-collective
+            const int s = s0 + lane;
+            Bilerp bA, bB; float3 cA = f3(0, 0, 0), cB = f3(0, 0, 0); bool aA = false, aB = false;   // this lane's envmap-gradient updates
+            bA.i00 = bB.i00 = 0; bA.w0x = bA.w1x = bA.w0y = bA.w1y = bB.w0x = bB.w1x = bB.w0y = bB.w1y = 0.f;
+            do {
+            if (s >= P.spp) break;
             Pcg32 rng; rng.seed(P.seed, (uint32_t)gpix * (uint32_t)P.spp + (uint32_t)s);
             const float jx = rng.next_float(), jy = rng.next_float();
             // film adjoint: dl = sum_taps wx_i wy_j G[p + (i,j)]
@@ -201,41 +230,58 @@ __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_BWD) shade_bwd_kernel(
                 if (WANT_ENV) {
                     const float3 d = primary_dir(P.cam, XADD((float)px, jx), XADD((float)py, jy));
                     float u, v; dir_to_uv(d, u, v);
-                    env_scatter(genv, P.env.Wi, env_lookup(P.env, u, v), dl);
+                    bA = env_lookup(P.env, u, v); cA = dl; aA = true;
+                    if (!ENVAGG) env_scatter(genv, P.env.Wi, bA, cA);
                 }
-                continue;
+                break;
             }
-            if (P.max_depth < 2) continue;
+            if (P.max_depth < 2) break;
             const float uex = rng.next_float(), uey = rng.next_float();
             const float s1 = rng.next_float();
             const float s2x = rng.next_float(), s2y = rng.next_float();
             // ---- emitter term: L1 = f(d_em) * Le/pdf * mis
-            const EmSample em = env_sample_direction(P.hier, P.env, uex, uey);
+            const EmSample em = env_sample_direction(P.hier, P.env, uex, uey, S.hier);
             if (em.pdf != 0.f) {
-                const BsdfVal fv = eval_brdf(em.d, c.view, c.mt);
+                BrdfGradCtx gc;
+                const BsdfVal fv = WANT_MAT ? eval_brdf_ctx<WANT_N>(em.d, c.view, c.mt, gc) : eval_brdf(em.d, c.view, c.mt);
                 const float k = mis_weight(em.pdf, fv.pdf) / em.pdf;
                 if (WANT_MAT) {
-                    const float3 le = env_value(P.env, em.b);
-                    const BsdfGrad bg = eval_brdf_grad<WANT_N>(em.d, c.view, c.mt, dl * le * k);
+                    const float3 le = env_value(P.env, em.b, S.tex);
+                    const BsdfGrad bg = brdf_grad_apply<WANT_N>(gc, em.d, c.view, c.mt, dl * le * k);
                     ga = ga + bg.ga; gr += bg.gr; gm += bg.gm; if (WANT_N) gn = gn + bg.gn;
                 }
-                if (WANT_ENV) env_scatter(genv, P.env.Wi, em.b, dl * fv.f * k);
+                if (WANT_ENV) { bA = em.b; cA = dl * fv.f * k; aA = true; if (!ENVAGG) env_scatter(genv, P.env.Wi, bA, cA); }
             }
-            // ---- BSDF term: L2 = f(d_bs)/detach(p2) * Le(d_bs) * mis
-            const BsdfSample bs = sample_brdf(s1, s2x, s2y, c.view, c.mt, c.fshade);
-            const float3 d_bs = (P.flags & MB200_FLAG_WO_WORLD_QUIRK) ? to_world(c.fgeo, bs.wi) : bs.wi;
-            const BsdfVal b2 = eval_brdf(d_bs, c.view, c.mt);
-            const float3 w_bs = b2.pdf > 0.f ? b2.f * (1.f / b2.pdf) : bs.weight;
-            if (fmax3(w_bs.x, w_bs.y, w_bs.z) != 0.f && bs.pdf > 0.f) {
+            // ---- BSDF term: L2 = f(d_bs)/detach(p2) * Le(d_bs) * mis.  Of the lobe sample itself only the direction and its pdf
+            // are needed (the primal weight f/(pdf+eps) only where the re-evaluated pdf is 0: a rare fallback, evaluated lazily)
+            int lobe;
+            const float3 wi_bs = sample_lobe_direction(s1, s2x, s2y, c.view, c.mt.r, c.fshade, lobe);
+            const float pdf_s = eval_brdf_pdf(wi_bs, c.view, c.mt);
+            const float bs_pdf = pdf_s > 0.f ? pdf_s : 0.f;
+            const float3 d_bs = (P.flags & MB200_FLAG_WO_WORLD_QUIRK) ? to_world(c.fgeo, wi_bs) : wi_bs;
+            BrdfGradCtx gc2;
+            const BsdfVal b2 = WANT_MAT ? eval_brdf_ctx<WANT_N>(d_bs, c.view, c.mt, gc2) : eval_brdf(d_bs, c.view, c.mt);
+            float3 w_bs;
+            if (b2.pdf > 0.f) w_bs = b2.f * (1.f / b2.pdf);
+            else {
+                const BsdfVal bv = eval_brdf(wi_bs, c.view, c.mt);
+                w_bs = bv.pdf > 1e-6f ? bv.f * (1.f / (bv.pdf + 1e-6f)) : f3(0.f, 0.f, 0.f);
+            }
+            if (fmax3(w_bs.x, w_bs.y, w_bs.z) != 0.f && bs_pdf > 0.f) {
                 float u, v; dir_to_uv(d_bs, u, v);
-                const float mis = mis_weight(bs.pdf, env_pdf_direction(P.hier, P.env, d_bs, u, v));
+                const float mis = mis_weight(bs_pdf, env_pdf_direction(P.hier, P.env, d_bs, u, v, S.hier));
                 const Bilerp bb = env_lookup(P.env, u, v);
                 if (WANT_MAT && b2.pdf > 0.f) {
-                    const float3 le = env_value(P.env, bb);
-                    const BsdfGrad bg = eval_brdf_grad<WANT_N>(d_bs, c.view, c.mt, dl * le * (mis / b2.pdf));
+                    const float3 le = env_value(P.env, bb, S.tex);
+                    const BsdfGrad bg = brdf_grad_apply<WANT_N>(gc2, d_bs, c.view, c.mt, dl * le * (mis / b2.pdf));
                     ga = ga + bg.ga; gr += bg.gr; gm += bg.gm; if (WANT_N) gn = gn + bg.gn;
                 }
-                if (WANT_ENV) env_scatter(genv, P.env.Wi, bb, dl * w_bs * mis);
+                if (WANT_ENV) { bB = bb; cB = dl * w_bs * mis; aB = true; if (!ENVAGG) env_scatter(genv, P.env.Wi, bB, cB); }
+            }
+            } while (false);
+            if (WANT_ENV && ENVAGG) {
+                env_scatter_agg(genv, senv, P.env.Wi, bA, cA, aA);
+                if (c.valid) env_scatter_agg(genv, senv, P.env.Wi, bB, cB, aB);      // (warp-uniform: all samples of a pixel share its validity)
             }
         }
         if (WANT_MAT) {
@@ -255,6 +301,13 @@ __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_BWD) shade_bwd_kernel(
                 if (P.g_m) atomicAdd(P.g_m + c.flat, gm);
                 if (WANT_N && P.g_n) { atomicAdd(P.g_n + 3 * c.flat, gn.x); atomicAdd(P.g_n + 3 * c.flat + 1, gn.y); atomicAdd(P.g_n + 3 * c.flat + 2, gn.z); }
             }
+        }
+    }
+    if (WANT_ENV && ENVAGG && senv) {  // flush the CTA's shared-memory gradient map into its slab: one 16-byte reduction per touched texel
+        __syncthreads();
+        for (int i = threadIdx.x; i < (int)P.env_slab_stride; i += blockDim.x) {
+            const float x = senv[3 * i], y = senv[3 * i + 1], z = senv[3 * i + 2];
+            if (x != 0.f || y != 0.f || z != 0.f) atomicAdd(genv + i, make_float4(x, y, z, 0.f));
         }
     }
 }
@@ -306,14 +359,20 @@ __global__ void sample_record_kernel(const __grid_constant__ RenderParams P, int
 }
 
 template <int FILTER>
-int launch_bwd(const RenderParams& P, bool want_mat, bool want_n, bool want_env, cudaStream_t st) {
-    const int grid = grid_for(P.prows * P.W);
-#define MB_BWD(M, N, E) shade_bwd_kernel<FILTER, M, N, E><<<grid, kThreads, 0, st>>>(P)
-    if (want_mat && want_n && want_env) MB_BWD(true, true, true);
-    else if (want_mat && want_n) MB_BWD(true, true, false);
-    else if (want_mat && want_env) MB_BWD(true, false, true);
-    else if (want_mat) MB_BWD(true, false, false);
-    else if (want_env) MB_BWD(false, false, true);
+int launch_bwd(const RenderParams& P, bool want_mat, bool want_n, bool want_env, size_t dyn, cudaStream_t st) {
+    const int npix = P.prows * P.W;
+#define MB_BWD(M, N, E, A) shade_bwd_kernel<FILTER, M, N, E, A><<<persistent_grid(shade_bwd_kernel<FILTER, M, N, E, A>, npix, dyn), kThreads, dyn, st>>>(P)
+    const bool agg = want_env && env_scatter_aggregated();
+    if (agg) {
+        if (want_mat && want_n) MB_BWD(true, true, true, true);
+        else if (want_mat) MB_BWD(true, false, true, true);
+        else MB_BWD(false, false, true, true);
+    }
+    else if (want_mat && want_n && want_env) MB_BWD(true, true, true, false);
+    else if (want_mat && want_n) MB_BWD(true, true, false, false);
+    else if (want_mat && want_env) MB_BWD(true, false, true, false);
+    else if (want_mat) MB_BWD(true, false, false, false);
+    else if (want_env) MB_BWD(false, false, true, false);
 #undef MB_BWD
     return mb200_check_launch();
 }
@@ -344,16 +403,14 @@ int mb200_shade_fwd(const mb200_cfg* c, const float* gpos, const float* gnrm, co
     if (rc) return rc;
     if (!partials) return MB200_EINVAL;
     P.prows = mb200_fwd_partial_rows(c, &P.prow0); P.partials = partials;
-    const int grid = grid_for(P.prows * P.W);
+    const int npix = P.prows * P.W;
     cudaStream_t st = (cudaStream_t)stream;
     const bool ad = (c->flags & MB200_FLAG_AD_WEIGHTS) != 0;
-    if (c->filter == MB200_FILTER_GAUSSIAN) {
-        if (ad) shade_fwd_kernel<MB200_FILTER_GAUSSIAN, true><<<grid, kThreads, 0, st>>>(P);
-        else    shade_fwd_kernel<MB200_FILTER_GAUSSIAN, false><<<grid, kThreads, 0, st>>>(P);
-    } else {
-        if (ad) shade_fwd_kernel<MB200_FILTER_BOX, true><<<grid, kThreads, 0, st>>>(P);
-        else    shade_fwd_kernel<MB200_FILTER_BOX, false><<<grid, kThreads, 0, st>>>(P);
-    }
+    const size_t dyn = plan_env_staging(P, d, env_staging_budget(kStageBudgetFwd));
+#define MB_FWD(F, A) shade_fwd_kernel<F, A><<<persistent_grid(shade_fwd_kernel<F, A>, npix, dyn), kThreads, dyn, st>>>(P)
+    if (c->filter == MB200_FILTER_GAUSSIAN) { if (ad) MB_FWD(MB200_FILTER_GAUSSIAN, true); else MB_FWD(MB200_FILTER_GAUSSIAN, false); }
+    else                                    { if (ad) MB_FWD(MB200_FILTER_BOX, true);      else MB_FWD(MB200_FILTER_BOX, false); }
+#undef MB_FWD
     return mb200_check_launch();
 }
 
@@ -366,10 +423,11 @@ int mb200_trans_shade_fwd(const mb200_cfg* c, const mb200_trans* t, const float*
     if (!partials) return MB200_EINVAL;
     if (c->flags & MB200_FLAG_AD_WEIGHTS) return MB200_EUNSUPPORTED;      // the reference never differentiates TransBSDF
     P.prows = mb200_fwd_partial_rows(c, &P.prow0); P.partials = partials;
-    const int grid = grid_for(P.prows * P.W);
+    const int npix = P.prows * P.W;
     cudaStream_t st = (cudaStream_t)stream;
-    if (c->filter == MB200_FILTER_GAUSSIAN) shade_fwd_kernel<MB200_FILTER_GAUSSIAN, false, true><<<grid, kThreads, 0, st>>>(P);
-    else                                    shade_fwd_kernel<MB200_FILTER_BOX, false, true><<<grid, kThreads, 0, st>>>(P);
+    const size_t dyn = plan_env_staging(P, d, env_staging_budget(kStageBudgetFwd));
+    if (c->filter == MB200_FILTER_GAUSSIAN) shade_fwd_kernel<MB200_FILTER_GAUSSIAN, false, true><<<persistent_grid(shade_fwd_kernel<MB200_FILTER_GAUSSIAN, false, true>, npix, dyn), kThreads, dyn, st>>>(P);
+    else                                    shade_fwd_kernel<MB200_FILTER_BOX, false, true><<<persistent_grid(shade_fwd_kernel<MB200_FILTER_BOX, false, true>, npix, dyn), kThreads, dyn, st>>>(P);
     return mb200_check_launch();
 }
 
@@ -391,7 +449,7 @@ int mb200_film_weights(const mb200_cfg* c, float* wpart, void* stream) {
     if (!wpart) return MB200_EINVAL;
     if ((double)c->H * (double)c->W * (double)c->spp >= 4294967296.0) return MB200_ERANGE;
     int wrow0; const int wrows = mb200_bwd_wpart_rows(c, &wrow0);
-    film_weights_kernel<<<grid_for(wrows * c->W), kThreads, 0, (cudaStream_t)stream>>>(c->W, c->spp, c->seed, wrow0, wrows, wpart);
+    film_weights_kernel<<<persistent_grid(film_weights_kernel, wrows * c->W), kThreads, 0, (cudaStream_t)stream>>>(c->W, c->spp, c->seed, wrow0, wrows, wpart);
     return mb200_check_launch();
 }
 
@@ -425,8 +483,13 @@ int mb200_shade_bwd(const mb200_cfg* c, const float* gpos, const float* gnrm, co
     const bool want_env = g_env4 != nullptr;
     if (!want_mat && !want_env) return MB200_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    return c->filter == MB200_FILTER_GAUSSIAN ? launch_bwd<MB200_FILTER_GAUSSIAN>(P, want_mat, want_n, want_env, st)
-                                              : launch_bwd<MB200_FILTER_BOX>(P, want_mat, want_n, want_env, st);
+    const size_t budget = env_staging_budget(kStageBudgetBwd);
+    size_t dyn = plan_env_staging(P, d, budget);
+    const size_t gbytes = ((size_t)3 * sizeof(float) * (size_t)P.env_slab_stride + 15) & ~(size_t)15;
+    P.env_grad_smem = (want_env && env_scatter_aggregated() == 2 && dyn + gbytes <= budget) ? 1 : 0;   // block-privatised gradient map (small envmaps)
+    if (P.env_grad_smem) dyn += gbytes;
+    return c->filter == MB200_FILTER_GAUSSIAN ? launch_bwd<MB200_FILTER_GAUSSIAN>(P, want_mat, want_n, want_env, dyn, st)
+                                              : launch_bwd<MB200_FILTER_BOX>(P, want_mat, want_n, want_env, dyn, st);
 }
 
 int mb200_debug_sample_indices(const mb200_cfg* c, const float* gpos, const float* r, const float* hier,

@@ -11,6 +11,27 @@ struct SampleDbg {
     uint32_t ox, oy; long long flat; int lobe; int em_i00, bs_i00; float3 d_em, d_bs;
 };
 
+// Shared-memory staging of the emitter's sampling pyramid (levels >= P.hier.smem_from; ALL levels and the float4 texels for the
+// small envmaps the reference really optimises: 16x32 learned, envmaps/0.hdr 32x16) — north_star: "the envmap marginal/conditional
+// CDFs and mip levels are staged in shared memory".  Called by every thread of the CTA before its pixel loop.
+__device__ __forceinline__ StagedEnv stage_env(const RenderParams& P, float4* dyn) {
+    StagedEnv S{nullptr, nullptr};
+    const int nf = P.hier.smem_floats, nh4 = (nf + 3) >> 2;
+    if (nf > 0) {
+        const float4* src = reinterpret_cast<const float4*>(P.hier.data + P.hier.smem_off0);      // level offsets are 16-byte aligned
+        for (int i = threadIdx.x; i < (nf >> 2); i += blockDim.x) dyn[i] = __ldg(src + i);
+        if (threadIdx.x < (nf & 3)) reinterpret_cast<float*>(dyn)[(nf & ~3) + threadIdx.x] = __ldg(P.hier.data + P.hier.smem_off0 + (nf & ~3) + threadIdx.x);
+        S.hier = reinterpret_cast<const float*>(dyn);
+    }
+    if (P.env_smem_texels > 0) {
+        float4* t = dyn + nh4;
+        for (int i = threadIdx.x; i < P.env_smem_texels; i += blockDim.x) t[i] = __ldg(P.env.tex + i);
+        S.tex = t;
+    }
+    if (nf > 0 || P.env_smem_texels > 0) __syncthreads();
+    return S;
+}
+
 struct PixelCtx {
     bool valid; long long flat; Material mt; float3 view; Frame fgeo, fshade; TransMat tm;
 };
@@ -38,7 +59,7 @@ __device__ __forceinline__ PixelCtx load_pixel(const RenderParams& P, int gpix) 
 // ---------------------------------------------------------------- one forward sample
 template <bool AD_W, bool TRANS = false, bool DBG = false>
 __device__ __forceinline__ float3 shade_sample(const RenderParams& P, const PixelCtx& c, int px, int py, uint32_t lane_id,
-                                               float& jx, float& jy, SampleDbg* dbg = nullptr) {
+                                               float& jx, float& jy, SampleDbg* dbg = nullptr, const StagedEnv S = StagedEnv{nullptr, nullptr}) {
     Pcg32 rng; rng.seed(P.seed, lane_id);
     jx = rng.next_float(); jy = rng.next_float();
     if (DBG) { dbg->ox = dbg->oy = 0; dbg->flat = -1; dbg->lobe = -1; dbg->em_i00 = dbg->bs_i00 = -1; dbg->d_em = dbg->d_bs = f3(0.f, 0.f, 0.f); }
@@ -47,7 +68,7 @@ __device__ __forceinline__ float3 shade_sample(const RenderParams& P, const Pixe
         float u, v; dir_to_uv(d, u, v);
         const Bilerp bm = env_lookup(P.env, u, v);
         if (DBG) { dbg->d_bs = d; dbg->bs_i00 = (int)bm.i00; }
-        return env_value(P.env, bm);
+        return env_value(P.env, bm, S.tex);
     }
     float3 L = f3(0.f, 0.f, 0.f);
     if (P.max_depth < 2) return L;
@@ -56,10 +77,10 @@ __device__ __forceinline__ float3 shade_sample(const RenderParams& P, const Pixe
     const float s2x = rng.next_float(), s2y = rng.next_float();
     // (the russian-roulette draw that follows is never consumed: rr_depth 5 > max_depth)
     // ---- emitter sampling
-    const EmSample em = env_sample_direction(P.hier, P.env, uex, uey);
+    const EmSample em = env_sample_direction(P.hier, P.env, uex, uey, S.hier);
     if (DBG) { dbg->ox = em.ox; dbg->oy = em.oy; dbg->flat = c.flat; dbg->em_i00 = (int)em.b.i00; dbg->d_em = em.d; }
     if (em.pdf != 0.f) {
-        const float3 le = env_value(P.env, em.b);
+        const float3 le = env_value(P.env, em.b, S.tex);
         const BsdfVal fv = TRANS ? trans_eval_brdf(em.d, c.view, c.mt, c.tm, P.trans) : eval_brdf(em.d, c.view, c.mt);
         const float k = mis_weight(em.pdf, fv.pdf) / em.pdf;
         L = fv.f * le * k;
@@ -78,8 +99,8 @@ __device__ __forceinline__ float3 shade_sample(const RenderParams& P, const Pixe
     }
     if (fmax3(w_bs.x, w_bs.y, w_bs.z) != 0.f && bs.pdf > 0.f) {
         float u, v; dir_to_uv(d_bs, u, v);
-        const float em_pdf = env_pdf_direction(P.hier, P.env, d_bs, u, v);
-        const float3 le = env_value(P.env, env_lookup(P.env, u, v));
+        const float em_pdf = env_pdf_direction(P.hier, P.env, d_bs, u, v, S.hier);
+        const float3 le = env_value(P.env, env_lookup(P.env, u, v), S.tex);
         L = L + w_bs * le * mis_weight(bs.pdf, em_pdf);
     }
     return L;

@@ -3,7 +3,7 @@ CPU with explicit seeds so that the CPU oracle and the GPU path see identical bi
 import numpy as np
 import torch
 
-from .scene import Camera
+from .camera import Camera
 
 
 def gbuffer(H, W, camera=None, invalid_border=0):

@@ -57,6 +57,7 @@ typedef double real;
 #define COPYSIGN copysign
 /* float64 build (error measurement / finite differences): libm */
 static inline void SINCOSPI(double x, double* s, double* c) { *s = sin(x * 3.14159265358979323846); *c = cos(x * 3.14159265358979323846); }
+#define RSQRT(x) (1.0 / sqrt(x))
 #else
 typedef float real;
 #define R(x) x##f
@@ -80,6 +81,7 @@ typedef float real;
 #define ACOS mbx_acos
 #define ATAN2 mbx_atan2
 #define SINCOSPI mbx_sincospi
+#define RSQRT mbx_rsqrt      /* correctly rounded 1/sqrt: one rounding, bit-identical to the device's __frsqrt_rn */
 #endif
 
 #define PI_R      ((real)3.14159265358979323846)
@@ -93,7 +95,9 @@ static inline v3 vadd(v3 a, v3 b) { return V3(a.x + b.x, a.y + b.y, a.z + b.z); 
 static inline v3 vsub(v3 a, v3 b) { return V3(a.x - b.x, a.y - b.y, a.z - b.z); }
 static inline v3 vmul(v3 a, real s) { return V3(a.x * s, a.y * s, a.z * s); }
 static inline real vdot(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-static inline v3 vnormalize(v3 a) { real inv = R(1.0) / SQRT(vdot(a, a)); return vmul(a, inv); }
+/* dr::dot on a 3-vector: a0 b0, then two fmadd (the shading geometry uses this form; Moeller-Trumbore keeps the plain vdot) */
+static inline real vdotf(v3 a, v3 b) { return FMA(a.z, b.z, FMA(a.y, b.y, a.x * b.x)); }
+static inline v3 vnormalize(v3 a) { real inv = RSQRT(vdotf(a, a)); return vmul(a, inv); }
 static inline real safe_sqrt(real x) { return SQRT(FMAX(x, R(0.0))); }
 static inline real safe_acos(real x) { return ACOS(FMIN(FMAX(x, R(-1.0)), R(1.0))); }
 static inline real pow5(real x) { real x2 = x * x; return x * (x2 * x2); }   /* drjit int pow: square-and-multiply */
@@ -468,8 +472,8 @@ static inline bsdf_val eval_brdf(v3 wi, v3 wo, const material* mt) {
     if (g_trans_on) return trans_eval_brdf(wi, wo, mt);
     v3 n = mt->n; bsdf_val o;
     v3 h = vnormalize(vadd(wi, wo));
-    real NoL = FMAX(vdot(n, wi), R(0.0)), NoV = FMAX(vdot(n, wo), R(0.0));
-    real VoH = FMAX(vdot(wo, h), R(0.0)), NoH = FMAX(vdot(n, h), R(0.0));
+    real NoL = FMAX(vdotf(n, wi), R(0.0)), NoV = FMAX(vdotf(n, wo), R(0.0));
+    real VoH = FMAX(vdotf(wo, h), R(0.0)), NoH = FMAX(vdotf(n, h), R(0.0));
     real D = D_GGX(NoH, mt->r);
     real pdf_spec = D / (R(4.0) * FMAX(VoH, R(1e-6))) * NoH;
     real pdf_diff = NoL / PI_R;
@@ -493,8 +497,8 @@ static inline bsdf_val eval_brdf(v3 wi, v3 wo, const material* mt) {
 static inline void eval_brdf_grad(v3 wi, v3 wo, const material* mt, const real w[3], bsdf_grad* g) {
     v3 n = mt->n; real r = mt->r, m = mt->m;
     v3 h = vnormalize(vadd(wi, wo));
-    real dNL = vdot(n, wi), dNV = vdot(n, wo), dNH = vdot(n, h);
-    real NoL = FMAX(dNL, R(0.0)), NoV = FMAX(dNV, R(0.0)), VoH = FMAX(vdot(wo, h), R(0.0)), NoH = FMAX(dNH, R(0.0));
+    real dNL = vdotf(n, wi), dNV = vdotf(n, wo), dNH = vdotf(n, h);
+    real NoL = FMAX(dNL, R(0.0)), NoV = FMAX(dNV, R(0.0)), VoH = FMAX(vdotf(wo, h), R(0.0)), NoH = FMAX(dNH, R(0.0));
     real alpha = r * r, alpha2 = alpha * alpha;
     real den0 = (NoH * NoH * (alpha2 - R(1.0)) + R(1.0)) + R(1e-6);
     real D = alpha2 / (PI_R * den0 * den0);
@@ -575,9 +579,9 @@ static inline bsdf_val trans_eval_brdf(v3 wi, v3 wo, const material* mt) {
     v3 n = mt->n; bsdf_val o;
     const real ior = (real)g_trans.ior, st = (real)g_trans.spec_trans;
     v3 h = vnormalize(vadd(wi, wo));
-    real dNL = vdot(n, wi), dNV = vdot(n, wo);
+    real dNL = vdotf(n, wi), dNV = vdotf(n, wo);
     real NoL = FMAX(dNL, R(0.0)), NoV = FMAX(dNV, R(0.0));
-    real VoH = FMAX(vdot(wo, h), R(0.0)), NoH = FMAX(vdot(n, h), R(0.0));
+    real VoH = FMAX(vdotf(wo, h), R(0.0)), NoH = FMAX(vdotf(n, h), R(0.0));
     real D = D_GGX(NoH, mt->r);
     real pdf_spec = D / (R(4.0) * FMAX(VoH, R(1e-4))) * NoH;
     real pdf_diff = NoL / PI_R;
@@ -596,7 +600,7 @@ static inline bsdf_val trans_eval_brdf(v3 wi, v3 wo, const material* mt) {
             o.f[c] = brdf_diff + D * G * F_m / R(4.0) * NoL;
         }
     } else {                              /* bsdf_edit */
-        real LoH = FMAX(vdot(wi, h), R(0.0));
+        real LoH = FMAX(vdotf(wi, h), R(0.0));
         real hw_in = R(1.0) / (LoH + R(1e-6)), hw_out = R(1.0) / (VoH + R(1e-6));
         real nw_in = R(1.0) / (NoL + R(1e-6)), nw_out = R(1.0) / (NoV + R(1e-6));
         real R_s = (hw_in - ior * hw_out) / (hw_in + ior * hw_out);
@@ -639,7 +643,7 @@ static inline v3 specular_sampler(real u0, real u1, real roughness, v3 wo, v3 no
     v3 wh = V3(sin_theta * cp, sin_theta * sp, cos_theta);
     frame f = make_frame(normal);
     wh = to_world(&f, wh);
-    v3 wi = vsub(vmul(wh, R(2.0) * vdot(wo, wh)), wo);
+    v3 wi = vsub(vmul(wh, R(2.0) * vdotf(wo, wh)), wo);
     wi = nan_to_zero(wi);
     return vnormalize(wi);
 }

@@ -34,3 +34,14 @@ static inline int __float_as_int(float f) { int u; memcpy(&u, &f, 4); return u; 
 static inline float __int_as_float(int u) { float f; memcpy(&f, &u, 4); return f; }
 static inline float atomicAdd(float* p, float v) { float o = *p; *p += v; return o; }
 static inline float4 atomicAdd(float4* p, float4 v) { float4 o = *p; p->x += v.x; p->y += v.y; p->z += v.z; p->w += v.w; return o; }
+// one "thread" per block on the host: the CTA-cooperative staging loops degenerate to serial copies
+static const uint3 threadIdx = {0, 0, 0};
+static const dim3 blockDim = {1, 1, 1};
+static inline void __syncthreads() {}
+// warp primitives for a "warp" of one lane (the aggregated scatter code must compile; the emulation never calls it)
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
+static inline int __any_sync(unsigned, int p) { return p != 0; }
+static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
+static inline unsigned __match_any_sync(unsigned, unsigned) { return 1u; }
+static inline float __shfl_sync(unsigned, float v, int) { return v; }
