@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 strong-scaling rider of the default (c2) run")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "autograd"],
                     help="fused: csrc/mb200_optim.cu loss + Adam kernels (9 launches/step); autograd: torch ops + torch.optim.Adam")
     return ap.parse_args()
@@ -117,7 +118,7 @@ def build_case(wl, world):
     import numpy as np
     import torch
     from materialist_b200 import synthetic
-    from materialist_b200.scene import Camera
+    from materialist_b200.camera import Camera
     H = wl["H"] * (world if (wl["scaling"] == "weak" and not wl.get("rolling")) else 1)
     W = wl["W"]
     cam = Camera(width=W, height=H)
@@ -137,19 +138,90 @@ def alg_bytes_per_pixel():
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
+def _host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def _stub_product_package():
+    """The reference arm must not load the product: `materialist_b200/__init__` dlopens libmaterialist_b200.so.  Register an empty
+    package object whose __path__ points at the directory, so that the two lib-free host modules the workload generators live in
+    (materialist_b200.camera, materialist_b200.synthetic) import without running __init__."""
+    import types
+    if "materialist_b200" not in sys.modules:
+        pkg = types.ModuleType("materialist_b200"); pkg.__path__ = [os.path.join(ROOT, "materialist_b200")]
+        sys.modules["materialist_b200"] = pkg
+
+
+REF_FLAGS = 1 | 2 | 4          # oracle.FLAG_WO_WORLD_QUIRK | FLAG_ROW_STRIDE_H | FLAG_ENV_HALF_TEXEL
+
+
+def try_mitsuba_reference(args, wl):
+    """when `import mitsuba` works AND the reference tree is reachable (MATERIALIST_REF), time the reference's
+    own path — Mitsuba llvm_ad_rgb with its MatDiffBSDF plugin — instead of the restatement.  Neither exists in the build image or on
+    the bench boxes of this pool (no wheel, no network, /root/reference is not shipped), so this returns None there."""
+    ref = os.environ.get("MATERIALIST_REF", "/root/reference")
+    try:
+        import mitsuba as mi
+        import drjit as dr
+    except Exception:
+        return None
+    if not os.path.isdir(ref) or wl.get("real") or wl.get("mesh") or wl.get("rolling") or wl.get("pos_mlp"):
+        return None
+    try:
+        import numpy as np
+        mi.set_variant("llvm_ad_rgb")
+        sys.path.insert(0, ref)
+        import myutils.mi_plugin as mp
+        mi.register_bsdf("MatDiffBSDF", lambda props: mp.MatDiffBSDF(props))
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import upstream_check as uc                                   # scene construction shared with the guarded parity check
+        scene, params, leaves = uc.build_reference_scene(mi, dr, mp, ref, wl["He"], wl["We"])
+        spp = wl["spp"]
+
+        def step(i):
+            img = mi.render(scene, params, spp=spp, seed=i)
+            dr.backward(dr.sum(img))
+            for t in leaves:
+                dr.grad(t)
+        for i in range(args.warmup):
+            step(i)
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            step(100 + i)
+        dt = (time.perf_counter() - t0) / args.steps
+        return {"dt": dt, "samples": 512 * 512 * spp, "kind": "mitsuba", "sample": f"whole 512x512 image, {spp} spp, mi.render + dr.backward (llvm_ad_rgb)"}
+    except Exception as e:                                            # API drift: fall back to the restatement, say why
+        sys.stderr.write(f"[bench] mitsuba reference arm failed ({e!r}); using the oracle\n")
+        return None
+
+
 def run_reference(args, wl):
     """The reference's CPU path (restated: oracle/) on the host cores, on a bounded row-sample of the workload."""
-    import numpy as np
-    from oracle import oracle as orc
-    from helpers import REF_FLAGS
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cores = _host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(cores)        # explicit: torchrun exports OMP_NUM_THREADS=1 to its workers (must precede dlopen)
+    os.environ.pop("OMP_PROC_BIND", None)
+    _stub_product_package()
+    import numpy as np
+    from oracle import oracle as orc
     O = orc.Oracle()
+    cores = int(O.lib.mbo_omp_max_threads())          # what the OpenMP runtime will actually use
+    mts = try_mitsuba_reference(args, wl)
+    if mts is not None:
+        val = mts["samples"] / mts["dt"] / 1e9
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": mts["dt"] * 1e3, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
+                          "dtype": "f32", "data": "synthetic", "config": {"workload": wl["desc"], "sample": mts["sample"]},
+                          "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "mitsuba", "sample": mts["sample"]},
+                          "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
     if wl.get("real"):                                             # C1: forward render of the shipped scene, traced (as run_real)
-        from test_reference_render_pin import pin_cfg
+        from test_reference_render_pin import pin_cfg             # (tests/: imports oracle + the lib-free camera module only)
         g = np.load(os.path.join(ROOT, "tests", "golden", "indoor_pin.npz"))
         om = O.mesh_create(g["verts"], g["tris"])
         env_int, hier, d = O.env_prepare(g["env"], orc.ENV_ASSIGNED)
@@ -211,7 +283,11 @@ def run_reference(args, wl):
     dt = (time.perf_counter() - t0) / args.steps
     val = rows * W * spp / dt / 1e9
     sample = f"rows [{row0},{row0 + rows}) of the {H}x{W} image, {spp} spp, fwd + adjoint render per step (no loss/optimiser)"
-    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    try:
+        lib_loaded = "libmaterialist_b200" in open("/proc/self/maps").read()
+    except Exception:
+        lib_loaded = None
+    out = {"impl": "reference", "product_lib_loaded": lib_loaded, "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
            "dtype": "f32", "data": "synthetic", "config": {"workload": wl["desc"], "sample": sample},
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
@@ -398,6 +474,257 @@ def run_real(args, wl, dev, world, rank, local):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ measurement helpers
+def _max_over_ranks(ms, dev, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _sync(world):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier(); torch.cuda.synchronize()
+
+
+def _timed(fn, steps, warmup, dev, world, seed0=2000):
+    """W warm-up calls, then K calls between CUDA events on the current stream, barrier + synchronize on both sides; max over ranks."""
+    import torch
+    for i in range(warmup):
+        fn(i)
+    _sync(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(seed0 + i)
+    e1.record()
+    _sync(world)
+    return _max_over_ranks(e0.elapsed_time(e1), dev, world) / steps / 1e3
+
+
+def load_ncu_counters(workload):
+    """profiles/ncu_counters.json: per-kernel counters of one `ncu --set full` capture (tools/ncu_counters.py), with the commit and
+    the workload it was taken on.  None when absent or taken on another workload."""
+    try:
+        c = json.load(open(os.path.join(ROOT, "profiles", "ncu_counters.json")))
+        return c if c.get("workload") == workload else None
+    except Exception:
+        return None
+
+
+def build_roofline(args, wl, scene, shard, dom, kavg, t_step, dev, world):
+    """achieved = max(bytes_alg / BW, flops / peak) / t — both roofs reported, `bound` names the binding one.
+    bytes: the algorithmic per-pixel figures of §8d.  FLOPs: EXECUTED FP32 operations per sample (2 FFMA + FADD + FMUL thread
+    instructions) counted by ncu on this kernel and committed in profiles/ncu_counters.json (not an estimate); the FP32 peak is an
+    FFMA loop timed in this run.  DRAM traffic and issue-slot utilisation come from the same capture."""
+    import torch
+    from materialist_b200 import _abi
+    if not dom:
+        return None, None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md 6.65 TB/s)"
+    W, spp = scene.W, wl["spp"]
+    npix_rank = shard.rows * W
+    env_bytes = wl["He"] * (wl["We"] + 1) * 16 + scene.prepared_env()[2].total_floats * 4
+    per_px = {"shade_bwd": 88.0, "shade_fwd": 96.0, "mesh_bwd": 88.0 - 32.0, "mesh_fwd": 96.0 - 32.0}.get(dom.replace("_wf", ""), 184.0)
+    alg_bytes = npix_rank * per_px + env_bytes
+    if scene.mesh is not None:
+        alg_bytes += scene.mesh.desc.total_bytes
+    t_k = kavg[dom] * 1e-3
+    hbm_ach = alg_bytes / t_k / 1e9
+    # FP32 peak: FFMA loop, measured now
+    peak_tf = None
+    try:
+        buf = torch.zeros(1 << 20, device=dev)
+        fl = _abi.C.c_double(0.0)
+        for _ in range(2):
+            _abi.check(_abi.lib.mb200_probe_ffma(_abi.ptr(buf), 4096, _abi.C.byref(fl), _abi.stream_ptr()), "probe")
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        _abi.check(_abi.lib.mb200_probe_ffma(_abi.ptr(buf), 16384, _abi.C.byref(fl), _abi.stream_ptr()), "probe")
+        p1.record(); torch.cuda.synchronize()
+        peak_tf = fl.value / (p0.elapsed_time(p1) * 1e-3) / 1e12
+    except Exception:
+        pass
+    cnt = load_ncu_counters(args.workload)
+    kc = (cnt or {}).get("kernels", {}).get(dom)
+    fp32 = {"peak_tflops": peak_tf, "peak_source": "measured here: FFMA loop (mb200_probe_ffma)"}
+    fp_frac = None
+    if kc and peak_tf:
+        flops = kc["flops_per_sample"] * npix_rank * spp
+        ach = flops / t_k / 1e12
+        fp_frac = ach / peak_tf
+        fp32.update({"achieved_tflops": ach, "frac": fp_frac, "flops_per_sample_executed": kc["flops_per_sample"],
+                     "thread_inst_per_sample": kc["thread_inst_per_sample"], "fp32_pipe_inst_frac_ncu": kc["fp32_pipe_inst_frac"],
+                     "issue_active_frac_ncu": kc["issue_active_frac"],
+                     "counters_from": {"file": "profiles/ncu_counters.json", "commit": cnt["commit"], "source": cnt.get("source")},
+                     "note": "FLOPs = 2 FFMA + FADD + FMUL thread instructions executed (ncu), per sample, times the samples of this launch; "
+                             "a kernel of non-contracted IEEE multiplies and adds (the bit-exact direction chain) can reach at most half of the FFMA peak"})
+    else:
+        fp32["note"] = "no ncu counters committed for this workload / kernel: FLOP rate not reported"
+    hbm_frac = hbm_ach / hbm_peak
+    bound_fp = fp_frac is not None and fp_frac >= hbm_frac
+    roofline = {"bound": "fp32" if bound_fp else "hbm", "kernel": dom,
+                "achieved": fp32.get("achieved_tflops") if bound_fp else hbm_ach, "peak": peak_tf if bound_fp else hbm_peak,
+                "unit": "TFLOP/s" if bound_fp else "GB/s", "frac": fp_frac if bound_fp else hbm_frac,
+                "traffic": kc["dram_bytes"] * (npix_rank * spp / float(cnt["samples_per_launch"])) if (kc and world == 1) else None,
+                "hbm": {"achieved_gbs": hbm_ach, "peak_gbs": hbm_peak, "frac": hbm_frac, "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src},
+                "fp32": fp32, "kernel_ms": kavg[dom], "kernel_share_of_step": t_k / t_step,
+                "note": "bound = the larger of the two roofline fractions (SURVEY 8d: max(bytes/BW, flops/peak)); the fused path is instruction-issue "
+                        "bound at 64-256 spp (~830 FLOP/B against a ridge of ~11): the HBM fraction is ~0.3 % by construction and is reported beside it; "
+                        "'bound: fp32' is the non-tensor FP32 roof (this path has no contraction to put on tensor cores)"}
+    return roofline, fp32
+
+
+def run_e2e_iteration(args, opt, shard, dev, world, samples_per_step):
+    """SAME step as `value` — forward render, loss, adjoint render, Adam — through FusedBRDFOptimizer with the step's input image on
+    the HOST: every step uploads the target image rows (pinned -> device) and reads back the step's result (the two loss scalars and
+    the predicted sRGB image rows).  The material maps are the optimised parameters and stay on the device, like the weights of any
+    training step."""
+    import torch
+    if not all(hasattr(opt, k) for k in ("gt_srgb", "pred_srgb", "sums2")):
+        return None
+    hgt = opt.gt_srgb.detach().cpu().pin_memory()
+    hpred = torch.empty_like(hgt).pin_memory()
+    hloss = torch.empty(2).pin_memory()
+
+    def serial(seed):
+        opt.gt_srgb.copy_(hgt, non_blocking=True)
+        opt.step(seed)
+        hpred.copy_(opt.pred_srgb, non_blocking=True)
+        hloss.copy_(opt.sums2, non_blocking=True)
+    t_serial = _timed(serial, args.steps, 3, dev, world)
+
+    # the same transfers on their own streams: the upload of step i+1 runs under step i (two target buffers), the download of step
+    # i's results under step i+1's forward render (the loss kernels of step i+1 wait for it before they overwrite pred_srgb / sums2)
+    main = torch.cuda.current_stream(dev)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    gts = [opt.gt_srgb, torch.empty_like(opt.gt_srgb)]
+    ev_in = [torch.cuda.Event(), torch.cuda.Event()]; ev_used = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_step, ev_out = torch.cuda.Event(), torch.cuda.Event()
+    state = {"i": 0}
+
+    def upload(slot):
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_used[slot])
+            gts[slot].copy_(hgt, non_blocking=True)
+            ev_in[slot].record(s_in)
+    upload(0)
+
+    def piped(seed):
+        slot = state["i"] % 2; state["i"] += 1
+        main.wait_event(ev_in[slot])
+        opt.gt_srgb = gts[slot]
+        upload(1 - slot)
+        main.wait_event(ev_out)                                  # the previous step's results have left pred_srgb / sums2
+        opt.step(seed)
+        ev_used[slot].record(main); ev_step.record(main)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_step)
+            hpred.copy_(opt.pred_srgb, non_blocking=True); hloss.copy_(opt.sums2, non_blocking=True)
+            ev_out.record(s_out)
+    for i in range(3):
+        piped(i)
+    main.wait_event(ev_out); _sync(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        piped(3000 + i)
+    main.wait_event(ev_out)
+    e1.record(); s_in.synchronize(); s_out.synchronize(); _sync(world)
+    t_pipe = _max_over_ranks(e0.elapsed_time(e1), dev, world) / args.steps / 1e3
+    opt.gt_srgb = gts[0]
+    return {"value": samples_per_step / t_pipe / 1e9, "unit": UNIT, "h2d_bytes_per_step": hgt.numel() * 4, "d2h_bytes_per_step": (hpred.numel() + 2) * 4,
+            "ms_per_step": t_pipe * 1e3, "ms_per_step_copies_serialised": t_serial * 1e3, "value_copies_serialised": samples_per_step / t_serial / 1e9,
+            "bytes_are": "per rank",
+            "what": "the full iteration (fwd render, loss, adjoint render, Adam: the step `value` times) with its input on the host: H2D of the "
+                    "target image rows every step, D2H of the loss sums and of the predicted image rows; copies on their own streams "
+                    "(the figure with the copies serialised on the compute stream is listed beside it)"}
+
+
+def run_e2e_operator(args, case, scene, shard, spp, dev, world, samples_per_step):
+    """The operator boundary for a HOST-side optimiser: render_w_brdf forward + backward with pinned host maps in and image + material
+    gradients out, every step; shard-local rows only (hostpipe).  Serial copies and copies on their own streams, both listed."""
+    import torch
+    import materialist_b200 as mb
+    from materialist_b200.hostpipe import HostPipelinedRenderWBRDF
+    H, W = scene.H, scene.W
+    with scene.shard(shard.row0, shard.rows):
+        pipe = HostPipelinedRenderWBRDF(scene, spp, halo_exchange=shard.halo_exchange if world > 1 else None)
+        (m0, m1), (o0, o1) = pipe.map_rows, pipe.out_rows
+        ha, hr, hm = (case[k][m0:m1].contiguous().pin_memory() for k in ("a", "r", "m"))
+        himg = torch.empty(shard.rows, W, 3).pin_memory(); hgrad = torch.ones(shard.rows, W, 3).pin_memory()
+        hga, hgr, hgm = (torch.empty(o1 - o0, W, c).pin_memory() for c in (3, 1, 1))
+        da, dr_, dm = (torch.zeros(H, W, c, device=dev) for c in (3, 1, 1))
+
+        def serial(seed):
+            da[m0:m1].copy_(ha, non_blocking=True); dr_[m0:m1].copy_(hr, non_blocking=True); dm[m0:m1].copy_(hm, non_blocking=True)
+            a = da.detach().requires_grad_(True); r = dr_.detach().requires_grad_(True); m = dm.detach().requires_grad_(True)
+            img = mb.render(scene, spp=spp, seed=seed, albedo=a, roughness=r, metallic=m, halo_exchange=shard.halo_exchange if world > 1 else None)
+            himg.copy_(img.detach(), non_blocking=True)
+            img.backward(hgrad.to(dev, non_blocking=True))
+            hga.copy_(a.grad[o0:o1], non_blocking=True); hgr.copy_(r.grad[o0:o1], non_blocking=True); hgm.copy_(m.grad[o0:o1], non_blocking=True)
+        t_serial = _timed(serial, args.steps, 3, dev, world)
+        inputs = (ha, hr, hm, hgrad)
+        pipe.stage(0, *inputs)
+        for i in range(3):
+            pipe.step(i, i % 2, himg, hga, hgr, hgm, next_inputs=inputs)
+        pipe.synchronize(); _sync(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            pipe.step(2000 + i, (3 + i) % 2, himg, hga, hgr, hgm, next_inputs=inputs)
+        torch.cuda.current_stream().wait_event(pipe.last_out)
+        e1.record(); pipe.synchronize(); _sync(world)
+        t_pipe = _max_over_ranks(e0.elapsed_time(e1), dev, world) / args.steps / 1e3
+    h2d = (ha.numel() + hr.numel() + hm.numel() + hgrad.numel()) * 4
+    d2h = (himg.numel() + hga.numel() + hgr.numel() + hgm.numel()) * 4
+    return {"value_copies_serialised": samples_per_step / t_serial / 1e9, "value_copies_overlapped": samples_per_step / t_pipe / 1e9, "unit": UNIT,
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "bytes_are": "per rank (own rows + 2-row film halo of the maps up; own rows down)",
+            "ms_per_step_copies_serialised": t_serial * 1e3, "ms_per_step_copies_overlapped": t_pipe * 1e3,
+            "what": "render_w_brdf forward + backward (no loss / optimiser: a host-side optimiser owns them) with pinned HOST buffers: H2D a/r/m + "
+                    "d(loss)/d(image), D2H image + material gradients, every step"}
+
+
+def run_c5_leg(args, dev, world, rank):
+    """BASELINE.json configs[4] at this N: the FIXED 3840x2160 image (256 spp, 2048x1024 envmap) row-sharded over the ranks — strong
+    scaling, the north-star '>= 7x at 8 GPUs on 4K G-buffers'.  Same iteration, same timing rules, fewer steps (one step is ~0.4 s of
+    GPU time at N = 1)."""
+    import torch
+    import materialist_b200 as mb
+    from materialist_b200.inverse import FusedBRDFOptimizer
+    from materialist_b200.parallel import ShardContext
+    wl = WORKLOADS["c5"]
+    case = build_case(wl, world)
+    H, W, spp = case["H"], case["W"], wl["spp"]
+    shard = ShardContext(H, W, rank, world)
+    scene = mb.Scene(case["pos"], case["nrm"], case["valid"], camera=case["cam"], envmap=case["env"], device=dev)
+    to = lambda t: t.to(dev)
+    with scene.shard(shard.row0, shard.rows):         # every rank renders its own rows of the target, then the rows are gathered
+        gt_rows = mb.render(scene, spp=64, seed=999, albedo=to(case["a2"]), roughness=to(case["r2"]), metallic=to(case["m2"]))
+    gt = torch.zeros(H, W, 3, device=dev)
+    gt[shard.row0:shard.row0 + shard.rows] = gt_rows
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(gt)
+    opt = FusedBRDFOptimizer(scene, {"albedo": to(case["a"]), "roughness": to(case["r"]), "metallic": to(case["m"])}, gt, "arm", spp=spp, shard=shard)
+    steps, warmup = max(2, min(args.steps, 4)), 3
+    t = _timed(lambda s: opt.step(s), steps, warmup, dev, world, seed0=1000)
+    return {"workload": wl["desc"], "scaling": "strong", "image": [H, W], "spp": spp, "envmap": [wl["He"], wl["We"]], "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": t * 1e3, "value": H * W * spp / t / 1e9, "unit": UNIT, "iters_per_s": 1.0 / t,
+            "rows_per_rank": shard.rows, "loss_mse_last": float(opt.last["loss_mse"].item())}
+
+
 # ------------------------------------------------------------------------------------------------ b200 arm
 def run_b200(args, wl):
     import numpy as np
@@ -477,111 +804,23 @@ def run_b200(args, wl):
     for name, a, b in kev:
         ktime.setdefault(name, []).append(a.elapsed_time(b))
     kavg = {k: sum(v) / len(v) for k, v in ktime.items()}
-    dom = max(kavg, key=kavg.get) if kavg else None
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md 6.65 TB/s)"
-    npix_rank = shard.rows * W
-    env_bytes = wl["He"] * (wl["We"] + 1) * 16 + scene.prepared_env()[2].total_floats * 4
-    # bytes one launch of the dominant kernel must move (SURVEY §8d itemisation): bwd 88 B/px, fwd 96 B/px, + envmap + hierarchy once
-    per_px = {"shade_bwd": 88.0, "shade_fwd": 96.0, "mesh_bwd": 88.0 - 32.0, "mesh_fwd": 96.0 - 32.0}.get(dom, 184.0)
-    alg_bytes = npix_rank * per_px + env_bytes
-    if scene.mesh is not None:       # mesh mode: no G-buffer (-32 B/px); sorted triangles (+ normals) and BVH boxes read once
-        alg_bytes += scene.mesh.desc.total_bytes
-    roofline = None
-    if dom:
-        achieved = alg_bytes / (kavg[dom] * 1e-3) / 1e9
-        # DRAM bytes per launch from one `ncu --set full` capture of the C2 workload (profiles/r1c_ncu_summary.txt); other shapes: null
-        ncu_traffic = {"shade_bwd": 23.95e6 + 0.05e6, "shade_fwd": 14.55e6 + 60.95e6}
-        traffic = ncu_traffic.get(dom) if (args.workload == "c2" and world == 1) else None
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": traffic,
-                    "issue_frac_ncu": {"shade_bwd": 0.699, "shade_fwd": 0.727}.get(dom) if scene.mesh is None else None, "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes, "kernel_ms": kavg[dom],
-                    "kernel_share_of_step": kavg[dom] * 1e-3 / t_step,
-                    "note": "at 64-256 spp the fused path is instruction-issue bound, not HBM bound (SURVEY §8d: ~830 FLOP/B): ncu shows issue-active "
-                            "70-73 %, L1 LSU wavefronts 51-72 %, DRAM < 1 % (issue_frac_ncu, profiles/); see also fp32"}
-    # ---- FP32 (non-tensor) peak, measured with an FFMA loop, and the kernel's algorithmic FLOP rate
-    fp32 = None
-    try:
-        buf = torch.zeros(1 << 20, device=dev)
-        fl = _abi.C.c_double(0.0)
-        for _ in range(2):
-            _abi.check(_abi.lib.mb200_probe_ffma(_abi.ptr(buf), 4096, _abi.C.byref(fl), _abi.stream_ptr()), "probe")
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        p0.record()
-        _abi.check(_abi.lib.mb200_probe_ffma(_abi.ptr(buf), 16384, _abi.C.byref(fl), _abi.stream_ptr()), "probe")
-        p1.record(); torch.cuda.synchronize()
-        peak_tf = fl.value / (p0.elapsed_time(p1) * 1e-3) / 1e12
-        flops_sample = {"shade_bwd": 1600.0, "shade_fwd": 800.0, "mesh_bwd": None, "mesh_fwd": None}     # SURVEY §8d estimate (2.4 kFLOP fwd+adjoint)
-        if dom and flops_sample.get(dom, 2400.0) is None:
-            fp32 = {"peak_tflops": peak_tf, "note": "no algorithmic FLOP figure for traced paths (data-dependent traversal length)"}
-        elif dom:
-            ach = npix_rank * spp * flops_sample.get(dom, 2400.0) / (kavg[dom] * 1e-3) / 1e12
-            fp32 = {"achieved_tflops": ach, "peak_tflops": peak_tf, "frac": ach / peak_tf,
-                    "alg_flops_per_sample": flops_sample.get(dom), "peak_source": "measured here: FFMA loop (mb200_probe_ffma)"}
-    except Exception as e:                                            # measurement aid only
-        fp32 = {"error": str(e)}
+    shade = {k: v for k, v in kavg.items() if k != "film_weights"}
+    dom = max(shade, key=shade.get) if shade else None
+    roofline, fp32 = build_roofline(args, wl, scene, shard, dom, kavg, t_step, dev, world)
 
-    # ---- e2e through the public API with HOST buffers (H2D of a/r/m + grad image, D2H of image + gradients)
-    e2e = None
-    if not args.no_e2e:
-        rows = slice(shard.row0, shard.row0 + shard.rows)
-        ha, hr, hm = (case[k].pin_memory() for k in ("a", "r", "m"))
-        himg = torch.empty(shard.rows, W, 3).pin_memory(); hgrad = torch.ones(shard.rows, W, 3).pin_memory()
-        hga, hgr, hgm = torch.empty(H, W, 3).pin_memory(), torch.empty(H, W, 1).pin_memory(), torch.empty(H, W, 1).pin_memory()
-        scene.set_shard(shard.row0, shard.rows)
+    # ---- e2e through the public API with HOST buffers
+    e2e = e2e_op = None
+    if not args.no_e2e and not wl.get("pos_mlp"):
+        e2e = run_e2e_iteration(args, opt, shard, dev, world, samples_per_step)
+        e2e_op = run_e2e_operator(args, case, scene, shard, spp, dev, world, samples_per_step)
 
-        def e2e_step(seed):
-            a = ha.to(dev, non_blocking=True).requires_grad_(True); r = hr.to(dev, non_blocking=True).requires_grad_(True)
-            m = hm.to(dev, non_blocking=True).requires_grad_(True)
-            # render_w_brdf(scene, a, r, m, None, spp) of the reference; mb.render is the same call + the shard halo hook
-            img = mb.render(scene, spp=spp, seed=seed, albedo=a, roughness=r, metallic=m,
-                            halo_exchange=shard.halo_exchange if world > 1 else None)
-            himg.copy_(img.detach(), non_blocking=True)
-            img.backward(hgrad.to(dev, non_blocking=True))
-            hga.copy_(a.grad, non_blocking=True); hgr.copy_(r.grad, non_blocking=True); hgm.copy_(m.grad, non_blocking=True)
-
-        for i in range(max(3, min(3, args.warmup))):
-            e2e_step(i)
-        sync(); e0.record()
-        for i in range(args.steps):
-            e2e_step(2000 + i)
-        e1.record(); sync()
-        te = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        t_serial = float(te.item()) / args.steps / 1e3
-        # the same work with the copies on their own streams (materialist_b200.hostpipe): uploads of step i+1 and downloads of
-        # step i overlap the render kernels; every step still moves its own inputs and outputs across PCIe
-        from materialist_b200.hostpipe import HostPipelinedRenderWBRDF
-        pipe = HostPipelinedRenderWBRDF(scene, spp, halo_exchange=shard.halo_exchange if world > 1 else None)
-        inputs = (ha, hr, hm, hgrad)
-        pipe.stage(0, *inputs)
-        for i in range(3):
-            pipe.step(i, i % 2, himg, hga, hgr, hgm, next_inputs=inputs)
-        pipe.synchronize(); sync(); e0.record()
-        for i in range(args.steps):
-            pipe.step(2000 + i, (3 + i) % 2, himg, hga, hgr, hgm, next_inputs=inputs)
-        torch.cuda.current_stream().wait_event(pipe.last_out)
-        e1.record(); pipe.synchronize(); sync()
-        te = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        t_pipe = float(te.item()) / args.steps / 1e3
-        # two supported call patterns of the same public API; the pipelined one needs a host thread fast enough to keep three
-        # streams fed (it is host-bound on a loaded box), so the better of the two is the end-to-end figure and both are listed
-        t_e = min(t_pipe, t_serial)
-        h2d = (ha.numel() + hr.numel() + hm.numel() + hgrad.numel()) * 4
-        d2h = (himg.numel() + hga.numel() + hgr.numel() + hgm.numel()) * 4
-        e2e = {"value": samples_per_step / t_e / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "ms_per_step": t_e * 1e3, "bytes_are": "per rank", "ms_per_step_copies_serialised": t_serial * 1e3,
-               "ms_per_step_copies_overlapped": t_pipe * 1e3,
-               "what": "render_w_brdf forward + backward through the public API with pinned HOST buffers, every step: H2D a/r/m + d(loss)/d(image), "
-                       "D2H image + material gradients; better of: copies on their own streams (materialist_b200.hostpipe) overlapping the render kernels / copies serialised on the compute stream"}
+    # ---- the north-star scaling target rides along: C5 (4K, 256 spp, 2048x1024 envmap), STRONG scaling, at this N
+    c5 = None
+    if args.workload == "c2" and not args.no_c5:
+        try:
+            c5 = run_c5_leg(args, dev, world, rank)
+        except Exception as e:                                        # never lose the headline line to the rider
+            c5 = {"error": repr(e)}
 
     clk = clocks.stop() if rank == 0 else None
     # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle on a bounded row sample
@@ -601,7 +840,7 @@ def run_b200(args, wl):
                "config": {"workload": wl["desc"], "image": [H, W], "spp": spp, "envmap": [wl["He"], wl["We"]], "filter": "gaussian",
                           "max_depth": 4, "parallelism": f"rows sharded over {world} GPU(s)",
                           "l2": f"no explicit flush: each step streams {(shard.rows * W * (400 + 100 + 32 + 20 + 16 + 12 + 12 + 40)) / 1e6:.0f} MB of inputs + per-step intermediates (film tap partials 400 B/px, weight partials 100 B/px, G-buffer, maps, gradients) per rank; >126 MB L2 for C2/C5. The 0.6 MB envmap + hierarchy is L2/L1-resident by design"},
-               "iters_per_s": 1.0 / t_step, "e2e": e2e, "gpu_launches": (9 if args.optimizer == "fused" else 5) * args.steps,
+               "iters_per_s": 1.0 / t_step, "e2e": e2e, "e2e_operator": e2e_op, "c5_strong": c5, "gpu_launches": (9 if args.optimizer == "fused" else 5) * args.steps,
                "gpu_launches_note": "own kernels per step: " + ("mesh_fwd" if scene.mesh is not None else "shade_fwd") + ", film_develop, film_weights, film_adjoint, "
                                     + ("mesh_bwd" if scene.mesh is not None else "shade_bwd")
                                     + (", image_sum, loss_srgb_sums, loss_srgb_grad, adam_clamped" if args.optimizer == "fused"

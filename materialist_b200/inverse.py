@@ -32,7 +32,16 @@ def brdf_phase_lr(k, lr0=3e-4, step_size=100, gamma=0.8, floor=1.5e-4):
     return lr
 
 
-class DirectBRDFOptimizer:
+class _ShardedStep:
+    """`step(seed)` renders this rank's rows and leaves the Scene's shard as it found it (a Scene is shared between phases and with
+    plain `render(scene)` calls, which must keep seeing the whole image)."""
+
+    def step(self, seed):
+        with self.scene.shard(self.shard.row0, self.shard.rows):
+            return self._step(seed)
+
+
+class DirectBRDFOptimizer(_ShardedStep):
     """`Directly optimizing {a,r,m} without neural network` (inverse_img_w_mi.py:346-446).
 
     mat: dict of full-image CUDA tensors albedo (H,W,3), roughness (H,W,1), metallic (H,W,1);
@@ -42,7 +51,6 @@ class DirectBRDFOptimizer:
     def __init__(self, scene, mat, gt_image, optimize_part="arm", spp=64, lr=3e-4, scale_delta=0.1, shard=None):
         self.scene, self.spp, self.scale_delta, self.part = scene, spp, scale_delta, optimize_part
         self.shard = shard or ShardContext(scene.H, scene.W)
-        scene.set_shard(self.shard.row0, self.shard.rows)
         self.mat = {k: v.detach().clone() for k, v in mat.items()}
         self.ori = {k: v.detach().clone() for k, v in mat.items()}
         self.params = {}
@@ -59,7 +67,7 @@ class DirectBRDFOptimizer:
         self.gt_sum = self.shard.all_reduce_sum(self.gt.sum().reshape(1).clone())
         self.last = {}
 
-    def step(self, seed):
+    def _step(self, seed):
         p, sh, rows = self.params, self.shard, self.rows
         mat = dict(self.mat)
         if "albedo" in p: mat["albedo"] = p["albedo"].clamp(0, 1)
@@ -83,21 +91,33 @@ class DirectBRDFOptimizer:
         scale_ratio = sums[1] / sums[0]                        # loss_l1.detach() / loss_mse.detach()
         loss = 3 * scale_ratio * loss_mse_l + loss_l1_l + aux * self.scale_delta
         loss.backward()
+        if sh.world_size > 1 and self.scene.mesh is not None:
+            # traced scene: a path that starts in this rank's rows reads the maps — and scatters their gradients — at whatever texels
+            # its secondary vertices hit, in any shard: sum the map gradients over the ranks, every rank steps the whole image
+            for q in p.values():
+                sh.all_reduce_sum(q.grad)
         self.opt.step()
         self.opt.zero_grad(set_to_none=True)
+        if sh.world_size > 1 and self.scene.mesh is None:
+            # G-buffer mode: only this rank's rows were stepped; its forward also READS the 2-row film halo of the neighbours'
+            # maps, which they have just stepped -> fetch them (parameters, so that the clamps above apply next iteration)
+            with torch.no_grad():
+                sh.map_halo_exchange([q.data for q in p.values()])
         if self.opt.param_groups[0]["lr"] > 1.5e-4:            # :431-432 (a host-side float, no device read)
             self.sched.step()
         self.last = {"loss_mse": sums[0] / self.n_img, "loss_l1": sums[1] / self.n_img, "pred": pred_srgb}
         return loss.detach()
 
 
-class FusedBRDFOptimizer:
+class FusedBRDFOptimizer(_ShardedStep):
     """Same iteration as DirectBRDFOptimizer (inverse_img_w_mi.py:346-446, `model_name == 'none'`), with everything
     between the two render kernels done by the fused loss / Adam kernels of csrc/mb200_optim.cu instead of ~100
     elementwise torch launches + autograd: 9 kernel launches per iteration, no host sync, scalars stay on the device.
 
     Per iteration: shade_fwd -> film_develop -> image_sum [all-reduce] -> loss_srgb_sums [all-reduce] ->
-    loss_srgb_grad [halo exchange] -> film_weights -> film_adjoint -> shade_bwd -> adam_clamped.
+    loss_srgb_grad [halo exchange of d loss / d image] -> film_adjoint -> shade_bwd -> adam_clamped [halo exchange of the stepped
+    maps]; film_weights (a function of seed_grad alone) runs on a side stream from the end of shade_fwd, under the loss kernels
+    and the collectives.
     """
 
     _RANGE = {"albedo": (0.0, 1.0), "roughness": (0.07, 1.0), "metallic": (0.0, 1.0)}
@@ -109,7 +129,6 @@ class FusedBRDFOptimizer:
         self.scene, self.spp, self.scale_delta, self.part = scene, spp, scale_delta, optimize_part
         self.lr0, self.betas, self.eps = lr, betas, eps
         self.shard = sh = shard or ShardContext(scene.H, scene.W)
-        scene.set_shard(sh.row0, sh.rows)
         dev, H, W = scene.device, scene.H, scene.W
         self.names = [n for n, k in (("albedo", "a"), ("roughness", "r"), ("metallic", "m")) if k in optimize_part]
         # the maps the kernels render with (full image; this rank only ever touches its own rows)
@@ -135,10 +154,11 @@ class FusedBRDFOptimizer:
         self.scal[0:1] = sh.all_reduce_sum(self.gt.sum().reshape(1).clone())
         self.sums2 = torch.zeros(2, device=dev)
         self.scratch = torch.zeros(_abi.lib.mb200_reduce_scratch_bytes() // 4 + 1, dtype=torch.int32, device=dev)
-        self.grad_img = torch.empty(sh.rows, W, 3, device=dev)
+        self.grad_full, self.grad_img = sh.halo_buffer(3, dev)         # d loss / d image: own rows (a view) inside the rows + film-halo buffer
         self.pred_srgb = torch.empty(sh.rows, W, 3, device=dev)
         self.k, self._lr, self._epoch = 0, lr, 0
         self.last = {}
+        self._side, self._wpart = None, None                  # side stream + film-weight buffer of the adjoint render (see _step)
         # Adam segments over this rank's rows (contiguous in the row-major maps).  Mesh mode under sharding: a path that starts in
         # this rank's rows scatters material gradients to whatever texels its secondary vertices hit, and reads the maps there —
         # so the map gradients are summed over the ranks and every rank steps the WHOLE image (replicated state, 5 floats / pixel).
@@ -156,11 +176,25 @@ class FusedBRDFOptimizer:
             segs[i].aux_coeff = scale_delta / (npx * c)
         self.segs = segs
 
-    def step(self, seed):
+    def _step(self, seed):
         sc, sh, lib, st = self.scene, self.shard, _abi.lib, _abi.stream_ptr()
         a, r, m = self.mat["albedo"], self.mat["roughness"], self.mat["metallic"]
         env_pack = sc.prepared_env()
+        seed_grad = _rop.default_seed_grad(int(seed))
         img = _rop._forward(sc, self.spp, int(seed), a, r, m, None, env_pack)
+        # The film weights of the adjoint render depend on nothing but seed_grad: they run on a side stream, UNDER the loss kernels
+        # and — with several ranks — under the latency of the scalar all-reduces and of the halo exchange that sit between the two
+        # render kernels (~30 us each over NVLink, during which this GPU would otherwise idle).
+        main = torch.cuda.current_stream(sc.device)
+        if sc.filter == _abi.FILTER_GAUSSIAN:
+            if self._side is None:
+                self._side = torch.cuda.Stream(sc.device)
+                self._ev_fwd, self._ev_w = torch.cuda.Event(), torch.cuda.Event()
+            self._ev_fwd.record(main)
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(self._ev_fwd)
+                self._wpart = _rop._film_weights(sc, self.spp, seed_grad, env_pack[2].res_x, out=self._wpart)
+                self._ev_w.record(self._side)
         n = img.numel()
         _abi.check(lib.mb200_image_sum(_abi.ptr(img), n, C.c_void_p(self.scal.data_ptr() + 4), _abi.ptr(self.scratch), st), "mb200_image_sum")
         if sh.world_size > 1:
@@ -171,11 +205,13 @@ class FusedBRDFOptimizer:
             sh.all_reduce_sum(self.sums2)
         _abi.check(lib.mb200_loss_srgb_grad(_abi.ptr(img), _abi.ptr(self.gt_srgb), n, _abi.ptr(self.scal), _abi.ptr(self.sums2),
                                             self.n_total, _abi.ptr(self.grad_img), st), "mb200_loss_srgb_grad")
-        grad = sh.halo_exchange(self.grad_img) if sh.world_size > 1 else self.grad_img
+        grad = sh.halo_exchange_inplace(self.grad_full) if sh.world_size > 1 else self.grad_img
         self.gflat.zero_()
-        _rop._backward(sc, self.spp, _rop.default_seed_grad(int(seed)), a, r, m, None, env_pack, grad,
+        if sc.filter == _abi.FILTER_GAUSSIAN:
+            main.wait_event(self._ev_w)
+        _rop._backward(sc, self.spp, seed_grad, a, r, m, None, env_pack, grad,
                        "albedo" in self.names, "roughness" in self.names, "metallic" in self.names, False, False,
-                       out=(self.grads["albedo"], self.grads["roughness"], self.grads["metallic"]))
+                       out=(self.grads["albedo"], self.grads["roughness"], self.grads["metallic"]), wpart=self._wpart)
         if self.replicated:
             sh.all_reduce_sum(self.gflat)
         self.k += 1
@@ -186,11 +222,15 @@ class FusedBRDFOptimizer:
                 self._lr *= 0.8
         _abi.check(lib.mb200_adam_clamped(self.segs, len(self.names), lr, self.betas[0], self.betas[1], self.eps, self.k, st),
                    "mb200_adam_clamped")
+        if sh.world_size > 1 and not self.replicated:
+            # only this rank's rows were stepped; its next forward READS the neighbours' maps in the 2-row film halo, and they have
+            # just stepped those rows: fetch them (without this the sharded run drifts from the single-GPU run after iteration 1)
+            sh.map_halo_exchange([self.mat[k] for k in self.names])
         self.last = {"loss_mse": self.sums2[0] / self.n_total, "loss_l1": self.sums2[1] / self.n_total, "pred": self.pred_srgb}
         return self.last["loss_mse"]
 
 
-class PosMLPBRDFOptimizer:
+class PosMLPBRDFOptimizer(_ShardedStep):
     """BRDF phase with `model_name == 'pos_mlp'` (inverse_img_w_mi.py:471-552): the maps are the output of `brdf_net`
     (PosMLP on the tensor cores, mymodels/mlps.py) applied to the initial estimate `start_arm`; the network weights are
     optimised with AdamW(lr=3e-4) + the guarded StepLR(100, 0.8).
@@ -204,7 +244,6 @@ class PosMLPBRDFOptimizer:
         from .mymodels.mlps import PosMLP
         self.scene, self.spp, self.scale_delta, self.part = scene, spp, scale_delta, optimize_part
         self.shard = sh = shard or ShardContext(scene.H, scene.W)
-        scene.set_shard(sh.row0, sh.rows)
         dev, H, W = scene.device, scene.H, scene.W
         self.net = net if net is not None else PosMLP(in_dims=7, out_dims=5, dims=[256] * 4, skip_connection=[1, 3], weight_norm=False,
                                                       multires_view=2, output_type="arm", color_ch=5).to(dev)   # :163
@@ -238,7 +277,7 @@ class PosMLPBRDFOptimizer:
                     mat[key] = torch.cat([self.mat[key][:e0], val.reshape(e1 - e0, W, c), self.mat[key][e1:]], 0)
         return mat
 
-    def step(self, seed):
+    def _step(self, seed):
         sh = self.shard
         mat = self._maps()
         pred = render(self.scene, spp=self.spp, seed=seed, albedo=mat["albedo"], roughness=mat["roughness"], metallic=mat["metallic"],
@@ -288,7 +327,7 @@ class _SumGradOverRanks(torch.autograd.Function):
         return g, None
 
 
-class EnvmapNetOptimizer:
+class EnvmapNetOptimizer(_ShardedStep):
     """Envmap phase exactly as the reference runs it (inverse_img_w_mi.py:117-124, :222-256): `envmap_net` = PosMLP(in_dims=5,
     out_dims=3, 'envmap') applied to a constant all-ones (env_h*env_w, 3) input gives the (16, 32, 3) envmap that
     `render_envmap` shades with; loss = mse + l1 in sRGB; Adam(lr=1e-3) + StepLR(100, 0.8) in the first outer loop.
@@ -299,7 +338,6 @@ class EnvmapNetOptimizer:
         from .mymodels.mlps import PosMLP
         self.scene, self.spp, self.env_h, self.env_w = scene, spp, env_h, env_w
         self.shard = shard or ShardContext(scene.H, scene.W)
-        scene.set_shard(self.shard.row0, self.shard.rows)
         dev = scene.device
         self.net = net if net is not None else PosMLP(in_dims=5, out_dims=3, dims=[256] * 4, skip_connection=[1, 3], weight_norm=False,
                                                       multires_view=2, output_type="envmap", color_ch=3).to(dev)      # :117-124
@@ -311,7 +349,7 @@ class EnvmapNetOptimizer:
         self.n_img = float(scene.H * scene.W * 3)
         self.last = {}
 
-    def step(self, seed):
+    def _step(self, seed):
         sh = self.shard
         envmap_pred = self.net(self.start_envmap, hw=(self.env_h, self.env_w)).reshape(self.env_h, self.env_w, 3)           # :238-239
         env = _SumGradOverRanks.apply(envmap_pred, sh) if sh.world_size > 1 else envmap_pred
@@ -326,7 +364,7 @@ class EnvmapNetOptimizer:
         return loss.detach()
 
 
-class EnvmapOptimizer:
+class EnvmapOptimizer(_ShardedStep):
     """Envmap phase (inverse_img_w_mi.py:237-256) with the envmap texels as direct parameters (the reference
     drives them through `envmap_net`; see mymodels/mlps.py for that module).  Gradients of the envmap are summed
     over ranks once per iteration."""
@@ -334,14 +372,13 @@ class EnvmapOptimizer:
     def __init__(self, scene, env_init, gt_image, spp=64, lr=1e-3, shard=None):
         self.scene, self.spp = scene, spp
         self.shard = shard or ShardContext(scene.H, scene.W)
-        scene.set_shard(self.shard.row0, self.shard.rows)
         self.env = torch.nn.Parameter(env_init.detach().clone())
         self.opt = torch.optim.Adam([self.env], lr=lr)
         self.rows = slice(self.shard.row0, self.shard.row0 + self.shard.rows)
         self.gt_srgb = linear_to_srgb(gt_image[self.rows].contiguous())
         self.n_img = float(scene.H * scene.W * 3)
 
-    def step(self, seed):
+    def _step(self, seed):
         sh = self.shard
         env = NF.softplus(self.env)
         pred = render(self.scene, spp=self.spp, seed=seed, envmap=env,

@@ -112,9 +112,26 @@ def _forward(scene, spp, seed, a, r, m, n, env_pack, extra_flags=0):
     return img
 
 
-def _backward(scene, spp, seed_grad, a, r, m, n, env_pack, grad_img_halo, want_a, want_r, want_m, want_n, want_env, out=None):
+def _film_weights(scene, spp, seed_grad, env_res_x, out=None):
+    """Film-weight taps of the seed_grad render (needs nothing but the seed: callers may run it on a side stream while the loss
+    of the forward image is still being reduced).  Returns the (wrows, W, 25) buffer, or None for the box filter."""
+    cfg = scene.make_cfg(spp, seed_grad, env_res_x)
+    if cfg.filter != _abi.FILTER_GAUSSIAN:
+        return None
+    first = C.c_int(0)
+    wrows = _abi.lib.mb200_bwd_wpart_rows(C.byref(cfg), C.byref(first))
+    wpart = out if out is not None else torch.empty(wrows, scene.W, _abi.FILM_TAPS, device=scene.device)
+    if tuple(wpart.shape) != (wrows, scene.W, _abi.FILM_TAPS):
+        raise ValueError("film-weight buffer has the wrong shape")
+    with _ktime("film_weights"):
+        _abi.check(_abi.lib.mb200_film_weights(C.byref(cfg), _abi.ptr(wpart), _abi.stream_ptr()), "mb200_film_weights")
+    return wpart
+
+
+def _backward(scene, spp, seed_grad, a, r, m, n, env_pack, grad_img_halo, want_a, want_r, want_m, want_n, want_env, out=None, wpart=None):
     """grad_img_halo: (gadj_rows, W, 3) — gradient w.r.t. the image for the shard rows plus the film halo.
-    out: optional pre-zeroed (g_a, g_r, g_m) full-image buffers to accumulate into (fused optimiser path)."""
+    out: optional pre-zeroed (g_a, g_r, g_m) full-image buffers to accumulate into (fused optimiser path).
+    wpart: film weights of this seed_grad render if the caller already computed them (_film_weights)."""
     env4, hier, desc, He, We, mode = env_pack
     cfg = scene.make_cfg(spp, seed_grad, desc.res_x)
     st = _abi.stream_ptr()
@@ -124,11 +141,8 @@ def _backward(scene, spp, seed_grad, a, r, m, n, env_pack, grad_img_halo, want_a
     if tuple(grad_img_halo.shape) != (grows, scene.W, 3):
         raise ValueError(f"grad image (with film halo) must be {(grows, scene.W, 3)}, got {tuple(grad_img_halo.shape)}")
     grad_img_halo = grad_img_halo.contiguous().float()
-    wpart = None
-    if cfg.filter == _abi.FILTER_GAUSSIAN:
-        wrows = _abi.lib.mb200_bwd_wpart_rows(C.byref(cfg), C.byref(first))
-        wpart = torch.empty(wrows, scene.W, _abi.FILM_TAPS, device=dev)
-        _abi.check(_abi.lib.mb200_film_weights(C.byref(cfg), _abi.ptr(wpart), st), "mb200_film_weights")
+    if cfg.filter == _abi.FILTER_GAUSSIAN and wpart is None:
+        wpart = _film_weights(scene, spp, seed_grad, desc.res_x)
     gadj = torch.empty(grows, scene.W, 4, device=dev)
     _abi.check(_abi.lib.mb200_film_adjoint(C.byref(cfg), _abi.ptr(wpart), _abi.ptr(grad_img_halo), _abi.ptr(gadj), st), "mb200_film_adjoint")
     H, W = scene.H, scene.W

@@ -123,6 +123,22 @@ class Scene:
             raise ValueError("shard rows out of range")
         self.row0, self.rows = int(row0), int(rows)
 
+    def shard(self, row0, rows):
+        """Context manager: render rows [row0, row0 + rows) inside the block, restore the previous shard on exit (the optimisers
+        use it per step, so a Scene shared between phases is never left sharded)."""
+        scene = self
+
+        class _Shard:
+            def __enter__(self_):
+                self_.prev = (scene.row0, scene.rows)
+                scene.set_shard(row0, rows)
+                return scene
+
+            def __exit__(self_, *exc):
+                scene.row0, scene.rows = self_.prev
+                return False
+        return _Shard()
+
     # ---------------------------------------------------------------- envmap
     def set_envmap(self, env, mode):
         """env: (He, We, 3). mode ENV_FILE = bitmap loaded from file (column appended), ENV_ASSIGNED = tensor

@@ -1064,6 +1064,13 @@ int mbo_render_bwd(const mb200_cfg* c, const float* gpos, const float* gnrm, con
     return MB200_OK;
 }
 
+#ifdef _OPENMP
+#include <omp.h>
+int mbo_omp_max_threads(void) { return omp_get_max_threads(); }
+#else
+int mbo_omp_max_threads(void) { return 1; }
+#endif
+
 int mbo_is_double(void) {
 #ifdef MBO_DOUBLE
     return 1;

@@ -4,7 +4,7 @@ import torch
 
 from oracle import oracle as orc
 from materialist_b200 import synthetic
-from materialist_b200.scene import Camera
+from materialist_b200.camera import Camera
 
 REF_FLAGS = orc.FLAG_WO_WORLD_QUIRK | orc.FLAG_ROW_STRIDE_H | orc.FLAG_ENV_HALF_TEXEL
 

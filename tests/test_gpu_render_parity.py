@@ -160,6 +160,37 @@ def test_host_pipelined_front_end_equals_direct_calls():
             assert rel_l2(got.numpy(), ref.cpu().numpy()) < 1e-5          # float atomics: order-dependent in the last bits
 
 
+def test_host_pipelined_front_end_row_shard():
+    """With a row shard the pipe moves only the shard's rows (+ the 2-row film halo of the maps): same image rows and gradients as
+    the direct sharded call with whole maps."""
+    import materialist_b200 as mb
+    from materialist_b200.hostpipe import HostPipelinedRenderWBRDF
+    c = Case(H=40, W=40, spp=32, He=16, We=32, gaussian=True)
+    s = c.scene()
+    row0, rows = 13, 14
+    a, r, m = (torch.from_numpy(x) for x in (c.a, c.r, c.m))
+    g = torch.from_numpy(np.random.RandomState(3).randn(rows, c.W, 3).astype(np.float32))
+    # stand-in for ShardContext.halo_exchange in one process: the neighbours' image-gradient rows are zero
+    halo = lambda gr: torch.cat([torch.zeros_like(gr[:2]), gr, torch.zeros_like(gr[:2])], 0)
+    with s.shard(row0, rows):
+        pipe = HostPipelinedRenderWBRDF(s, c.spp, halo_exchange=halo)
+        (m0, m1), (o0, o1) = pipe.map_rows, pipe.out_rows
+        assert (m0, m1) == (row0 - 2, row0 + rows + 2) and (o0, o1) == (row0, row0 + rows)
+        ins = tuple(t[m0:m1].contiguous().pin_memory() for t in (a, r, m)) + (g.pin_memory(),)
+        outs = tuple(torch.empty(*sh).pin_memory() for sh in ((rows, c.W, 3), (rows, c.W, 3), (rows, c.W, 1), (rows, c.W, 1)))
+        pipe.stage(0, *ins)
+        pipe.step(77, 0, *outs)
+        pipe.synchronize()
+        da, dr, dm = (t.cuda().requires_grad_(True) for t in (a, r, m))
+        img = mb.render(s, spp=c.spp, seed=77, albedo=da, roughness=dr, metallic=dm, halo_exchange=halo)
+        img.backward(g.cuda())
+    assert (s.row0, s.rows) == (0, c.H)
+    assert torch.equal(outs[0], img.detach().cpu())
+    for got, ref in zip(outs[1:], (da.grad, dr.grad, dm.grad)):
+        assert rel_l2(got.numpy(), ref[row0:row0 + rows].cpu().numpy()) < 1e-5
+        assert float(ref[:row0].abs().sum() + ref[row0 + rows:].abs().sum()) == 0.0      # G-buffer mode: gradients stay in the shard's rows
+
+
 def test_no_cpu_fallback():
     import materialist_b200 as mb
     c = Case(H=8, W=8, spp=4, He=8, We=16)

@@ -4,7 +4,7 @@ import pytest
 
 from oracle import oracle as orc
 from materialist_b200 import synthetic
-from materialist_b200.scene import Camera
+from materialist_b200.camera import Camera
 from test_reference_render_pin import pin_cfg, rel_l2
 
 

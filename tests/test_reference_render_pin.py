@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as orc
-from materialist_b200.scene import Camera
+from materialist_b200.camera import Camera
 
 FIX = os.path.join(os.path.dirname(__file__), "golden", "indoor_pin.npz")
 REF_FLAGS = orc.FLAG_WO_WORLD_QUIRK | orc.FLAG_ROW_STRIDE_H | orc.FLAG_ENV_HALF_TEXEL

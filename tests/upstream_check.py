@@ -108,6 +108,34 @@ def _write_ply(path, verts, tris):
             f.write(struct.pack("<B3I", 3, *[int(i) for i in t]))
 
 
+def build_reference_scene(mi, dr, mp, ref, He=16, We=32, tmpdir=None):
+    """The reference's scene dict (inverse_img_w_mi.py:40-56) around a synthetic 512 x 512 height-field PLY, with its own MatDiffBSDF
+    plugin and differentiable a / r / m leaves attached.  Also used by bench.py's guarded mitsuba reference arm."""
+    import tempfile
+    from materialist_b200 import synthetic
+    from materialist_b200.camera import Camera
+    H = W = 512
+    cam = Camera(width=W, height=H)
+    verts, tris = synthetic.grid_mesh(synthetic.bumpy_positions(H, W, cam))
+    ply = os.path.join(tmpdir or tempfile.mkdtemp(), "scene.ply"); _write_ply(ply, verts, tris)
+    env = synthetic.envmap(He, We, seed=4).numpy()
+    scene = mi.load_dict({
+        "type": "scene", "integrator": {"type": "path", "max_depth": 4},
+        "sensor": {"type": "perspective", "fov": 35, "to_world": mi.ScalarTransform4f(cam.to_world.tolist()),
+                   "film": {"type": "hdrfilm", "width": W, "height": H}},
+        "emitter": {"type": "envmap", "bitmap": mi.Bitmap(env)},
+        "shape": {"type": "ply", "filename": ply, "bsdf": {"type": "MatDiffBSDF", "cam_meta": os.path.join(ref, "myutils", "default_cam.json"),
+                                                            "use_mesh_normal": True}}})
+    a, r, m = (t.numpy() for t in synthetic.materials(H, W, seed_base=1))
+    params = mi.traverse(scene)
+    leaves = [mi.TensorXf(a), mi.TensorXf(r), mi.TensorXf(m)]
+    for t in leaves:
+        dr.enable_grad(t)
+    params["shape.bsdf.a"], params["shape.bsdf.r"], params["shape.bsdf.m"] = leaves
+    params.update()
+    return scene, params, leaves
+
+
 def test_render_and_backward_against_mitsuba(O, tmp_path):
     """32 x 32 height-field scene through the reference's own scene dict + MatDiffBSDF plugin, forward and dr.backward."""
     if not os.path.isdir(REF):
@@ -116,7 +144,7 @@ def test_render_and_backward_against_mitsuba(O, tmp_path):
     import myutils.mi_plugin as mp                                   # registers nothing by itself
     mi.register_bsdf("MatDiffBSDF", lambda props: mp.MatDiffBSDF(props))
     from materialist_b200 import synthetic
-    from materialist_b200.scene import Camera
+    from materialist_b200.camera import Camera
     H = W = 512                                                      # the plugin hard-codes 512 x 512 maps (mi_plugin.py:1238-1241)
     cam = Camera(width=W, height=H)
     verts, tris = synthetic.grid_mesh(synthetic.bumpy_positions(H, W, cam))

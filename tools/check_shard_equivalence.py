@@ -3,6 +3,8 @@
 Row sharding must reproduce the 1-GPU run:
   * mesh mode, FusedBRDFOptimizer: paths cross shard borders at their secondary vertices -> the map gradients are all-reduced
     and every rank steps the whole image;
+  * G-buffer mode, FusedBRDFOptimizer / DirectBRDFOptimizer: a rank steps its own rows; its forward reads the neighbours' maps in the
+    2-row film halo, so the stepped boundary rows are exchanged after every iteration (ShardContext.map_halo_exchange);
   * G-buffer mode, PosMLPBRDFOptimizer (model_name=pos_mlp): every rank evaluates brdf_net on its own rows + film halo only
     (PosMLP row0), weight gradients summed over the ranks."""
 import os
@@ -15,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import materialist_b200 as mb  # noqa: E402
 from materialist_b200 import synthetic  # noqa: E402
-from materialist_b200.inverse import FusedBRDFOptimizer, PosMLPBRDFOptimizer  # noqa: E402
+from materialist_b200.inverse import DirectBRDFOptimizer, FusedBRDFOptimizer, PosMLPBRDFOptimizer  # noqa: E402
 from materialist_b200.parallel import ShardContext  # noqa: E402
 
 
@@ -32,6 +34,22 @@ def run(dev, shard, K=3, H=64, W=64, spp=32):
     for k in range(K):
         opt.step(100 + k)
     return {k: v.clone() for k, v in opt.mat.items()}, shard
+
+
+def run_gbuffer(dev, shard, cls, K=5, H=64, W=64, spp=32):
+    """G-buffer mode with the maps as direct parameters: returns this rank's OWN rows of the optimised maps."""
+    cam = mb.Camera(width=W, height=H)
+    pos, nrm, valid = synthetic.gbuffer(H, W, cam)
+    scene = mb.Scene(pos, nrm, valid, camera=cam, envmap=synthetic.envmap(16, 32, seed=4), device=dev)
+    a, r, m = (t.to(dev) for t in synthetic.materials(H, W, seed_base=1))
+    a2, r2, m2 = (t.to(dev) for t in synthetic.materials(H, W, seed_base=5))
+    gt = mb.render(scene, spp=spp, seed=999, albedo=a2, roughness=r2, metallic=m2)
+    opt = cls(scene, {"albedo": a, "roughness": r, "metallic": m}, gt, "arm", spp=spp, lr=0.02, shard=shard)
+    for k in range(K):
+        opt.step(100 + k)
+    assert (scene.row0, scene.rows) == (0, H)                 # the optimiser leaves the scene unsharded
+    maps = opt.mat if cls is FusedBRDFOptimizer else {k: v.detach() for k, v in opt.params.items()}
+    return {k: v.clone() for k, v in maps.items()}
 
 
 def run_posmlp(dev, shard, K=3, H=64, W=64, spp=32):
@@ -63,6 +81,16 @@ def main():
         d = float((sharded[k] - single[k]).norm() / single[k].norm())
         print(f"rank {rank} {k}: max |sharded - single| = {e:.3e}, rel-L2 {d:.3e}", flush=True)
         ok &= d < 1e-5
+    for cls in (FusedBRDFOptimizer, DirectBRDFOptimizer):
+        shc = ShardContext(64, 64, rank, world)
+        sharded = run_gbuffer(dev, shc, cls)
+        single = run_gbuffer(dev, ShardContext(64, 64, 0, 1), cls)
+        rows = slice(shc.row0, shc.row0 + shc.rows)
+        for k in sharded:
+            d = float((sharded[k][rows] - single[k][rows]).norm() / single[k][rows].norm())
+            lim = 1e-5
+            print(f"rank {rank} G-buffer {cls.__name__} {k}: own rows rel-L2 sharded vs single {d:.3e}", flush=True)
+            ok &= d < lim
     sharded, _ = run_posmlp(dev, ShardContext(64, 64, rank, world))
     single, _ = run_posmlp(dev, ShardContext(64, 64, 0, 1))
     d = float((sharded["params"] - single["params"]).norm() / single["params"].norm())
@@ -74,7 +102,7 @@ def main():
     if not ok:
         raise SystemExit("a sharded optimisation differs from the single-GPU run")
     if rank == 0:
-        print("OK: 2-rank mesh-mode and pos_mlp optimisations == 1-GPU runs")
+        print("OK: 2-rank mesh-mode, G-buffer (fused / direct) and pos_mlp optimisations == 1-GPU runs")
 
 
 if __name__ == "__main__":

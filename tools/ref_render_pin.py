@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
 from oracle import oracle as orc  # noqa: E402
-from materialist_b200.scene import Camera  # noqa: E402  (host-side camera maths only; no GPU needed)
+from materialist_b200.camera import Camera  # noqa: E402  (host-side camera maths only; no GPU needed)
 
 
 def read_ply(path):
