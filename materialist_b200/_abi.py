@@ -154,17 +154,26 @@ def check(rc, what=""):
         raise MB200Error(f"{what}: {msg} (rc={rc})")
 
 
-def ptr(t):
-    """Device pointer of a contiguous CUDA tensor (None -> NULL). Raises on CPU tensors: no fallback."""
+def ptr(t, dtype=None):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL). Raises on CPU tensors: no fallback.
+    dtype: when given, the tensor must have exactly this dtype (the kernels reinterpret nothing)."""
     if t is None:
         return None
     if not isinstance(t, torch.Tensor):
         raise TypeError(f"expected a torch.Tensor, got {type(t)}")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"expected a {dtype} tensor, got {t.dtype}")
     if not t.is_cuda:
         raise ValueError("materialist_b200 runs on CUDA tensors only (no CPU fallback); got a CPU tensor")
     if not t.is_contiguous():
         raise ValueError("tensor must be contiguous")
     return C.c_void_p(t.data_ptr())
+
+
+def fptr(t):
+    """ptr() for the float32 buffers of the render / optimiser entry points (user tensors arrive here: a float64 or half map
+    would otherwise be reinterpreted bit-wise by a float* kernel)."""
+    return ptr(t, torch.float32)
 
 
 def stream_ptr():

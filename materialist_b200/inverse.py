@@ -57,6 +57,15 @@ class DirectBRDFOptimizer(_ShardedStep):
         if "a" in optimize_part: self.params["albedo"] = torch.nn.Parameter(mat["albedo"].clone())
         if "r" in optimize_part: self.params["roughness"] = torch.nn.Parameter(mat["roughness"].clone())
         if "m" in optimize_part: self.params["metallic"] = torch.nn.Parameter(mat["metallic"].clone())
+        self.normal_ori = None
+        if not scene.use_mesh_normal:                          # :356-357: the normal map is a parameter only with 'n' in the part
+            if "normal" not in mat:
+                raise ValueError("use_mesh_normal=False needs mat['normal'] (H, W, 3)")
+            self.normal_ori = NF.normalize(mat["normal"].detach(), p=2, dim=-1)            # :196
+            if "n" in optimize_part:
+                if scene.mesh is not None and self.shard.world_size > 1:
+                    raise NotImplementedError("'n' with a traced scene under sharding is not supported")
+                self.params["normal"] = torch.nn.Parameter(mat["normal"].clone())
         self.opt = torch.optim.Adam(self.params.values(), lr=lr)
         self.sched = torch.optim.lr_scheduler.StepLR(self.opt, step_size=100, gamma=0.8)
         r0, r1 = self.shard.row0, self.shard.row0 + self.shard.rows
@@ -73,8 +82,11 @@ class DirectBRDFOptimizer(_ShardedStep):
         if "albedo" in p: mat["albedo"] = p["albedo"].clamp(0, 1)
         if "roughness" in p: mat["roughness"] = p["roughness"].clamp(0.07, 1)
         if "metallic" in p: mat["metallic"] = p["metallic"].clamp(0, 1)
+        normal = None
+        if not self.scene.use_mesh_normal:                     # :375-376, :384
+            normal = NF.normalize(p["normal"], p=2, dim=-1) if "normal" in p else mat["normal"]
         pred = render(self.scene, spp=self.spp, seed=seed, albedo=mat["albedo"], roughness=mat["roughness"],
-                      metallic=mat["metallic"], halo_exchange=sh.halo_exchange if sh.world_size > 1 else None)
+                      metallic=mat["metallic"], normal=normal, halo_exchange=sh.halo_exchange if sh.world_size > 1 else None)
         # ratio = gt.mean() / pred.detach().mean()  — a GLOBAL scalar over all pixels (:388-389)
         pred_sum = sh.all_reduce_sum(pred.detach().sum().reshape(1))
         pred = pred * (self.gt_sum / pred_sum)
@@ -88,6 +100,7 @@ class DirectBRDFOptimizer(_ShardedStep):
         if "albedo" in p: aux = aux + (mat["albedo"][rows] - self.ori["albedo"][rows]).abs().sum() / (npx * 3)
         if "roughness" in p: aux = aux + (mat["roughness"][rows] - self.ori["roughness"][rows]).abs().sum() / npx
         if "metallic" in p: aux = aux + (mat["metallic"][rows] - self.ori["metallic"][rows]).abs().sum() / npx
+        if "normal" in p: aux = aux + (normal[rows] - self.normal_ori[rows]).abs().sum() / (npx * 3)      # :407-408
         scale_ratio = sums[1] / sums[0]                        # loss_l1.detach() / loss_mse.detach()
         loss = 3 * scale_ratio * loss_mse_l + loss_l1_l + aux * self.scale_delta
         loss.backward()
@@ -124,19 +137,17 @@ class FusedBRDFOptimizer(_ShardedStep):
 
     def __init__(self, scene, mat, gt_image, optimize_part="arm", spp=64, lr=3e-4, scale_delta=0.1, shard=None,
                  betas=(0.9, 0.999), eps=1e-8):
-        if not scene.use_mesh_normal:
-            raise ValueError("FusedBRDFOptimizer covers the use_mesh_normal=True schedule (a/r/m); use DirectBRDFOptimizer for 'n'")
         self.scene, self.spp, self.scale_delta, self.part = scene, spp, scale_delta, optimize_part
         self.lr0, self.betas, self.eps = lr, betas, eps
         self.shard = sh = shard or ShardContext(scene.H, scene.W)
         dev, H, W = scene.device, scene.H, scene.W
         self.names = [n for n, k in (("albedo", "a"), ("roughness", "r"), ("metallic", "m")) if k in optimize_part]
         # the maps the kernels render with (full image; this rank only ever touches its own rows)
-        self.mat = {k: mat[k].detach().clone().contiguous() for k in ("albedo", "roughness", "metallic")}
+        self.mat = {k: mat[k].detach().float().clone().contiguous() for k in ("albedo", "roughness", "metallic")}
         for k in self.names:
             self.mat[k].clamp_(*self._RANGE[k])
-        self.ori = {k: mat[k].detach().clone().contiguous() for k in self.names}
-        self.params = {k: mat[k].detach().clone().contiguous() for k in self.names}
+        self.ori = {k: mat[k].detach().float().clone().contiguous() for k in self.names}
+        self.params = {k: mat[k].detach().float().clone().contiguous() for k in self.names}
         ch = {"albedo": 3, "roughness": 1, "metallic": 1}
         # one flat gradient buffer (one memset per iteration) and one flat Adam state
         sizes = [H * W * ch[k] for k in ("albedo", "roughness", "metallic")]
@@ -146,7 +157,7 @@ class FusedBRDFOptimizer(_ShardedStep):
         self.exp_avg = {k: torch.zeros_like(self.params[k]) for k in self.names}
         self.exp_avg_sq = {k: torch.zeros_like(self.params[k]) for k in self.names}
         self.rows = slice(sh.row0, sh.row0 + sh.rows)
-        self.gt = gt_image[self.rows].contiguous()
+        self.gt = gt_image[self.rows].float().contiguous()
         self.gt_srgb = linear_to_srgb(self.gt)
         self.n_total = H * W * 3
         # device scalars: scal = (Σ gt, Σ pred), sums2 = (Σ diff², Σ |diff|)
@@ -159,6 +170,22 @@ class FusedBRDFOptimizer(_ShardedStep):
         self.k, self._lr, self._epoch = 0, lr, 0
         self.last = {}
         self._side, self._wpart = None, None                  # side stream + film-weight buffer of the adjoint render (see _step)
+        # Normal map (use_mesh_normal False, inverse_img_w_mi.py:356-357, :375-376, :384, :407-410): rendered with mat['normal']; with
+        # 'n' in optimize_part the PARAMETER is the un-normalised map, the kernels see normalize(p), and the aux term is
+        # l1(normalize(p), normal_ori).  The a / r / m part stays in the fused kernels; the normal's chain rule through the
+        # normalisation and its Adam step are a handful of elementwise torch ops on one (H, W, 3) tensor.
+        self.normal = self.normal_ori = self.n_param = self.n_opt = None
+        if not scene.use_mesh_normal:
+            if "normal" not in mat:
+                raise ValueError("use_mesh_normal=False needs mat['normal'] (H, W, 3)")
+            self.normal = mat["normal"].detach().float().clone().contiguous()
+            if "n" in optimize_part:
+                if scene.mesh is not None and sh.world_size > 1:
+                    raise NotImplementedError("'n' with a traced scene under sharding: use DirectBRDFOptimizer")
+                self.normal_ori = NF.normalize(self.normal, p=2, dim=-1)
+                self.n_param = torch.nn.Parameter(self.normal.clone())
+                self.n_opt = torch.optim.Adam([self.n_param], lr=lr, betas=betas, eps=eps)
+                self.normal = NF.normalize(self.n_param.detach(), p=2, dim=-1).contiguous()
         # Adam segments over this rank's rows (contiguous in the row-major maps).  Mesh mode under sharding: a path that starts in
         # this rank's rows scatters material gradients to whatever texels its secondary vertices hit, and reads the maps there —
         # so the map gradients are summed over the ranks and every rank steps the WHOLE image (replicated state, 5 floats / pixel).
@@ -181,7 +208,8 @@ class FusedBRDFOptimizer(_ShardedStep):
         a, r, m = self.mat["albedo"], self.mat["roughness"], self.mat["metallic"]
         env_pack = sc.prepared_env()
         seed_grad = _rop.default_seed_grad(int(seed))
-        img = _rop._forward(sc, self.spp, int(seed), a, r, m, None, env_pack)
+        nmap = self.normal
+        img = _rop._forward(sc, self.spp, int(seed), a, r, m, nmap, env_pack)
         # The film weights of the adjoint render depend on nothing but seed_grad: they run on a side stream, UNDER the loss kernels
         # and — with several ranks — under the latency of the scalar all-reduces and of the halo exchange that sit between the two
         # render kernels (~30 us each over NVLink, during which this GPU would otherwise idle).
@@ -209,11 +237,21 @@ class FusedBRDFOptimizer(_ShardedStep):
         self.gflat.zero_()
         if sc.filter == _abi.FILTER_GAUSSIAN:
             main.wait_event(self._ev_w)
-        _rop._backward(sc, self.spp, seed_grad, a, r, m, None, env_pack, grad,
-                       "albedo" in self.names, "roughness" in self.names, "metallic" in self.names, False, False,
-                       out=(self.grads["albedo"], self.grads["roughness"], self.grads["metallic"]), wpart=self._wpart)
+        g = _rop._backward(sc, self.spp, seed_grad, a, r, m, nmap, env_pack, grad,
+                           "albedo" in self.names, "roughness" in self.names, "metallic" in self.names, self.n_param is not None, False,
+                           out=(self.grads["albedo"], self.grads["roughness"], self.grads["metallic"]), wpart=self._wpart)
         if self.replicated:
             sh.all_reduce_sum(self.gflat)
+        if self.n_param is not None:
+            # d loss / d p through n = p / |p|, with the aux term scale_delta * l1(n, n_ori) (mean over H*W*3) added on n first
+            rows = self.rows
+            gn = g[3][rows] + (self.scale_delta / float(sc.H * sc.W * 3)) * torch.sign(self.normal[rows] - self.normal_ori[rows])
+            p = self.n_param.data[rows]
+            inv = 1.0 / p.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+            nn_ = p * inv
+            gp = torch.zeros_like(self.n_param.data)
+            gp[rows] = (gn - nn_ * (nn_ * gn).sum(-1, keepdim=True)) * inv
+            self.n_param.grad = gp
         self.k += 1
         lr = self._lr
         if self._lr > 1.5e-4:                                  # StepLR(100, 0.8), advanced only above the floor (:431-432)
@@ -222,10 +260,15 @@ class FusedBRDFOptimizer(_ShardedStep):
                 self._lr *= 0.8
         _abi.check(lib.mb200_adam_clamped(self.segs, len(self.names), lr, self.betas[0], self.betas[1], self.eps, self.k, st),
                    "mb200_adam_clamped")
+        if self.n_param is not None:
+            for gr_ in self.n_opt.param_groups:
+                gr_["lr"] = lr
+            self.n_opt.step()
+            self.normal = NF.normalize(self.n_param.detach(), p=2, dim=-1).contiguous()
         if sh.world_size > 1 and not self.replicated:
             # only this rank's rows were stepped; its next forward READS the neighbours' maps in the 2-row film halo, and they have
             # just stepped those rows: fetch them (without this the sharded run drifts from the single-GPU run after iteration 1)
-            sh.map_halo_exchange([self.mat[k] for k in self.names])
+            sh.map_halo_exchange([self.mat[k] for k in self.names] + ([self.normal] if self.n_param is not None else []))
         self.last = {"loss_mse": self.sums2[0] / self.n_total, "loss_l1": self.sums2[1] / self.n_total, "pred": self.pred_srgb}
         return self.last["loss_mse"]
 

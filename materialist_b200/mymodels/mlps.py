@@ -56,7 +56,7 @@ class _PosMLPFn(torch.autograd.Function):
             cache = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=img.device)
         wbytes = _abi.lib.mb200_posmlp_workspace_bytes(C.byref(desc))
         work = torch.empty((wbytes + 3) // 4, dtype=torch.float32, device=img.device) if wbytes else None
-        _abi.check(_abi.lib.mb200_posmlp_fwd(C.byref(desc), _abi.ptr(flat), _abi.ptr(img), N, _abi.ptr(out), _abi.ptr(cache),
+        _abi.check(_abi.lib.mb200_posmlp_fwd(C.byref(desc), _abi.fptr(flat), _abi.fptr(img), N, _abi.fptr(out), _abi.ptr(cache),
                                              _abi.ptr(work), _abi.stream_ptr()), "mb200_posmlp_fwd")
         ctx.desc, ctx.cache, ctx.N, ctx.work = desc, cache, N, work
         ctx.save_for_backward(img, flat)
@@ -67,7 +67,7 @@ class _PosMLPFn(torch.autograd.Function):
         img, flat = ctx.saved_tensors
         g_flat = torch.zeros_like(flat)
         g_img = torch.empty_like(img) if ctx.needs_input_grad[1] else None
-        _abi.check(_abi.lib.mb200_posmlp_bwd(C.byref(ctx.desc), _abi.ptr(flat), _abi.ptr(img), ctx.N, _abi.ptr(ctx.cache),
+        _abi.check(_abi.lib.mb200_posmlp_bwd(C.byref(ctx.desc), _abi.fptr(flat), _abi.fptr(img), ctx.N, _abi.ptr(ctx.cache),
                                              _abi.ptr(g_out.contiguous().float()), _abi.ptr(g_flat), _abi.ptr(g_img), _abi.ptr(ctx.work),
                                              _abi.stream_ptr()),
                    "mb200_posmlp_bwd")

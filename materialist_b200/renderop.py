@@ -82,33 +82,33 @@ def _forward(scene, spp, seed, a, r, m, n, env_pack, extra_flags=0):
             scene._wf_scratch = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=scene.device)
         with _ktime("mesh_fwd_wf"):
             _abi.check(_abi.lib.mb200_mesh_shade_fwd_wf(C.byref(cfg), C.byref(td) if td is not None else None, C.byref(scene.mesh.desc),
-                                                        _abi.ptr(scene.mesh.buf), _abi.ptr(a), _abi.ptr(r), _abi.ptr(m), _abi.ptr(nmap),
-                                                        _abi.ptr(env4), _abi.ptr(hier), C.byref(desc), _abi.ptr(partials),
+                                                        _abi.ptr(scene.mesh.buf), _abi.fptr(a), _abi.fptr(r), _abi.fptr(m), _abi.fptr(nmap),
+                                                        _abi.fptr(env4), _abi.fptr(hier), C.byref(desc), _abi.fptr(partials),
                                                         _abi.ptr(scene._wf_scratch), scene._wf_scratch.numel() * 8, st), "mb200_mesh_shade_fwd_wf")
     elif scene.trans is not None:               # TransBSDF plugin (trans_edit.py): forward only
         td = scene.trans.desc()
         if scene.mesh is not None:
             with _ktime("mesh_fwd_trans"):
                 _abi.check(_abi.lib.mb200_trans_mesh_shade_fwd(C.byref(cfg), C.byref(td), C.byref(scene.mesh.desc), _abi.ptr(scene.mesh.buf),
-                                                               _abi.ptr(a), _abi.ptr(r), _abi.ptr(m), _abi.ptr(nmap), _abi.ptr(env4), _abi.ptr(hier),
-                                                               C.byref(desc), _abi.ptr(partials), st), "mb200_trans_mesh_shade_fwd")
+                                                               _abi.fptr(a), _abi.fptr(r), _abi.fptr(m), _abi.fptr(nmap), _abi.fptr(env4), _abi.fptr(hier),
+                                                               C.byref(desc), _abi.fptr(partials), st), "mb200_trans_mesh_shade_fwd")
         else:
             with _ktime("shade_fwd_trans"):
-                _abi.check(_abi.lib.mb200_trans_shade_fwd(C.byref(cfg), C.byref(td), _abi.ptr(scene.gpos), _abi.ptr(scene.gnrm), _abi.ptr(a),
-                                                          _abi.ptr(r), _abi.ptr(m), _abi.ptr(nmap), _abi.ptr(env4), _abi.ptr(hier), C.byref(desc),
-                                                          _abi.ptr(partials), st), "mb200_trans_shade_fwd")
+                _abi.check(_abi.lib.mb200_trans_shade_fwd(C.byref(cfg), C.byref(td), _abi.fptr(scene.gpos), _abi.fptr(scene.gnrm), _abi.fptr(a),
+                                                          _abi.fptr(r), _abi.fptr(m), _abi.fptr(nmap), _abi.fptr(env4), _abi.fptr(hier), C.byref(desc),
+                                                          _abi.fptr(partials), st), "mb200_trans_shade_fwd")
     elif scene.mesh is not None:
         with _ktime("mesh_fwd"):
-            _abi.check(_abi.lib.mb200_mesh_shade_fwd(C.byref(cfg), C.byref(scene.mesh.desc), _abi.ptr(scene.mesh.buf), _abi.ptr(a), _abi.ptr(r),
-                                                     _abi.ptr(m), _abi.ptr(nmap), _abi.ptr(env4), _abi.ptr(hier), C.byref(desc),
-                                                     _abi.ptr(partials), st), "mb200_mesh_shade_fwd")
+            _abi.check(_abi.lib.mb200_mesh_shade_fwd(C.byref(cfg), C.byref(scene.mesh.desc), _abi.ptr(scene.mesh.buf), _abi.fptr(a), _abi.fptr(r),
+                                                     _abi.fptr(m), _abi.fptr(nmap), _abi.fptr(env4), _abi.fptr(hier), C.byref(desc),
+                                                     _abi.fptr(partials), st), "mb200_mesh_shade_fwd")
     else:
         with _ktime("shade_fwd"):
-            _abi.check(_abi.lib.mb200_shade_fwd(C.byref(cfg), _abi.ptr(scene.gpos), _abi.ptr(scene.gnrm), _abi.ptr(a), _abi.ptr(r),
-                                                _abi.ptr(m), _abi.ptr(nmap), _abi.ptr(env4), _abi.ptr(hier), C.byref(desc),
-                                                _abi.ptr(partials), st), "mb200_shade_fwd")
+            _abi.check(_abi.lib.mb200_shade_fwd(C.byref(cfg), _abi.fptr(scene.gpos), _abi.fptr(scene.gnrm), _abi.fptr(a), _abi.fptr(r),
+                                                _abi.fptr(m), _abi.fptr(nmap), _abi.fptr(env4), _abi.fptr(hier), C.byref(desc),
+                                                _abi.fptr(partials), st), "mb200_shade_fwd")
     img = torch.empty(cfg.rows, scene.W, 3, device=scene.device)
-    _abi.check(_abi.lib.mb200_film_develop(C.byref(cfg), _abi.ptr(partials), _abi.ptr(img), st), "mb200_film_develop")
+    _abi.check(_abi.lib.mb200_film_develop(C.byref(cfg), _abi.fptr(partials), _abi.fptr(img), st), "mb200_film_develop")
     return img
 
 
@@ -124,7 +124,7 @@ def _film_weights(scene, spp, seed_grad, env_res_x, out=None):
     if tuple(wpart.shape) != (wrows, scene.W, _abi.FILM_TAPS):
         raise ValueError("film-weight buffer has the wrong shape")
     with _ktime("film_weights"):
-        _abi.check(_abi.lib.mb200_film_weights(C.byref(cfg), _abi.ptr(wpart), _abi.stream_ptr()), "mb200_film_weights")
+        _abi.check(_abi.lib.mb200_film_weights(C.byref(cfg), _abi.fptr(wpart), _abi.stream_ptr()), "mb200_film_weights")
     return wpart
 
 
@@ -144,7 +144,7 @@ def _backward(scene, spp, seed_grad, a, r, m, n, env_pack, grad_img_halo, want_a
     if cfg.filter == _abi.FILTER_GAUSSIAN and wpart is None:
         wpart = _film_weights(scene, spp, seed_grad, desc.res_x)
     gadj = torch.empty(grows, scene.W, 4, device=dev)
-    _abi.check(_abi.lib.mb200_film_adjoint(C.byref(cfg), _abi.ptr(wpart), _abi.ptr(grad_img_halo), _abi.ptr(gadj), st), "mb200_film_adjoint")
+    _abi.check(_abi.lib.mb200_film_adjoint(C.byref(cfg), _abi.fptr(wpart), _abi.fptr(grad_img_halo), _abi.fptr(gadj), st), "mb200_film_adjoint")
     H, W = scene.H, scene.W
     if out is not None:
         g_a, g_r, g_m = (o if w else None for o, w in zip(out, (want_a, want_r, want_m)))
@@ -163,27 +163,27 @@ def _backward(scene, spp, seed_grad, a, r, m, n, env_pack, grad_img_halo, want_a
         if scene._wf_scratch is None or scene._wf_scratch.numel() * 8 < nbytes:
             scene._wf_scratch = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=scene.device)
         with _ktime("mesh_bwd_wf"):
-            _abi.check(_abi.lib.mb200_mesh_shade_bwd_wf(C.byref(cfg), C.byref(scene.mesh.desc), _abi.ptr(scene.mesh.buf), _abi.ptr(a), _abi.ptr(r),
-                                                        _abi.ptr(m), _abi.ptr(nmap), _abi.ptr(env4), _abi.ptr(hier), C.byref(desc),
-                                                        _abi.ptr(gadj), _abi.ptr(g_a), _abi.ptr(g_r), _abi.ptr(g_m), _abi.ptr(g_n),
-                                                        _abi.ptr(g_env4), n_slabs, _abi.ptr(scene._wf_scratch), scene._wf_scratch.numel() * 8, st),
+            _abi.check(_abi.lib.mb200_mesh_shade_bwd_wf(C.byref(cfg), C.byref(scene.mesh.desc), _abi.ptr(scene.mesh.buf), _abi.fptr(a), _abi.fptr(r),
+                                                        _abi.fptr(m), _abi.fptr(nmap), _abi.fptr(env4), _abi.fptr(hier), C.byref(desc),
+                                                        _abi.fptr(gadj), _abi.fptr(g_a), _abi.fptr(g_r), _abi.fptr(g_m), _abi.fptr(g_n),
+                                                        _abi.fptr(g_env4), n_slabs, _abi.ptr(scene._wf_scratch), scene._wf_scratch.numel() * 8, st),
                        "mb200_mesh_shade_bwd_wf")
     elif scene.mesh is not None:
         with _ktime("mesh_bwd"):
-            _abi.check(_abi.lib.mb200_mesh_shade_bwd(C.byref(cfg), C.byref(scene.mesh.desc), _abi.ptr(scene.mesh.buf), _abi.ptr(a), _abi.ptr(r),
-                                                     _abi.ptr(m), _abi.ptr(nmap), _abi.ptr(env4), _abi.ptr(hier), C.byref(desc),
-                                                     _abi.ptr(gadj), _abi.ptr(g_a), _abi.ptr(g_r), _abi.ptr(g_m), _abi.ptr(g_n),
-                                                     _abi.ptr(g_env4), n_slabs, st), "mb200_mesh_shade_bwd")
+            _abi.check(_abi.lib.mb200_mesh_shade_bwd(C.byref(cfg), C.byref(scene.mesh.desc), _abi.ptr(scene.mesh.buf), _abi.fptr(a), _abi.fptr(r),
+                                                     _abi.fptr(m), _abi.fptr(nmap), _abi.fptr(env4), _abi.fptr(hier), C.byref(desc),
+                                                     _abi.fptr(gadj), _abi.fptr(g_a), _abi.fptr(g_r), _abi.fptr(g_m), _abi.fptr(g_n),
+                                                     _abi.fptr(g_env4), n_slabs, st), "mb200_mesh_shade_bwd")
     else:
         with _ktime("shade_bwd"):
-            _abi.check(_abi.lib.mb200_shade_bwd(C.byref(cfg), _abi.ptr(scene.gpos), _abi.ptr(scene.gnrm), _abi.ptr(a), _abi.ptr(r),
-                                                _abi.ptr(m), _abi.ptr(nmap), _abi.ptr(env4), _abi.ptr(hier), C.byref(desc),
-                                                _abi.ptr(gadj), _abi.ptr(g_a), _abi.ptr(g_r), _abi.ptr(g_m), _abi.ptr(g_n),
-                                                _abi.ptr(g_env4), n_slabs, st), "mb200_shade_bwd")
+            _abi.check(_abi.lib.mb200_shade_bwd(C.byref(cfg), _abi.fptr(scene.gpos), _abi.fptr(scene.gnrm), _abi.fptr(a), _abi.fptr(r),
+                                                _abi.fptr(m), _abi.fptr(nmap), _abi.fptr(env4), _abi.fptr(hier), C.byref(desc),
+                                                _abi.fptr(gadj), _abi.fptr(g_a), _abi.fptr(g_r), _abi.fptr(g_m), _abi.fptr(g_n),
+                                                _abi.fptr(g_env4), n_slabs, st), "mb200_shade_bwd")
     g_env = None
     if want_env:
         g_env = torch.empty(He, We, 3, device=dev)
-        _abi.check(_abi.lib.mb200_env_grad_finish(_abi.ptr(g_env4), n_slabs, He, We, mode, _abi.ptr(g_env), st), "mb200_env_grad_finish")
+        _abi.check(_abi.lib.mb200_env_grad_finish(_abi.fptr(g_env4), n_slabs, He, We, mode, _abi.fptr(g_env), st), "mb200_env_grad_finish")
     if want_n and g_n is None:
         g_n = torch.zeros(H, W, 3, device=dev)
     return g_a, g_r, g_m, g_n, g_env
@@ -275,7 +275,7 @@ def sample_indices(scene, spp, seed):
     env4, hier, desc, He, We, mode = scene.prepared_env()
     cfg = scene.make_cfg(spp, seed, desc.res_x)
     out = torch.empty(cfg.rows * scene.W * spp, 4, dtype=torch.int32, device=scene.device)
-    _abi.check(_abi.lib.mb200_debug_sample_indices(C.byref(cfg), _abi.ptr(scene.gpos), _abi.ptr(scene.r), _abi.ptr(hier),
+    _abi.check(_abi.lib.mb200_debug_sample_indices(C.byref(cfg), _abi.fptr(scene.gpos), _abi.ptr(scene.r), _abi.fptr(hier),
                                                    C.byref(desc), _abi.ptr(out), _abi.stream_ptr()), "mb200_debug_sample_indices")
     return out
 
@@ -290,7 +290,7 @@ def sample_record(scene, spp, seed, ad_weights=False, want_radiance=False):
     out = torch.empty(S, 12, dtype=torch.int32, device=scene.device)
     rad = torch.empty(S, 3, device=scene.device) if want_radiance else None
     nmap = None if scene.use_mesh_normal else scene.n
-    _abi.check(_abi.lib.mb200_debug_sample_record(C.byref(cfg), _abi.ptr(scene.gpos), _abi.ptr(scene.gnrm), _abi.ptr(scene.a), _abi.ptr(scene.r),
-                                                  _abi.ptr(scene.m), _abi.ptr(nmap), _abi.ptr(env4), _abi.ptr(hier), C.byref(desc),
+    _abi.check(_abi.lib.mb200_debug_sample_record(C.byref(cfg), _abi.fptr(scene.gpos), _abi.fptr(scene.gnrm), _abi.ptr(scene.a), _abi.ptr(scene.r),
+                                                  _abi.ptr(scene.m), _abi.fptr(nmap), _abi.fptr(env4), _abi.fptr(hier), C.byref(desc),
                                                   _abi.ptr(out), _abi.ptr(rad), _abi.stream_ptr()), "mb200_debug_sample_record")
     return (out, rad) if want_radiance else out

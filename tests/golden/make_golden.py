@@ -173,6 +173,59 @@ def helpers_and_rotate(sh, eu):
     np.savez_compressed(os.path.join(HERE, "helpers_rotate.npz"), **out)
 
 
+def e5_and_s5(eu, sh):
+    """E5: sample_env1 / sample_brdf1 (envmap_utils.py:7-28) with the random numbers they draw recorded (torch.rand is patched to
+    replay them on the CUDA side).  S5: the torch SH variants are broken as shipped; the fixture is their INTENDED
+    maths in float64 — a Riemann sum 4 pi / (W H) * sum L Y sin(theta) on the (phi, theta) = linspace grids of :410-430, with the
+    reference's own working numpy building blocks for Y: computeK (:58-68) and the associated Legendre functions P_l_m (:13-56)."""
+    out = {}
+    n = 1500
+    env = 0.2 + torch.exp(torch.randn(16, 32, 3, generator=g(600)))
+    d = eu.build_envmap(env)
+    normals = torch.nn.functional.normalize(torch.randn(n, 3, generator=g(601)), dim=-1)
+    wo = torch.nn.functional.normalize(normals + 0.7 * torch.randn(n, 3, generator=g(602)), dim=-1)
+    mat = {"albedo": torch.rand(n, 3, generator=g(603)), "roughness": torch.rand(n, 1, generator=g(604)) * 0.93 + 0.07,
+           "metallic": torch.rand(n, 1, generator=g(605)), "normal": normals}
+    draws = []
+    real_rand = torch.rand
+
+    def rec_rand(*shape, **kw):
+        kw.pop("device", None)
+        t = real_rand(*shape, generator=g(700 + len(draws)))
+        draws.append(t)
+        return t
+    torch.rand = rec_rand
+    try:
+        wi, pdf, w = eu.sample_env1(wo, normals, mat, True, "cpu", d)
+        wi2, pdf2, w2 = eu.sample_brdf1(wo, normals, mat, True, "cpu")
+    finally:
+        torch.rand = real_rand
+    out.update(e5_env=env.numpy(), e5_normals=normals.numpy(), e5_wo=wo.numpy(), e5_albedo=mat["albedo"].numpy(), e5_rough=mat["roughness"].numpy(),
+               e5_metal=mat["metallic"].numpy(), e5_draw0=draws[0].numpy(), e5_draw1=draws[1].numpy(), e5_draw2=draws[2].numpy(),
+               e5_env_wi=wi.numpy(), e5_env_pdf=pdf.numpy(), e5_env_w=w.numpy(), e5_brdf_wi=wi2.numpy(), e5_brdf_pdf=pdf2.numpy(), e5_brdf_w=w2.numpy())
+    # ---- S5
+    rs = np.random.RandomState(800)
+    H, W, l_max = 12, 24, 2
+    img = rs.rand(H, W, 3)
+    phis, thetas = np.meshgrid(np.linspace(0, 2 * np.pi, W), np.linspace(0, np.pi, H), indexing="xy")
+    P = {(0, 0): sh.P_0_0, (1, 0): sh.P_1_0, (1, 1): sh.P_1_1, (2, 0): sh.P_2_0, (2, 1): sh.P_2_1, (2, 2): sh.P_2_2}
+    coeffs = np.zeros((l_max + 1, 2 * l_max + 1, 3))
+    Y = {}
+    for l in range(l_max + 1):
+        for m in range(-l, l + 1):
+            K = float(sh.computeK(np.array([l]), np.array([m]))[0])
+            plm = P[(l, abs(m))](thetas.astype(np.float64))
+            y = K * plm * (np.sqrt(2) * np.cos(m * phis) if m > 0 else (np.sqrt(2) * np.sin(-m * phis) if m < 0 else 1.0))
+            Y[(l, m)] = y
+            coeffs[l, m + l] = (img * (y * np.sin(thetas))[..., None]).sum((0, 1))
+    coeffs *= 4 * np.pi / (W * H)
+    rec = np.zeros((H, W, 3))
+    for (l, m), y in Y.items():
+        rec += coeffs[l, m + l][None, None, :] * y[..., None]
+    out.update(s5_img=img, s5_coeffs=coeffs, s5_rec=rec)
+    np.savez_compressed(os.path.join(HERE, "e5_s5.npz"), **out)
+
+
 def main():
     install_stubs()
     import myutils.mi_plugin as mp
@@ -184,6 +237,7 @@ def main():
     envmap_utils(eu); print("envmap_utils.npz")
     compute_sh(sh); print("compute_sh.npz")
     helpers_and_rotate(sh, eu); print("helpers_rotate.npz")
+    e5_and_s5(eu, sh); print("e5_s5.npz")
 
 
 if __name__ == "__main__":

@@ -165,6 +165,53 @@ def test_envmap_utils_match_reference_golden(tag):
     assert torch.isfinite(d2).all() and torch.isfinite(p2).all()
 
 
+def test_sample_env1_and_sample_brdf1_match_reference_golden(monkeypatch):
+    """E5: the two sampling wrappers (envmap_utils.py:7-28) on the CUDA path against the reference's own outputs; the random numbers
+    they draw with torch.rand(..., device) are replayed from the fixture (tests/golden/make_golden.py::e5_and_s5)."""
+    from materialist_b200.myutils import envmap_utils as eu
+    g = load("e5_s5.npz")
+    cu = lambda k: torch.from_numpy(g[k]).cuda()
+    env = cu("e5_env")
+    d = eu.build_envmap(env)
+    mat = {"albedo": cu("e5_albedo"), "roughness": cu("e5_rough"), "metallic": cu("e5_metal"), "normal": cu("e5_normals")}
+    draws = [cu("e5_draw0"), cu("e5_draw1"), cu("e5_draw2")]
+    it = iter(draws)
+    real_rand = torch.rand
+
+    def replay(*shape, **kw):
+        t = next(it)
+        assert tuple(t.shape) == tuple(shape if not (len(shape) == 1 and isinstance(shape[0], (tuple, list))) else shape[0])
+        return t
+    monkeypatch.setattr(torch, "rand", replay)
+    wi, pdf, w = eu.sample_env1(cu("e5_wo"), cu("e5_normals"), mat, True, "cuda", d)
+    wi2, pdf2, w2 = eu.sample_brdf1(cu("e5_wo"), cu("e5_normals"), mat, True, "cuda")
+    monkeypatch.setattr(torch, "rand", real_rand)
+    np.testing.assert_allclose(wi.cpu().numpy(), g["e5_env_wi"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(pdf.cpu().numpy().reshape(-1), g["e5_env_pdf"].reshape(-1), rtol=5e-5, atol=1e-7)
+    e = np.abs(w.cpu().numpy() - g["e5_env_w"]) / np.maximum(np.abs(g["e5_env_w"]), 1e-4)
+    assert np.median(e) < 2e-6 and np.percentile(e, 99) < 1e-3, (np.median(e), np.percentile(e, 99))
+    np.testing.assert_allclose(wi2.cpu().numpy(), g["e5_brdf_wi"], rtol=0, atol=5e-5)
+    for got, ref, nm in ((pdf2, g["e5_brdf_pdf"], "pdf"), (w2, g["e5_brdf_w"], "weight")):
+        e = np.abs(got.cpu().numpy().reshape(ref.shape) - ref) / np.maximum(np.abs(ref), 1e-4)
+        assert np.median(e) < 5e-6 and np.percentile(e, 99) < 5e-3, (nm, np.median(e), np.percentile(e, 99))
+
+
+def test_torch_sh_variants_match_intended_maths_golden():
+    """S5: compute_sh_coeff_torch / reconstruct_envmap_from_sh (broken as shipped) against the float64 fixture of their
+    intended maths built from the reference's own computeK and P_l_m (tests/golden/make_golden.py::e5_and_s5)."""
+    from materialist_b200.myutils import computeSH as sh
+    g = load("e5_s5.npz")
+    img = torch.from_numpy(g["s5_img"]).float().cuda()
+    c = sh.compute_sh_coeff_torch(img, l_max=2)
+    ref = g["s5_coeffs"]
+    valid = np.zeros(ref.shape[:2], bool)
+    for l in range(3):
+        valid[l, :2 * l + 1] = True
+    np.testing.assert_allclose(c.cpu().numpy()[valid], ref[valid], rtol=0, atol=2e-6 * np.abs(ref).max())
+    rec = sh.reconstruct_envmap_from_sh(torch.from_numpy(ref).float().cuda(), 24, 12, l_max=2)
+    np.testing.assert_allclose(rec.cpu().numpy(), g["s5_rec"], rtol=0, atol=3e-6 * np.abs(g["s5_rec"]).max())
+
+
 def test_cdf_build_large_vs_oracle():
     from materialist_b200 import synthetic
     from materialist_b200.myutils import envmap_utils as eu

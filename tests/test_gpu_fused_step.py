@@ -100,6 +100,34 @@ def test_fused_iteration_matches_autograd_iteration(part):
         assert torch.equal(f.mat[k], f.params[k].clamp(*f._RANGE[k]))
 
 
+@pytest.mark.parametrize("part", ["arm", "armn"])
+def test_fused_iteration_with_normal_map_matches_autograd_iteration(part):
+    """use_mesh_normal=False (inverse_img_w_mi.py:384: render_w_brdf(..., mat['normal'], spp)): the normal map is rendered with, and
+    with 'n' in the part it is optimised through normalize(p) with its l1 aux term (:356-357, :375-376, :407-410)."""
+    import materialist_b200 as mb
+    from materialist_b200.inverse import DirectBRDFOptimizer, FusedBRDFOptimizer
+    c = Case(H=48, W=48, spp=32, He=16, We=32, use_mesh_normal=False)
+    s = c.scene()
+    a, r, m, n = c.torch_maps()
+    a2, r2, m2, _ = Case(H=48, W=48, spp=32, He=16, We=32, mat_seed=5).torch_maps()
+    gt = mb.render(s, spp=32, seed=999, albedo=a2, roughness=r2, metallic=m2, normal=n)
+    # un-normalised on purpose where the map is a parameter (the kernels then see normalize(p)); with 'arm' the reference renders
+    # with mat['normal'] as loaded (:384), i.e. a unit map
+    mat = {"albedo": a, "roughness": r, "metallic": m, "normal": n * 1.7 if "n" in part else n}
+    d = DirectBRDFOptimizer(s, mat, gt, part, spp=c.spp, lr=1e-3)
+    f = FusedBRDFOptimizer(s, mat, gt, part, spp=c.spp, lr=1e-3)
+    for i in range(4):
+        d.step(20 + i); f.step(20 + i)
+        assert torch.allclose(f.last["loss_mse"], d.last["loss_mse"], rtol=2e-5), i
+        assert torch.allclose(f.last["loss_l1"], d.last["loss_l1"], rtol=2e-5), i
+    if "n" in part:
+        diff = (f.n_param.detach() - d.params["normal"].detach()).abs()
+        assert (diff < 2e-6).float().mean() > 0.99 and diff.max() < 4 * 4 * 1e-3, (diff.max(), (diff < 2e-6).float().mean())
+        assert float((f.n_param.detach() - mat["normal"]).abs().max()) > 1e-4       # it moved
+    else:
+        assert f.n_param is None and torch.equal(f.normal, mat["normal"])
+
+
 def test_envmap_net_phase_reduces_loss():
     """Envmap phase as the reference runs it (inverse_img_w_mi.py:222-256): envmap_net(ones) -> (16, 32, 3) envmap ->
     render_envmap -> mse + l1 -> Adam.  The zero-initialised head starts at softplus(0) = ln 2 everywhere; a few dozen
