@@ -315,6 +315,12 @@ int mb200_trans_refracted_texel(const mb200_cfg* cfg_host, const mb200_trans* tr
                                 const float* p, const float* n_geo, const float* wi_world,
                                 float* out_screen, int64_t* out_flat, void* stream);
 
+/* Debug / parity: the shared reproducible float32 functions (include/mb200_exact_math.h) and the branch-free exact division /
+ * square root of the hierarchy descent, evaluated on the device over arrays.  op: 0 sincospi(x) -> (out0 = sin, out1 = cos),
+ * 1 atan2(x, y), 2 acos(x), 3 asin01(x), 4 rsqrt(x) (out0 = the kernels' mbx_rsqrt, out1 = __frsqrt_rn),
+ * 5 x / y (out0 = fast path with its deferred fallback, out1 = __fdiv_rn), 6 sqrt(x) (likewise vs __fsqrt_rn).  out1 may be NULL. */
+int mb200_debug_exact_math(int op, const float* x, const float* y, int64_t n, float* out0, float* out1, void* stream);
+
 /* Wavefront formulation of mb200_mesh_shade_fwd / mb200_trans_mesh_shade_fwd (trans_host may be NULL = MatDiffBSDF): the path
  * loop is cut into kernels at its rays (traversal-only kernels at high occupancy, coherent shading kernels); path state lives
  * in `scratch` (device, 256-byte aligned, mb200_mesh_fwd_wf_scratch_bytes(cfg) bytes: 156 bytes per path, <= 4 Mi paths at a

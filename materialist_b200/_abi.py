@@ -115,6 +115,7 @@ def _load():
         "mb200_trans_eval_pdf": (i32, [pc, pt, i64] + [vp] * 11),
         "mb200_trans_sample": (i32, [pc, pt, i64] + [vp] * 13),
         "mb200_trans_refracted_texel": (i32, [pc, pt, i64] + [vp] * 6),
+        "mb200_debug_exact_math": (i32, [i32, vp, vp, i64, vp, vp, vp]),
         "mb200_image_info": (i32, [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "mb200_image_read": (i32, [C.c_char_p, vp, i32, i32, i32]),
         "mb200_image_write": (i32, [C.c_char_p, vp, i32, i32, i32]),

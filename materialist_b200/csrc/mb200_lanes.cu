@@ -64,6 +64,26 @@ __global__ void trans_sample_kernel(const __grid_constant__ LaneParams P) {
     const BsdfSample s = trans_sample_brdf(P.s1[i], P.s2[2 * i], P.s2[2 * i + 1], view, mt, tm, P.trans, make_frame(mt.n));
     st3(P.o3, i, s.wi); P.o1[i] = s.pdf; st3(P.ow, i, s.weight);
 }
+// the shared reproducible functions of include/mb200_exact_math.h (and the branch-free division / square root of the hierarchy
+// descent) as nvcc compiles them, on arrays: tests compare them bit for bit with the gcc build (oracle) and with the IEEE intrinsics
+__global__ void exact_math_kernel(int op, const float* __restrict__ x, const float* __restrict__ y, long long n, float* __restrict__ o0, float* __restrict__ o1) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float a = x[i], b = y ? y[i] : 0.f;
+    float r0 = 0.f, r1 = 0.f; bool bad = false;
+    switch (op) {
+        case 0: mbx_sincospi(a, &r0, &r1); break;
+        case 1: r0 = mbx_atan2(a, b); break;
+        case 2: r0 = mbx_acos(a); break;
+        case 3: r0 = mbx_asin01(a); break;
+        case 4: r0 = mbx_rsqrt(a); r1 = __frsqrt_rn(a); break;
+        case 5: r0 = xdiv_pos(a, b, bad); r1 = __fdiv_rn(a, b); if (bad) r0 = r1; break;
+        case 6: r0 = xsqrt_pos(a, bad); r1 = __fsqrt_rn(a); if (bad) r0 = r1; break;
+        default: break;
+    }
+    o0[i] = r0; if (o1) o1[i] = r1;
+}
+
 __global__ void trans_refracted_kernel(const __grid_constant__ LaneParams P) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.L) return;
@@ -159,6 +179,14 @@ int mb200_trans_refracted_texel(const mb200_cfg* c, const mb200_trans* t, int64_
     if (L == 0) return MB200_OK;
     P.L = L; P.p = p; P.n_geo = n_geo; P.wi = wi_world; P.o3 = out_screen; P.oflat = (long long*)out_flat;
     trans_refracted_kernel<<<(unsigned)((L + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P);
+    return mb200_check_launch();
+}
+
+int mb200_debug_exact_math(int op, const float* x, const float* y, int64_t n, float* out0, float* out1, void* stream) {
+    if (op < 0 || op > 6 || !x || !out0 || n < 0) return MB200_EINVAL;
+    if ((op == 1 || op == 5) && !y) return MB200_EINVAL;
+    if (n == 0) return MB200_OK;
+    exact_math_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(op, x, y, (long long)n, out0, out1);
     return mb200_check_launch();
 }
 

@@ -151,33 +151,44 @@ __device__ __forceinline__ SurfacePoint hit_point(const MeshView& M, const Hit& 
     const Frame g = make_frame(s.ng);
     if (!M.tn) { s.sh = g; return s; }
     const float4 a0 = __ldg(M.tn + 3 * (size_t)h.slot), a1 = __ldg(M.tn + 3 * (size_t)h.slot + 1), a2 = __ldg(M.tn + 3 * (size_t)h.slot + 2);
-    float3 ns = f3(fmaf(a0.x, b0, fmaf(a1.x, b1, a2.x * b2)), fmaf(a0.y, b0, fmaf(a1.y, b1, a2.y * b2)), fmaf(a0.z, b0, fmaf(a1.z, b1, a2.z * b2)));
-    ns = ns * (1.f / sqrtf(dot(ns, ns)));
+    // exact chain (the oracle's hit_point, operation for operation): the shading frame turns the sampled lobe direction into the next
+    // ray, so an ulp here is an ulp of the next hit — and a different radiance wherever the next vertex sits on a GGX peak
+    float3 ns = f3(XFMA(a0.x, b0, XFMA(a1.x, b1, XMUL(a2.x, b2))), XFMA(a0.y, b0, XFMA(a1.y, b1, XMUL(a2.y, b2))), XFMA(a0.z, b0, XFMA(a1.z, b1, XMUL(a2.z, b2))));
+    ns = xnormalize3(ns);
     // SurfaceInteraction::initialize_sh_frame: Gram-Schmidt of dp_du (= coordinate_system(n).s) against the shading normal
-    const float dd = dot(ns, g.s);
-    float3 ss = f3(fmaf(-ns.x, dd, g.s.x), fmaf(-ns.y, dd, g.s.y), fmaf(-ns.z, dd, g.s.z));
-    ss = ss * (1.f / sqrtf(dot(ss, ss)));
-    s.sh.n = ns; s.sh.s = ss; s.sh.t = cross3(ns, ss);
+    const float dd = xdot3(ns, g.s);
+    float3 ss = f3(XFMA(-ns.x, dd, g.s.x), XFMA(-ns.y, dd, g.s.y), XFMA(-ns.z, dd, g.s.z));
+    ss = xnormalize3(ss);
+    s.sh.n = ns; s.sh.s = ss; s.sh.t = xcross3(ns, ss);
     return s;
 }
-// SurfaceInteraction::offset_p
+// SurfaceInteraction::offset_p (exact: the oracle's offset_p)
 __device__ __forceinline__ float3 offset_p(float3 p, float3 n, float3 d) {
-    float mag = (1.f + fmaxf(fabsf(p.x), fmaxf(fabsf(p.y), fabsf(p.z)))) * kRayEps;
-    if (dot(n, d) < 0.f) mag = -mag;
-    return f3(fmaf(mag, n.x, p.x), fmaf(mag, n.y, p.y), fmaf(mag, n.z, p.z));
+    float mag = XMUL(XADD(1.f, fmaxf(fabsf(p.x), fmaxf(fabsf(p.y), fabsf(p.z)))), kRayEps);
+    if (xdot3(n, d) < 0.f) mag = -mag;
+    return f3(XFMA(mag, n.x, p.x), XFMA(mag, n.y, p.y), XFMA(mag, n.z, p.z));
 }
-// Scene::sample_emitter_direction(test_visibility) for an envmap: ray_test towards it.p + d * 2 * max(radius, |it.p - centre|)
-__device__ __forceinline__ bool shadow_visible(const MeshView& M, float3 p, float3 n, float3 d) {
+// Scene::sample_emitter_direction(test_visibility) for an envmap: ray_test towards it.p + d * 2 * max(radius, |it.p - centre|).
+// Origin, direction and length of the visibility ray, bit-identical to the oracle's shadow_visible (a grazing shadow ray is a
+// discrete decision).
+struct ShadowRay { float3 o, d; float maxt; };
+__device__ __forceinline__ ShadowRay shadow_ray(const MeshView& M, float3 p, float3 n, float3 d) {
     const float3 c = f3(__ldg(M.header), __ldg(M.header + 1), __ldg(M.header + 2));
-    const float3 pc = p - c;
-    const float rad = fmaxf(__ldg(M.header + 3), sqrtf(dot(pc, pc)));
-    const float3 target = p + d * (2.f * rad);
-    const float3 o = offset_p(p, n, target - p);
-    float3 dd = target - o;
-    const float dist = sqrtf(dot(dd, dd));
-    dd = dd * (1.f / dist);
+    const float3 pc = xsub3(p, c);
+    const float rad = fmaxf(__ldg(M.header + 3), XSQRT(xdot3(pc, pc)));
+    const float3 target = xadd3(p, xscale3(d, XMUL(2.f, rad)));
+    ShadowRay r;
+    r.o = offset_p(p, n, xsub3(target, p));
+    float3 dd = xsub3(target, r.o);
+    const float dist = XSQRT(xdot3(dd, dd));
+    r.d = xscale3(dd, XDIV(1.f, dist));
+    r.maxt = XMUL(dist, XSUB(1.f, kShadowEps));
+    return r;
+}
+__device__ __forceinline__ bool shadow_visible(const MeshView& M, float3 p, float3 n, float3 d) {
+    const ShadowRay r = shadow_ray(M, p, n, d);
     Hit h;
-    return !mesh_intersect<true>(M, o, dd, dist * (1.f - kShadowEps), h);
+    return !mesh_intersect<true>(M, r.o, r.d, r.maxt, h);
 }
 
 __device__ __forceinline__ Material fetch_material(const RenderParams& P, float3 p, float3 ng, long long& flat) {
@@ -319,15 +330,8 @@ __device__ __forceinline__ void trav_step(const MeshView& M, Trav& T, TStack<SM,
 }
 // Scene::sample_emitter_direction's visibility ray (see shadow_visible) as a resumable any-hit query
 __device__ __forceinline__ void trav_begin_shadow(const MeshView& M, Trav& T, float3 p, float3 n, float3 d) {
-    const float3 c = f3(__ldg(M.header), __ldg(M.header + 1), __ldg(M.header + 2));
-    const float3 pc = p - c;
-    const float rad = fmaxf(__ldg(M.header + 3), sqrtf(dot(pc, pc)));
-    const float3 target = p + d * (2.f * rad);
-    const float3 o = offset_p(p, n, target - p);
-    float3 dd = target - o;
-    const float dist = sqrtf(dot(dd, dd));
-    dd = dd * (1.f / dist);
-    trav_begin(M, T, o, dd, dist * (1.f - kShadowEps), true);
+    const ShadowRay r = shadow_ray(M, p, n, d);
+    trav_begin(M, T, r.o, r.d, r.maxt, true);
 }
 
 // ---------------------------------------------------------------- forward: PathIntegrator::sample, persistent lanes
@@ -742,16 +746,9 @@ __global__ void __launch_bounds__(kThreads, 2) wf_shade_kernel(const __grid_cons
                         const float3 cem = beta * fv.f * env_value(P.env, em.b) * (mis_weight(em.pdf, fv.pdf) / em.pdf);
                         B.cem[pid] = make_float4(cem.x, cem.y, cem.z, 0.f);
                         // Scene::sample_emitter_direction's visibility ray (trav_begin_shadow)
-                        const float3 c = f3(__ldg(M.header), __ldg(M.header + 1), __ldg(M.header + 2));
-                        const float3 pc = sp.p - c;
-                        const float rad = fmaxf(__ldg(M.header + 3), sqrtf(dot(pc, pc)));
-                        const float3 target = sp.p + em.d * (2.f * rad);
-                        const float3 o = offset_p(sp.p, sp.ng, target - sp.p);
-                        float3 dd = target - o;
-                        const float dist = sqrtf(dot(dd, dd));
-                        dd = dd * (1.f / dist);
-                        B.sray_o[pid] = make_float4(o.x, o.y, o.z, 0.f); B.sray_d[pid] = make_float4(dd.x, dd.y, dd.z, dist * (1.f - kShadowEps));
-                        shadow = true; sbin = wf_octant(dd.x, dd.y, dd.z);
+                        const ShadowRay sr = shadow_ray(M, sp.p, sp.ng, em.d);
+                        B.sray_o[pid] = make_float4(sr.o.x, sr.o.y, sr.o.z, 0.f); B.sray_d[pid] = make_float4(sr.d.x, sr.d.y, sr.d.z, sr.maxt);
+                        shadow = true; sbin = wf_octant(sr.d.x, sr.d.y, sr.d.z);
                     }
                 }
                 const BsdfSample bs = TRANS ? trans_sample_brdf(s1, s2x, s2y, view, mt, tm, P.trans, make_frame(mt.n)) : sample_brdf_ool(s1, s2x, s2y, view, mt);
@@ -1108,16 +1105,9 @@ __global__ void __launch_bounds__(kThreads, 2) wf_shade_bwd_kernel(const __grid_
                         B.scat[pid] = make_float4(sc.x, sc.y, sc.z, __uint_as_float(em.b.i00));
                         B.pbw[pid] = make_float4(em.b.w0x, em.b.w1x, em.b.w0y, em.b.w1y);
                     }
-                    const float3 c = f3(__ldg(M.header), __ldg(M.header + 1), __ldg(M.header + 2));
-                    const float3 pc = sp.p - c;
-                    const float rad = fmaxf(__ldg(M.header + 3), sqrtf(dot(pc, pc)));
-                    const float3 target = sp.p + em.d * (2.f * rad);
-                    const float3 o = offset_p(sp.p, sp.ng, target - sp.p);
-                    float3 dd = target - o;
-                    const float dist = sqrtf(dot(dd, dd));
-                    dd = dd * (1.f / dist);
-                    B.sray_o[pid] = make_float4(o.x, o.y, o.z, 0.f); B.sray_d[pid] = make_float4(dd.x, dd.y, dd.z, dist * (1.f - kShadowEps));
-                    shadow = true; sbin = wf_octant(dd.x, dd.y, dd.z);
+                    const ShadowRay sr = shadow_ray(M, sp.p, sp.ng, em.d);
+                    B.sray_o[pid] = make_float4(sr.o.x, sr.o.y, sr.o.z, 0.f); B.sray_d[pid] = make_float4(sr.d.x, sr.d.y, sr.d.z, sr.maxt);
+                    shadow = true; sbin = wf_octant(sr.d.x, sr.d.y, sr.d.z);
                 }
                 const BsdfSample bs = sample_brdf_ool(s1, s2x, s2y, view, mt);
                 const float3 d_bs = (P.flags & MB200_FLAG_WO_WORLD_QUIRK) ? to_world(sp.sh, bs.wi) : bs.wi;
@@ -1315,10 +1305,11 @@ __global__ void mesh_morton_kernel(const float* __restrict__ verts, const int32_
     vals[t] = t;
 }
 // Mesh::recompute_vertex_normals: face normals weighted by the corner angle, accumulated in double
+// (exact chain: the oracle's unit_angle with the shared mbx_asin01, so that the interpolated shading normals are bit-identical)
 __device__ __forceinline__ float unit_angle(float3 u, float3 v) {
-    const float3 dm = v - u, dp = v + u;
-    const float t = 2.f * asinf(fminf(0.5f * sqrtf(dot(dm, dm)), 1.f));
-    return dot(u, v) >= 0.f ? t : MB_PI - 2.f * asinf(fminf(0.5f * sqrtf(dot(dp, dp)), 1.f));
+    const float3 dm = xsub3(v, u), dp = xadd3(v, u);
+    const float t = XMUL(2.f, mbx_asin01(fminf(XMUL(0.5f, XSQRT(xdot3(dm, dm))), 1.f)));
+    return xdot3(u, v) >= 0.f ? t : XSUB(MB_PI, XMUL(2.f, mbx_asin01(fminf(XMUL(0.5f, XSQRT(xdot3(dp, dp))), 1.f))));
 }
 __global__ void mesh_vn_accum_kernel(const float* __restrict__ verts, const int32_t* __restrict__ tris, int nt, double* __restrict__ acc) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;

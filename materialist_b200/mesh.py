@@ -86,6 +86,17 @@ class Mesh:
         h = self.buf.view(torch.float32)[self.desc.off_header // 4: self.desc.off_header // 4 + 12].cpu().numpy()
         return h[:3], float(h[3]), h[4:7], h[8:11]
 
+    def corner_normals(self):
+        """(tri_id (n_slots,), normals (n_slots, 3, 3)) as stored for the shading frames: per Morton-ordered slot the original triangle id
+        (-1: padding) and the angle-weighted vertex normal of each of its three corners (None with face normals)."""
+        if self.desc.face_normals:
+            return None
+        n = self.desc.n_slots
+        f = self.buf.view(torch.float32)
+        tv = f[self.desc.off_tv // 4: self.desc.off_tv // 4 + n * 12].view(n, 3, 4)
+        tn = f[self.desc.off_tn // 4: self.desc.off_tn // 4 + n * 12].view(n, 3, 4)
+        return tv[:, 0, 3].contiguous().view(torch.int32), tn[..., :3].contiguous()
+
     def intersect(self, o, d, maxt=None, any_hit=False):
         o = torch.as_tensor(o, dtype=torch.float32).to(self.device).contiguous()
         d = torch.as_tensor(d, dtype=torch.float32).to(self.device).contiguous()

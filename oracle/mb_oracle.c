@@ -78,6 +78,8 @@ typedef float real;
  * are the shared reproducible implementations of include/mb200_exact_math.h, bit-identical to the kernels' */
 #undef ACOS
 #undef ATAN2
+#undef ASIN
+#define ASIN mbx_asin01      /* only dr::unit_angle uses it (argument in [0, 1]) */
 #define ACOS mbx_acos
 #define ATAN2 mbx_atan2
 #define SINCOSPI mbx_sincospi

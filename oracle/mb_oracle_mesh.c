@@ -334,6 +334,30 @@ static void film_splat_setup(const mb200_cfg* c, int* r0, int* r1) {
     *r0 = c->row0 - halo; *r1 = c->row0 + c->rows + halo; if (*r0 < 0) *r0 = 0; if (*r1 > c->H) *r1 = c->H;
 }
 
+/* Debug (tools/debug_mesh_paths.py): per-path record of the shard rows, path = (pixel of the shard, sample) in lane order:
+ * out (npaths, 16) floats = L.rgb, nv, miss_k, then per vertex k < 3: tri, visible (active_em ? visible : -1), lobe; + 2 spare */
+int mbo_mesh_path_records(const mb200_cfg* c, const void* mesh, const float* a, const float* r, const float* m, const float* n_opt,
+                          const float* env_int, const float* hier, const mb200_hier_desc* d, float* out) {
+    mscene S = { c, (const mbo_mesh*)mesh, a, r, m, n_opt, env_int, hier, d };
+    const int W = c->W, spp = c->spp;
+    const int ad = (c->flags & MB200_FLAG_AD_WEIGHTS) != 0;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int py = c->row0; py < c->row0 + c->rows; ++py)
+        for (int px = 0; px < W; ++px)
+            for (int s = 0; s < spp; ++s) {
+                mpath o; trace_path_mesh(&S, px, py, s, ad, &o);
+                float* q = out + (((size_t)(py - c->row0) * W + px) * spp + s) * 16;
+                q[0] = (float)o.L[0]; q[1] = (float)o.L[1]; q[2] = (float)o.L[2]; q[3] = (float)o.nv; q[4] = (float)o.miss_k;
+                for (int k = 0; k < 3; ++k) {
+                    q[5 + 3 * k] = k < o.nv ? (float)o.v[k].tri : -1.f;
+                    q[6 + 3 * k] = k < o.nv ? (o.v[k].active_em ? (float)o.v[k].visible : -1.f) : -2.f;
+                    q[7 + 3 * k] = k < o.nv ? (float)o.v[k].lobe : -1.f;
+                }
+                q[14] = (float)o.jx; q[15] = (float)o.jy;
+            }
+    return MB200_OK;
+}
+
 /* img: (rows, W, 3).  stats (optional, 5 int64): paths, scattering vertices, occluded emitter samples, escaped paths,
  * AD-weight fallbacks */
 int mbo_mesh_render_fwd(const mb200_cfg* c, const void* mesh, const float* a, const float* r, const float* m, const float* n_opt,

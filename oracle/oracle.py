@@ -256,6 +256,14 @@ class Oracle:
             raise RuntimeError(f"mbo_mesh_render_fwd rc={rc}")
         return (img, stats) if want_stats else img
 
+    def mesh_path_records(self, cfg, mesh, a, r, m, n_opt, env_int, hier, d):
+        """Debug: (rows*W*spp, 16) per-path records (L.rgb, nv, miss_k, 3 x (tri, visible, lobe), jx, jy)."""
+        out = np.zeros((cfg.rows * cfg.W * cfg.spp, 16), np.float32)
+        rc = self.lib.mbo_mesh_path_records(C.byref(cfg), mesh, _p(a), _p(r), _p(m), _p(n_opt), _p(env_int), _p(hier), C.byref(d), _p(out))
+        if rc != 0:
+            raise RuntimeError(f"mbo_mesh_path_records rc={rc}")
+        return out
+
     def mesh_render_bwd(self, cfg, mesh, a, r, m, n_opt, env_int, hier, d, grad_img, want=("a", "r", "m", "env")):
         H, W = cfg.H, cfg.W
         grad_img = _f32(grad_img)

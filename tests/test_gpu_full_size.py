@@ -114,6 +114,40 @@ def test_c5_full_size_rows_vs_oracle_and_adjoint_identity(oracle32):
         assert np.array_equal(rref[:, k], rgot[:, k]), (nm, int((rref[:, k] != rgot[:, k]).sum()))
 
 
+def test_mesh_adjoint_rows_vs_oracle_at_c2m_size(oracle32):
+    """C2m (512x512 height-field mesh, 521 k triangles, 64 spp, max_depth 4, 256x128 envmap, gaussian film): the forward image and
+    the adjoint of a 2-row sample of the image against the oracle.  In mesh mode a path scatters material gradients to whatever
+    texels its secondary vertices hit, so the WHOLE gradient maps of that row sample are compared (radiance 1e-4, gradients 1e-3)."""
+    import materialist_b200 as mb
+    from materialist_b200 import renderop as mbr
+    from oracle import oracle as orc
+    from test_gpu_mesh_parity import _scene, _cuda_scene
+    from test_reference_render_pin import REF_FLAGS, pin_cfg
+    H = W = 512; spp = 64; row0, rows = 255, 2
+    cam, verts, tris, a, r, m, env = _scene(H, W, env_hw=(128, 256))
+    assert tris.shape[0] > 520_000
+    om = oracle32.mesh_create(verts, tris)
+    env_int, hier, d = oracle32.env_prepare(env, orc.ENV_ASSIGNED)
+    seed = 17; sg = mb.default_seed_grad(seed)
+    s = _cuda_scene(cam, verts, tris, env, REF_FLAGS)
+    ta, tr, tm = (torch.from_numpy(x).cuda() for x in (a, r, m))
+    ref = oracle32.mesh_render_fwd(pin_cfg(d, seed, row0, rows, spp=spp, H=H, W=W), om, a, r, m, None, env_int, hier, d)
+    G = np.random.RandomState(5).randn(H, W, 3).astype(np.float32)
+    gref = oracle32.mesh_render_bwd(pin_cfg(d, sg, row0, rows, spp=spp, H=H, W=W), om, a, r, m, None, env_int, hier, d, G, want=("a", "r", "m", "env"))
+    gref["env"] = oracle32.env_grad_finish(gref.pop("env_int"), env.shape[1], orc.ENV_ASSIGNED)
+    oracle32.mesh_destroy(om)
+    with s.shard(row0, rows):
+        img = mbr._forward(s, spp, seed, ta, tr, tm, None, s.prepared_env())
+        e = rel_l2(img.cpu().numpy(), ref)
+        assert e <= 1e-4, e
+        Gh = torch.from_numpy(G[row0 - 2:row0 + rows + 2]).cuda().contiguous()
+        g_a, g_r, g_m, _, g_env = mbr._backward(s, spp, sg, ta, tr, tm, None, s.prepared_env(), Gh, True, True, True, False, True)
+    for key, got in (("a", g_a), ("r", g_r), ("m", g_m), ("env", g_env)):
+        e = rel_l2(got.cpu().numpy().reshape(gref[key].shape), gref[key])
+        assert e <= 1e-3, (key, e)
+    assert float(g_a[:row0 - 8].abs().max()) > 0          # gradients did reach texels far outside the sampled rows (secondary vertices)
+
+
 def test_mesh_mode_at_1080p_scale():
     """Mesh mode on a 1920x1080 height-field mesh (4.1 M triangles, 12 BVH levels): GPU-built BVH == brute force (float64-free
     restatement of the same Moeller-Trumbore in numpy, smallest t wins) on random rays; a forward render is finite, deterministic
