@@ -720,9 +720,13 @@ def run_c5_leg(args, dev, world, rank):
     opt = FusedBRDFOptimizer(scene, {"albedo": to(case["a"]), "roughness": to(case["r"]), "metallic": to(case["m"])}, gt, "arm", spp=spp, shard=shard)
     steps, warmup = max(2, min(args.steps, 4)), 3
     t = _timed(lambda s: opt.step(s), steps, warmup, dev, world, seed0=1000)
-    return {"workload": wl["desc"], "scaling": "strong", "image": [H, W], "spp": spp, "envmap": [wl["He"], wl["We"]], "n_gpus": world,
+    loss_last = float(opt.last["loss_mse"].item())
+    exchange = "peer memory (NVLink stores + in-kernel mailboxes)" if getattr(opt, "peer", None) is not None else ("nccl" if world > 1 else None)
+    if hasattr(opt, "close"):
+        opt.close()
+    return {"workload": wl["desc"], "scaling": "strong", "exchange": exchange, "image": [H, W], "spp": spp, "envmap": [wl["He"], wl["We"]], "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": t * 1e3, "value": H * W * spp / t / 1e9, "unit": UNIT, "iters_per_s": 1.0 / t,
-            "rows_per_rank": shard.rows, "loss_mse_last": float(opt.last["loss_mse"].item())}
+            "rows_per_rank": shard.rows, "loss_mse_last": loss_last}
 
 
 # ------------------------------------------------------------------------------------------------ b200 arm
@@ -847,8 +851,12 @@ def run_b200(args, wl):
                                        else " (+ ~100 torch elementwise/reduce launches for loss and Adam)"),
                "optimizer": args.optimizer,
                "kernel_ms": kavg, "roofline": roofline, "fp32": fp32, "cpu_baseline": cpu, "clocks": clk,
-               "loss_mse_last": float(opt.last["loss_mse"].item())}
+               "loss_mse_last": float(opt.last["loss_mse"].item()),
+               "exchange": ("peer memory (NVLink stores + in-kernel mailboxes; no NCCL call in the iteration)" if getattr(opt, "peer", None) is not None
+                            else ("nccl" if world > 1 else None))}
         print(json.dumps(out), flush=True)
+    if hasattr(opt, "close"):
+        opt.close()
     if world > 1:
         dist.destroy_process_group()
 

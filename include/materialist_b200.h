@@ -421,6 +421,40 @@ int mb200_loss_srgb_grad(const float* img, const float* gt_srgb, int64_t n, cons
 int mb200_adam_clamped(const mb200_adam_seg* segs_host, int nseg, float lr, float beta1, float beta2, float eps,
                        int step /* 1-based */, void* stream);
 
+/* ---------------------------------------------------------------- multi-GPU: exchange steps over peer memory (NVLink / NVSwitch)
+ * One process per GPU.  Every rank owns a mailbox of mb200_peer_box_bytes() bytes in peer-visible device memory
+ * (mb200_peer_alloc; the 64-byte IPC handle goes to the other ranks through any host channel, who map it with mb200_peer_open).
+ * The *_peer variants of the loss kernels exchange the three scalar sums of an iteration THROUGH those mailboxes from inside the
+ * kernels (the producer's last block stores its partial into every peer's mailbox and raises a flag; the consumer — the next kernel
+ * of the iteration — waits for all flags and adds the partials in rank order): what the reference's single process gets from
+ * `gt.mean() / pred.mean()`, `loss_mse`, `loss_l1` (inverse_img_w_mi.py:388-395) without a collective library in the loop.
+ * mb200_peer_push / mb200_peer_wait move the 2-row film halo of d(loss)/d(image) and the stepped boundary rows of the material
+ * maps between neighbouring row shards the same way.  peer->seq: > 0, incremented by the caller once per iteration, identical on
+ * all ranks. */
+#define MB200_MAX_PEERS 16
+#define MB200_PEER_MAX_PUSH 8
+#define MB200_PEER_HALO 0
+#define MB200_PEER_MAP  1
+typedef struct mb200_peer {
+    int32_t  rank, world;
+    uint32_t seq, reserved;
+    void*    box[MB200_MAX_PEERS];       /* mailbox of every rank as mapped into THIS process (box[rank] = its own) */
+} mb200_peer;
+typedef struct mb200_push_seg { const void* src; void* dst; int64_t n_float4; } mb200_push_seg;
+size_t mb200_peer_box_bytes(void);
+int mb200_peer_alloc(size_t bytes, void** dev_ptr_host, void* ipc_handle_64_host);   /* cudaMalloc + zero + IPC handle */
+int mb200_peer_open(const void* ipc_handle_64_host, void** dev_ptr_host);
+int mb200_peer_close(void* dev_ptr);
+int mb200_peer_free(void* dev_ptr);
+int mb200_image_sum_peer(const float* img, int64_t n, float* out_local /*1*/, void* scratch, const mb200_peer* peer_host, void* stream);
+int mb200_loss_srgb_sums_peer(const float* img, const float* gt_srgb, int64_t n, float* gt_pred_sums /* [1] receives the global sum */,
+                              float* out2_local, float* pred_srgb_opt, void* scratch, const mb200_peer* peer_host, void* stream);
+int mb200_loss_srgb_grad_peer(const float* img, const float* gt_srgb, int64_t n, const float* gt_pred_sums, float* sums2 /* receives the global sums */,
+                              int64_t n_total, float* grad, const mb200_peer* peer_host, void* stream);
+int mb200_peer_push(const mb200_peer* peer_host, int which, const mb200_push_seg* segs_host, int nseg, int to_up, int to_down,
+                    void* ticket, void* stream);
+int mb200_peer_wait(const mb200_peer* peer_host, int which, int from_up, int from_down, void* stream);
+
 /* ---------------------------------------------------------------- measurement aid (bench.py only) */
 /* Runs `iters` rounds of 16 independent FFMA chains per thread on SMs*8 blocks of 256 threads and writes a
  * checksum to out[0..]; returns the number of FLOPs issued (2 per FFMA) through *flops_host.  Used to MEASURE

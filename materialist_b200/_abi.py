@@ -63,6 +63,18 @@ class AdamSeg(C.Structure):
                 ("n", C.c_int64), ("lo", C.c_float), ("hi", C.c_float), ("aux_coeff", C.c_float)]
 
 
+MAX_PEERS, PEER_MAX_PUSH, PEER_HALO, PEER_MAP = 16, 8, 0, 1
+
+
+class Peer(C.Structure):
+    """mb200_peer: this rank, the world, the iteration's sequence number and every rank's mailbox as mapped into this process."""
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("seq", C.c_uint32), ("reserved", C.c_uint32), ("box", C.c_void_p * MAX_PEERS)]
+
+
+class PushSeg(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("n_float4", C.c_int64)]
+
+
 class MB200Error(RuntimeError):
     pass
 
@@ -134,6 +146,16 @@ def _load():
         "mb200_loss_srgb_grad": (i32, [vp, vp, i64, vp, vp, i64, vp, vp]),
         "mb200_adam_clamped": (i32, [C.POINTER(AdamSeg), i32, C.c_float, C.c_float, C.c_float, C.c_float, i32, vp]),
         "mb200_probe_ffma": (i32, [vp, i32, C.POINTER(C.c_double), vp]),
+        "mb200_peer_box_bytes": (sz, []),
+        "mb200_peer_alloc": (i32, [sz, C.POINTER(C.c_void_p), vp]),
+        "mb200_peer_open": (i32, [vp, C.POINTER(C.c_void_p)]),
+        "mb200_peer_close": (i32, [vp]),
+        "mb200_peer_free": (i32, [vp]),
+        "mb200_image_sum_peer": (i32, [vp, i64, vp, vp, C.POINTER(Peer), vp]),
+        "mb200_loss_srgb_sums_peer": (i32, [vp, vp, i64, vp, vp, vp, vp, C.POINTER(Peer), vp]),
+        "mb200_loss_srgb_grad_peer": (i32, [vp, vp, i64, vp, vp, i64, vp, C.POINTER(Peer), vp]),
+        "mb200_peer_push": (i32, [C.POINTER(Peer), i32, C.POINTER(PushSeg), i32, i32, i32, vp, vp]),
+        "mb200_peer_wait": (i32, [C.POINTER(Peer), i32, i32, i32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)           # AttributeError here = header / library mismatch

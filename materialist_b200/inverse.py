@@ -10,7 +10,7 @@ import torch.nn.functional as NF
 
 from . import _abi
 from . import renderop as _rop
-from .parallel import ShardContext
+from .parallel import PeerArena, ShardContext, peer_exchange_available, shard_rows
 from .renderop import render
 
 
@@ -142,13 +142,32 @@ class FusedBRDFOptimizer(_ShardedStep):
         self.shard = sh = shard or ShardContext(scene.H, scene.W)
         dev, H, W = scene.device, scene.H, scene.W
         self.names = [n for n, k in (("albedo", "a"), ("roughness", "r"), ("metallic", "m")) if k in optimize_part]
+        # Multi-GPU, G-buffer mode: the exchange steps of the iteration go over peer memory from inside / between the kernels
+        # (parallel.PeerArena) instead of through NCCL; the buffers the neighbours write into — the rendered-with maps and the
+        # d(loss)/d(image) buffer with its film halo — then live in this rank's peer-visible arena.
+        ch = {"albedo": 3, "roughness": 1, "metallic": 1}
+        self.peer = None
+        if (sh.world_size > 1 and scene.mesh is None and W % 4 == 0 and scene.filter == _abi.FILTER_GAUSSIAN
+                and scene.use_mesh_normal and peer_exchange_available(sh, dev)):
+            top = sh.halo if sh.rank > 0 else 0
+            bot = sh.halo if sh.rank < sh.world_size - 1 else 0
+            ar = PeerArena(sh, dev)
+            for k in ("albedo", "roughness", "metallic"):
+                ar.alloc(k, (H, W, ch[k]))
+            ar.alloc("grad_full", (top + sh.rows + bot, W, 3))
+            ar.alloc("ticket", (64,), torch.int32)
+            self.peer = ar.finalize()
         # the maps the kernels render with (full image; this rank only ever touches its own rows)
-        self.mat = {k: mat[k].detach().float().clone().contiguous() for k in ("albedo", "roughness", "metallic")}
+        if self.peer is not None:
+            self.mat = {k: self.peer.tensor(k) for k in ("albedo", "roughness", "metallic")}
+            for k in self.mat:
+                self.mat[k].copy_(mat[k].detach().float())
+        else:
+            self.mat = {k: mat[k].detach().float().clone().contiguous() for k in ("albedo", "roughness", "metallic")}
         for k in self.names:
             self.mat[k].clamp_(*self._RANGE[k])
         self.ori = {k: mat[k].detach().float().clone().contiguous() for k in self.names}
         self.params = {k: mat[k].detach().float().clone().contiguous() for k in self.names}
-        ch = {"albedo": 3, "roughness": 1, "metallic": 1}
         # one flat gradient buffer (one memset per iteration) and one flat Adam state
         sizes = [H * W * ch[k] for k in ("albedo", "roughness", "metallic")]
         self.gflat = torch.zeros(sum(sizes), device=dev)
@@ -165,7 +184,12 @@ class FusedBRDFOptimizer(_ShardedStep):
         self.scal[0:1] = sh.all_reduce_sum(self.gt.sum().reshape(1).clone())
         self.sums2 = torch.zeros(2, device=dev)
         self.scratch = torch.zeros(_abi.lib.mb200_reduce_scratch_bytes() // 4 + 1, dtype=torch.int32, device=dev)
-        self.grad_full, self.grad_img = sh.halo_buffer(3, dev)         # d loss / d image: own rows (a view) inside the rows + film-halo buffer
+        if self.peer is not None:                                      # d loss / d image: own rows (a view) inside the rows + film-halo buffer
+            self.grad_full = self.peer.tensor("grad_full")
+            self.grad_img = self.grad_full[top:top + sh.rows]
+            self._peer_plan(top)
+        else:
+            self.grad_full, self.grad_img = sh.halo_buffer(3, dev)
         self.pred_srgb = torch.empty(sh.rows, W, 3, device=dev)
         self.k, self._lr, self._epoch = 0, lr, 0
         self.last = {}
@@ -203,7 +227,44 @@ class FusedBRDFOptimizer(_ShardedStep):
             segs[i].aux_coeff = scale_delta / (npx * c)
         self.segs = segs
 
+    def _peer_plan(self, top):
+        """Push descriptors of the two halo exchanges (constant over the optimisation): where this rank's boundary rows land in the
+        neighbours' arenas."""
+        sh, ar, W, h = self.shard, self.peer, self.scene.W, self.shard.halo
+        up = sh.rank - 1 if sh.rank > 0 else -1
+        down = sh.rank + 1 if sh.rank < sh.world_size - 1 else -1
+        self._nb = (up, down)
+        row_b = W * 3 * 4
+        segs = []
+        if up >= 0:       # my first h rows -> the upper neighbour's bottom halo
+            up_top = h if up > 0 else 0
+            up_rows = shard_rows(sh.H, sh.world_size, up)[1]
+            segs.append((self.grad_full[top:top + h].data_ptr(), ar.remote_ptr(up, "grad_full", (up_top + up_rows) * row_b), h * row_b // 16))
+        if down >= 0:     # my last h rows -> the lower neighbour's top halo
+            segs.append((self.grad_full[top + sh.rows - h:top + sh.rows].data_ptr(), ar.remote_ptr(down, "grad_full", 0), h * row_b // 16))
+        self._push_halo = (_abi.PushSeg * max(1, len(segs)))(*[_abi.PushSeg(a, b, n) for a, b, n in segs]); self._n_push_halo = len(segs)
+        segs = []
+        chn = {"albedo": 3, "roughness": 1, "metallic": 1}
+        r0, r1 = sh.row0, sh.row0 + sh.rows
+        for k in self.names:
+            rb = W * chn[k] * 4
+            if up >= 0:
+                segs.append((self.mat[k][r0:r0 + h].data_ptr(), ar.remote_ptr(up, k, r0 * rb), h * rb // 16))
+            if down >= 0:
+                segs.append((self.mat[k][r1 - h:r1].data_ptr(), ar.remote_ptr(down, k, (r1 - h) * rb), h * rb // 16))
+        self._push_map = (_abi.PushSeg * max(1, len(segs)))(*[_abi.PushSeg(a, b, n) for a, b, n in segs]); self._n_push_map = len(segs)
+        self._ticket = self.peer.tensor("ticket")
+
+    def close(self):
+        """Unmaps / frees the peer arena (collective; call on every rank when the optimisation is over)."""
+        if self.peer is not None:
+            keep = {k: v.clone() for k, v in self.mat.items()}
+            self.peer.close(); self.peer = None
+            self.mat = keep
+
     def _step(self, seed):
+        if self.peer is not None:
+            return self._step_peer(seed)
         sc, sh, lib, st = self.scene, self.shard, _abi.lib, _abi.stream_ptr()
         a, r, m = self.mat["albedo"], self.mat["roughness"], self.mat["metallic"]
         env_pack = sc.prepared_env()
@@ -269,6 +330,59 @@ class FusedBRDFOptimizer(_ShardedStep):
             # only this rank's rows were stepped; its next forward READS the neighbours' maps in the 2-row film halo, and they have
             # just stepped those rows: fetch them (without this the sharded run drifts from the single-GPU run after iteration 1)
             sh.map_halo_exchange([self.mat[k] for k in self.names] + ([self.normal] if self.n_param is not None else []))
+        self.last = {"loss_mse": self.sums2[0] / self.n_total, "loss_l1": self.sums2[1] / self.n_total, "pred": self.pred_srgb}
+        return self.last["loss_mse"]
+
+
+    def _step_peer(self, seed):
+        """The iteration with its exchange steps over peer memory (see __init__): shade_fwd -> film_develop -> image_sum [publishes
+        Σ pred] -> loss_srgb_sums [collects Σ pred; publishes Σ diff², Σ |diff|] -> loss_srgb_grad [collects] -> push of the film halo of
+        d loss / d image into the neighbours -> wait for theirs -> film_adjoint -> shade_bwd -> adam_clamped -> push of the stepped
+        boundary rows of the maps into the neighbours (awaited at the start of the next iteration).  No NCCL call."""
+        sc, sh, lib, st, ar = self.scene, self.shard, _abi.lib, _abi.stream_ptr(), self.peer
+        a, r, m = self.mat["albedo"], self.mat["roughness"], self.mat["metallic"]
+        env_pack = sc.prepared_env()
+        seed_grad = _rop.default_seed_grad(int(seed))
+        seq = self.k + 1
+        up, down = self._nb
+        pr = ar.peer(seq)
+        if seq > 1:       # the neighbours' stepped boundary rows of the previous iteration have landed in my maps
+            prev = ar.peer(seq - 1)
+            _abi.check(lib.mb200_peer_wait(C.byref(prev), _abi.PEER_MAP, up, down, st), "mb200_peer_wait")
+        img = _rop._forward(sc, self.spp, int(seed), a, r, m, None, env_pack)
+        main = torch.cuda.current_stream(sc.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(sc.device)
+            self._ev_fwd, self._ev_w = torch.cuda.Event(), torch.cuda.Event()
+        self._ev_fwd.record(main)
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(self._ev_fwd)
+            self._wpart = _rop._film_weights(sc, self.spp, seed_grad, env_pack[2].res_x, out=self._wpart)
+            self._ev_w.record(self._side)
+        n = img.numel()
+        _abi.check(lib.mb200_image_sum_peer(_abi.ptr(img), n, C.c_void_p(self.scal.data_ptr() + 4), _abi.ptr(self.scratch), C.byref(pr), st),
+                   "mb200_image_sum_peer")
+        _abi.check(lib.mb200_loss_srgb_sums_peer(_abi.ptr(img), _abi.ptr(self.gt_srgb), n, _abi.ptr(self.scal), _abi.ptr(self.sums2),
+                                                 _abi.ptr(self.pred_srgb), _abi.ptr(self.scratch), C.byref(pr), st), "mb200_loss_srgb_sums_peer")
+        _abi.check(lib.mb200_loss_srgb_grad_peer(_abi.ptr(img), _abi.ptr(self.gt_srgb), n, _abi.ptr(self.scal), _abi.ptr(self.sums2),
+                                                 self.n_total, _abi.ptr(self.grad_img), C.byref(pr), st), "mb200_loss_srgb_grad_peer")
+        _abi.check(lib.mb200_peer_push(C.byref(pr), _abi.PEER_HALO, self._push_halo, self._n_push_halo, up, down, _abi.ptr(self._ticket), st),
+                   "mb200_peer_push")
+        self.gflat.zero_()
+        main.wait_event(self._ev_w)
+        _abi.check(lib.mb200_peer_wait(C.byref(pr), _abi.PEER_HALO, up, down, st), "mb200_peer_wait")
+        _rop._backward(sc, self.spp, seed_grad, a, r, m, None, env_pack, self.grad_full,
+                       "albedo" in self.names, "roughness" in self.names, "metallic" in self.names, False, False,
+                       out=(self.grads["albedo"], self.grads["roughness"], self.grads["metallic"]), wpart=self._wpart)
+        self.k += 1
+        lr = self._lr
+        if self._lr > 1.5e-4:
+            self._epoch += 1
+            if self._epoch % 100 == 0:
+                self._lr *= 0.8
+        _abi.check(lib.mb200_adam_clamped(self.segs, len(self.names), lr, self.betas[0], self.betas[1], self.eps, self.k, st), "mb200_adam_clamped")
+        _abi.check(lib.mb200_peer_push(C.byref(pr), _abi.PEER_MAP, self._push_map, self._n_push_map, up, down,
+                                       C.c_void_p(self._ticket.data_ptr() + 64), st), "mb200_peer_push")
         self.last = {"loss_mse": self.sums2[0] / self.n_total, "loss_l1": self.sums2[1] / self.n_total, "pred": self.pred_srgb}
         return self.last["loss_mse"]
 

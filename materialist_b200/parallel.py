@@ -11,7 +11,15 @@ steps of an iteration:
      have just stepped them.
 
 RNG streams are indexed by the GLOBAL lane id, so any sharding reproduces the single-GPU samples exactly.
+
+On GPUs the fused BRDF iteration does steps 1, 2 and 4 WITHOUT a collective library in the loop (`PeerArena`): every rank maps
+the other ranks' peer-visible memory (CUDA IPC over NVLink / NVSwitch), the loss kernels exchange their scalar sums through
+mailboxes from inside the kernels, and the halo rows are stored straight into the neighbours' buffers (include/materialist_b200.h,
+"multi-GPU: exchange steps over peer memory").  NCCL remains for set-up, for the envmap / MLP gradient sums and as the fallback.
 """
+import ctypes as C
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -110,3 +118,101 @@ class ShardContext:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
         return full
+
+
+class _DevMem:
+    """A raw device allocation as a CUDA-array-interface object (torch.as_tensor wraps it without copying)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class PeerArena:
+    """Peer-visible device memory of this rank (mailbox + named buffers) and the mappings of every other rank's arena.
+
+    Collective: all ranks of the shard's group construct it together, `alloc` the same names, then `finalize()` (which exchanges the
+    IPC handles and the offset tables through torch.distributed — set-up only).  `tensor(name)` is this rank's buffer;
+    `remote_ptr(rank, name, byte_offset)` is where that buffer of another rank is mapped in this process."""
+
+    def __init__(self, shard, device):
+        from . import _abi
+        if shard.world_size < 2 or shard.world_size > _abi.MAX_PEERS:
+            raise ValueError("PeerArena needs 2..%d ranks" % _abi.MAX_PEERS)
+        self._abi, self.shard, self.device = _abi, shard, torch.device(device)
+        self.box_bytes = int(_abi.lib.mb200_peer_box_bytes())
+        self._plan, self._cursor = {}, self.box_bytes
+        self.base, self._own, self._mem, self._tensors = None, None, None, {}
+
+    def alloc(self, name, shape, dtype=torch.float32):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        self._plan[name] = (self._cursor, tuple(int(d) for d in shape), dtype, nbytes)
+        self._cursor += (nbytes + 255) & ~255
+
+    def finalize(self):
+        _abi, sh = self._abi, self.shard
+        with torch.cuda.device(self.device):
+            ptr = C.c_void_p(); handle = (C.c_ubyte * 64)()
+            _abi.check(_abi.lib.mb200_peer_alloc(self._cursor, C.byref(ptr), handle), "mb200_peer_alloc")
+            self._own = ptr.value
+            mine = (bytes(handle), {k: v[0] for k, v in self._plan.items()})
+            everyone = [None] * sh.world_size
+            dist.all_gather_object(everyone, mine, group=sh.group)
+            self.base, self.offsets = [None] * sh.world_size, [e[1] for e in everyone]
+            for r, (h, _) in enumerate(everyone):
+                if r == sh.rank:
+                    self.base[r] = self._own
+                else:
+                    q = C.c_void_p(); hb = (C.c_ubyte * 64).from_buffer_copy(h)
+                    _abi.check(_abi.lib.mb200_peer_open(hb, C.byref(q)), "mb200_peer_open")
+                    self.base[r] = q.value
+            self._mem = torch.as_tensor(_DevMem(self._own, self._cursor), device=self.device)
+            for name, (off, shape, dtype, nbytes) in self._plan.items():
+                self._tensors[name] = self._mem[off:off + nbytes].view(dtype).view(shape)
+            dist.barrier(group=sh.group)          # every mailbox is zeroed and mapped before anyone's first kernel writes into it
+        return self
+
+    def tensor(self, name):
+        return self._tensors[name]
+
+    def remote_ptr(self, rank, name, byte_offset=0):
+        return self.base[rank] + self.offsets[rank][name] + int(byte_offset)
+
+    def peer(self, seq):
+        p = self._abi.Peer()
+        p.rank, p.world, p.seq = self.shard.rank, self.shard.world_size, int(seq)
+        for r in range(self.shard.world_size):
+            p.box[r] = self.base[r]
+        return p
+
+    def close(self):
+        if self.base is None:
+            return
+        lib = self._abi.lib
+        try:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.shard.group)   # nobody unmaps / frees while a peer's kernel may still write here
+        except Exception:
+            pass
+        for r, b in enumerate(self.base):
+            if r != self.shard.rank and b:
+                lib.mb200_peer_close(C.c_void_p(b))
+        self._tensors, self._mem = {}, None
+        lib.mb200_peer_free(C.c_void_p(self._own))
+        self.base = None
+
+
+def peer_exchange_available(shard, device):
+    """The peer-memory exchange needs one GPU per rank on one node with peer access (NVLink / NVSwitch) and the NCCL-era set-up
+    channel; MB200_PEER=0 forces the NCCL path."""
+    if os.environ.get("MB200_PEER", "1") == "0" or shard.world_size < 2 or shard.world_size > 16:
+        return False
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_backend(shard.group) != "nccl":
+        return False
+    dev = torch.device(device)
+    if dev.type != "cuda" or torch.cuda.device_count() < shard.world_size:
+        return False
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    return all(p == idx or torch.cuda.can_device_access_peer(idx, p) for p in range(shard.world_size))

@@ -49,7 +49,12 @@ def run_gbuffer(dev, shard, cls, K=5, H=64, W=64, spp=32):
         opt.step(100 + k)
     assert (scene.row0, scene.rows) == (0, H)                 # the optimiser leaves the scene unsharded
     maps = opt.mat if cls is FusedBRDFOptimizer else {k: v.detach() for k, v in opt.params.items()}
-    return {k: v.clone() for k, v in maps.items()}
+    out = {k: v.clone() for k, v in maps.items()}
+    if getattr(opt, "peer", None) is not None:
+        print(f"rank {shard.rank}: {cls.__name__} exchanged over peer memory (no NCCL in the iteration)", flush=True)
+    if hasattr(opt, "close"):
+        opt.close()
+    return out
 
 
 def run_posmlp(dev, shard, K=3, H=64, W=64, spp=32):
