@@ -4,6 +4,7 @@
 with a ShardContext the three scalar sums and the image-gradient halo are exchanged between ranks.
 """
 import ctypes as C
+import os
 
 import torch
 import torch.nn.functional as NF
@@ -255,6 +256,38 @@ class FusedBRDFOptimizer(_ShardedStep):
         self._push_map = (_abi.PushSeg * max(1, len(segs)))(*[_abi.PushSeg(a, b, n) for a, b, n in segs]); self._n_push_map = len(segs)
         self._ticket = self.peer.tensor("ticket")
 
+    def _launch_film_weights(self, main, seed_grad, env_pack):
+        """The film weights of the adjoint render depend on nothing but seed_grad: they run on a side stream.  Default: launched right
+        AFTER the forward render, under the loss kernels and (multi-GPU) the latency of the exchange steps that sit between the two
+        render kernels.  MB200_FILM_WEIGHTS_EARLY=1 launches them BEFORE the forward render instead, co-resident with it (shade_fwd
+        leaves ~20 % of the issue slots idle); measured at C2 (profiles/r5h): step 2.736 -> 2.726 ms, the forward kernel slows from
+        1.19 to 1.25 ms while the weights take 0.94 ms beside it — issue slots are conserved, so the gain is the 10 us tail only; left
+        off so that the per-kernel times of the bench stay clean."""
+        sc = self.scene
+        if sc.filter != _abi.FILTER_GAUSSIAN:
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream(sc.device)
+            self._ev_fwd, self._ev_w = torch.cuda.Event(), torch.cuda.Event()
+            self._fw_late = os.environ.get("MB200_FILM_WEIGHTS_EARLY", "0") != "1"
+        if self._fw_late:
+            self._pending_fw = (seed_grad, env_pack)
+            return
+        self._ev_fwd.record(main)                 # after the previous iteration's adjoint render (which read the weight buffer)
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(self._ev_fwd)
+            self._wpart = _rop._film_weights(sc, self.spp, seed_grad, env_pack[2].res_x, out=self._wpart)
+            self._ev_w.record(self._side)
+
+    def _late_film_weights(self, main):
+        if self.scene.filter == _abi.FILTER_GAUSSIAN and self._fw_late:
+            seed_grad, env_pack = self._pending_fw
+            self._ev_fwd.record(main)
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(self._ev_fwd)
+                self._wpart = _rop._film_weights(self.scene, self.spp, seed_grad, env_pack[2].res_x, out=self._wpart)
+                self._ev_w.record(self._side)
+
     def close(self):
         """Unmaps / frees the peer arena (collective; call on every rank when the optimisation is over)."""
         if self.peer is not None:
@@ -270,20 +303,10 @@ class FusedBRDFOptimizer(_ShardedStep):
         env_pack = sc.prepared_env()
         seed_grad = _rop.default_seed_grad(int(seed))
         nmap = self.normal
-        img = _rop._forward(sc, self.spp, int(seed), a, r, m, nmap, env_pack)
-        # The film weights of the adjoint render depend on nothing but seed_grad: they run on a side stream, UNDER the loss kernels
-        # and — with several ranks — under the latency of the scalar all-reduces and of the halo exchange that sit between the two
-        # render kernels (~30 us each over NVLink, during which this GPU would otherwise idle).
         main = torch.cuda.current_stream(sc.device)
-        if sc.filter == _abi.FILTER_GAUSSIAN:
-            if self._side is None:
-                self._side = torch.cuda.Stream(sc.device)
-                self._ev_fwd, self._ev_w = torch.cuda.Event(), torch.cuda.Event()
-            self._ev_fwd.record(main)
-            with torch.cuda.stream(self._side):
-                self._side.wait_event(self._ev_fwd)
-                self._wpart = _rop._film_weights(sc, self.spp, seed_grad, env_pack[2].res_x, out=self._wpart)
-                self._ev_w.record(self._side)
+        self._launch_film_weights(main, seed_grad, env_pack)
+        img = _rop._forward(sc, self.spp, int(seed), a, r, m, nmap, env_pack)
+        self._late_film_weights(main)
         n = img.numel()
         _abi.check(lib.mb200_image_sum(_abi.ptr(img), n, C.c_void_p(self.scal.data_ptr() + 4), _abi.ptr(self.scratch), st), "mb200_image_sum")
         if sh.world_size > 1:
@@ -349,16 +372,10 @@ class FusedBRDFOptimizer(_ShardedStep):
         if seq > 1:       # the neighbours' stepped boundary rows of the previous iteration have landed in my maps
             prev = ar.peer(seq - 1)
             _abi.check(lib.mb200_peer_wait(C.byref(prev), _abi.PEER_MAP, up, down, st), "mb200_peer_wait")
-        img = _rop._forward(sc, self.spp, int(seed), a, r, m, None, env_pack)
         main = torch.cuda.current_stream(sc.device)
-        if self._side is None:
-            self._side = torch.cuda.Stream(sc.device)
-            self._ev_fwd, self._ev_w = torch.cuda.Event(), torch.cuda.Event()
-        self._ev_fwd.record(main)
-        with torch.cuda.stream(self._side):
-            self._side.wait_event(self._ev_fwd)
-            self._wpart = _rop._film_weights(sc, self.spp, seed_grad, env_pack[2].res_x, out=self._wpart)
-            self._ev_w.record(self._side)
+        self._launch_film_weights(main, seed_grad, env_pack)
+        img = _rop._forward(sc, self.spp, int(seed), a, r, m, None, env_pack)
+        self._late_film_weights(main)
         n = img.numel()
         _abi.check(lib.mb200_image_sum_peer(_abi.ptr(img), n, C.c_void_p(self.scal.data_ptr() + 4), _abi.ptr(self.scratch), C.byref(pr), st),
                    "mb200_image_sum_peer")
