@@ -25,24 +25,36 @@ constexpr size_t kStageBudgetFwd = 27 * 1024, kStageBudgetBwd = 44 * 1024;
 
 
 // ---------------------------------------------------------------- forward kernel
-template <int FILTER, bool AD_W, bool TRANS = false>
+// LPP = lanes per pixel (32 or 8): a warp shades 32 / LPP pixels at a time, lane l = (pixel group l / LPP, sample slot l % LPP), and a
+// lane walks the samples slot, slot + LPP, ... of ITS pixel.  LPP = 8 amortises everything that is per pixel — G-buffer and map
+// loads, the texel projection, the view vector, two frames, index arithmetic, the final stores: ~170 instructions a lane, 6-8 % of
+// the kernel at 64 spp with a whole warp per pixel — over 4x as many samples per lane, and keeps all lanes busy from 8 spp up
+// (a warp per pixel idles lanes below 32 spp).  The film-tap reduction is unchanged in cost: still 32 staged records per batch,
+// lanes 0..24 each own one tap, now with one accumulator per pixel group.
+template <int FILTER, bool AD_W, bool TRANS = false, int LPP = 32>
 __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_FWD) shade_fwd_kernel(const __grid_constant__ RenderParams P) {
+    constexpr int PPW = 32 / LPP;
     __shared__ __align__(16) float s_rec[FILTER == MB200_FILTER_GAUSSIAN ? kWarpsPerBlock * 32 * kRecStride : 4];
     extern __shared__ float4 s_dyn[];
     const StagedEnv S = stage_env(P, s_dyn);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane / LPP, sl = lane % LPP;
     float* rec = s_rec + (FILTER == MB200_FILTER_GAUSSIAN ? warp * 32 * kRecStride : 0);
     const int npix = P.prows * P.W;
     const int ti = lane % 5, tj = lane / 5;              // tap owned by this lane (lanes 0..24)
-    for (int pix = blockIdx.x * kWarpsPerBlock + warp; pix < npix; pix += gridDim.x * kWarpsPerBlock) {
+    for (int pix0 = (blockIdx.x * kWarpsPerBlock + warp) * PPW; pix0 < npix; pix0 += gridDim.x * kWarpsPerBlock * PPW) {
+        const bool pix_ok = pix0 + grp < npix;           // (a ragged last warp: the extra groups shade nothing)
+        const int pix = pix_ok ? pix0 + grp : npix - 1;
         const int py = P.prow0 + pix / P.W, px = pix % P.W;
         const int gpix = py * P.W + px;
         const PixelCtx c = load_pixel<TRANS>(P, gpix);
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s0 = 0; s0 < P.spp; s0 += 32) {
-            const int s = s0 + lane;
+        float4 acc[PPW];
+#pragma unroll
+        for (int g = 0; g < PPW; ++g) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s0 = 0; s0 < P.spp; s0 += LPP) {
+            const int s = s0 + sl;
             float3 L = f3(0.f, 0.f, 0.f); float jx = 0.f, jy = 0.f;
-            const bool act = s < P.spp;
+            const bool act = pix_ok && s < P.spp;
             if (act) L = shade_sample<AD_W, TRANS>(P, c, px, py, (uint32_t)gpix * (uint32_t)P.spp + (uint32_t)s, jx, jy, nullptr, S);
             if (FILTER == MB200_FILTER_GAUSSIAN) {
                 float wx[5], wy[5]; film_taps(jx, wx); film_taps(jy, wy);
@@ -54,31 +66,38 @@ __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_FWD) shade_fwd_kernel(
                 r4[3] = make_float4(L.x, L.y, L.z, 1.f);
                 __syncwarp();
                 if (lane < MB200_FILM_TAPS) {
-                    // inactive lanes of a ragged last batch staged wx = 0 -> w = 0: always 32 records, fully unrollable
+                    // inactive lanes staged wx = 0 -> w = 0: always 32 records (LPP per pixel group), fully unrollable
                     const float* rt = rec + ti; const float* ru = rec + 5 + tj;
+#pragma unroll
+                    for (int g = 0; g < PPW; ++g) {
 #pragma unroll 8
-                    for (int k = 0; k < 32; ++k) {
-                        const float w = rt[k * kRecStride] * ru[k * kRecStride];
-                        const float4 l4 = *reinterpret_cast<const float4*>(rec + k * kRecStride + 12);
-                        acc.x = fmaf(w, l4.x, acc.x); acc.y = fmaf(w, l4.y, acc.y); acc.z = fmaf(w, l4.z, acc.z); acc.w += w;
+                        for (int kk = 0; kk < LPP; ++kk) {
+                            const int k = g * LPP + kk;
+                            const float w = rt[k * kRecStride] * ru[k * kRecStride];
+                            const float4 l4 = *reinterpret_cast<const float4*>(rec + k * kRecStride + 12);
+                            acc[g].x = fmaf(w, l4.x, acc[g].x); acc[g].y = fmaf(w, l4.y, acc[g].y); acc[g].z = fmaf(w, l4.z, acc[g].z); acc[g].w += w;
+                        }
                     }
                 }
                 __syncwarp();
             } else {
-                acc.x += L.x; acc.y += L.y; acc.z += L.z;
+                acc[0].x += L.x; acc[0].y += L.y; acc[0].z += L.z;
             }
         }
         if (FILTER == MB200_FILTER_GAUSSIAN) {
-            if (lane < MB200_FILM_TAPS)
-                reinterpret_cast<float4*>(P.partials)[(size_t)pix * MB200_FILM_TAPS + lane] = acc;
+            if (lane < MB200_FILM_TAPS) {
+#pragma unroll
+                for (int g = 0; g < PPW; ++g)
+                    if (pix0 + g < npix) reinterpret_cast<float4*>(P.partials)[(size_t)(pix0 + g) * MB200_FILM_TAPS + lane] = acc[g];
+            }
         } else {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-                acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+            for (int o = LPP / 2; o > 0; o >>= 1) {
+                acc[0].x += __shfl_xor_sync(0xffffffffu, acc[0].x, o);
+                acc[0].y += __shfl_xor_sync(0xffffffffu, acc[0].y, o);
+                acc[0].z += __shfl_xor_sync(0xffffffffu, acc[0].z, o);
             }
-            if (lane == 0) reinterpret_cast<float4*>(P.partials)[pix] = make_float4(acc.x, acc.y, acc.z, (float)P.spp);
+            if (sl == 0 && pix_ok) reinterpret_cast<float4*>(P.partials)[pix] = make_float4(acc[0].x, acc[0].y, acc[0].z, (float)P.spp);
         }
     }
 }
@@ -166,13 +185,17 @@ __global__ void film_adjoint_kernel(const float* __restrict__ wpart, int H, int 
 // (the default: the kernel is instruction-issue bound and the L2 atomic units absorb the updates, profiles/r4b_envphase*.log);
 // true = warp-aggregated (match.any + register peer reduction) and, for small maps, block-privatised in shared memory — what
 // north_star prescribes; measured SLOWER on B200 (16x32 + sun: 1.55 / 1.64 ms against 1.40 ms) and kept selectable (MB200_ENV_SCATTER=agg).
-template <int FILTER, bool WANT_MAT, bool WANT_N, bool WANT_ENV, bool ENVAGG = false>
+// LPP: lanes per pixel, as in shade_fwd_kernel (each pixel group of a warp has its own 5x5 film cotangent in shared memory; the
+// material gradients are reduced over the LPP lanes of a group).
+template <int FILTER, bool WANT_MAT, bool WANT_N, bool WANT_ENV, bool ENVAGG = false, int LPP = 32>
 __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_BWD) shade_bwd_kernel(const __grid_constant__ RenderParams P) {
-    __shared__ float4 s_g[FILTER == MB200_FILTER_GAUSSIAN ? kWarpsPerBlock * MB200_FILM_TAPS : 1];
+    constexpr int PPW = 32 / LPP;
+    __shared__ float4 s_g[FILTER == MB200_FILTER_GAUSSIAN ? kWarpsPerBlock * PPW * MB200_FILM_TAPS : 1];
     extern __shared__ float4 s_dyn[];
     const StagedEnv S = stage_env(P, s_dyn);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float4* gt = s_g + (FILTER == MB200_FILTER_GAUSSIAN ? warp * MB200_FILM_TAPS : 0);
+    const int grp = lane / LPP, sl = lane % LPP;
+    float4* gt = s_g + (FILTER == MB200_FILTER_GAUSSIAN ? (warp * PPW + grp) * MB200_FILM_TAPS : 0);
     const int npix = P.prows * P.W;
     // this CTA's privatised copy of the envmap-gradient grid (mb200_env_grad_slabs) and, for small maps, its shared-memory accumulator
     float4* const genv = WANT_ENV ? P.g_env4 + (long long)(blockIdx.x % P.env_slabs) * P.env_slab_stride : nullptr;
@@ -182,19 +205,21 @@ __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_BWD) shade_bwd_kernel(
         for (int i = threadIdx.x; i < 3 * (int)P.env_slab_stride; i += blockDim.x) senv[i] = 0.f;
         __syncthreads();
     }
-    for (int pix = blockIdx.x * kWarpsPerBlock + warp; pix < npix; pix += gridDim.x * kWarpsPerBlock) {
+    for (int pix0 = (blockIdx.x * kWarpsPerBlock + warp) * PPW; pix0 < npix; pix0 += gridDim.x * kWarpsPerBlock * PPW) {
+        const bool pix_ok = pix0 + grp < npix;
+        const int pix = pix_ok ? pix0 + grp : npix - 1;
         const int py = P.prow0 + pix / P.W, px = pix % P.W;
         const int gpix = py * P.W + px;
         const PixelCtx c = load_pixel(P, gpix);
         float3 gbox = f3(0, 0, 0);
         if (FILTER == MB200_FILTER_GAUSSIAN) {
             __syncwarp();
-            if (lane < MB200_FILM_TAPS) {
-                const int qy = py + (lane / 5 - 2), qx = px + (lane % 5 - 2);
+            for (int t = sl; t < MB200_FILM_TAPS; t += LPP) {
+                const int qy = py + (t / 5 - 2), qx = px + (t % 5 - 2);
                 float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (qx >= 0 && qx < P.W && qy >= P.grow0 && qy < P.grow0 + P.grows && qy >= 0 && qy < P.H)
                     g = __ldg(P.gadj + (size_t)(qy - P.grow0) * P.W + qx);
-                gt[lane] = g;
+                gt[t] = g;
             }
             __syncwarp();
         } else {
@@ -202,12 +227,12 @@ __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_BWD) shade_bwd_kernel(
             gbox = f3(g.x, g.y, g.z);
         }
         float3 ga = f3(0, 0, 0), gn = f3(0, 0, 0); float gr = 0.f, gm = 0.f;
-        for (int s0 = 0; s0 < P.spp; s0 += 32) {          // uniform trip count: the aggregated envmap scatter below is warp-collective
-            const int s = s0 + lane;
+        for (int s0 = 0; s0 < P.spp; s0 += LPP) {         // uniform trip count: the aggregated envmap scatter below is warp-collective
+            const int s = s0 + sl;
             Bilerp bA, bB; float3 cA = f3(0, 0, 0), cB = f3(0, 0, 0); bool aA = false, aB = false;   // this lane's envmap-gradient updates
             bA.i00 = bB.i00 = 0; bA.w0x = bA.w1x = bA.w0y = bA.w1y = bB.w0x = bB.w1x = bB.w0y = bB.w1y = 0.f;
             do {
-            if (s >= P.spp) break;
+            if (s >= P.spp || !pix_ok) break;
             Pcg32 rng; rng.seed(P.seed, (uint32_t)gpix * (uint32_t)P.spp + (uint32_t)s);
             const float jx = rng.next_float(), jy = rng.next_float();
             // film adjoint: dl = sum_taps wx_i wy_j G[p + (i,j)]
@@ -281,12 +306,12 @@ __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_BWD) shade_bwd_kernel(
             } while (false);
             if (WANT_ENV && ENVAGG) {
                 env_scatter_agg(genv, senv, P.env.Wi, bA, cA, aA);
-                if (c.valid) env_scatter_agg(genv, senv, P.env.Wi, bB, cB, aB);      // (warp-uniform: all samples of a pixel share its validity)
+                if (LPP < 32 || c.valid) env_scatter_agg(genv, senv, P.env.Wi, bB, cB, aB);   // (one pixel per warp: validity is warp-uniform)
             }
         }
         if (WANT_MAT) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
+            for (int o = LPP / 2; o > 0; o >>= 1) {
                 ga.x += __shfl_xor_sync(0xffffffffu, ga.x, o); ga.y += __shfl_xor_sync(0xffffffffu, ga.y, o);
                 ga.z += __shfl_xor_sync(0xffffffffu, ga.z, o);
                 gr += __shfl_xor_sync(0xffffffffu, gr, o); gm += __shfl_xor_sync(0xffffffffu, gm, o);
@@ -295,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_BWD) shade_bwd_kernel(
                     gn.z += __shfl_xor_sync(0xffffffffu, gn.z, o);
                 }
             }
-            if (lane == 0 && c.valid && P.max_depth >= 2) {
+            if (sl == 0 && pix_ok && c.valid && P.max_depth >= 2) {
                 if (P.g_a) { atomicAdd(P.g_a + 3 * c.flat, ga.x); atomicAdd(P.g_a + 3 * c.flat + 1, ga.y); atomicAdd(P.g_a + 3 * c.flat + 2, ga.z); }
                 if (P.g_r) atomicAdd(P.g_r + c.flat, gr);
                 if (P.g_m) atomicAdd(P.g_m + c.flat, gm);
@@ -358,10 +383,25 @@ __global__ void sample_record_kernel(const __grid_constant__ RenderParams P, int
     if (out_L) { out_L[3 * i] = L.x; out_L[3 * i + 1] = L.y; out_L[3 * i + 2] = L.z; }
 }
 
-template <int FILTER>
+// Lanes per pixel of the G-buffer kernels.  Measured at C2 (64 spp, profiles/r5i_lpp_ab.log):
+//   adjoint  warp per pixel 1.291 ms -> 8 lanes per pixel 1.207 ms (-6.5 %): default 8 up to 128 spp (above, the per-pixel work no
+//            longer shows and a whole warp per pixel keeps the film cotangents of ONE pixel in shared memory);
+//   forward  1.189 ms -> 1.232 ms at its 64-register cap (four tap accumulators instead of one: spills), 1.195 ms at 80 registers /
+//            3 CTAs per SM: no gain, so the forward keeps a warp per pixel from 32 spp up and uses 8 lanes per pixel only below
+//            (where a warp per pixel would idle lanes).
+// MB200_LPP=8|32 forces both kernels (measurements).
+inline int lanes_per_pixel(int spp, bool adjoint) {
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("MB200_LPP"); forced = e ? atoi(e) : 0; }
+    if (forced == 8 || forced == 32) return forced;
+    if (adjoint) return spp <= 128 ? 8 : 32;
+    return spp < 32 ? 8 : 32;
+}
+
+template <int FILTER, int LPP>
 int launch_bwd(const RenderParams& P, bool want_mat, bool want_n, bool want_env, size_t dyn, cudaStream_t st) {
-    const int npix = P.prows * P.W;
-#define MB_BWD(M, N, E, A) shade_bwd_kernel<FILTER, M, N, E, A><<<persistent_grid(shade_bwd_kernel<FILTER, M, N, E, A>, npix, dyn), kThreads, dyn, st>>>(P)
+    const int npix = (P.prows * P.W + (32 / LPP) - 1) / (32 / LPP);        // warps' worth of pixel groups
+#define MB_BWD(M, N, E, A) shade_bwd_kernel<FILTER, M, N, E, A, LPP><<<persistent_grid(shade_bwd_kernel<FILTER, M, N, E, A, LPP>, npix, dyn), kThreads, dyn, st>>>(P)
     const bool agg = want_env && env_scatter_aggregated();
     if (agg) {
         if (want_mat && want_n) MB_BWD(true, true, true, true);
@@ -407,9 +447,14 @@ int mb200_shade_fwd(const mb200_cfg* c, const float* gpos, const float* gnrm, co
     cudaStream_t st = (cudaStream_t)stream;
     const bool ad = (c->flags & MB200_FLAG_AD_WEIGHTS) != 0;
     const size_t dyn = plan_env_staging(P, d, env_staging_budget(kStageBudgetFwd));
-#define MB_FWD(F, A) shade_fwd_kernel<F, A><<<persistent_grid(shade_fwd_kernel<F, A>, npix, dyn), kThreads, dyn, st>>>(P)
-    if (c->filter == MB200_FILTER_GAUSSIAN) { if (ad) MB_FWD(MB200_FILTER_GAUSSIAN, true); else MB_FWD(MB200_FILTER_GAUSSIAN, false); }
-    else                                    { if (ad) MB_FWD(MB200_FILTER_BOX, true);      else MB_FWD(MB200_FILTER_BOX, false); }
+#define MB_FWD(F, A, L) shade_fwd_kernel<F, A, false, L><<<persistent_grid(shade_fwd_kernel<F, A, false, L>, (npix + 32 / L - 1) / (32 / L), dyn), kThreads, dyn, st>>>(P)
+    if (lanes_per_pixel(c->spp, false) == 8) {
+        if (c->filter == MB200_FILTER_GAUSSIAN) { if (ad) MB_FWD(MB200_FILTER_GAUSSIAN, true, 8); else MB_FWD(MB200_FILTER_GAUSSIAN, false, 8); }
+        else                                    { if (ad) MB_FWD(MB200_FILTER_BOX, true, 8);      else MB_FWD(MB200_FILTER_BOX, false, 8); }
+    } else {
+        if (c->filter == MB200_FILTER_GAUSSIAN) { if (ad) MB_FWD(MB200_FILTER_GAUSSIAN, true, 32); else MB_FWD(MB200_FILTER_GAUSSIAN, false, 32); }
+        else                                    { if (ad) MB_FWD(MB200_FILTER_BOX, true, 32);      else MB_FWD(MB200_FILTER_BOX, false, 32); }
+    }
 #undef MB_FWD
     return mb200_check_launch();
 }
@@ -488,8 +533,11 @@ int mb200_shade_bwd(const mb200_cfg* c, const float* gpos, const float* gnrm, co
     const size_t gbytes = ((size_t)3 * sizeof(float) * (size_t)P.env_slab_stride + 15) & ~(size_t)15;
     P.env_grad_smem = (want_env && env_scatter_aggregated() == 2 && dyn + gbytes <= budget) ? 1 : 0;   // block-privatised gradient map (small envmaps)
     if (P.env_grad_smem) dyn += gbytes;
-    return c->filter == MB200_FILTER_GAUSSIAN ? launch_bwd<MB200_FILTER_GAUSSIAN>(P, want_mat, want_n, want_env, dyn, st)
-                                              : launch_bwd<MB200_FILTER_BOX>(P, want_mat, want_n, want_env, dyn, st);
+    if (lanes_per_pixel(c->spp, true) == 8)
+        return c->filter == MB200_FILTER_GAUSSIAN ? launch_bwd<MB200_FILTER_GAUSSIAN, 8>(P, want_mat, want_n, want_env, dyn, st)
+                                                  : launch_bwd<MB200_FILTER_BOX, 8>(P, want_mat, want_n, want_env, dyn, st);
+    return c->filter == MB200_FILTER_GAUSSIAN ? launch_bwd<MB200_FILTER_GAUSSIAN, 32>(P, want_mat, want_n, want_env, dyn, st)
+                                              : launch_bwd<MB200_FILTER_BOX, 32>(P, want_mat, want_n, want_env, dyn, st);
 }
 
 int mb200_debug_sample_indices(const mb200_cfg* c, const float* gpos, const float* r, const float* hier,

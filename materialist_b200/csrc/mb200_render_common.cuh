@@ -193,6 +193,8 @@ inline int persistent_grid(K kernel, int npix, size_t dyn_smem = 0) {
     int resident = 0;
     for (int i = 0; i < n_keys; ++i) if (keys[i] == (const void*)kernel) { resident = vals[i]; break; }
     if (resident <= 0) {
+        // static + dynamic shared memory may pass 48 KB (adjoint, 8 lanes per pixel: 12.5 KB of film cotangents + 44 KB of staging)
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         int n = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, dyn_smem) != cudaSuccess || n <= 0) n = 2;
         resident = n;

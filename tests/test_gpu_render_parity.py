@@ -19,6 +19,10 @@ CASES = {
     "gauss_invalid_border_nmap": dict(H=36, W=36, spp=40, He=16, We=32, gaussian=True, invalid_border=3, use_mesh_normal=False),
     "gauss_nonsquare": dict(H=24, W=40, spp=32, He=16, We=32, gaussian=True),
     "spp_below_warp": dict(H=20, W=20, spp=5, He=8, We=16, gaussian=True),
+    # 8 lanes per pixel (four pixels per warp): pixel count not a multiple of 4, spp = the group width / a single sample
+    "lpp_ragged_pixels_nmap": dict(H=21, W=21, spp=8, He=16, We=32, gaussian=True, use_mesh_normal=False, invalid_border=2),
+    "spp_one_box": dict(H=18, W=18, spp=1, He=8, We=16, gaussian=False),
+    "spp_above_128": dict(H=16, W=16, spp=160, He=16, We=32, gaussian=True),          # adjoint back on a warp per pixel
 }
 
 
