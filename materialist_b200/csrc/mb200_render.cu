@@ -31,7 +31,7 @@ constexpr size_t kStageBudgetFwd = 27 * 1024, kStageBudgetBwd = 44 * 1024;
 // the kernel at 64 spp with a whole warp per pixel — over 4x as many samples per lane, and keeps all lanes busy from 8 spp up
 // (a warp per pixel idles lanes below 32 spp).  The film-tap reduction is unchanged in cost: still 32 staged records per batch,
 // lanes 0..24 each own one tap, now with one accumulator per pixel group.
-template <int FILTER, bool AD_W, bool TRANS = false, int LPP = 32>
+template <int FILTER, bool AD_W, bool TRANS = false, int LPP = 32, bool NMAP = true>
 __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_FWD) shade_fwd_kernel(const __grid_constant__ RenderParams P) {
     constexpr int PPW = 32 / LPP;
     __shared__ __align__(16) float s_rec[FILTER == MB200_FILTER_GAUSSIAN ? kWarpsPerBlock * 32 * kRecStride : 4];
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_FWD) shade_fwd_kernel(
         const int pix = pix_ok ? pix0 + grp : npix - 1;
         const int py = P.prow0 + pix / P.W, px = pix % P.W;
         const int gpix = py * P.W + px;
-        const PixelCtx c = load_pixel<TRANS>(P, gpix);
+        const PixelCtx c = load_pixel<TRANS, NMAP>(P, gpix);
         float4 acc[PPW];
 #pragma unroll
         for (int g = 0; g < PPW; ++g) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -187,7 +187,7 @@ __global__ void film_adjoint_kernel(const float* __restrict__ wpart, int H, int 
 // north_star prescribes; measured SLOWER on B200 (16x32 + sun: 1.55 / 1.64 ms against 1.40 ms) and kept selectable (MB200_ENV_SCATTER=agg).
 // LPP: lanes per pixel, as in shade_fwd_kernel (each pixel group of a warp has its own 5x5 film cotangent in shared memory; the
 // material gradients are reduced over the LPP lanes of a group).
-template <int FILTER, bool WANT_MAT, bool WANT_N, bool WANT_ENV, bool ENVAGG = false, int LPP = 32>
+template <int FILTER, bool WANT_MAT, bool WANT_N, bool WANT_ENV, bool ENVAGG = false, int LPP = 32, bool NMAP = true>
 __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_BWD) shade_bwd_kernel(const __grid_constant__ RenderParams P) {
     constexpr int PPW = 32 / LPP;
     __shared__ float4 s_g[FILTER == MB200_FILTER_GAUSSIAN ? kWarpsPerBlock * PPW * MB200_FILM_TAPS : 1];
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_BWD) shade_bwd_kernel(
         const int pix = pix_ok ? pix0 + grp : npix - 1;
         const int py = P.prow0 + pix / P.W, px = pix % P.W;
         const int gpix = py * P.W + px;
-        const PixelCtx c = load_pixel(P, gpix);
+        const PixelCtx c = load_pixel<false, NMAP>(P, gpix);
         float3 gbox = f3(0, 0, 0);
         if (FILTER == MB200_FILTER_GAUSSIAN) {
             __syncwarp();
@@ -383,36 +383,39 @@ __global__ void sample_record_kernel(const __grid_constant__ RenderParams P, int
     if (out_L) { out_L[3 * i] = L.x; out_L[3 * i + 1] = L.y; out_L[3 * i + 2] = L.z; }
 }
 
-// Lanes per pixel of the G-buffer kernels.  Measured at C2 (64 spp, profiles/r5i_lpp_ab.log):
-//   adjoint  warp per pixel 1.291 ms -> 8 lanes per pixel 1.207 ms (-6.5 %): default 8 up to 128 spp (above, the per-pixel work no
-//            longer shows and a whole warp per pixel keeps the film cotangents of ONE pixel in shared memory);
-//   forward  1.189 ms -> 1.232 ms at its 64-register cap (four tap accumulators instead of one: spills), 1.195 ms at 80 registers /
-//            3 CTAs per SM: no gain, so the forward keeps a warp per pixel from 32 spp up and uses 8 lanes per pixel only below
-//            (where a warp per pixel would idle lanes).
-// MB200_LPP=8|32 forces both kernels (measurements).
+// Lanes per pixel of the G-buffer kernels.  Measured at C2 (64 spp; profiles/r5i_lpp_ab.log, r5j, r5k):
+//   adjoint  warp per pixel 1.291 ms -> 8 lanes per pixel 1.207 ms (-6.5 %; 4 lanes: 1.209): default 8 up to 128 spp (above, the
+//            per-pixel work no longer shows and a whole warp per pixel keeps the film cotangents of ONE pixel in shared memory);
+//   forward  8 lanes per pixel needs four tap accumulators: 1.232 ms at the kernel's 64-register cap (spills) against 1.189 ms for a
+//            warp per pixel, 1.195 ms at 80 registers / 3 CTAs per SM; 16 lanes per pixel (two accumulators) 1.165 ms against 1.173
+//            ms -> default 16 for 16..128 spp, 8 below (so that no lane idles from 8 spp up), a warp per pixel above.
+// MB200_LPP=8|32 forces both kernels, 16 the forward (measurements).
 inline int lanes_per_pixel(int spp, bool adjoint) {
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("MB200_LPP"); forced = e ? atoi(e) : 0; }
-    if (forced == 8 || forced == 32) return forced;
+    if (forced == 8 || forced == 32 || (forced == 16 && !adjoint)) return forced;
     if (adjoint) return spp <= 128 ? 8 : 32;
-    return spp < 32 ? 8 : 32;
+    return spp < 16 ? 8 : (spp <= 128 ? 16 : 32);
 }
 
 template <int FILTER, int LPP>
 int launch_bwd(const RenderParams& P, bool want_mat, bool want_n, bool want_env, size_t dyn, cudaStream_t st) {
     const int npix = (P.prows * P.W + (32 / LPP) - 1) / (32 / LPP);        // warps' worth of pixel groups
-#define MB_BWD(M, N, E, A) shade_bwd_kernel<FILTER, M, N, E, A, LPP><<<persistent_grid(shade_bwd_kernel<FILTER, M, N, E, A, LPP>, npix, dyn), kThreads, dyn, st>>>(P)
+    const bool nmap = !P.use_mesh_normal && P.n_opt != nullptr;
+#define MB_BWD_(M, N, E, A, NM) shade_bwd_kernel<FILTER, M, N, E, A, LPP, NM><<<persistent_grid(shade_bwd_kernel<FILTER, M, N, E, A, LPP, NM>, npix, dyn), kThreads, dyn, st>>>(P)
+#define MB_BWD(M, N, E, A) do { if ((N) || nmap) MB_BWD_(M, N, E, A, true); else MB_BWD_(M, false, E, A, false); } while (0)
     const bool agg = want_env && env_scatter_aggregated();
     if (agg) {
-        if (want_mat && want_n) MB_BWD(true, true, true, true);
-        else if (want_mat) MB_BWD(true, false, true, true);
-        else MB_BWD(false, false, true, true);
+        if (want_mat && want_n) MB_BWD_(true, true, true, true, true);
+        else if (want_mat) MB_BWD_(true, false, true, true, true);
+        else MB_BWD_(false, false, true, true, true);
     }
-    else if (want_mat && want_n && want_env) MB_BWD(true, true, true, false);
-    else if (want_mat && want_n) MB_BWD(true, true, false, false);
+    else if (want_mat && want_n && want_env) MB_BWD_(true, true, true, false, true);
+    else if (want_mat && want_n) MB_BWD_(true, true, false, false, true);
     else if (want_mat && want_env) MB_BWD(true, false, true, false);
     else if (want_mat) MB_BWD(true, false, false, false);
     else if (want_env) MB_BWD(false, false, true, false);
+#undef MB_BWD_
 #undef MB_BWD
     return mb200_check_launch();
 }
@@ -447,8 +450,13 @@ int mb200_shade_fwd(const mb200_cfg* c, const float* gpos, const float* gnrm, co
     cudaStream_t st = (cudaStream_t)stream;
     const bool ad = (c->flags & MB200_FLAG_AD_WEIGHTS) != 0;
     const size_t dyn = plan_env_staging(P, d, env_staging_budget(kStageBudgetFwd));
-#define MB_FWD(F, A, L) shade_fwd_kernel<F, A, false, L><<<persistent_grid(shade_fwd_kernel<F, A, false, L>, (npix + 32 / L - 1) / (32 / L), dyn), kThreads, dyn, st>>>(P)
-    if (lanes_per_pixel(c->spp, false) == 8) {
+    const bool nmap = !P.use_mesh_normal && P.n_opt != nullptr;
+#define MB_FWD_(F, A, L, NM) shade_fwd_kernel<F, A, false, L, NM><<<persistent_grid(shade_fwd_kernel<F, A, false, L, NM>, (npix + 32 / L - 1) / (32 / L), dyn), kThreads, dyn, st>>>(P)
+#define MB_FWD(F, A, L) do { if (nmap) MB_FWD_(F, A, L, true); else MB_FWD_(F, A, L, false); } while (0)
+    if (lanes_per_pixel(c->spp, false) == 16) {
+        if (c->filter == MB200_FILTER_GAUSSIAN) { if (ad) MB_FWD(MB200_FILTER_GAUSSIAN, true, 16); else MB_FWD(MB200_FILTER_GAUSSIAN, false, 16); }
+        else                                    { if (ad) MB_FWD(MB200_FILTER_BOX, true, 16);      else MB_FWD(MB200_FILTER_BOX, false, 16); }
+    } else if (lanes_per_pixel(c->spp, false) == 8) {
         if (c->filter == MB200_FILTER_GAUSSIAN) { if (ad) MB_FWD(MB200_FILTER_GAUSSIAN, true, 8); else MB_FWD(MB200_FILTER_GAUSSIAN, false, 8); }
         else                                    { if (ad) MB_FWD(MB200_FILTER_BOX, true, 8);      else MB_FWD(MB200_FILTER_BOX, false, 8); }
     } else {
@@ -456,6 +464,7 @@ int mb200_shade_fwd(const mb200_cfg* c, const float* gpos, const float* gnrm, co
         else                                    { if (ad) MB_FWD(MB200_FILTER_BOX, true, 32);      else MB_FWD(MB200_FILTER_BOX, false, 32); }
     }
 #undef MB_FWD
+#undef MB_FWD_
     return mb200_check_launch();
 }
 
