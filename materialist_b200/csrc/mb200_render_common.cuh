@@ -20,6 +20,9 @@ namespace {
 constexpr int kWarpsPerBlock = 8;
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr int kRecStride = 20;            // floats per staged sample record (bank-conflict-free for 16B stores)
+// (measured and rejected, profiles/r5m: row weight folded into the radiance by the staging lane — records of 5 x (L.rgb * wy_j, wy_j) +
+// wx[5], 6 instead of 8 instructions per record in the tap loop — shade_fwd 1.166 -> 1.202 ms: 7 instead of 4 16-byte stores per
+// sample and more spills at the 64-register cap outweigh the shorter loop; a 28-float record stride alone costs +0.65 %)
 // (measured and rejected, profiles/r5c: weights staged as (w,w) pairs + FMUL2 / 2 x FFMA2 per record in the forward tap loop — 6
 // instead of 8 instructions per record — made shade_fwd SLOWER, 1.205 -> 1.270 ms: the records grow 20 -> 28 floats, 8.7 KB more
 // shared memory per CTA taken from the L1 that serves the two un-staged pyramid levels and the envmap texels)
