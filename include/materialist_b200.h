@@ -71,6 +71,7 @@ extern "C" {
 #define MB200_ERANGE        -2   /* size out of supported range (e.g. H*W*spp >= 2^32)   */
 #define MB200_ELAUNCH       -3   /* CUDA launch / runtime error (see mb200_last_cuda_error) */
 #define MB200_EUNSUPPORTED  -4   /* valid request, not implemented by this build */
+#define MB200_EIO           -5   /* a file could not be written completely (fwrite / fclose failed) */
 
 /* ---------------------------------------------------------------- flags  */
 /* cfg.flags — reference-exact quirks, all ON by default in the Python host. */
@@ -385,7 +386,11 @@ int mb200_sh_reconstruct(const double* coef, int nrows, int ncols, int clip, dou
  * Images are (H, W, C) fp32 row-major in R,G,B(,A) order; single-channel files are C = 1. */
 int mb200_image_info(const char* path, int* H, int* W, int* C);
 int mb200_image_read(const char* path, float* out_host, int H, int W, int C);
-int mb200_image_write(const char* path, const float* img_host, int H, int W, int C);   /* by extension: .hdr (C = 3), .exr, .png */
+int mb200_image_write(const char* path, const float* img_host, int H, int W, int C);   /* by extension: .hdr (C = 3), .exr, .png (raw values) */
+/* flags: MB200_IMG_SRGB = 8-bit PNG colour channels through the sRGB transfer curve, alpha linear — what mi.util.write_bitmap does for
+ * 8-bit files (Bitmap::convert(..., srgb_gamma = true); trans_edit.py:47); ignored for .hdr / .exr (linear float formats). */
+#define MB200_IMG_SRGB 1
+int mb200_image_write_ex(const char* path, const float* img_host, int H, int W, int C, int flags);
 
 /* ---------------------------------------------------------------- fused loss + optimiser step (BRDF phase) */
 /* What sits between the forward and the adjoint render of one iteration of `optimize_envmap_ARMN`

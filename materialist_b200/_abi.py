@@ -15,7 +15,8 @@ LIB_PATH = os.environ.get("MB200_LIB") or os.path.join(_HERE, "libmaterialist_b2
 MAX_LEVELS = 24
 FILM_TAPS = 25
 
-OK, EINVAL, ERANGE, ELAUNCH, EUNSUPPORTED = 0, -1, -2, -3, -4
+OK, EINVAL, ERANGE, ELAUNCH, EUNSUPPORTED, EIO = 0, -1, -2, -3, -4, -5
+IMG_SRGB = 1
 FLAG_WO_WORLD_QUIRK, FLAG_ROW_STRIDE_H, FLAG_ENV_HALF_TEXEL, FLAG_AD_WEIGHTS = 1, 2, 4, 8
 FILTER_BOX, FILTER_GAUSSIAN = 0, 1
 ENV_ASSIGNED, ENV_FILE = 0, 1
@@ -131,6 +132,7 @@ def _load():
         "mb200_image_info": (i32, [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "mb200_image_read": (i32, [C.c_char_p, vp, i32, i32, i32]),
         "mb200_image_write": (i32, [C.c_char_p, vp, i32, i32, i32]),
+        "mb200_image_write_ex": (i32, [C.c_char_p, vp, i32, i32, i32, i32]),
         "mb200_posmlp_param_count": (i64, [pm]),
         "mb200_posmlp_cache_bytes": (sz, [pm, i64]),
         "mb200_posmlp_workspace_bytes": (sz, [pm]),

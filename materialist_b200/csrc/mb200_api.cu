@@ -57,6 +57,7 @@ const char* mb200_strerror(int code) {
         case MB200_ERANGE: return "size out of supported range";
         case MB200_ELAUNCH: return "CUDA launch/runtime error";
         case MB200_EUNSUPPORTED: return "not supported by this build";
+        case MB200_EIO: return "file could not be written completely";
         default: return "unknown error";
     }
 }

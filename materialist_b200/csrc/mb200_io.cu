@@ -103,14 +103,23 @@ inline void float_to_rgbe(const float* c, uint8_t* q) {
     q[0] = (uint8_t)(c[0] > 0.f ? c[0] * s : 0.f); q[1] = (uint8_t)(c[1] > 0.f ? c[1] * s : 0.f); q[2] = (uint8_t)(c[2] > 0.f ? c[2] * s : 0.f);
     q[3] = (uint8_t)(e + 128);
 }
+// fwrite / fclose with the error remembered: a full disk must not come back as MB200_OK
+struct OutFile {
+    FILE* f; bool ok;
+    explicit OutFile(const char* path) : f(fopen(path, "wb")), ok(f != nullptr) {}
+    void put(const void* p, size_t n) { if (ok && n && fwrite(p, 1, n, f) != n) ok = false; }
+    int close() { if (f && fclose(f) != 0) ok = false; f = nullptr; return ok ? MB200_OK : MB200_EIO; }
+    ~OutFile() { if (f) fclose(f); }
+};
 int hdr_write(const char* path, const float* img, int H, int W) {
-    FILE* f = fopen(path, "wb");
-    if (!f) return MB200_EINVAL;
-    fprintf(f, "#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y %d +X %d\n", H, W);
+    OutFile of(path);
+    if (!of.f) return MB200_EINVAL;
+    char head[128]; const int hl = snprintf(head, sizeof(head), "#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y %d +X %d\n", H, W);
+    of.put(head, (size_t)hl);
     std::vector<uint8_t> px((size_t)W * 4), out;
     for (int y = 0; y < H; ++y) {
         for (int x = 0; x < W; ++x) float_to_rgbe(img + ((size_t)y * W + x) * 3, &px[(size_t)x * 4]);
-        if (W < 8 || W >= 32768) { fwrite(px.data(), 1, px.size(), f); continue; }
+        if (W < 8 || W >= 32768) { of.put(px.data(), px.size()); continue; }
         out.clear();
         out.push_back(2); out.push_back(2); out.push_back((uint8_t)(W >> 8)); out.push_back((uint8_t)(W & 255));
         for (int c = 0; c < 4; ++c) {
@@ -132,10 +141,9 @@ int hdr_write(const char* path, const float* img, int H, int W) {
                 x += lit;
             }
         }
-        fwrite(out.data(), 1, out.size(), f);
+        of.put(out.data(), out.size());
     }
-    fclose(f);
-    return MB200_OK;
+    return of.close();
 }
 
 // ------------------------------------------------------------------------------------------------ OpenEXR
@@ -440,17 +448,16 @@ int exr_write(const char* path, const float* img, int H, int W, int C) {
         zip_do(raw.data(), raw.size(), blocks[blk]);
         if (blocks[blk].size() >= raw.size()) blocks[blk] = raw;     // stored raw when compression does not help (reader: size == raw size)
     }
-    FILE* f = fopen(path, "wb");
-    if (!f) return MB200_EINVAL;
-    fwrite(h.data(), 1, h.size(), f);
+    OutFile of(path);
+    if (!of.f) return MB200_EINVAL;
+    of.put(h.data(), h.size());
     uint64_t off = h.size() + (uint64_t)nblocks * 8;
-    for (int blk = 0; blk < nblocks; ++blk) { fwrite(&off, 8, 1, f); off += 8 + blocks[blk].size(); }
+    for (int blk = 0; blk < nblocks; ++blk) { of.put(&off, 8); off += 8 + blocks[blk].size(); }
     for (int blk = 0; blk < nblocks; ++blk) {
         const int32_t y = blk * lpb, sz = (int32_t)blocks[blk].size();
-        fwrite(&y, 4, 1, f); fwrite(&sz, 4, 1, f); fwrite(blocks[blk].data(), 1, blocks[blk].size(), f);
+        of.put(&y, 4); of.put(&sz, 4); of.put(blocks[blk].data(), blocks[blk].size());
     }
-    fclose(f);
-    return MB200_OK;
+    return of.close();
 }
 
 
@@ -510,34 +517,38 @@ int png_read(const std::vector<uint8_t>& b, const PngInfo& pi, float* out) {
     }
     return MB200_OK;
 }
-void png_chunk(FILE* f, const char* type, const uint8_t* data, uint32_t len) {
+void png_chunk(OutFile& of, const char* type, const uint8_t* data, uint32_t len) {
     uint8_t hdr[8] = {(uint8_t)(len >> 24), (uint8_t)(len >> 16), (uint8_t)(len >> 8), (uint8_t)len, (uint8_t)type[0], (uint8_t)type[1], (uint8_t)type[2], (uint8_t)type[3]};
-    fwrite(hdr, 1, 8, f); if (len) fwrite(data, 1, len, f);
+    of.put(hdr, 8); of.put(data, len);
     uLong crc = crc32(0L, hdr + 4, 4); if (len) crc = crc32(crc, data, len);
     const uint8_t c4[4] = {(uint8_t)(crc >> 24), (uint8_t)(crc >> 16), (uint8_t)(crc >> 8), (uint8_t)crc};
-    fwrite(c4, 1, 4, f);
+    of.put(c4, 4);
 }
-int png_write(const char* path, const float* img, int H, int W, int C) {
+// srgb: colour channels through the sRGB transfer curve, as Mitsuba's Bitmap::convert(UInt8, srgb_gamma = true) does behind
+// mi.util.write_bitmap for 8-bit files (trans_edit.py:47, the preview PNGs); alpha stays linear.  Raw (srgb = false) for data files
+// such as bg.png / mask.png fixtures whose values must come back unchanged.
+inline float srgb_oetf(float x) { return x <= 0.0031308f ? 12.92f * x : 1.055f * powf(x, 1.0f / 2.4f) - 0.055f; }
+int png_write(const char* path, const float* img, int H, int W, int C, bool srgb) {
     if (C != 1 && C != 3 && C != 4) return MB200_EINVAL;
     std::vector<uint8_t> raw((size_t)H * ((size_t)W * C + 1));
     for (int y = 0; y < H; ++y) {
         uint8_t* row = raw.data() + (size_t)y * ((size_t)W * C + 1); row[0] = 0;
         for (size_t i = 0; i < (size_t)W * C; ++i) {
             float v = img[(size_t)y * W * C + i]; v = v != v ? 0.f : (v < 0.f ? 0.f : (v > 1.f ? 1.f : v));
+            if (srgb && !(C == 4 && i % 4 == 3)) v = srgb_oetf(v);
             row[1 + i] = (uint8_t)(v * 255.0f + 0.5f);
         }
     }
     uLongf cap = compressBound((uLong)raw.size()); std::vector<uint8_t> z(cap);
     if (compress2(z.data(), &cap, raw.data(), (uLong)raw.size(), Z_DEFAULT_COMPRESSION) != Z_OK) return MB200_EINVAL;
-    FILE* f = fopen(path, "wb");
-    if (!f) return MB200_EINVAL;
+    OutFile of(path);
+    if (!of.f) return MB200_EINVAL;
     static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
-    fwrite(sig, 1, 8, f);
+    of.put(sig, 8);
     const uint8_t ihdr[13] = {(uint8_t)(W >> 24), (uint8_t)(W >> 16), (uint8_t)(W >> 8), (uint8_t)W, (uint8_t)(H >> 24), (uint8_t)(H >> 16), (uint8_t)(H >> 8), (uint8_t)H,
                               8, (uint8_t)(C == 1 ? 0 : C == 3 ? 2 : 6), 0, 0, 0};
-    png_chunk(f, "IHDR", ihdr, 13); png_chunk(f, "IDAT", z.data(), (uint32_t)cap); png_chunk(f, "IEND", nullptr, 0);
-    fclose(f);
-    return MB200_OK;
+    png_chunk(of, "IHDR", ihdr, 13); png_chunk(of, "IDAT", z.data(), (uint32_t)cap); png_chunk(of, "IEND", nullptr, 0);
+    return of.close();
 }
 
 }  // namespace
@@ -566,12 +577,13 @@ int mb200_image_read(const char* path, float* out, int H, int W, int C) {
     return MB200_EUNSUPPORTED;
 }
 
-int mb200_image_write(const char* path, const float* img, int H, int W, int C) {
+int mb200_image_write_ex(const char* path, const float* img, int H, int W, int C, int flags) {
     if (!path || !img || H <= 0 || W <= 0) return MB200_EINVAL;
     if (ends_with(path, ".hdr")) return C == 3 ? hdr_write(path, img, H, W) : MB200_EINVAL;
     if (ends_with(path, ".exr")) return exr_write(path, img, H, W, C);
-    if (ends_with(path, ".png")) return png_write(path, img, H, W, C);
+    if (ends_with(path, ".png")) return png_write(path, img, H, W, C, (flags & MB200_IMG_SRGB) != 0);
     return MB200_EUNSUPPORTED;
 }
+int mb200_image_write(const char* path, const float* img, int H, int W, int C) { return mb200_image_write_ex(path, img, H, W, C, 0); }
 
 }  // extern "C"

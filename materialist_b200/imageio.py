@@ -23,8 +23,10 @@ def read_bitmap(path):
     return out[..., 0] if Cn == 1 else out
 
 
-def write_bitmap(path, img):
-    """`mi.util.write_bitmap(path, img)` for .hdr (RGBE, 3 channels) and .exr (ZIP, float32; 1, 3 or 4 channels)."""
+def write_bitmap(path, img, srgb=True):
+    """`mi.util.write_bitmap(path, img)` for .hdr (RGBE, 3 channels), .exr (ZIP, float32; 1, 3 or 4 channels) and 8-bit .png.
+    PNG: like Mitsuba, the colour channels go through the sRGB transfer curve (alpha stays linear); `srgb=False` stores the clamped
+    values as they are (data files: masks, backgrounds that must read back unchanged).  .hdr / .exr are linear float formats."""
     if hasattr(img, "detach"):
         img = img.detach().cpu().numpy()
     a = np.ascontiguousarray(img, dtype=np.float32)
@@ -33,4 +35,5 @@ def write_bitmap(path, img):
     if a.ndim != 3:
         raise ValueError("image must be (H, W) or (H, W, C)")
     H, W, Cn = a.shape
-    _abi.check(_abi.lib.mb200_image_write(str(path).encode(), a.ctypes.data_as(C.c_void_p), H, W, Cn), f"mb200_image_write({path})")
+    _abi.check(_abi.lib.mb200_image_write_ex(str(path).encode(), a.ctypes.data_as(C.c_void_p), H, W, Cn, _abi.IMG_SRGB if srgb else 0),
+               f"mb200_image_write({path})")

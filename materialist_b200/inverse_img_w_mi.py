@@ -9,7 +9,6 @@ B200 operator with `import materialist_b200.inverse_img_w_mi as ...` in place of
     img    = render(scene, spp=64, seed=i)                                            # render_final.py:194 (mi.render)
     frames = render_rolling_envmap(scene, envmap, frames=36, rotation_step=10)        # render_final.py:300-418 (intended behaviour)
 """
-import os
 
 import numpy as np
 import torch
@@ -19,7 +18,6 @@ from .gbuffer import gbuffer_from_ply, load_estimated_brdf, read_image
 from .renderop import render, render_envmap, render_w_brdf  # noqa: F401  (re-exported under the reference's names)
 from .scene import Camera, Scene, traverse  # noqa: F401
 
-_ENV0 = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "envmaps", "0.hdr")
 
 
 def load_estimated_mesh(mesh_path, use_mesh_normal, max_path=4, envmap=None, width=512, height=512, device="cuda", mode="mesh"):

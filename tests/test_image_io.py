@@ -124,12 +124,21 @@ def test_png_reader_and_writer_match_opencv(tmp_path):
     for C in (1, 3, 4):
         img = rs.rand(19, 23, C).astype(np.float32) if C > 1 else rs.rand(19, 23).astype(np.float32)
         p = str(tmp_path / f"w{C}.png")
-        io.write_bitmap(p, img)
+        io.write_bitmap(p, img, srgb=False)                                     # data file: raw values
         back = cv2.imread(p, cv2.IMREAD_UNCHANGED)
         if back.ndim == 3:
             back = back[..., [2, 1, 0] + ([3] if back.shape[2] == 4 else [])]
         assert np.array_equal(back, np.floor(np.clip(img, 0, 1) * 255.0 + 0.5).astype(np.uint8))
         assert np.array_equal(io.read_bitmap(p), back.astype(np.float32) / 255.0)
+        io.write_bitmap(p, img)                                                 # default, as mi.util.write_bitmap: sRGB transfer, alpha linear
+        back = cv2.imread(p, cv2.IMREAD_UNCHANGED)
+        if back.ndim == 3:
+            back = back[..., [2, 1, 0] + ([3] if back.shape[2] == 4 else [])]
+        x = np.clip(img, 0, 1).astype(np.float64)
+        want = np.where(x <= 0.0031308, 12.92 * x, 1.055 * x ** (1 / 2.4) - 0.055)
+        if C == 4:
+            want[..., 3] = x[..., 3]
+        assert np.abs(back.astype(np.float64) - want * 255.0).max() <= 0.5 + 1e-3
 
 
 def test_errors():
@@ -149,7 +158,8 @@ def test_load_estimated_brdf_goes_through_the_native_readers(tmp_path):
     for name, img in (("albedo", a), ("roughness", r), ("metallic", m), ("normal", n)):
         io.write_bitmap(str(tmp_path / f"{name}.exr"), img)
     bg = rs.rand(7, 9, 4).astype(np.float32); mk = (rs.rand(12, 12, 4) > 0.5).astype(np.float32); env = (rs.rand(4, 8, 3) + 0.5).astype(np.float32)
-    io.write_bitmap(str(tmp_path / "bg.png"), bg); io.write_bitmap(str(tmp_path / "mask.png"), mk); io.write_bitmap(str(tmp_path / "envmap.hdr"), env)
+    io.write_bitmap(str(tmp_path / "bg.png"), bg, srgb=False); io.write_bitmap(str(tmp_path / "mask.png"), mk, srgb=False)
+    io.write_bitmap(str(tmp_path / "envmap.hdr"), env)
     mat = gbuffer.load_estimated_brdf(str(tmp_path))
     assert mat["bg"].shape == (12, 12, 3) and mat["mask"].dtype == np.bool_ and np.array_equal(mat["mask"], mk[..., 0] > 0.5)
     assert mat["envmap"].shape == (4, 8, 3) and np.allclose(mat["envmap"], env, rtol=1 / 64)
