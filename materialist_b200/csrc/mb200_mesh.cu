@@ -576,6 +576,10 @@ inline void launch_mesh_fwd(K kernel, int filter, int grid, cudaStream_t st, con
 #define MB200_WF_TRACE_BLOCKS 4          // CTAs per SM of the traversal kernels: 64 registers, no spills (5: 94 ms, 4: 84 ms, 3: 87 ms, 6: 122 ms)
 #endif
 constexpr int kWfBatch = 1 << MB200_WF_BATCH_LOG2;
+#ifndef MB200_WF_CHUNK
+#define MB200_WF_CHUNK 64               // queue entries a traversal warp draws per global atomic
+#endif
+constexpr int kWfChunk = MB200_WF_CHUNK;
 // Ray queues can be binned by direction octant (MB200_WF_BINS = 8: bin b of queue q at q + b * nb, counts in
 // counters[8 * (1 + queue) + b]; the traversal kernel drains bin after bin, so the lanes of a warp hold rays of one octant).
 // Measured (profiles/r3p): C2m 155 -> 167 ms, C1 42.9 -> 46.9 ms — queue order = pixel order keeps the ORIGINS of a warp's rays
@@ -674,26 +678,46 @@ __global__ void __launch_bounds__(kThreads, MB200_WF_TRACE_BLOCKS) wf_trace_kern
     TStack<0> stack; stack.loc = stack_loc; stack.sh = nullptr;
     const QView qv = wf_qview(count);
     const uint32_t n = qv.pre[kBins];
-    Trav T; T.active = false; uint32_t pid = 0; bool done = false;
+    Trav T; T.active = false; uint32_t pid = 0;
+    // The warp draws rays from the queue in CHUNKS of kWfChunk consecutive entries (one global atomic per chunk) and hands them to
+    // its lanes from registers.  (One atomicAdd on the cursor per loop iteration — some lane finishes a ray in almost every
+    // iteration — put a ~600-cycle L2 round trip on the critical path of every traversal step: profiles/r5o.)
+    uint32_t pool = 0, pool_end = 0; bool drained = false;          // warp-uniform
+    const int lane = threadIdx.x & 31;
+#ifdef MB200_TRAV_STATS
+    unsigned long long st_node = 0, st_leaf = 0, st_iter = 0;       // tuning build: box steps / triangle tests per lane, loop iterations per warp
+    struct StatFlush { unsigned long long &a, &b, &c; uint32_t* cnt; int mode; __device__ ~StatFlush() {
+        atomicAdd((unsigned long long*)(cnt + 40 + 8 * 0) + 3 * mode + 0, a); atomicAdd((unsigned long long*)(cnt + 40) + 3 * mode + 1, b);
+        atomicAdd((unsigned long long*)(cnt + 40) + 3 * mode + 2, c); } } st_flush{st_node, st_leaf, st_iter, B.counters, MODE};
+#endif
     for (;;) {
-        // lanes without a ray take the next ones of the queue
-        const bool want = !T.active && !done;
-        const unsigned wm = __ballot_sync(0xffffffffu, want);
-        if (wm) {
-            uint32_t base = 0; const int lane = threadIdx.x & 31;
-            if (lane == 0) base = atomicAdd(cursor, (uint32_t)__popc(wm));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (want) {
-                const uint32_t i = base + (uint32_t)__popc(wm & ((1u << lane) - 1u));
-                if (i < n) {
+        // lanes without a ray take the next ones of the warp's chunk
+        const unsigned wm = __ballot_sync(0xffffffffu, !T.active);
+        if (wm && !drained) {
+            if (pool == pool_end) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(cursor, (uint32_t)kWfChunk);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= n) drained = true;
+                else { pool = base; pool_end = min(base + (uint32_t)kWfChunk, n); }
+            }
+            if (!drained) {
+                const uint32_t rank = (uint32_t)__popc(wm & ((1u << lane) - 1u));
+                const uint32_t i = pool + rank;
+                if (!T.active && i < pool_end) {
                     pid = wf_qget(q, qv, i, B.nb);
                     const float4 o = ANY ? B.sray_o[pid] : B.ray_o[pid], d = ANY ? B.sray_d[pid] : B.ray_d[pid];
                     trav_begin(M, T, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), ANY ? d.w : kInf, ANY);
-                } else done = true;
+                }
+                pool = min(pool + (uint32_t)__popc(wm), pool_end);
             }
         }
-        if (!__ballot_sync(0xffffffffu, T.active)) break;
+        if (!__ballot_sync(0xffffffffu, T.active)) { if (drained) break; else continue; }
         const bool was = T.active;
+#ifdef MB200_TRAV_STATS
+        if (was) { if ((T.cur >> 27) == 0) ++st_leaf; else ++st_node; }
+        if (lane == 0) ++st_iter;
+#endif
         trav_step<MB200_WF_LEAF_MIN>(M, T, stack);
         if (was && !T.active) {                                                    // this lane's ray has finished
             if (MODE == 1) {
@@ -1289,11 +1313,41 @@ __device__ __forceinline__ uint32_t expand10(uint32_t v) {
     v = (v * 0x00000011u) & 0xC30C30C3u; v = (v * 0x00000005u) & 0x49249249u;
     return v;
 }
+__device__ __forceinline__ uint32_t expand15(uint32_t v) {        // 15 bits -> every second bit of 30
+    v &= 0x7fffu;
+    v = (v | (v << 8)) & 0x00FF00FFu; v = (v | (v << 4)) & 0x0F0F0F0Fu;
+    v = (v | (v << 2)) & 0x33333333u; v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+// ORDER 0: 30-bit 3-D Morton code of the centroid in the scene box (any mesh).
+// ORDER 1: 30-bit 2-D Morton code of the DIRECTION of the centroid as seen from the origin (octahedral map, 15 bits per axis).
+//   The reference's meshes are depth maps unprojected from a camera at the origin (mesh_recon.py:184-258: vertex k <-> pixel k), i.e.
+//   sheets that a 3-D curve threads badly — depth bits interleave with the two screen axes, neighbouring quads end up far apart and
+//   the implicit tree's mid-level boxes overlap (measured, profiles/r5o_trav_stats.log: 63 box steps per closest-hit ray).  Ordered
+//   by viewing direction the implicit 4-ary tree IS the screen-space quadtree of the depth map.
+template <int ORDER>
 __global__ void mesh_morton_kernel(const float* __restrict__ verts, const int32_t* __restrict__ tris, int nt, const float* __restrict__ header,
                                    uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nt) return;
     float lo[3], hi[3]; tri_bounds(verts, tris, t, lo, hi);
+    if (ORDER == 1) {
+        const float cx = 0.5f * (lo[0] + hi[0]), cy = 0.5f * (lo[1] + hi[1]), cz = 0.5f * (lo[2] + hi[2]);
+        const float l1 = fabsf(cx) + fabsf(cy) + fabsf(cz);
+        float u = 0.f, v = 0.f;
+        if (l1 > 0.f) {
+            u = cx / l1; v = cy / l1;
+            if (cz > 0.f) {          // the hemisphere behind a camera that looks down -z: folded over the diagonals
+                const float fu = (1.f - fabsf(v)) * (u >= 0.f ? 1.f : -1.f), fv = (1.f - fabsf(u)) * (v >= 0.f ? 1.f : -1.f);
+                u = fu; v = fv;
+            }
+        }
+        const uint32_t qu = (uint32_t)fminf(fmaxf((u * 0.5f + 0.5f) * 32768.f, 0.f), 32767.f);
+        const uint32_t qv = (uint32_t)fminf(fmaxf((v * 0.5f + 0.5f) * 32768.f, 0.f), 32767.f);
+        keys[t] = (expand15(qv) << 1) | expand15(qu);
+        vals[t] = t;
+        return;
+    }
     uint32_t q[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -1510,7 +1564,10 @@ int mb200_mesh_build(const float* verts, const int32_t* tris, const mb200_mesh_d
     mesh_header_kernel<<<1, 1, 0, st>>>(bbox, header);
     uint32_t* k0 = reinterpret_cast<uint32_t*>(sb + S.keys0); uint32_t* k1 = reinterpret_cast<uint32_t*>(sb + S.keys1);
     int32_t* v0 = reinterpret_cast<int32_t*>(sb + S.vals0); int32_t* v1 = reinterpret_cast<int32_t*>(sb + S.vals1);
-    mesh_morton_kernel<<<grid, tb, 0, st>>>(verts, tris, nt, header, k0, v0);
+    static int order = -1;
+    if (order < 0) { const char* e = getenv("MB200_MESH_ORDER"); order = e ? atoi(e) : 0; }
+    if (order == 1) mesh_morton_kernel<1><<<grid, tb, 0, st>>>(verts, tris, nt, header, k0, v0);
+    else            mesh_morton_kernel<0><<<grid, tb, 0, st>>>(verts, tris, nt, header, k0, v0);
     cub::DoubleBuffer<uint32_t> kb(k0, k1); cub::DoubleBuffer<int32_t> vb(v0, v1);
     size_t cub_bytes = S.cub_bytes;
     if (cub::DeviceRadixSort::SortPairs(sb + S.cub, cub_bytes, kb, vb, nt, 0, 30, st) != cudaSuccess) return mb200_check_launch();
