@@ -570,6 +570,24 @@ def build_roofline(args, wl, scene, shard, dom, kavg, t_step, dev, world):
                      "counters_from": {"file": "profiles/ncu_counters.json", "commit": cnt["commit"], "source": cnt.get("source")},
                      "note": "FLOPs = 2 FFMA + FADD + FMUL thread instructions executed (ncu), per sample, times the samples of this launch; "
                              "a kernel of non-contracted IEEE multiplies and adds (the bit-exact direction chain) can reach at most half of the FFMA peak"})
+        # the roof this kernel actually sits under: one warp instruction per scheduler per cycle (4 schedulers per SM).  Executed warp
+        # instructions per sample are ncu's count (same capture); the rate is this run's kernel time; the clock is what nvidia-smi
+        # reported for this GPU.
+        try:
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            mhz = float(subprocess.run(["nvidia-smi", "--query-gpu=clocks.max.sm", "--format=csv,noheader,nounits", "-i", str(dev.index or 0)],
+                                       capture_output=True, text=True, timeout=10).stdout.strip().splitlines()[0])
+            winst = kc["warp_inst"] * (npix_rank * spp / float(cnt["samples_per_launch"]))
+            peak_i = sms * 4 * mhz * 1e6
+            fp32["issue"] = {"warp_inst_per_launch": winst, "achieved_ginst_s": winst / t_k / 1e9, "peak_ginst_s": peak_i / 1e9,
+                             "frac": winst / t_k / peak_i, "peak_is": f"{sms} SMs x 4 schedulers x {mhz:.0f} MHz (max SM clock)",
+                             "note": "issue-slot roof: the shading kernels are bound by instruction issue, not by FP32 lanes or HBM"}
+            # SURVEY 8d's algorithmic convention (1.6 k FLOP per adjoint sample, 0.8 k per forward sample) for comparison with round 1
+            alg = {"shade_bwd": 1600.0, "shade_fwd": 800.0}.get(dom)
+            if alg:
+                fp32["frac_algorithmic_flops"] = alg * npix_rank * spp / t_k / 1e12 / peak_tf
+        except Exception:
+            pass
     else:
         fp32["note"] = "no ncu counters committed for this workload / kernel: FLOP rate not reported"
     hbm_frac = hbm_ach / hbm_peak

@@ -24,9 +24,14 @@
  *     render/scene.cpp.  PINNED on the forward render by the reference's OWN saved output: with the recovered sampler seed
  *     (993) the mesh-mode oracle reproduces output_imgs/indoor/best_results/rendered_img.exr down to its Monte-Carlo noise
  *     pattern (0.5 % / 1.2 % rel-L2 on absolute radiance vs 6-7 % for any other seed; tests/test_reference_render_pin.py),
- *     plus the official PCG32 and Mitsuba TEA known answers.  The ADJOINT has no reference output to pin against (Mitsuba is
- *     not installable here): it is checked against an independent float64 autograd mirror (tests/torch_mirror.py) ==>
- *     "parity unpinned" for the adjoint pass only.
+ *     plus the official PCG32 and Mitsuba TEA known answers; a second shipped render (output_imgs/jinjya, seed 705) confirms it.
+ *   - ADJOINT: the BSDF derivatives (eval_brdf_grad) are PINNED against the Jacobian of the reference's own MatDiffBSDF.eval_pdf
+ *     source, taken by float64 central differences through the numpy Dr.Jit stand-ins (tests/golden/make_bsdf_grad_golden.py ->
+ *     matdiff_bsdf_grad.npz, tests/test_bsdf_grad_pin.py).  The operator-level structure of render_backward (second render with
+ *     seed_grad, f2 / detach(p2) weights, detached pdf / MIS / film weights) is restated from Mitsuba's published source and
+ *     checked by adjoint identities and a float64 autograd mirror (tests/torch_mirror.py); it has no Mitsuba OUTPUT to pin
+ *     against here (not installable) ==> "parity unpinned" for that structure only, until tests/upstream_check.py (guarded,
+ *     unit by unit against real mitsuba) can run on a box that has it.
  *
  * Build: see oracle/Makefile.  -ffp-contract=off is REQUIRED (integer decisions must not depend on
  * FMA contraction); fmaf() is used only where upstream writes fmadd.
