@@ -14,21 +14,52 @@ struct SampleDbg {
 // Shared-memory staging of the emitter's sampling pyramid (levels >= P.hier.smem_from; ALL levels and the float4 texels for the
 // small envmaps the reference really optimises: 16x32 learned, envmaps/0.hdr 32x16) — north_star: "the envmap marginal/conditional
 // CDFs and mip levels are staged in shared memory".  Called by every thread of the CTA before its pixel loop.
+// The copy itself is the bulk-copy engine's (cp.async.bulk global -> shared, completion counted on an mbarrier — the TMA path for
+// 1-D data): ONE thread issues two copies per CTA and everybody waits on the barrier, instead of ~11 load/store iterations by all 256
+// threads of each of the grid's 4 736 CTAs (the plain loop was 2.5 % of the adjoint kernel's executed instructions, profiles/r5l).
+#if defined(__CUDACC__)
+__device__ __forceinline__ uint32_t mb_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void stage_bulk(uint32_t bar, float4* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(mb_smem_u32(dst)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+#endif
 __device__ __forceinline__ StagedEnv stage_env(const RenderParams& P, float4* dyn) {
     StagedEnv S{nullptr, nullptr};
     const int nf = P.hier.smem_floats, nh4 = (nf + 3) >> 2;
-    if (nf > 0) {
-        const float4* src = reinterpret_cast<const float4*>(P.hier.data + P.hier.smem_off0);      // level offsets are 16-byte aligned
-        for (int i = threadIdx.x; i < (nf >> 2); i += blockDim.x) dyn[i] = __ldg(src + i);
-        if (threadIdx.x < (nf & 3)) reinterpret_cast<float*>(dyn)[(nf & ~3) + threadIdx.x] = __ldg(P.hier.data + P.hier.smem_off0 + (nf & ~3) + threadIdx.x);
-        S.hier = reinterpret_cast<const float*>(dyn);
+    if (nf <= 0 && P.env_smem_texels <= 0) return S;
+    const float* hsrc = P.hier.data + P.hier.smem_off0;                  // level offsets are 16-byte aligned
+    float4* t = dyn + nh4;
+#if defined(__CUDACC__)
+    __shared__ __align__(8) unsigned long long s_bar;
+    const uint32_t bar = mb_smem_u32(&s_bar);
+    const uint32_t hbytes = (uint32_t)(nf >> 2) * 16u, tbytes = (uint32_t)P.env_smem_texels * 16u;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (P.env_smem_texels > 0) {
-        float4* t = dyn + nh4;
-        for (int i = threadIdx.x; i < P.env_smem_texels; i += blockDim.x) t[i] = __ldg(P.env.tex + i);
-        S.tex = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(hbytes + tbytes) : "memory");
+        if (hbytes) stage_bulk(bar, dyn, hsrc, hbytes);
+        if (tbytes) stage_bulk(bar, t, P.env.tex, tbytes);
     }
-    if (nf > 0 || P.env_smem_texels > 0) __syncthreads();
+    if (threadIdx.x < (nf & 3)) reinterpret_cast<float*>(dyn)[(nf & ~3) + threadIdx.x] = __ldg(hsrc + (nf & ~3) + threadIdx.x);   // < 16-byte tail
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(0) : "memory");
+    __syncthreads();                                                      // the tail stores
+#else       // host emulation build: plain copies
+    for (int i = threadIdx.x; i < nf; i += blockDim.x) reinterpret_cast<float*>(dyn)[i] = hsrc[i];
+    for (int i = threadIdx.x; i < P.env_smem_texels; i += blockDim.x) t[i] = P.env.tex[i];
+    __syncthreads();
+#endif
+    if (nf > 0) S.hier = reinterpret_cast<const float*>(dyn);
+    if (P.env_smem_texels > 0) S.tex = t;
     return S;
 }
 
