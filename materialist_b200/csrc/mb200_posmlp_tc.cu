@@ -113,6 +113,8 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 << 4), A = B = F16 (0), both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(NPIX >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+constexpr int NSUB = 2, SPIX = NPIX / NSUB;        // sub-tiles of 64 pixels: the MMAs of one run under the epilogue of the other
+constexpr uint32_t kIdescSub = (1u << 4) | ((uint32_t)(SPIX >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 // smem -> global bulk store (async proxy); completion of the smem READS is awaited with wait_group.read
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
@@ -225,16 +227,29 @@ __device__ __forceinline__ void embed_pixel(const Dims& D, const float* __restri
 }
 
 // ---------------------------------------------------------------- pipeline pieces shared by the forward and the data-gradient kernels
-struct Pipe { uint32_t wfull, wempty, xready, dfull, sdone; uint32_t* tmem_slot; };
+// Two 64-pixel SUB-TILES per 128-pixel tile, each with its own barriers: while the 16 epilogue warps turn the accumulators of
+// sub-tile s into the next layer's operand rows, the MMA issuer is already working on sub-tile 1 - s (its operand rows and its TMEM
+// columns are disjoint).  Before, MMA and epilogue of a tile strictly alternated: the tensor pipe was busy 22 % of the time and the
+// epilogue warps waited for it the rest of that (ncu: profiles/r5q).  Price: the weight chunks of a layer are streamed from L2 once
+// per sub-tile (2.1 MB per tile instead of 1.05 MB).
+struct Pipe {
+    uint32_t wfull, wempty, xready0, dfull0, sdone0; uint32_t* tmem_slot;
+    __device__ __forceinline__ uint32_t xready(int u) const { return xready0 + 8u * (uint32_t)u; }
+    __device__ __forceinline__ uint32_t dfull(int u) const { return dfull0 + 8u * (uint32_t)u; }
+    __device__ __forceinline__ uint32_t sdone(int u) const { return sdone0 + 8u * (uint32_t)u; }
+};
 
 __device__ __forceinline__ Pipe pipe_setup(uint8_t* smem, int tid, int warp) {
     Pipe P;
     const uint32_t bar0 = smem_u32(smem + SM_BAR);
-    P.wfull = bar0; P.wempty = bar0 + 8 * NSTAGE; P.xready = bar0 + 16 * NSTAGE; P.dfull = P.xready + 8; P.sdone = P.xready + 16;
-    P.tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 16 * NSTAGE + 32);
+    P.wfull = bar0; P.wempty = bar0 + 8 * NSTAGE;
+    const uint32_t b1 = bar0 + 16 * NSTAGE;
+    P.xready0 = b1; P.dfull0 = b1 + 8 * NSUB; P.sdone0 = b1 + 16 * NSUB;
+    P.tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 16 * NSTAGE + 24 * NSUB);
+    static_assert(16 * NSTAGE + 24 * NSUB + 4 <= 128, "barrier area");
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(P.wfull + 8 * s, 1); mbar_init(P.wempty + 8 * s, 1); }
-        mbar_init(P.xready, NEPI); mbar_init(P.dfull, 1); mbar_init(P.sdone, 1);
+        for (int u = 0; u < NSUB; ++u) { mbar_init(P.xready(u), NEPI); mbar_init(P.dfull(u), 1); mbar_init(P.sdone(u), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == WARP_MMA) {
@@ -263,16 +278,17 @@ template <bool FWD>
 __device__ __forceinline__ void producer_loop(const Pipe& P, uint8_t* smem, const __half* wimg, long long ntiles) {
     uint32_t it = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-        for (int ph = 0; ph < n_phase<FWD>(); ++ph) {
-            const int nch = phase_chunks<FWD>(ph);
-            for (int c = 0; c < nch; ++c, ++it) {
-                const uint32_t s = it % NSTAGE, par = (it / NSTAGE) & 1;
-                mbar_wait(P.wempty + 8 * s, par ^ 1);
-                mbar_expect_tx(P.wfull + 8 * s, W_STAGE);
-                bulk_g2s(smem_u32(smem + SM_W + s * W_STAGE), reinterpret_cast<const uint8_t*>(wimg) + ((size_t)ph * NCHUNK + c) * W_STAGE,
-                         W_STAGE, P.wfull + 8 * s);
+        for (int ph = 0; ph < n_phase<FWD>(); ++ph)
+            for (int u = 0; u < NSUB; ++u) {
+                const int nch = phase_chunks<FWD>(ph);
+                for (int c = 0; c < nch; ++c, ++it) {
+                    const uint32_t s = it % NSTAGE, par = (it / NSTAGE) & 1;
+                    mbar_wait(P.wempty + 8 * s, par ^ 1);
+                    mbar_expect_tx(P.wfull + 8 * s, W_STAGE);
+                    bulk_g2s(smem_u32(smem + SM_W + s * W_STAGE), reinterpret_cast<const uint8_t*>(wimg) + ((size_t)ph * NCHUNK + c) * W_STAGE,
+                             W_STAGE, P.wfull + 8 * s);
+                }
             }
-        }
 }
 // MMA issuer: one thread; per phase waits for the operand image, then 3 split-term MMAs per K = 16 step and half
 template <bool FWD>
@@ -280,31 +296,33 @@ __device__ __forceinline__ void mma_loop(const Pipe& P, uint8_t* smem, uint32_t 
     uint32_t it = 0, ph_x = 0;
     const uint32_t xa = smem_u32(smem + SM_X), wa = smem_u32(smem + SM_W);
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-        for (int ph = 0; ph < n_phase<FWD>(); ++ph) {
-            mbar_wait(P.xready, ph_x); ph_x ^= 1;
-            tc_fence_after();
-            const int nhalf = (FWD && ph == NLAYER - 1) ? 1 : 2;      // lin4: n_out <= 8 rows live in half 0
-            const int nch = phase_chunks<FWD>(ph), nj = (FWD && ph == 0) ? 1 : KCH / 16;
-            for (int c = 0; c < nch; ++c, ++it) {
-                const uint32_t s = it % NSTAGE, par = (it / NSTAGE) & 1;
-                mbar_wait(P.wfull + 8 * s, par);
+        for (int ph = 0; ph < n_phase<FWD>(); ++ph, ph_x ^= 1)
+            for (int u = 0; u < NSUB; ++u) {
+                mbar_wait(P.xready(u), ph_x);
                 tc_fence_after();
-                const uint32_t wst = wa + s * W_STAGE;
-                for (int h = 0; h < nhalf; ++h)
-                    for (int j = 0; j < nj; ++j) {
-                        const uint32_t kb = (uint32_t)(c * (KCH / 8) + 2 * j);          // first k8 block of this K = 16 step
-                        const uint64_t b1 = umma_desc(xa + kb * X_BLK, X_BLK, 128), b2 = umma_desc(xa + X_SPLIT + kb * X_BLK, X_BLK, 128);
-                        const uint64_t a1 = umma_desc(wst + (uint32_t)((0 * 2 + h) * (KCH / 8) + 2 * j) * W_BLK, W_BLK, 128);
-                        const uint64_t a2 = umma_desc(wst + (uint32_t)((1 * 2 + h) * (KCH / 8) + 2 * j) * W_BLK, W_BLK, 128);
-                        const uint32_t d = tmem_base + (uint32_t)(h * NPIX);
-                        umma_f16(d, a1, b1, kIdesc, (c | j) != 0);        // w1 x1
-                        umma_f16(d, a1, b2, kIdesc, 1);                   // w1 x2
-                        umma_f16(d, a2, b1, kIdesc, 1);                   // w2 x1
-                    }
-                tc_commit(P.wempty + 8 * s);                  // stage free once these MMAs have read it
+                const int nhalf = (FWD && ph == NLAYER - 1) ? 1 : 2;      // lin4: n_out <= 8 rows live in half 0
+                const int nch = phase_chunks<FWD>(ph), nj = (FWD && ph == 0) ? 1 : KCH / 16;
+                const uint32_t xu = xa + (uint32_t)(u * SPIX * 16);       // operand rows (pixels) of this sub-tile
+                for (int c = 0; c < nch; ++c, ++it) {
+                    const uint32_t s = it % NSTAGE, par = (it / NSTAGE) & 1;
+                    mbar_wait(P.wfull + 8 * s, par);
+                    tc_fence_after();
+                    const uint32_t wst = wa + s * W_STAGE;
+                    for (int h = 0; h < nhalf; ++h)
+                        for (int j = 0; j < nj; ++j) {
+                            const uint32_t kb = (uint32_t)(c * (KCH / 8) + 2 * j);          // first k8 block of this K = 16 step
+                            const uint64_t b1 = umma_desc(xu + kb * X_BLK, X_BLK, 128), b2 = umma_desc(xu + X_SPLIT + kb * X_BLK, X_BLK, 128);
+                            const uint64_t a1 = umma_desc(wst + (uint32_t)((0 * 2 + h) * (KCH / 8) + 2 * j) * W_BLK, W_BLK, 128);
+                            const uint64_t a2 = umma_desc(wst + (uint32_t)((1 * 2 + h) * (KCH / 8) + 2 * j) * W_BLK, W_BLK, 128);
+                            const uint32_t d = tmem_base + (uint32_t)(h * NPIX + u * SPIX);
+                            umma_f16(d, a1, b1, kIdescSub, (c | j) != 0);        // w1 x1
+                            umma_f16(d, a1, b2, kIdescSub, 1);                   // w1 x2
+                            umma_f16(d, a2, b1, kIdescSub, 1);                   // w2 x1
+                        }
+                    tc_commit(P.wempty + 8 * s);                  // stage free once these MMAs have read it
+                }
+                tc_commit(P.dfull(u));                            // accumulators of this sub-tile complete, its operand rows free
             }
-            tc_commit(P.dfull);                               // accumulators complete, operand image free
-        }
 }
 // image-store warp: after every operand image is complete, optionally bulk-copy it to global as 4 pixel-quarter pieces
 // ([split][k8][32 px][8 halves], 32 KB each; lane <-> k8 block), then release the image for the next writer.
@@ -314,22 +332,23 @@ __device__ __forceinline__ void store_loop(const Pipe& P, uint8_t* smem, uint8_t
     uint32_t ph_x = 0;
     const uint32_t xa = smem_u32(smem + SM_X);
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-        for (int ph = 0; ph < n_phase<FWD>(); ++ph) {
-            mbar_wait(P.xready, ph_x); ph_x ^= 1;
-            // FWD: phases 1,2,3 hold X_1, X_2, X_3 (inputs of lin1..lin3) -> slots 0,1,2.  BWD: phases 0,1,2 hold G_3, G_2, G_1 -> slots 2,1,0
-            const int slot = FWD ? ((ph >= 1 && ph <= 3) ? ph - 1 : -1) : 2 - ph;
-            if (imgs && slot >= 0) {
-                uint8_t* dst = imgs + ((size_t)slot * ntiles + tile) * IMG_TILE;
+        for (int ph = 0; ph < n_phase<FWD>(); ++ph, ph_x ^= 1)
+            for (int u = 0; u < NSUB; ++u) {
+                mbar_wait(P.xready(u), ph_x);
+                // FWD: phases 1,2,3 hold X_1, X_2, X_3 (inputs of lin1..lin3) -> slots 0,1,2.  BWD: phases 0,1,2 hold G_3, G_2, G_1 -> slots 2,1,0
+                const int slot = FWD ? ((ph >= 1 && ph <= 3) ? ph - 1 : -1) : 2 - ph;
+                if (imgs && slot >= 0) {
+                    uint8_t* dst = imgs + ((size_t)slot * ntiles + tile) * IMG_TILE;
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
+                    for (int q = u * (4 / NSUB); q < (u + 1) * (4 / NSUB); ++q)          // the pixel quarters of this sub-tile
 #pragma unroll
-                    for (int sp = 0; sp < 2; ++sp)
-                        bulk_s2g(dst + (size_t)q * IMG_PIECE + sp * (IMG_PIECE / 2) + lane * 512, xa + sp * X_SPLIT + lane * X_BLK + q * 512, 512);
-                bulk_commit_wait_read();
+                        for (int sp = 0; sp < 2; ++sp)
+                            bulk_s2g(dst + (size_t)q * IMG_PIECE + sp * (IMG_PIECE / 2) + lane * 512, xa + sp * X_SPLIT + lane * X_BLK + q * 512, 512);
+                    bulk_commit_wait_read();
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(P.sdone(u));
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(P.sdone);
-        }
 }
 
 // ---------------------------------------------------------------- forward
@@ -347,9 +366,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) posmlp_fwd_tc_kernel(const __grid
     const long long ntiles = (A.N + NPIX - 1) / NPIX;
 
     if (warp < NEPI / 32) {
-        // ===================================================== epilogue: thread <-> (feature f, pixel half)
+        // ===================================================== epilogue: thread <-> (feature f, pixel quarter of each sub-tile)
         const int f = 128 * ((warp >> 2) & 1) + 32 * (warp & 3) + lane;
-        const int pbeg = (warp >> 3) * (NPIX / 2), pend = pbeg + NPIX / 2;
+        const int pq = (warp >> 3) * (SPIX / 2);                     // first pixel of this thread's 32 inside a sub-tile
         const uint32_t t_lane = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(((warp >> 2) & 1) * NPIX);
         uint32_t ph_d = 0, ph_s = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -365,8 +384,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) posmlp_fwd_tc_kernel(const __grid
             }
             tc_fence_before();
             fence_proxy_async();
-            mbar_arrive(P.xready);
-            named_bar_sync(1, NEPI);                                  // sPT visible to every epilogue thread
+            named_bar_sync(1, NEPI);                                  // sPT and the lin0 image complete (written by warps 0..3 for both sub-tiles)
+#pragma unroll
+            for (int u = 0; u < NSUB; ++u) mbar_arrive(P.xready(u));
             // ---- lin0 .. lin3: z = acc + b + w_row row + w_col col ; cache z ; x = sin z -> input image of the next layer
             for (int L = 0; L < 4; ++L) {
                 const int n_out = (L == 0 || L == 2) ? D.h0 : HID;
@@ -378,28 +398,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) posmlp_fwd_tc_kernel(const __grid
                     if (L != 2) { w_row = __ldg(A.params + D.oW[L] + f * ld + emb0); w_col = __ldg(A.params + D.oW[L] + f * ld + emb0 + 1); }
                 }
                 const int ke = f - n_out;                             // embedding index carried by this feature slot when !live
-                mbar_wait(P.dfull, ph_d); ph_d ^= 1; tc_fence_after();
-                mbar_wait(P.sdone, ph_s); ph_s ^= 1;                  // the previous image has been copied out
-                for (int p0 = pbeg; p0 < pend; p0 += 16) {
-                    float acc[16];
-                    tmem_ld16(t_lane + (uint32_t)p0, acc);
+                for (int u = 0; u < NSUB; ++u) {
+                    mbar_wait(P.dfull(u), ph_d); tc_fence_after();
+                    mbar_wait(P.sdone(u), ph_s);                      // the previous image rows of this sub-tile have been copied out
+                    const int pbeg = u * SPIX + pq;
+                    for (int p0 = pbeg; p0 < pbeg + SPIX / 2; p0 += 16) {
+                        float acc[16];
+                        tmem_ld16(t_lane + (uint32_t)p0, acc);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int p = p0 + i;
-                        const float2 rc = *reinterpret_cast<const float2*>(sPT + p * 16);
-                        const float z = fmaf(w_row, rc.x, fmaf(w_col, rc.y, acc[i] + bias));
-                        if (A.zc && n0 + p < A.N) A.zc[(n0 + p) * ZSTRIDE + L * HID + f] = live ? z : 0.f;
-                        // features >= n_out of the next layer's input are the concatenated embedding (coordinates: FP32 side term)
-                        const float x = live ? sin_cw(z) : (ke >= 2 ? sPT[p * 16 + ke] : 0.f);
-                        store_x(sX, f, p, x);
+                        for (int i = 0; i < 16; ++i) {
+                            const int p = p0 + i;
+                            const float2 rc = *reinterpret_cast<const float2*>(sPT + p * 16);
+                            const float z = fmaf(w_row, rc.x, fmaf(w_col, rc.y, acc[i] + bias));
+                            if (A.zc && n0 + p < A.N) A.zc[(n0 + p) * ZSTRIDE + L * HID + f] = live ? z : 0.f;
+                            // features >= n_out of the next layer's input are the concatenated embedding (coordinates: FP32 side term)
+                            const float x = live ? sin_cw(z) : (ke >= 2 ? sPT[p * 16 + ke] : 0.f);
+                            store_x(sX, f, p, x);
+                        }
                     }
+                    tc_fence_before();
+                    fence_proxy_async();                              // generic-proxy smem writes -> visible to the async proxy (UMMA, bulk store)
+                    mbar_arrive(P.xready(u));
                 }
-                tc_fence_before();
-                fence_proxy_async();                                  // generic-proxy smem writes -> visible to the async proxy (UMMA, bulk store)
-                mbar_arrive(P.xready);
+                ph_d ^= 1; ph_s ^= 1;
             }
             // ---- lin4 accumulators (half 0, lanes 0..n_out-1) -> sOB, then the output activation on all epilogue threads
-            mbar_wait(P.dfull, ph_d); ph_d ^= 1; tc_fence_after();
+#pragma unroll
+            for (int u = 0; u < NSUB; ++u) { mbar_wait(P.dfull(u), ph_d); }
+            ph_d ^= 1;
+            tc_fence_after();
             if (warp == 0) {
                 for (int p0 = 0; p0 < NPIX; p0 += 16) {
                     float acc[16];
@@ -423,7 +450,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) posmlp_fwd_tc_kernel(const __grid
                     A.out[n * D.n_out + o] = y;
                 }
             }
-            mbar_wait(P.sdone, ph_s); ph_s ^= 1;
+#pragma unroll
+            for (int u = 0; u < NSUB; ++u) { mbar_wait(P.sdone(u), ph_s); }
+            ph_s ^= 1;
             named_bar_sync(1, NEPI);                                  // sOB / sPT / the image are rewritten by the next tile
         }
     } else if (warp == WARP_PROD) {
@@ -466,7 +495,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) posmlp_bwd_data_tc_kernel(const _
 
     if (warp < NEPI / 32) {
         const int f = 128 * ((warp >> 2) & 1) + 32 * (warp & 3) + lane;
-        const int pbeg = (warp >> 3) * (NPIX / 2), pend = pbeg + NPIX / 2;
+        const int pq = (warp >> 3) * (SPIX / 2);                     // first pixel of this thread's 32 inside a sub-tile
         const uint32_t t_lane = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(((warp >> 2) & 1) * NPIX);
         uint32_t ph_d = 0, ph_s = 0;
         float w4[OSTRIDE];
@@ -501,60 +530,67 @@ __global__ void __launch_bounds__(NTHREADS, 1) posmlp_bwd_data_tc_kernel(const _
             named_bar_sync(1, NEPI);
             if (tid < OSTRIDE) { float sum = 0.f; for (int p = 0; p < NPIX; ++p) sum += sG4[p * OSTRIDE + tid]; gb4 += sum; }
             // ---- through lin4 and the sine of lin3 (no MMA):  gz3 = (W4^T G4) * cos z3 ; gW4 += G4 sin z3
-            for (int p0 = pbeg; p0 < pend; p0 += 16) {
-                float zv[16];
+            for (int u = 0; u < NSUB; ++u) {
+                const int pbeg = u * SPIX + pq;
+                for (int p0 = pbeg; p0 < pbeg + SPIX / 2; p0 += 16) {
+                    float zv[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) zv[i] = (n0 + p0 + i < A.N) ? __ldg(A.zc + (n0 + p0 + i) * ZSTRIDE + 3 * HID + f) : 0.f;
+                    for (int i = 0; i < 16; ++i) zv[i] = (n0 + p0 + i < A.N) ? __ldg(A.zc + (n0 + p0 + i) * ZSTRIDE + 3 * HID + f) : 0.f;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int p = p0 + i;
-                    const float4 ga = *reinterpret_cast<const float4*>(sG4 + p * OSTRIDE), gb_ = *reinterpret_cast<const float4*>(sG4 + p * OSTRIDE + 4);
-                    const float g4[OSTRIDE] = {ga.x, ga.y, ga.z, ga.w, gb_.x, gb_.y, gb_.z, gb_.w};
-                    float gx = 0.f;
+                    for (int i = 0; i < 16; ++i) {
+                        const int p = p0 + i;
+                        const float4 ga = *reinterpret_cast<const float4*>(sG4 + p * OSTRIDE), gb_ = *reinterpret_cast<const float4*>(sG4 + p * OSTRIDE + 4);
+                        const float g4[OSTRIDE] = {ga.x, ga.y, ga.z, ga.w, gb_.x, gb_.y, gb_.z, gb_.w};
+                        float gx = 0.f;
 #pragma unroll
-                    for (int o = 0; o < OSTRIDE; ++o) gx = fmaf(w4[o], g4[o], gx);
-                    float sn, cs; sincos_cw(zv[i], sn, cs);
-                    const float gz = gx * cs;
+                        for (int o = 0; o < OSTRIDE; ++o) gx = fmaf(w4[o], g4[o], gx);
+                        float sn, cs; sincos_cw(zv[i], sn, cs);
+                        const float gz = gx * cs;
 #pragma unroll
-                    for (int o = 0; o < OSTRIDE; ++o) gW4a[o] = fmaf(g4[o], sn, gW4a[o]);
-                    const float2 rc = *reinterpret_cast<const float2*>(sPT + p * 16);
-                    gb[3] += gz; gWc3[0] = fmaf(gz, rc.x, gWc3[0]); gWc3[1] = fmaf(gz, rc.y, gWc3[1]);
-                    store_x(sX, f, p, gz);
+                        for (int o = 0; o < OSTRIDE; ++o) gW4a[o] = fmaf(g4[o], sn, gW4a[o]);
+                        const float2 rc = *reinterpret_cast<const float2*>(sPT + p * 16);
+                        gb[3] += gz; gWc3[0] = fmaf(gz, rc.x, gWc3[0]); gWc3[1] = fmaf(gz, rc.y, gWc3[1]);
+                        store_x(sX, f, p, gz);
+                    }
                 }
+                tc_fence_before(); fence_proxy_async(); mbar_arrive(P.xready(u));
             }
-            tc_fence_before(); fence_proxy_async(); mbar_arrive(P.xready);
             // ---- lin3, lin2, lin1 backward: the accumulators hold W_L^T G_L (feature f = an INPUT of layer L = an output of layer L-1)
             for (int L = 3; L >= 1; --L) {
                 const int h_prev = (L == 3 || L == 1) ? D.h0 : HID;  // sine units feeding layer L; the rest of its input is the embedding
                 const bool live = f < h_prev;
-                mbar_wait(P.dfull, ph_d); ph_d ^= 1; tc_fence_after();
-                mbar_wait(P.sdone, ph_s); ph_s ^= 1;
-                for (int p0 = pbeg; p0 < pend; p0 += 16) {
-                    float acc[16], zv[16];
+                for (int u = 0; u < NSUB; ++u) {
+                    mbar_wait(P.dfull(u), ph_d); tc_fence_after();
+                    mbar_wait(P.sdone(u), ph_s);
+                    const int pbeg = u * SPIX + pq;
+                    for (int p0 = pbeg; p0 < pbeg + SPIX / 2; p0 += 16) {
+                        float acc[16], zv[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) zv[i] = (live && n0 + p0 + i < A.N) ? __ldg(A.zc + (n0 + p0 + i) * ZSTRIDE + (L - 1) * HID + f) : 0.f;
-                    tmem_ld16(t_lane + (uint32_t)p0, acc);
+                        for (int i = 0; i < 16; ++i) zv[i] = (live && n0 + p0 + i < A.N) ? __ldg(A.zc + (n0 + p0 + i) * ZSTRIDE + (L - 1) * HID + f) : 0.f;
+                        tmem_ld16(t_lane + (uint32_t)p0, acc);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int p = p0 + i;
-                        const float gz = live ? acc[i] * cos_cw(zv[i]) : 0.f;       // dL/dz_{L-1}
-                        gb[L - 1] += gz;
-                        if (L == 2) {                                                // z1: lin1's output -> coordinate columns of gW1
-                            const float2 rc = *reinterpret_cast<const float2*>(sPT + p * 16);
-                            gWc1[0] = fmaf(gz, rc.x, gWc1[0]); gWc1[1] = fmaf(gz, rc.y, gWc1[1]);
-                        }
-                        if (L > 1) store_x(sX, f, p, gz);
-                        else {                                                       // z0: lin0's weight gradient, K = embedding, exact FP32
-                            const float4* e4 = reinterpret_cast<const float4*>(sPT + p * 16);
-                            const float4 e0 = e4[0], e1 = e4[1], e2 = e4[2], e3 = e4[3];
-                            gW0a[0] = fmaf(gz, e0.x, gW0a[0]); gW0a[1] = fmaf(gz, e0.y, gW0a[1]); gW0a[2] = fmaf(gz, e0.z, gW0a[2]); gW0a[3] = fmaf(gz, e0.w, gW0a[3]);
-                            gW0a[4] = fmaf(gz, e1.x, gW0a[4]); gW0a[5] = fmaf(gz, e1.y, gW0a[5]); gW0a[6] = fmaf(gz, e1.z, gW0a[6]); gW0a[7] = fmaf(gz, e1.w, gW0a[7]);
-                            gW0a[8] = fmaf(gz, e2.x, gW0a[8]); gW0a[9] = fmaf(gz, e2.y, gW0a[9]); gW0a[10] = fmaf(gz, e2.z, gW0a[10]); gW0a[11] = fmaf(gz, e2.w, gW0a[11]);
-                            gW0a[12] = fmaf(gz, e3.x, gW0a[12]); gW0a[13] = fmaf(gz, e3.y, gW0a[13]); gW0a[14] = fmaf(gz, e3.z, gW0a[14]); gW0a[15] = fmaf(gz, e3.w, gW0a[15]);
+                        for (int i = 0; i < 16; ++i) {
+                            const int p = p0 + i;
+                            const float gz = live ? acc[i] * cos_cw(zv[i]) : 0.f;       // dL/dz_{L-1}
+                            gb[L - 1] += gz;
+                            if (L == 2) {                                                // z1: lin1's output -> coordinate columns of gW1
+                                const float2 rc = *reinterpret_cast<const float2*>(sPT + p * 16);
+                                gWc1[0] = fmaf(gz, rc.x, gWc1[0]); gWc1[1] = fmaf(gz, rc.y, gWc1[1]);
+                            }
+                            if (L > 1) store_x(sX, f, p, gz);
+                            else {                                                       // z0: lin0's weight gradient, K = embedding, exact FP32
+                                const float4* e4 = reinterpret_cast<const float4*>(sPT + p * 16);
+                                const float4 e0 = e4[0], e1 = e4[1], e2 = e4[2], e3 = e4[3];
+                                gW0a[0] = fmaf(gz, e0.x, gW0a[0]); gW0a[1] = fmaf(gz, e0.y, gW0a[1]); gW0a[2] = fmaf(gz, e0.z, gW0a[2]); gW0a[3] = fmaf(gz, e0.w, gW0a[3]);
+                                gW0a[4] = fmaf(gz, e1.x, gW0a[4]); gW0a[5] = fmaf(gz, e1.y, gW0a[5]); gW0a[6] = fmaf(gz, e1.z, gW0a[6]); gW0a[7] = fmaf(gz, e1.w, gW0a[7]);
+                                gW0a[8] = fmaf(gz, e2.x, gW0a[8]); gW0a[9] = fmaf(gz, e2.y, gW0a[9]); gW0a[10] = fmaf(gz, e2.z, gW0a[10]); gW0a[11] = fmaf(gz, e2.w, gW0a[11]);
+                                gW0a[12] = fmaf(gz, e3.x, gW0a[12]); gW0a[13] = fmaf(gz, e3.y, gW0a[13]); gW0a[14] = fmaf(gz, e3.z, gW0a[14]); gW0a[15] = fmaf(gz, e3.w, gW0a[15]);
+                            }
                         }
                     }
+                    if (L > 1) { tc_fence_before(); fence_proxy_async(); mbar_arrive(P.xready(u)); }
                 }
-                if (L > 1) { tc_fence_before(); fence_proxy_async(); mbar_arrive(P.xready); }
+                ph_d ^= 1; ph_s ^= 1;
             }
             tc_fence_before();
             named_bar_sync(1, NEPI);                                  // sPT / sG4 / the image are rewritten by the next tile
