@@ -33,9 +33,17 @@ namespace posmlp {
 namespace {
 
 constexpr int NPIX = 128;                 // pixels per tile (UMMA N)
-constexpr int KCH = 32;                   // k per weight stage
-constexpr int NCHUNK = HID / KCH;         // 8 chunks per layer
-constexpr int NSTAGE = 2;
+#ifndef MB200_POSMLP_KCH
+#define MB200_POSMLP_KCH 32
+#endif
+#ifndef MB200_POSMLP_NSTAGE
+#define MB200_POSMLP_NSTAGE 2
+#endif
+// (measured, profiles/r5s: 5 stages of 16 KB — all the shared memory that is left — instead of 2 of 32 KB: forward 0.740 -> 0.799 ms;
+// the weight stream is not what the kernel waits for, twice as many chunk barriers cost more than the deeper ring gains)
+constexpr int KCH = MB200_POSMLP_KCH;     // k per weight stage
+constexpr int NCHUNK = HID / KCH;         // chunks per layer
+constexpr int NSTAGE = MB200_POSMLP_NSTAGE;
 constexpr int NLAYER = 5;                 // lin0 .. lin4, all on the tensor cores
 constexpr int W_BLK = 128 * 16;           // one k8 block of a 128-row weight half (bytes) = LBO of the A operand
 constexpr int W_STAGE = 2 * 2 * (KCH / 8) * W_BLK;          // [term][half][k8][128 rows][8 halves] = 32768 B
@@ -46,7 +54,8 @@ constexpr int SM_W = SM_X + 2 * X_SPLIT;                     // 132096
 constexpr int SM_PT = SM_W + NSTAGE * W_STAGE;               // 197632
 constexpr int SM_OB = SM_PT + NPIX * 16 * 4;                 // 205824
 constexpr int SM_BAR = SM_OB + OSTRIDE * NPIX * 4;           // 209920
-constexpr int SM_TOTAL = SM_BAR + 128;
+constexpr int SM_TOTAL = SM_BAR + 256;
+static_assert(SM_TOTAL <= 232448, "shared memory per CTA");
 constexpr int NEPI = 512;                 // epilogue threads
 constexpr int NTHREADS = NEPI + 96;       // + producer warp, MMA warp, image-store warp
 constexpr int WARP_PROD = NEPI / 32, WARP_MMA = NEPI / 32 + 1, WARP_STORE = NEPI / 32 + 2;
@@ -246,7 +255,7 @@ __device__ __forceinline__ Pipe pipe_setup(uint8_t* smem, int tid, int warp) {
     const uint32_t b1 = bar0 + 16 * NSTAGE;
     P.xready0 = b1; P.dfull0 = b1 + 8 * NSUB; P.sdone0 = b1 + 16 * NSUB;
     P.tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 16 * NSTAGE + 24 * NSUB);
-    static_assert(16 * NSTAGE + 24 * NSUB + 4 <= 128, "barrier area");
+    static_assert(16 * NSTAGE + 24 * NSUB + 4 <= 256, "barrier area");
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(P.wfull + 8 * s, 1); mbar_init(P.wempty + 8 * s, 1); }
         for (int u = 0; u < NSUB; ++u) { mbar_init(P.xready(u), NEPI); mbar_init(P.dfull(u), 1); mbar_init(P.sdone(u), 1); }
