@@ -624,12 +624,16 @@ def run_e2e_iteration(args, opt, shard, dev, world, samples_per_step):
     t_serial = _timed(serial, args.steps, 3, dev, world)
 
     # the same transfers on their own streams: the upload of step i+1 runs under step i (two target buffers), the download of step
-    # i's results under step i+1's forward render (the loss kernels of step i+1 wait for it before they overwrite pred_srgb / sums2)
+    # i's results under step i+1 (two result buffers)
     main = torch.cuda.current_stream(dev)
     s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     gts = [opt.gt_srgb, torch.empty_like(opt.gt_srgb)]
     ev_in = [torch.cuda.Event(), torch.cuda.Event()]; ev_used = [torch.cuda.Event(), torch.cuda.Event()]
-    ev_step, ev_out = torch.cuda.Event(), torch.cuda.Event()
+    # results double-buffered too: step i+1 writes pred_srgb / sums2 into the other pair while step i's pair is still being read back
+    preds = [opt.pred_srgb, torch.empty_like(opt.pred_srgb)]; sums = [opt.sums2, torch.zeros_like(opt.sums2)]
+    ev_step = [torch.cuda.Event(), torch.cuda.Event()]; ev_out = [torch.cuda.Event(), torch.cuda.Event()]
+    for e in ev_out:
+        e.record(main)
     state = {"i": 0}
 
     def upload(slot):
@@ -642,26 +646,26 @@ def run_e2e_iteration(args, opt, shard, dev, world, samples_per_step):
     def piped(seed):
         slot = state["i"] % 2; state["i"] += 1
         main.wait_event(ev_in[slot])
-        opt.gt_srgb = gts[slot]
+        opt.gt_srgb = gts[slot]; opt.pred_srgb = preds[slot]; opt.sums2 = sums[slot]
         upload(1 - slot)
-        main.wait_event(ev_out)                                  # the previous step's results have left pred_srgb / sums2
+        main.wait_event(ev_out[slot])                            # the results of step i-2 have left this pair of buffers
         opt.step(seed)
-        ev_used[slot].record(main); ev_step.record(main)
+        ev_used[slot].record(main); ev_step[slot].record(main)
         with torch.cuda.stream(s_out):
-            s_out.wait_event(ev_step)
-            hpred.copy_(opt.pred_srgb, non_blocking=True); hloss.copy_(opt.sums2, non_blocking=True)
-            ev_out.record(s_out)
+            s_out.wait_event(ev_step[slot])
+            hpred.copy_(preds[slot], non_blocking=True); hloss.copy_(sums[slot], non_blocking=True)
+            ev_out[slot].record(s_out)
     for i in range(3):
         piped(i)
-    main.wait_event(ev_out); _sync(world)
+    main.wait_event(ev_out[0]); main.wait_event(ev_out[1]); _sync(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
         piped(3000 + i)
-    main.wait_event(ev_out)
+    main.wait_event(ev_out[0]); main.wait_event(ev_out[1])      # the last results are on the host when the clock stops
     e1.record(); s_in.synchronize(); s_out.synchronize(); _sync(world)
     t_pipe = _max_over_ranks(e0.elapsed_time(e1), dev, world) / args.steps / 1e3
-    opt.gt_srgb = gts[0]
+    opt.gt_srgb = gts[0]; opt.pred_srgb = preds[0]; opt.sums2 = sums[0]
     return {"value": samples_per_step / t_pipe / 1e9, "unit": UNIT, "h2d_bytes_per_step": hgt.numel() * 4, "d2h_bytes_per_step": (hpred.numel() + 2) * 4,
             "ms_per_step": t_pipe * 1e3, "ms_per_step_copies_serialised": t_serial * 1e3, "value_copies_serialised": samples_per_step / t_serial / 1e9,
             "bytes_are": "per rank",
