@@ -86,16 +86,19 @@ def main():
         d = float((sharded[k] - single[k]).norm() / single[k].norm())
         print(f"rank {rank} {k}: max |sharded - single| = {e:.3e}, rel-L2 {d:.3e}", flush=True)
         ok &= d < 1e-5
-    for cls in (FusedBRDFOptimizer, DirectBRDFOptimizer):
-        shc = ShardContext(64, 64, rank, world)
-        sharded = run_gbuffer(dev, shc, cls)
-        single = run_gbuffer(dev, ShardContext(64, 64, 0, 1), cls)
-        rows = slice(shc.row0, shc.row0 + shc.rows)
-        for k in sharded:
-            d = float((sharded[k][rows] - single[k][rows]).norm() / single[k][rows].norm())
-            lim = 1e-5
-            print(f"rank {rank} G-buffer {cls.__name__} {k}: own rows rel-L2 sharded vs single {d:.3e}", flush=True)
-            ok &= d < lim
+    # G-buffer mode: an even split (64 rows) and an UNEVEN one (70 rows x 68 columns: the ranks' halo buffers differ in size, so the
+    # peer arenas have different layouts and the neighbours' offset tables are what addresses them)
+    for (Hg, Wg) in ((64, 64), (70, 68)):
+        for cls in (FusedBRDFOptimizer, DirectBRDFOptimizer):
+            shc = ShardContext(Hg, Wg, rank, world)
+            sharded = run_gbuffer(dev, shc, cls, H=Hg, W=Wg)
+            single = run_gbuffer(dev, ShardContext(Hg, Wg, 0, 1), cls, H=Hg, W=Wg)
+            rows = slice(shc.row0, shc.row0 + shc.rows)
+            for k in sharded:
+                d = float((sharded[k][rows] - single[k][rows]).norm() / single[k][rows].norm())
+                lim = 1e-5
+                print(f"rank {rank} G-buffer {Hg}x{Wg} {cls.__name__} {k}: own rows rel-L2 sharded vs single {d:.3e}", flush=True)
+                ok &= d < lim
     sharded, _ = run_posmlp(dev, ShardContext(64, 64, rank, world))
     single, _ = run_posmlp(dev, ShardContext(64, 64, 0, 1))
     d = float((sharded["params"] - single["params"]).norm() / single["params"].norm())
@@ -107,7 +110,7 @@ def main():
     if not ok:
         raise SystemExit("a sharded optimisation differs from the single-GPU run")
     if rank == 0:
-        print("OK: 2-rank mesh-mode, G-buffer (fused / direct) and pos_mlp optimisations == 1-GPU runs")
+        print(f"OK: {world}-rank mesh-mode, G-buffer (fused / direct) and pos_mlp optimisations == 1-GPU runs")
 
 
 if __name__ == "__main__":
