@@ -103,6 +103,19 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same, with the descriptors as (low word, high word): the MMA issuer keeps the constant high words in registers and only ADDS
+// 16-byte-unit offsets to the low words (start address field) inside its loops — rebuilding four 64-bit descriptors per K step
+// with shifts and masks cost the single issuing thread ~12 k dependent instructions per tile (profiles/r5r), a serial bottleneck
+// that the epilogue warps ended up waiting for
+__device__ __forceinline__ void umma_f16_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -304,6 +317,11 @@ template <bool FWD>
 __device__ __forceinline__ void mma_loop(const Pipe& P, uint8_t* smem, uint32_t tmem_base, long long ntiles) {
     uint32_t it = 0, ph_x = 0;
     const uint32_t xa = smem_u32(smem + SM_X), wa = smem_u32(smem + SM_W);
+    // descriptor words (umma_desc): low = start >> 4 | (LBO >> 4) << 16, high = SBO >> 4 | version 1 << 14
+    const uint32_t b_hi = (128u >> 4) | (1u << 14), a_hi = b_hi;
+    const uint32_t b_lo0 = ((xa >> 4) & 0x3FFFu) | (((uint32_t)X_BLK >> 4) << 16);          // split term 1, k8 block 0, pixel row 0
+    const uint32_t a_lo0 = ((wa >> 4) & 0x3FFFu) | (((uint32_t)W_BLK >> 4) << 16);          // stage 0, term 1, half 0, k8 block 0
+    constexpr uint32_t kXBlk16 = X_BLK >> 4, kXSplit16 = X_SPLIT >> 4, kWBlk16 = W_BLK >> 4, kWStage16 = W_STAGE >> 4;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
         for (int ph = 0; ph < n_phase<FWD>(); ++ph, ph_x ^= 1)
             for (int u = 0; u < NSUB; ++u) {
@@ -311,22 +329,32 @@ __device__ __forceinline__ void mma_loop(const Pipe& P, uint8_t* smem, uint32_t 
                 tc_fence_after();
                 const int nhalf = (FWD && ph == NLAYER - 1) ? 1 : 2;      // lin4: n_out <= 8 rows live in half 0
                 const int nch = phase_chunks<FWD>(ph), nj = (FWD && ph == 0) ? 1 : KCH / 16;
-                const uint32_t xu = xa + (uint32_t)(u * SPIX * 16);       // operand rows (pixels) of this sub-tile
+                const uint32_t b_u = b_lo0 + (uint32_t)(u * SPIX);        // operand rows (pixels) of this sub-tile: 16 bytes per row
                 for (int c = 0; c < nch; ++c, ++it) {
                     const uint32_t s = it % NSTAGE, par = (it / NSTAGE) & 1;
                     mbar_wait(P.wfull + 8 * s, par);
                     tc_fence_after();
-                    const uint32_t wst = wa + s * W_STAGE;
+                    const uint32_t a_s = a_lo0 + s * kWStage16;
                     for (int h = 0; h < nhalf; ++h)
                         for (int j = 0; j < nj; ++j) {
                             const uint32_t kb = (uint32_t)(c * (KCH / 8) + 2 * j);          // first k8 block of this K = 16 step
-                            const uint64_t b1 = umma_desc(xu + kb * X_BLK, X_BLK, 128), b2 = umma_desc(xu + X_SPLIT + kb * X_BLK, X_BLK, 128);
-                            const uint64_t a1 = umma_desc(wst + (uint32_t)((0 * 2 + h) * (KCH / 8) + 2 * j) * W_BLK, W_BLK, 128);
-                            const uint64_t a2 = umma_desc(wst + (uint32_t)((1 * 2 + h) * (KCH / 8) + 2 * j) * W_BLK, W_BLK, 128);
+                            const uint32_t b1 = b_u + kb * kXBlk16, b2 = b1 + kXSplit16;
+                            const uint32_t a1 = a_s + (uint32_t)((0 * 2 + h) * (KCH / 8) + 2 * j) * kWBlk16;
+                            const uint32_t a2 = a_s + (uint32_t)((1 * 2 + h) * (KCH / 8) + 2 * j) * kWBlk16;
                             const uint32_t d = tmem_base + (uint32_t)(h * NPIX + u * SPIX);
-                            umma_f16(d, a1, b1, kIdescSub, (c | j) != 0);        // w1 x1
-                            umma_f16(d, a1, b2, kIdescSub, 1);                   // w1 x2
-                            umma_f16(d, a2, b1, kIdescSub, 1);                   // w2 x1
+                            if (FWD) {
+                                umma_f16_w(d, a1, a_hi, b1, b_hi, kIdescSub, (c | j) != 0);        // w1 x1
+                                umma_f16_w(d, a1, a_hi, b2, b_hi, kIdescSub, 1);                   // w1 x2
+                                umma_f16_w(d, a2, a_hi, b1, b_hi, kIdescSub, 1);                   // w2 x1
+                            } else {
+                                // (the data-gradient kernel keeps the descriptors as 64-bit values: with the split form its register
+                                // allocation tips into 1.7 KB of spills in the epilogue branch — measured 1.90 -> 2.31 ms fwd + bwd)
+                                const uint64_t A1 = ((uint64_t)a_hi << 32) | a1, A2 = ((uint64_t)a_hi << 32) | a2;
+                                const uint64_t B1 = ((uint64_t)b_hi << 32) | b1, B2 = ((uint64_t)b_hi << 32) | b2;
+                                umma_f16(d, A1, B1, kIdescSub, (c | j) != 0);
+                                umma_f16(d, A1, B2, kIdescSub, 1);
+                                umma_f16(d, A2, B1, kIdescSub, 1);
+                            }
                         }
                     tc_commit(P.wempty + 8 * s);                  // stage free once these MMAs have read it
                 }
@@ -414,12 +442,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) posmlp_fwd_tc_kernel(const __grid
                     for (int p0 = pbeg; p0 < pbeg + SPIX / 2; p0 += 16) {
                         float acc[16];
                         tmem_ld16(t_lane + (uint32_t)p0, acc);
+                        // pre-activation cache: one pointer per 16-pixel block, compile-time offsets inside it (the per-element 64-bit
+                        // index arithmetic was 14 % of the kernel's instructions, profiles/r5r)
+                        float* const zp = A.zc ? A.zc + (n0 + p0) * ZSTRIDE + L * HID + f : nullptr;
+                        const int nval = zp ? (int)min((long long)16, A.N - (n0 + p0)) : 0;
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const int p = p0 + i;
                             const float2 rc = *reinterpret_cast<const float2*>(sPT + p * 16);
                             const float z = fmaf(w_row, rc.x, fmaf(w_col, rc.y, acc[i] + bias));
-                            if (A.zc && n0 + p < A.N) A.zc[(n0 + p) * ZSTRIDE + L * HID + f] = live ? z : 0.f;
+                            if (i < nval) zp[i * ZSTRIDE] = live ? z : 0.f;
                             // features >= n_out of the next layer's input are the concatenated embedding (coordinates: FP32 side term)
                             const float x = live ? sin_cw(z) : (ke >= 2 ? sPT[p * 16 + ke] : 0.f);
                             store_x(sX, f, p, x);
@@ -543,8 +575,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) posmlp_bwd_data_tc_kernel(const _
                 const int pbeg = u * SPIX + pq;
                 for (int p0 = pbeg; p0 < pbeg + SPIX / 2; p0 += 16) {
                     float zv[16];
+                    const float* const zp = A.zc + (n0 + p0) * ZSTRIDE + 3 * HID + f;
+                    const int nval = (int)min((long long)16, A.N - (n0 + p0));
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) zv[i] = (n0 + p0 + i < A.N) ? __ldg(A.zc + (n0 + p0 + i) * ZSTRIDE + 3 * HID + f) : 0.f;
+                    for (int i = 0; i < 16; ++i) zv[i] = i < nval ? __ldg(zp + i * ZSTRIDE) : 0.f;
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const int p = p0 + i;
@@ -574,8 +608,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) posmlp_bwd_data_tc_kernel(const _
                     const int pbeg = u * SPIX + pq;
                     for (int p0 = pbeg; p0 < pbeg + SPIX / 2; p0 += 16) {
                         float acc[16], zv[16];
+                        const float* const zp = A.zc + (n0 + p0) * ZSTRIDE + (L - 1) * HID + f;
+                        const int nval = live ? (int)min((long long)16, A.N - (n0 + p0)) : 0;
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) zv[i] = (live && n0 + p0 + i < A.N) ? __ldg(A.zc + (n0 + p0 + i) * ZSTRIDE + (L - 1) * HID + f) : 0.f;
+                        for (int i = 0; i < 16; ++i) zv[i] = i < nval ? __ldg(zp + i * ZSTRIDE) : 0.f;
                         tmem_ld16(t_lane + (uint32_t)p0, acc);
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
