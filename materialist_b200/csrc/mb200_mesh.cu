@@ -584,6 +584,9 @@ inline void launch_mesh_fwd(K kernel, int filter, int grid, cudaStream_t st, con
 #define MB200_WF_TRACE_BLOCKS 4          // CTAs per SM of the traversal kernels: 64 registers, no spills (5: 94 ms, 4: 84 ms, 3: 87 ms, 6: 122 ms)
 #endif
 constexpr int kWfBatch = 1 << MB200_WF_BATCH_LOG2;
+#ifndef MB200_WF_SM_STACK
+#define MB200_WF_SM_STACK 16        // measured (profiles/r5w): 0 / 8 / 12 / 16 / 24 entries -> C2m 132.8 / 133.2 / 128.2 / 127.6 / 129.3 ms, C1 37.1 / 37.2 / 36.3 / 36.0 / 36.7 ms
+#endif
 #ifndef MB200_WF_CHUNK
 #define MB200_WF_CHUNK 64               // queue entries a traversal warp draws per global atomic
 #endif
@@ -683,7 +686,10 @@ __global__ void __launch_bounds__(kThreads, MB200_WF_TRACE_BLOCKS) wf_trace_kern
                                                                 const uint32_t* __restrict__ count, uint32_t* cursor) {
     constexpr bool ANY = MODE != 0;
     uint2 stack_loc[kStack];
-    TStack<0> stack; stack.loc = stack_loc; stack.sh = nullptr;
+    // the first MB200_WF_SM_STACK entries of a lane's traversal stack in shared memory (entry e of thread t at sh[e * 256 + t]: two
+    // wavefronts per push / pop whatever the lanes' stack depths), deeper ones in local memory (one 128-byte line per DISTINCT depth)
+    __shared__ uint2 s_stack[MB200_WF_SM_STACK > 0 ? MB200_WF_SM_STACK * kThreads : 1];
+    TStack<MB200_WF_SM_STACK> stack; stack.loc = stack_loc; stack.sh = s_stack + threadIdx.x;
     const QView qv = wf_qview(count);
     const uint32_t n = qv.pre[kBins];
     Trav T; T.active = false; uint32_t pid = 0;

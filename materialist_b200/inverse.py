@@ -294,6 +294,12 @@ class FusedBRDFOptimizer(_ShardedStep):
             keep = {k: v.clone() for k, v in self.mat.items()}
             self.peer.close(); self.peer = None
             self.mat = keep
+            # everything that lived in the arena moves to ordinary device memory, so that the optimiser stays usable (NCCL path)
+            self.grad_full, self.grad_img = self.shard.halo_buffer(3, self.scene.device)
+            for i, k in enumerate(self.names):
+                c = {"albedo": 3, "roughness": 1, "metallic": 1}[k]
+                off = self.shard.row0 * self.scene.W * c * 4
+                self.segs[i].mat = self.mat[k].data_ptr() + off
 
     def _step(self, seed):
         if self.peer is not None:
