@@ -327,11 +327,20 @@ int mb200_debug_exact_math(int op, const float* x, const float* y, int64_t n, fl
  * in `scratch` (device, 256-byte aligned, mb200_mesh_fwd_wf_scratch_bytes(cfg) bytes: 156 bytes per path, <= 4 Mi paths at a
  * time).  Same film partials as the one-kernel formulation. */
 size_t mb200_mesh_fwd_wf_scratch_bytes(const mb200_cfg* cfg_host);
+/* Primary-visibility index of a (mesh, camera) pair: every triangle binned into the pixels its projection (dilated by 0.01 pixel)
+ * touches, so that a primary ray tests — with the same exact Moeller-Trumbore, same closest-hit tie rule — only the candidates of
+ * its pixel instead of walking the BVH (bit-identical hits at ~1/5 of the cost; the reference's meshes are depth maps seen from the
+ * camera they were unprojected with, mesh_recon.py:184-258 / inverse_img_w_mi.py:40-56).  Pixels with too many candidates and
+ * meshes the index cannot represent (a triangle at or behind the camera plane, or covering > 64 pixels) fall back to the BVH
+ * transparently.  index: mb200_mesh_primary_index_bytes bytes of device memory (256-byte aligned); uses cfg's camera, H and W only;
+ * pass it as `primary_index` to the two wavefront entry points below (or NULL). */
+size_t mb200_mesh_primary_index_bytes(const mb200_cfg* cfg_host, const mb200_mesh_desc* desc_host);
+int mb200_mesh_primary_index_build(const mb200_cfg* cfg_host, const mb200_mesh_desc* desc_host, const void* mesh_buf, void* index, void* stream);
 int mb200_mesh_shade_fwd_wf(const mb200_cfg* cfg_host, const mb200_trans* trans_host,
                             const mb200_mesh_desc* desc_host, const void* mesh_buf,
                             const float* a, const float* r, const float* m, const float* n_opt,
                             const float* env4, const float* hier, const mb200_hier_desc* hdesc_host,
-                            float* partials, void* scratch, size_t scratch_bytes, void* stream);
+                            float* partials, void* scratch, size_t scratch_bytes, const void* primary_index, void* stream);
 
 /* Wavefront formulation of mb200_mesh_shade_bwd (same arguments + scratch: mb200_mesh_bwd_wf_scratch_bytes(cfg) bytes, device,
  * 256-byte aligned; 224 + 128 * (max_depth - 1) bytes per path, <= 8 Mi paths at a time). */
@@ -341,7 +350,7 @@ int mb200_mesh_shade_bwd_wf(const mb200_cfg* cfg_host, const mb200_mesh_desc* de
                             const float* env4, const float* hier, const mb200_hier_desc* hdesc_host,
                             const float* gadj,
                             float* g_a, float* g_r, float* g_m, float* g_n, float* g_env4, int n_env_slabs,
-                            void* scratch, size_t scratch_bytes, void* stream);
+                            void* scratch, size_t scratch_bytes, const void* primary_index, void* stream);
 
 /* ---------------------------------------------------------------- PosMLP */
 #define MB200_POSMLP_TCGEN05 0   /* 256-wide layers on tcgen05 tensor cores, FP16x2-split operands, FP32 TMEM accumulators */

@@ -122,9 +122,11 @@ def _load():
         "mb200_trans_shade_fwd": (i32, [pc, pt] + [vp] * 8 + [ph, vp, vp]),
         "mb200_trans_mesh_shade_fwd": (i32, [pc, pt, pd] + [vp] * 7 + [ph, vp, vp]),
         "mb200_mesh_fwd_wf_scratch_bytes": (sz, [pc]),
-        "mb200_mesh_shade_fwd_wf": (i32, [pc, pt, pd] + [vp] * 7 + [ph, vp, vp, sz, vp]),
+        "mb200_mesh_shade_fwd_wf": (i32, [pc, pt, pd] + [vp] * 7 + [ph, vp, vp, sz, vp, vp]),
+        "mb200_mesh_primary_index_bytes": (sz, [pc, pd]),
+        "mb200_mesh_primary_index_build": (i32, [pc, pd, vp, vp, vp]),
         "mb200_mesh_bwd_wf_scratch_bytes": (sz, [pc]),
-        "mb200_mesh_shade_bwd_wf": (i32, [pc, pd] + [vp] * 7 + [ph] + [vp] * 6 + [i32, vp, sz, vp]),
+        "mb200_mesh_shade_bwd_wf": (i32, [pc, pd] + [vp] * 7 + [ph] + [vp] * 6 + [i32, vp, sz, vp, vp]),
         "mb200_trans_eval_pdf": (i32, [pc, pt, i64] + [vp] * 11),
         "mb200_trans_sample": (i32, [pc, pt, i64] + [vp] * 13),
         "mb200_trans_refracted_texel": (i32, [pc, pt, i64] + [vp] * 6),

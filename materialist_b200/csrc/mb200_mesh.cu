@@ -668,7 +668,8 @@ __global__ void wf_gen_kernel(const __grid_constant__ RenderParams P, WfBuf B, l
         Pcg32 rng; rng.seed(P.seed, (uint32_t)(py * P.W + px) * (uint32_t)P.spp + (uint32_t)s);
         const float jx = rng.next_float(), jy = rng.next_float();
         const float3 d = primary_dir(P.cam, XADD((float)px, jx), XADD((float)py, jy));
-        B.ray_o[p] = make_float4(cam_o.x, cam_o.y, cam_o.z, 0.f); B.ray_d[p] = make_float4(d.x, d.y, d.z, 0.f);
+        // (.w of the two ray records: the film position of the primary ray, read by wf_primary_kernel)
+        B.ray_o[p] = make_float4(cam_o.x, cam_o.y, cam_o.z, XADD((float)px, jx)); B.ray_d[p] = make_float4(d.x, d.y, d.z, XADD((float)py, jy));
         B.beta[p] = make_float4(1.f, 1.f, 1.f, 1.f);                               // w = prev_pdf
         B.L[p] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x100));               // w = nv | prev_delta << 8
         B.rng[p] = make_uint4((uint32_t)rng.state, (uint32_t)(rng.state >> 32), (uint32_t)rng.inc, (uint32_t)(rng.inc >> 32));
@@ -679,6 +680,108 @@ __global__ void wf_gen_kernel(const __grid_constant__ RenderParams P, WfBuf B, l
         B.counters[CNT_A] = (uint32_t)nb;                                          // primary rays: one bin (they are coherent anyway)
     }
 }
+// ---------------------------------------------------------------- primary-visibility index
+// Primary rays all leave one point, so which triangles a ray CAN hit is a 2-D question: those whose projection onto the film contains
+// the ray's film position.  The index bins every triangle into the pixels its projected bounding box (dilated by kPIdxEps pixels:
+// far more than the float rounding of primary_dir / Moeller-Trumbore can move a hit) overlaps; a primary ray then runs the SAME exact
+// triangle test on the <= kPIdxK candidates of its pixel whose box contains its film position — the closest hit with the same tie
+// rule, hence bit-identical to the BVH traversal (and to brute force), at ~1/5 of its cost: for the reference's depth-map meshes
+// (vertex k <-> pixel k, mesh_recon.py:184-258) a pixel sees 8-18 candidates and a ray tests 2-4 of them.  Pixels with more than
+// kPIdxK candidates, and meshes with a triangle at or behind the camera plane or one that covers more than 64 pixels, fall back to the
+// BVH (per pixel / for the whole image).  Built once per (mesh, camera): mb200_mesh_primary_index_build.
+constexpr int kPIdxK = 20;
+constexpr float kPIdxEps = 0.01f;
+struct PIdxView { int* valid; int* counts; int* lists; float4* bbox; };
+__host__ __device__ inline size_t pidx_off_counts() { return 256; }
+inline size_t pidx_bytes(int H, int W, int n_slots) {
+    return 256 + (((size_t)H * W * (1 + kPIdxK) * 4 + 255) & ~(size_t)255) + (size_t)n_slots * 16;
+}
+inline PIdxView pidx_view(void* buf, int H, int W) {
+    PIdxView v; char* b = (char*)buf;
+    v.valid = (int*)b; v.counts = (int*)(b + 256); v.lists = v.counts + (size_t)H * W;
+    v.bbox = (float4*)(b + 256 + (((size_t)H * W * (1 + kPIdxK) * 4 + 255) & ~(size_t)255));
+    return v;
+}
+__global__ void pidx_bin_kernel(const __grid_constant__ MeshView M, const __grid_constant__ CamView cam, PIdxView I, int n_slots) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_slots) return;
+    const float4 q0 = __ldg(M.tv + 3 * (size_t)slot);
+    float4 bb = make_float4(1.f, 1.f, 0.f, 0.f);                     // empty
+    if (__float_as_int(q0.w) >= 0) {
+        const float4 q1 = __ldg(M.tv + 3 * (size_t)slot + 1), q2 = __ldg(M.tv + 3 * (size_t)slot + 2);
+        const double vx[3] = {q0.x, q1.x, q2.x}, vy[3] = {q0.y, q1.y, q2.y}, vz[3] = {q0.z, q1.z, q2.z};
+        const double ox = cam.c2w[3], oy = cam.c2w[7], oz = cam.c2w[11];
+        const double t = cam.tan_half_fov_x, aspect = (double)cam.W / (double)cam.H;
+        double x0 = 1e30, y0 = 1e30, x1 = -1e30, y1 = -1e30; bool ok = true;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double dx = vx[k] - ox, dy = vy[k] - oy, dz = vz[k] - oz;
+            // camera-local coordinates: columns of the rotation part of cam_to_world (primary_dir maps local (lx, ly, 1) through its rows)
+            const double lx = cam.c2w[0] * dx + cam.c2w[4] * dy + cam.c2w[8] * dz;
+            const double ly = cam.c2w[1] * dx + cam.c2w[5] * dy + cam.c2w[9] * dz;
+            const double lz = cam.c2w[2] * dx + cam.c2w[6] * dy + cam.c2w[10] * dz;
+            if (!(lz > 1e-6 * (fabs(lx) + fabs(ly) + fabs(lz)))) { ok = false; break; }
+            const double sx = 0.5 * cam.W * (1.0 - lx / (lz * t)), sy = 0.5 * cam.H * (1.0 - ly * aspect / (lz * t));
+            x0 = fmin(x0, sx); x1 = fmax(x1, sx); y0 = fmin(y0, sy); y1 = fmax(y1, sy);
+        }
+        if (!ok) { *I.valid = 0; }
+        else {
+            x0 -= kPIdxEps; y0 -= kPIdxEps; x1 += kPIdxEps; y1 += kPIdxEps;
+            bb = make_float4((float)x0, (float)y0, (float)x1, (float)y1);
+            const int px0 = max(0, (int)floor(x0)), px1 = min(cam.W - 1, (int)floor(x1));
+            const int py0 = max(0, (int)floor(y0)), py1 = min(cam.H - 1, (int)floor(y1));
+            if (px1 >= px0 && py1 >= py0) {
+                if ((long long)(px1 - px0 + 1) * (py1 - py0 + 1) > 64) *I.valid = 0;
+                else
+                    for (int y = py0; y <= py1; ++y)
+                        for (int x = px0; x <= px1; ++x) {
+                            const int pix = y * cam.W + x;
+                            const int pos = atomicAdd(I.counts + pix, 1);
+                            if (pos < kPIdxK) I.lists[(size_t)pix * kPIdxK + pos] = slot;
+                        }
+            }
+        }
+    }
+    I.bbox[slot] = bb;
+}
+// closest hit of the primary rays of a batch through the index; rays of pixels the index cannot serve go to the fallback queue
+__global__ void __launch_bounds__(256) wf_primary_kernel(const __grid_constant__ RenderParams P, const __grid_constant__ MeshView M, WfBuf B, PIdxView I,
+                                                         long long pix0, int nb, uint32_t* __restrict__ qfall, uint32_t* fall_count) {
+    const int valid = *I.valid;
+    const uint32_t nthreads = gridDim.x * blockDim.x;
+    for (uint32_t p0 = blockIdx.x * blockDim.x; p0 < (uint32_t)nb; p0 += nthreads) {      // warp-uniform trip count (queue appends are warp-wide)
+        const uint32_t p = p0 + threadIdx.x;
+        bool fall = false;
+        if (p < (uint32_t)nb) {
+            const long long pix = pix0 + p / P.spp;
+            const int py = P.prow0 + (int)(pix / P.W), px = (int)(pix % P.W);
+            const int gpix = py * P.W + px;
+            const int cnt = valid ? __ldg(I.counts + gpix) : kPIdxK + 1;
+            if (cnt > kPIdxK) fall = true;
+            else {
+                const float4 o4 = B.ray_o[p], d4 = B.ray_d[p];
+                const float3 o = f3(o4.x, o4.y, o4.z), d = f3(d4.x, d4.y, d4.z);
+                const float sx = o4.w, sy = d4.w;
+                float best = kInf; int bslot = -1, btri = -1; float bt = kInf, bu = 0.f, bv = 0.f;
+                const int* lst = I.lists + (size_t)gpix * kPIdxK;
+                for (int i = 0; i < cnt; ++i) {
+                    const int slot = __ldg(lst + i);
+                    const float4 bb = __ldg(I.bbox + slot);
+                    if (sx < bb.x || sx > bb.z || sy < bb.y || sy > bb.w) continue;
+                    const float4 q0 = __ldg(M.tv + 3 * (size_t)slot), q1 = __ldg(M.tv + 3 * (size_t)slot + 1), q2 = __ldg(M.tv + 3 * (size_t)slot + 2);
+                    float tt, uu, vv;
+                    if (!tri_intersect(f3(q0.x, q0.y, q0.z), f3(q1.x, q1.y, q1.z), f3(q2.x, q2.y, q2.z), o, d, best, tt, uu, vv)) continue;
+                    const int tri = __float_as_int(q0.w);
+                    if (bslot < 0 || tt < bt || (tt == bt && tri < btri)) { bslot = slot; btri = tri; bt = tt; bu = uu; bv = vv; best = tt; }
+                }
+                B.hit[p] = make_float4(__int_as_float(bslot), bt, bu, bv);
+            }
+        }
+        const uint32_t slot_q = wf_append(fall_count, fall);
+        if (fall) qfall[slot_q] = p;
+    }
+}
+
 // rays of queue q[0 .. *count): MODE 0 = closest hit -> hit record; 1 = any hit, L += cem when unoccluded (forward);
 // 2 = any hit, visibility flag (adjoint)
 template <int MODE>
@@ -1085,7 +1188,7 @@ __global__ void wf_gen_bwd_kernel(const __grid_constant__ RenderParams P, WfBuf 
             dl = f3(g.x, g.y, g.z);
         }
         const float3 d = primary_dir(P.cam, XADD((float)px, jx), XADD((float)py, jy));
-        B.ray_o[p] = make_float4(cam_o.x, cam_o.y, cam_o.z, 0.f); B.ray_d[p] = make_float4(d.x, d.y, d.z, 0.f);
+        B.ray_o[p] = make_float4(cam_o.x, cam_o.y, cam_o.z, XADD((float)px, jx)); B.ray_d[p] = make_float4(d.x, d.y, d.z, XADD((float)py, jy));
         B.beta[p] = make_float4(1.f, 1.f, 1.f, 1.f);
         B.L[p] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x100));               // (R.xyz, nv | prev_delta << 8)
         B.dl[p] = make_float4(dl.x, dl.y, dl.z, 0.f);
@@ -1645,10 +1748,33 @@ size_t mb200_mesh_fwd_wf_scratch_bytes(const mb200_cfg* c) {
     return wf_scratch_bytes(nb);
 }
 
+static void fill_cam(const mb200_cfg* c, CamView& cam) {
+    for (int i = 0; i < 16; ++i) { cam.view[i] = c->view[i]; cam.proj[i] = c->proj[i]; cam.c2w[i] = c->cam_to_world[i]; }
+    cam.tan_half_fov_x = c->tan_half_fov_x; cam.H = c->H; cam.W = c->W;
+    cam.stride = (c->flags & MB200_FLAG_ROW_STRIDE_H) ? c->H : c->W;
+}
+size_t mb200_mesh_primary_index_bytes(const mb200_cfg* c, const mb200_mesh_desc* md) {
+    if (!c || !md || c->H <= 0 || c->W <= 0 || md->n_slots <= 0) return 0;
+    return pidx_bytes(c->H, c->W, md->n_slots);
+}
+int mb200_mesh_primary_index_build(const mb200_cfg* c, const mb200_mesh_desc* md, const void* mesh_buf, void* index, void* stream) {
+    if (!c || !md || !mesh_buf || !index || c->H <= 0 || c->W <= 0) return MB200_EINVAL;
+    MeshView M; int rc = make_view(md, mesh_buf, M);
+    if (rc) return rc;
+    CamView cam; fill_cam(c, cam);
+    cudaStream_t st = (cudaStream_t)stream;
+    PIdxView I = pidx_view(index, c->H, c->W);
+    if (mb200_check(cudaMemsetAsync(index, 0, 256 + (size_t)c->H * c->W * 4, st)) != MB200_OK) return MB200_ELAUNCH;     // header + counts
+    const int one = 1;
+    if (mb200_check(cudaMemcpyAsync(I.valid, &one, 4, cudaMemcpyHostToDevice, st)) != MB200_OK) return MB200_ELAUNCH;
+    pidx_bin_kernel<<<(md->n_slots + 255) / 256, 256, 0, st>>>(M, cam, I, md->n_slots);
+    return mb200_check_launch();
+}
+
 int mb200_mesh_shade_fwd_wf(const mb200_cfg* c, const mb200_trans* t, const mb200_mesh_desc* md, const void* mesh_buf,
                             const float* a, const float* r, const float* m, const float* n_opt,
                             const float* env4, const float* hier, const mb200_hier_desc* d, float* partials,
-                            void* scratch, size_t scratch_bytes, void* stream) {
+                            void* scratch, size_t scratch_bytes, const void* primary_index, void* stream) {
     RenderParams P; int rc = mesh_render_params(c, a, r, m, n_opt, env4, hier, d, P);
     if (rc) return rc;
     if (t && (rc = fill_trans(t, P)) != MB200_OK) return rc;
@@ -1675,6 +1801,13 @@ int mb200_mesh_shade_fwd_wf(const mb200_cfg* c, const mb200_trans* t, const mb20
         bool any_pending = false;
         for (int it = 0; it <= (max_verts < 0 ? 0 : max_verts); ++it) {
             cudaMemsetAsync(B.counters + 3, 0, 4, st);
+            if (it == 0 && primary_index) {
+                // primary rays: closest hit among the candidates of the ray's pixel; what the index cannot serve goes through the BVH
+                const PIdxView I = pidx_view(const_cast<void*>(primary_index), c->H, c->W);
+                cudaMemsetAsync(B.counters + CNT_B, 0, 4 * kBins, st);                 // fallback queue (rays the index cannot serve)
+                wf_primary_kernel<<<sms * 8, 256, 0, st>>>(P, M, B, I, pix0, nb, B.qb, B.counters + CNT_B);
+                wf_trace_kernel<0><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, st>>>(M, B, B.qb, B.counters + CNT_B, B.counters + 3);
+            } else
             wf_trace_kernel<0><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, st>>>(M, B, qin, B.counters + cin, B.counters + 3);
             if (any_pending) { cudaStreamWaitEvent(st, side->any_done, 0); any_pending = false; }   // the shadow rays of the previous bounce
             cudaMemsetAsync(B.counters + cout, 0, 4 * kBins, st);
@@ -1751,7 +1884,7 @@ int mb200_mesh_shade_bwd_wf(const mb200_cfg* c, const mb200_mesh_desc* md, const
                             const float* a, const float* r, const float* m, const float* n_opt,
                             const float* env4, const float* hier, const mb200_hier_desc* d, const float* gadj,
                             float* g_a, float* g_r, float* g_m, float* g_n, float* g_env4, int n_env_slabs,
-                            void* scratch, size_t scratch_bytes, void* stream) {
+                            void* scratch, size_t scratch_bytes, const void* primary_index, void* stream) {
     RenderParams P; int rc = mesh_render_params(c, a, r, m, n_opt, env4, hier, d, P);
     if (rc) return rc;
     MeshView M; rc = make_view(md, mesh_buf, M);
@@ -1783,6 +1916,12 @@ int mb200_mesh_shade_bwd_wf(const mb200_cfg* c, const mb200_mesh_desc* md, const
         bool any_pending = false;
         for (int it = 0; it <= max_verts; ++it) {
             cudaMemsetAsync(B.counters + 3, 0, 4, st);
+            if (it == 0 && primary_index) {
+                const PIdxView I = pidx_view(const_cast<void*>(primary_index), c->H, c->W);
+                cudaMemsetAsync(B.counters + CNT_B, 0, 4 * kBins, st);                 // fallback queue (rays the index cannot serve)
+                wf_primary_kernel<<<sms * 8, 256, 0, st>>>(P, M, B, I, pix0, nb, B.qb, B.counters + CNT_B);
+                wf_trace_kernel<0><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, st>>>(M, B, B.qb, B.counters + CNT_B, B.counters + 3);
+            } else
             wf_trace_kernel<0><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, st>>>(M, B, qin, B.counters + cin, B.counters + 3);
             if (any_pending) { cudaStreamWaitEvent(st, side->any_done, 0); any_pending = false; }
             cudaMemsetAsync(B.counters + cout, 0, 4 * kBins, st);

@@ -64,6 +64,26 @@ def _check_map(name, t, shape):
     return t.detach().contiguous()
 
 
+def _primary_index(scene, cfg):
+    """Primary-visibility index of (scene.mesh, scene camera): built on first use, kept with the scene (both are static over an
+    optimisation).  MB200_PRIMARY_INDEX=0 disables it (every primary ray then walks the BVH)."""
+    import os
+    if os.environ.get("MB200_PRIMARY_INDEX", "1") == "0":
+        return None
+    key = (bytes(cfg.cam_to_world), float(cfg.tan_half_fov_x), int(cfg.H), int(cfg.W), int(scene.mesh.buf.data_ptr()))
+    cached = getattr(scene, "_primary_idx", None)
+    idx = cached[1] if cached is not None and cached[0] == key else None
+    if idx is None:
+        nbytes = _abi.lib.mb200_mesh_primary_index_bytes(C.byref(cfg), C.byref(scene.mesh.desc))
+        if nbytes == 0:
+            return None
+        idx = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=scene.device)
+        _abi.check(_abi.lib.mb200_mesh_primary_index_build(C.byref(cfg), C.byref(scene.mesh.desc), _abi.ptr(scene.mesh.buf), _abi.ptr(idx),
+                                                           _abi.stream_ptr()), "mb200_mesh_primary_index_build")
+        scene._primary_idx = (key, idx)
+    return _abi.ptr(idx)
+
+
 def _forward(scene, spp, seed, a, r, m, n, env_pack, extra_flags=0):
     env4, hier, desc, He, We, mode = env_pack
     cfg = scene.make_cfg(spp, seed, desc.res_x, extra_flags)
@@ -84,7 +104,8 @@ def _forward(scene, spp, seed, a, r, m, n, env_pack, extra_flags=0):
             _abi.check(_abi.lib.mb200_mesh_shade_fwd_wf(C.byref(cfg), C.byref(td) if td is not None else None, C.byref(scene.mesh.desc),
                                                         _abi.ptr(scene.mesh.buf), _abi.fptr(a), _abi.fptr(r), _abi.fptr(m), _abi.fptr(nmap),
                                                         _abi.fptr(env4), _abi.fptr(hier), C.byref(desc), _abi.fptr(partials),
-                                                        _abi.ptr(scene._wf_scratch), scene._wf_scratch.numel() * 8, st), "mb200_mesh_shade_fwd_wf")
+                                                        _abi.ptr(scene._wf_scratch), scene._wf_scratch.numel() * 8, _primary_index(scene, cfg), st),
+                       "mb200_mesh_shade_fwd_wf")
     elif scene.trans is not None:               # TransBSDF plugin (trans_edit.py): forward only
         td = scene.trans.desc()
         if scene.mesh is not None:
@@ -166,7 +187,8 @@ def _backward(scene, spp, seed_grad, a, r, m, n, env_pack, grad_img_halo, want_a
             _abi.check(_abi.lib.mb200_mesh_shade_bwd_wf(C.byref(cfg), C.byref(scene.mesh.desc), _abi.ptr(scene.mesh.buf), _abi.fptr(a), _abi.fptr(r),
                                                         _abi.fptr(m), _abi.fptr(nmap), _abi.fptr(env4), _abi.fptr(hier), C.byref(desc),
                                                         _abi.fptr(gadj), _abi.fptr(g_a), _abi.fptr(g_r), _abi.fptr(g_m), _abi.fptr(g_n),
-                                                        _abi.fptr(g_env4), n_slabs, _abi.ptr(scene._wf_scratch), scene._wf_scratch.numel() * 8, st),
+                                                        _abi.fptr(g_env4), n_slabs, _abi.ptr(scene._wf_scratch), scene._wf_scratch.numel() * 8,
+                                                        _primary_index(scene, cfg), st),
                        "mb200_mesh_shade_bwd_wf")
     elif scene.mesh is not None:
         with _ktime("mesh_bwd"):
