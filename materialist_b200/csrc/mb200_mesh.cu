@@ -336,6 +336,114 @@ __device__ __forceinline__ void trav_step(const MeshView& M, Trav& T, TStack<SM,
         if (!got) T.active = false;
     }
 }
+// ---------------------------------------------------------------- traversal step with DEFERRED triangle tests (wavefront kernels)
+// In trav_step a lane that reaches a leaf runs the ~170-instruction exact triangle test on the spot.  Only ~7 % of a ray's steps are
+// leaf steps, so in 9 of 10 warp steps SOME lane sits on a leaf and the whole warp pays for the test at 2-3 active lanes of 32 — more
+// issue slots than the box tests themselves.  Here a leaf is only NOTED (its slot goes on a short per-lane list in
+// shared memory) and the lane keeps walking its stack; the warp runs the triangle test when enough lanes hold one
+// (MB200_WF_LEAF_THRESH), when a lane's list is full, or when no lane has box work left.  The set of triangles a ray tests can only
+// grow (`best` shrinks a little later), every test is the same exact test with the same tie rule: hits are bit-identical.
+// MEASURED (profiles/r6d_defer_sweep.log, all mesh parity tests green): threshold 1 / 4 / 8 / 12 / 16 / 24 lanes -> C1 30.7 / 30.0 /
+// 29.8 / 29.8 / 29.8 / 29.8 ms, C2m 118.8 / 115.5 / 113.3 / 113.3 / 112.9 / 113.3 ms against 27.4 / 104.5 ms of trav_step: batching the
+// triangle tests is worth 3-5 %, the second dependent load per step (leaf data after the box data) and the list traffic cost 12 %.
+// The traversal is bound by its memory pipeline (divergent 32-lane loads), not by issue slots -> left OFF.
+#ifndef MB200_WF_DEFER
+#define MB200_WF_DEFER 0
+#endif
+#ifndef MB200_WF_LEAF_THRESH
+#define MB200_WF_LEAF_THRESH 8
+#endif
+#ifndef MB200_WF_PEND
+#define MB200_WF_PEND 3
+#endif
+constexpr uint32_t kNoNode = 0xffffffffu;
+static int wf_leaf_thresh() {       // lanes that must hold an untested leaf before the warp runs the triangle test (tuning: MB200_WF_LEAF_THRESH in the environment)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MB200_WF_LEAF_THRESH"); v = e ? atoi(e) : MB200_WF_LEAF_THRESH; if (v < 1) v = 1; if (v > 32) v = 32; }
+    return v;
+}
+template <int SM, int STRIDE>
+__device__ __forceinline__ void trav_step_deferred(const MeshView& M, Trav& T, TStack<SM, STRIDE> stack, uint32_t* __restrict__ pend, int& npend, int thresh) {
+    static_assert(kLeaf == 1, "deferred leaf tests assume one triangle per leaf");
+    const bool act = T.active;
+    const bool node = act && T.cur != kNoNode && (T.cur >> 27) != 0;
+    if (node) {
+        const uint32_t level = T.cur >> 27, idx = T.cur & 0x7ffffffu;
+        float4 d0, d1, d2, d3, d4, d5;
+        const float4* src = M.nodes + (size_t)(M.lvl_off[level - 1] + (int)idx) * 6;
+        ldg256(src, d0, d1); ldg256(src + 2, d2, d3); ldg256(src + 4, d4, d5);
+        const float lox[4] = {d0.x, d0.y, d0.z, d0.w}, loy[4] = {d1.x, d1.y, d1.z, d1.w}, loz[4] = {d2.x, d2.y, d2.z, d2.w};
+        const float hix[4] = {d3.x, d3.y, d3.z, d3.w}, hiy[4] = {d4.x, d4.y, d4.z, d4.w}, hiz[4] = {d5.x, d5.y, d5.z, d5.w};
+        uint32_t key[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float ax = fmaf(lox[k], T.inv.x, -T.oi.x), bx = fmaf(hix[k], T.inv.x, -T.oi.x);
+            const float ay = fmaf(loy[k], T.inv.y, -T.oi.y), by = fmaf(hiy[k], T.inv.y, -T.oi.y);
+            const float az = fmaf(loz[k], T.inv.z, -T.oi.z), bz = fmaf(hiz[k], T.inv.z, -T.oi.z);
+            const float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
+            const float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.0000004f;
+            const bool hit = t0 <= fminf(t1, T.best) && lox[k] <= hix[k];
+            key[k] = ((hit ? __float_as_uint(t0) : 0x7f800000u) & ~3u) | (uint32_t)k;
+        }
+#define MB_KSWAP(i, j) { const uint32_t lo_ = min(key[i], key[j]), hi_ = max(key[i], key[j]); key[i] = lo_; key[j] = hi_; }
+        MB_KSWAP(0, 1) MB_KSWAP(2, 3) MB_KSWAP(0, 2) MB_KSWAP(1, 3) MB_KSWAP(1, 2)
+#undef MB_KSWAP
+        const uint32_t cbase = ((level - 1) << 27) | (idx * 4u);
+        T.cur = kNoNode;
+        if (key[0] < 0x7f800000u) {
+            if (key[1] < 0x7f800000u) {
+                if (key[2] < 0x7f800000u) {
+                    if (key[3] < 0x7f800000u) stack.push(T.sp, make_uint2(cbase | (key[3] & 3u), key[3] & ~3u));
+                    stack.push(T.sp, make_uint2(cbase | (key[2] & 3u), key[2] & ~3u));
+                }
+                stack.push(T.sp, make_uint2(cbase | (key[1] & 3u), key[1] & ~3u));
+            }
+            T.cur = cbase | (key[0] & 3u);
+        }
+    }
+    __syncwarp();
+    // advance: every lane whose `cur` is not a box group moves leaves onto its list and pops until it holds a box group (or runs dry,
+    // or holds a leaf its full list cannot take: it keeps it in `cur` until the next triangle pass has made room)
+    if (act && (T.cur == kNoNode || (T.cur >> 27) == 0)) {
+        uint32_t c = T.cur;
+        for (;;) {
+            if (c == kNoNode) {
+                bool got = false;
+                while (T.sp > 0) {
+                    const uint2 e = stack.pop(T.sp);
+                    if (__uint_as_float(e.y) <= T.best) { c = e.x; got = true; break; }
+                }
+                if (!got) break;
+            }
+            if ((c >> 27) != 0) break;
+            if (npend >= MB200_WF_PEND) break;
+            pend[npend * kThreads] = c; ++npend; c = kNoNode;
+        }
+        T.cur = c;
+    }
+    __syncwarp();
+    const bool has_pend = act && npend > 0;
+    const bool held = act && T.cur != kNoNode && (T.cur >> 27) == 0;
+    const bool boxwork = act && T.cur != kNoNode && (T.cur >> 27) != 0;
+    const unsigned pm = __ballot_sync(0xffffffffu, has_pend);
+    const bool flush = pm != 0u && (__popc(pm) >= thresh || __any_sync(0xffffffffu, held) || !__any_sync(0xffffffffu, boxwork));
+    if (flush && has_pend) {
+        --npend;
+        const int slot = (int)pend[npend * kThreads];
+        const float4 q0 = __ldg(M.tv + 3 * (size_t)slot);
+        const int tri = __float_as_int(q0.w);
+        if (tri >= 0) {
+            const float4 q1 = __ldg(M.tv + 3 * (size_t)slot + 1), q2 = __ldg(M.tv + 3 * (size_t)slot + 2);
+            float tt, uu, vv;
+            if (tri_intersect(f3(q0.x, q0.y, q0.z), f3(q1.x, q1.y, q1.z), f3(q2.x, q2.y, q2.z), T.o, T.d, T.best, tt, uu, vv)) {
+                if (T.any) { T.found = true; npend = 0; T.sp = 0; T.cur = kNoNode; }
+                else if (!T.found || tt < T.h.t || (tt == T.h.t && tri < T.h.tri)) { T.h.slot = slot; T.h.tri = tri; T.h.t = tt; T.h.u = uu; T.h.v = vv; T.best = tt; T.found = true; }
+            }
+        }
+    }
+    __syncwarp();
+    if (act && T.cur == kNoNode && T.sp == 0 && npend == 0) T.active = false;
+}
 // Scene::sample_emitter_direction's visibility ray (see shadow_visible) as a resumable any-hit query
 __device__ __forceinline__ void trav_begin_shadow(const MeshView& M, Trav& T, float3 p, float3 n, float3 d) {
     const ShadowRay r = shadow_ray(M, p, n, d);
@@ -786,13 +894,17 @@ __global__ void __launch_bounds__(256) wf_primary_kernel(const __grid_constant__
 // 2 = any hit, visibility flag (adjoint)
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, MB200_WF_TRACE_BLOCKS) wf_trace_kernel(const __grid_constant__ MeshView M, WfBuf B, const uint32_t* __restrict__ q,
-                                                                const uint32_t* __restrict__ count, uint32_t* cursor) {
+                                                                const uint32_t* __restrict__ count, uint32_t* cursor, int leaf_thresh) {
     constexpr bool ANY = MODE != 0;
     uint2 stack_loc[kStack];
     // the first MB200_WF_SM_STACK entries of a lane's traversal stack in shared memory (entry e of thread t at sh[e * 256 + t]: two
     // wavefronts per push / pop whatever the lanes' stack depths), deeper ones in local memory (one 128-byte line per DISTINCT depth)
     __shared__ uint2 s_stack[MB200_WF_SM_STACK > 0 ? MB200_WF_SM_STACK * kThreads : 1];
     TStack<MB200_WF_SM_STACK> stack; stack.loc = stack_loc; stack.sh = s_stack + threadIdx.x;
+#if MB200_WF_DEFER
+    __shared__ uint32_t s_pend[MB200_WF_PEND * kThreads];            // leaves a lane has reached and not yet tested (trav_step_deferred)
+    int npend = 0;
+#endif
     const QView qv = wf_qview(count);
     const uint32_t n = qv.pre[kBins];
     Trav T; T.active = false; uint32_t pid = 0;
@@ -835,7 +947,11 @@ __global__ void __launch_bounds__(kThreads, MB200_WF_TRACE_BLOCKS) wf_trace_kern
         if (was) { if ((T.cur >> 27) == 0) ++st_leaf; else ++st_node; }
         if (lane == 0) ++st_iter;
 #endif
+#if MB200_WF_DEFER
+        trav_step_deferred(M, T, stack, s_pend + threadIdx.x, npend, leaf_thresh);
+#else
         trav_step<MB200_WF_LEAF_MIN>(M, T, stack);
+#endif
         if (was && !T.active) {                                                    // this lane's ray has finished
             if (MODE == 1) {
                 if (!T.found) { float4 L = B.L[pid]; const float4 c = B.cem[pid]; L.x += c.x; L.y += c.y; L.z += c.z; B.L[pid] = L; }
@@ -1806,9 +1922,9 @@ int mb200_mesh_shade_fwd_wf(const mb200_cfg* c, const mb200_trans* t, const mb20
                 const PIdxView I = pidx_view(const_cast<void*>(primary_index), c->H, c->W);
                 cudaMemsetAsync(B.counters + CNT_B, 0, 4 * kBins, st);                 // fallback queue (rays the index cannot serve)
                 wf_primary_kernel<<<sms * 8, 256, 0, st>>>(P, M, B, I, pix0, nb, B.qb, B.counters + CNT_B);
-                wf_trace_kernel<0><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, st>>>(M, B, B.qb, B.counters + CNT_B, B.counters + 3);
+                wf_trace_kernel<0><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, st>>>(M, B, B.qb, B.counters + CNT_B, B.counters + 3, wf_leaf_thresh());
             } else
-            wf_trace_kernel<0><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, st>>>(M, B, qin, B.counters + cin, B.counters + 3);
+            wf_trace_kernel<0><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, st>>>(M, B, qin, B.counters + cin, B.counters + 3, wf_leaf_thresh());
             if (any_pending) { cudaStreamWaitEvent(st, side->any_done, 0); any_pending = false; }   // the shadow rays of the previous bounce
             cudaMemsetAsync(B.counters + cout, 0, 4 * kBins, st);
             cudaMemsetAsync(B.counters + CNT_S, 0, 4 * kBins, st);
@@ -1818,7 +1934,7 @@ int mb200_mesh_shade_fwd_wf(const mb200_cfg* c, const mb200_trans* t, const mb20
             cudaStream_t sa = side ? side->s : st;
             if (side) { cudaEventRecord(side->shaded, st); cudaStreamWaitEvent(sa, side->shaded, 0); }
             cudaMemsetAsync(B.counters + 4, 0, 4, sa);
-            wf_trace_kernel<1><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, sa>>>(M, B, B.qs, B.counters + CNT_S, B.counters + 4);
+            wf_trace_kernel<1><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, sa>>>(M, B, B.qs, B.counters + CNT_S, B.counters + 4, wf_leaf_thresh());
             if (side) { cudaEventRecord(side->any_done, sa); any_pending = true; }
             uint32_t* tq = qin; qin = qout; qout = tq; const int tc = cin; cin = cout; cout = tc;
         }
@@ -1920,9 +2036,9 @@ int mb200_mesh_shade_bwd_wf(const mb200_cfg* c, const mb200_mesh_desc* md, const
                 const PIdxView I = pidx_view(const_cast<void*>(primary_index), c->H, c->W);
                 cudaMemsetAsync(B.counters + CNT_B, 0, 4 * kBins, st);                 // fallback queue (rays the index cannot serve)
                 wf_primary_kernel<<<sms * 8, 256, 0, st>>>(P, M, B, I, pix0, nb, B.qb, B.counters + CNT_B);
-                wf_trace_kernel<0><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, st>>>(M, B, B.qb, B.counters + CNT_B, B.counters + 3);
+                wf_trace_kernel<0><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, st>>>(M, B, B.qb, B.counters + CNT_B, B.counters + 3, wf_leaf_thresh());
             } else
-            wf_trace_kernel<0><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, st>>>(M, B, qin, B.counters + cin, B.counters + 3);
+            wf_trace_kernel<0><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, st>>>(M, B, qin, B.counters + cin, B.counters + 3, wf_leaf_thresh());
             if (any_pending) { cudaStreamWaitEvent(st, side->any_done, 0); any_pending = false; }
             cudaMemsetAsync(B.counters + cout, 0, 4 * kBins, st);
             cudaMemsetAsync(B.counters + CNT_S, 0, 4 * kBins, st);
@@ -1932,7 +2048,7 @@ int mb200_mesh_shade_bwd_wf(const mb200_cfg* c, const mb200_mesh_desc* md, const
             cudaStream_t sa = side ? side->s : st;
             if (side) { cudaEventRecord(side->shaded, st); cudaStreamWaitEvent(sa, side->shaded, 0); }
             cudaMemsetAsync(B.counters + 4, 0, 4, sa);
-            wf_trace_kernel<2><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, sa>>>(M, B, B.qs, B.counters + CNT_S, B.counters + 4);
+            wf_trace_kernel<2><<<sms * MB200_WF_TRACE_BLOCKS, kThreads, 0, sa>>>(M, B, B.qs, B.counters + CNT_S, B.counters + 4, wf_leaf_thresh());
             if (want_mat && want_env)  wf_apply_bwd_kernel<true, true><<<sms * 4, 256, 0, sa>>>(P, B);
             else if (want_mat)         wf_apply_bwd_kernel<true, false><<<sms * 4, 256, 0, sa>>>(P, B);
             else                       wf_apply_bwd_kernel<false, true><<<sms * 4, 256, 0, sa>>>(P, B);

@@ -65,22 +65,26 @@ def _check_map(name, t, shape):
 
 
 def _primary_index(scene, cfg):
-    """Primary-visibility index of (scene.mesh, scene camera): built on first use, kept with the scene (both are static over an
-    optimisation).  MB200_PRIMARY_INDEX=0 disables it (every primary ray then walks the BVH)."""
+    """Primary-visibility index of (scene.mesh, scene camera): built on first use and kept ON THE MESH OBJECT (a Mesh is immutable once
+    built, the camera is part of the key), so a new mesh — even one whose buffer lands on the old one's address — never sees a stale
+    index.  MB200_PRIMARY_INDEX=0 disables it (every primary ray then walks the BVH)."""
     import os
     if os.environ.get("MB200_PRIMARY_INDEX", "1") == "0":
         return None
-    key = (bytes(cfg.cam_to_world), float(cfg.tan_half_fov_x), int(cfg.H), int(cfg.W), int(scene.mesh.buf.data_ptr()))
-    cached = getattr(scene, "_primary_idx", None)
-    idx = cached[1] if cached is not None and cached[0] == key else None
+    mesh = scene.mesh
+    key = (bytes(cfg.cam_to_world), float(cfg.tan_half_fov_x), int(cfg.H), int(cfg.W))
+    cache = mesh.__dict__.setdefault("_primary_idx", {})
+    idx = cache.get(key)
     if idx is None:
-        nbytes = _abi.lib.mb200_mesh_primary_index_bytes(C.byref(cfg), C.byref(scene.mesh.desc))
+        nbytes = _abi.lib.mb200_mesh_primary_index_bytes(C.byref(cfg), C.byref(mesh.desc))
         if nbytes == 0:
             return None
         idx = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=scene.device)
-        _abi.check(_abi.lib.mb200_mesh_primary_index_build(C.byref(cfg), C.byref(scene.mesh.desc), _abi.ptr(scene.mesh.buf), _abi.ptr(idx),
+        _abi.check(_abi.lib.mb200_mesh_primary_index_build(C.byref(cfg), C.byref(mesh.desc), _abi.ptr(mesh.buf), _abi.ptr(idx),
                                                            _abi.stream_ptr()), "mb200_mesh_primary_index_build")
-        scene._primary_idx = (key, idx)
+        if len(cache) >= 4:                      # a handful of cameras per mesh at most (each index is ~22 ints per pixel)
+            cache.pop(next(iter(cache)))
+        cache[key] = idx
     return _abi.ptr(idx)
 
 
