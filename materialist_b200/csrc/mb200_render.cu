@@ -158,6 +158,51 @@ __global__ void __launch_bounds__(kThreads) film_weights_kernel(int W, int spp, 
         if (lane < MB200_FILM_TAPS) wpart[(size_t)pix * MB200_FILM_TAPS + lane] = v[0];
     }
 }
+// The same sums with T LANES PER PIXEL (T = 1: one thread per pixel) for images with enough pixels to fill the GPU that way: no
+// 31-shuffle butterfly (which costs about as many instructions per sample as the RNG and the taps together at 64 spp), and the 25
+// sums of a warp's 32 / T pixels leave through shared memory as coalesced rows (stride 25 is odd: conflict free).
+// Measured at C2 (profiles/r6g_fw_sweep.log): one warp per pixel 159 us; T = 1 / 2 / 4 / 8 -> 105 / 108 / 125 / 138 us; capping the
+// residency (4 CTAs per SM, persistent) so that the loss kernels beside it always find a free CTA slot: no gain (step 2.527 vs 2.514 ms).
+template <int T>
+__global__ void __launch_bounds__(kThreads) film_weights_px_kernel(int W, int spp, uint32_t seed, int wrow0, int wrows, float* __restrict__ wpart) {
+    constexpr int kPixPerWarp = 32 / T, kPixPerCta = kThreads / T;
+    __shared__ float s_out[kPixPerCta * MB200_FILM_TAPS];
+    const int npix = wrows * W, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane & (T - 1);
+    float* sw = s_out + warp * kPixPerWarp * MB200_FILM_TAPS;                  // this warp's pixels x 25
+    for (int base = blockIdx.x * kPixPerCta; base < npix; base += gridDim.x * kPixPerCta) {
+        const int wbase = base + warp * kPixPerWarp, pix = wbase + lane / T;
+        float acc[MB200_FILM_TAPS];
+#pragma unroll
+        for (int t = 0; t < MB200_FILM_TAPS; ++t) acc[t] = 0.f;
+        if (pix < npix) {
+            const uint32_t gpix = (uint32_t)((wrow0 + pix / W) * W + pix % W);
+            for (int s = sub; s < spp; s += T) {
+                Pcg32 rng; rng.seed(seed, gpix * (uint32_t)spp + (uint32_t)s);
+                const float jx = rng.next_float(), jy = rng.next_float();
+                float wx[5], wy[5]; film_taps(jx, wx); film_taps(jy, wy);
+#pragma unroll
+                for (int t = 0; t < MB200_FILM_TAPS; ++t) acc[t] = fmaf(wx[t % 5], wy[t / 5], acc[t]);
+            }
+        }
+#pragma unroll
+        for (int h = 1; h < T; h <<= 1) {
+#pragma unroll
+            for (int t = 0; t < MB200_FILM_TAPS; ++t) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], h);
+        }
+        if (sub == 0) {
+#pragma unroll
+            for (int t = 0; t < MB200_FILM_TAPS; ++t) sw[(lane / T) * MB200_FILM_TAPS + t] = acc[t];
+        }
+        __syncwarp();
+        const long long w0 = (long long)wbase * MB200_FILM_TAPS, wend = (long long)npix * MB200_FILM_TAPS;
+#pragma unroll
+        for (int i = 0; i < (kPixPerWarp * MB200_FILM_TAPS + 31) / 32; ++i) {
+            const int k = i * 32 + lane;
+            if (k < kPixPerWarp * MB200_FILM_TAPS && w0 + k < wend) wpart[w0 + k] = sw[k];
+        }
+        __syncwarp();
+    }
+}
 // G[q] = grad[q] / W_q
 template <int FILTER>
 __global__ void film_adjoint_kernel(const float* __restrict__ wpart, int H, int W, int wrow0, int wrows, int grow0, int grows,
@@ -503,7 +548,15 @@ int mb200_film_weights(const mb200_cfg* c, float* wpart, void* stream) {
     if (!wpart) return MB200_EINVAL;
     if ((double)c->H * (double)c->W * (double)c->spp >= 4294967296.0) return MB200_ERANGE;
     int wrow0; const int wrows = mb200_bwd_wpart_rows(c, &wrow0);
-    film_weights_kernel<<<persistent_grid(film_weights_kernel, wrows * c->W), kThreads, 0, (cudaStream_t)stream>>>(c->W, c->spp, c->seed, wrow0, wrows, wpart);
+    const int npix = wrows * c->W, sms = mb200_sm_count();
+    // one thread per pixel once that alone gives every SM two full CTAs; one warp per pixel below (small images / shards, high spp)
+    static int px_mode = -1;
+    if (px_mode < 0) { const char* e = getenv("MB200_FILM_WEIGHTS_PX"); px_mode = e ? atoi(e) : 1; }
+    if (px_mode && npix >= sms * 2 * kThreads) {
+        const int tiles = (npix + kThreads - 1) / kThreads, cap = sms * 8;
+        film_weights_px_kernel<1><<<tiles < cap ? tiles : cap, kThreads, 0, (cudaStream_t)stream>>>(c->W, c->spp, c->seed, wrow0, wrows, wpart);
+    } else
+        film_weights_kernel<<<persistent_grid(film_weights_kernel, npix), kThreads, 0, (cudaStream_t)stream>>>(c->W, c->spp, c->seed, wrow0, wrows, wpart);
     return mb200_check_launch();
 }
 
