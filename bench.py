@@ -831,7 +831,9 @@ def run_b200(args, wl):
         ktime.setdefault(name, []).append(a.elapsed_time(b))
     kavg = {k: sum(v) / len(v) for k, v in ktime.items()}
     shade = {k: v for k, v in kavg.items() if k != "film_weights"}
-    dom = max(shade, key=shade.get) if shade else None
+    # roofline kernel: the adjoint render kernel when it ran alone on the GPU (it is the largest kernel of the step; the forward
+    # kernel's event time includes the film-weights kernel that runs beside it on a side stream, see FusedBRDFOptimizer), else the largest
+    dom = "shade_bwd" if "shade_bwd" in shade else (max(shade, key=shade.get) if shade else None)
     roofline, fp32 = build_roofline(args, wl, scene, shard, dom, kavg, t_step, dev, world)
 
     # ---- e2e through the public API with HOST buffers
@@ -872,7 +874,10 @@ def run_b200(args, wl):
                                     + (", image_sum, loss_srgb_sums, loss_srgb_grad, adam_clamped" if args.optimizer == "fused"
                                        else " (+ ~100 torch elementwise/reduce launches for loss and Adam)"),
                "optimizer": args.optimizer,
-               "kernel_ms": kavg, "roofline": roofline, "fp32": fp32, "cpu_baseline": cpu, "clocks": clk,
+               "kernel_ms": kavg,
+               "kernel_ms_note": "CUDA events around each launch on its own stream; film_weights runs on a side stream BESIDE shade_fwd (launched behind it, "
+                                 "no dependency), so those two event times include each other's work; shade_bwd runs alone",
+               "roofline": roofline, "fp32": fp32, "cpu_baseline": cpu, "clocks": clk,
                "loss_mse_last": float(opt.last["loss_mse"].item()),
                "exchange": ("peer memory (NVLink stores + in-kernel mailboxes; no NCCL call in the iteration)" if getattr(opt, "peer", None) is not None
                             else ("nccl" if world > 1 else None))}

@@ -257,21 +257,24 @@ class FusedBRDFOptimizer(_ShardedStep):
         self._ticket = self.peer.tensor("ticket")
 
     def _launch_film_weights(self, main, seed_grad, env_pack):
-        """The film weights of the adjoint render depend on nothing but seed_grad: they run on a side stream.  Default: launched right
-        AFTER the forward render, under the loss kernels and (multi-GPU) the latency of the exchange steps that sit between the two
-        render kernels.  MB200_FILM_WEIGHTS_EARLY=1 launches them BEFORE the forward render instead, co-resident with it (shade_fwd
-        leaves ~20 % of the issue slots idle); measured at C2 (profiles/r5h): step 2.736 -> 2.726 ms, the forward kernel slows from
-        1.19 to 1.25 ms while the weights take 0.94 ms beside it — issue slots are conserved, so the gain is the 10 us tail only; left
-        off so that the per-kernel times of the bench stay clean."""
+        """The film weights of the adjoint render depend on nothing but seed_grad: they run on a side stream.  MB200_FILM_WEIGHTS_EARLY
+        selects where: "2" (default) launches them BEHIND the forward render with no dependency on it — the forward's CTAs are
+        dispatched first and leave no room for the weights' CTAs, which then fill the forward's tail and the idle slots under the
+        latency-bound loss kernels; "1" launches them before the forward render (co-resident from its start); "0" after it (a
+        dependency on the forward render: its per-kernel time in the bench stays clean).  Measured at C2 (profiles/r6h_prio_probe.log):
+        2.500 / 2.468 / 2.464 ms per iteration for "0" / "1" / "2"; a high-priority stream for everything else: within noise of that."""
         sc = self.scene
         if sc.filter != _abi.FILTER_GAUSSIAN:
             return
         if self._side is None:
             self._side = torch.cuda.Stream(sc.device)
             self._ev_fwd, self._ev_w = torch.cuda.Event(), torch.cuda.Event()
-            self._fw_late = os.environ.get("MB200_FILM_WEIGHTS_EARLY", "0") != "1"
+            self._fw_mode = os.environ.get("MB200_FILM_WEIGHTS_EARLY", "2")
+            self._fw_late = self._fw_mode != "1"
         if self._fw_late:
             self._pending_fw = (seed_grad, env_pack)
+            if self._fw_mode == "2":
+                self._ev_fwd.record(main)         # dependency: the previous iteration; the launch itself follows the forward render's
             return
         self._ev_fwd.record(main)                 # after the previous iteration's adjoint render (which read the weight buffer)
         with torch.cuda.stream(self._side):
@@ -282,7 +285,8 @@ class FusedBRDFOptimizer(_ShardedStep):
     def _late_film_weights(self, main):
         if self.scene.filter == _abi.FILTER_GAUSSIAN and self._fw_late:
             seed_grad, env_pack = self._pending_fw
-            self._ev_fwd.record(main)
+            if self._fw_mode != "2":
+                self._ev_fwd.record(main)
             with torch.cuda.stream(self._side):
                 self._side.wait_event(self._ev_fwd)
                 self._wpart = _rop._film_weights(self.scene, self.spp, seed_grad, env_pack[2].res_x, out=self._wpart)
