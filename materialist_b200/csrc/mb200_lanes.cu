@@ -70,15 +70,15 @@ __global__ void exact_math_kernel(int op, const float* __restrict__ x, const flo
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float a = x[i], b = y ? y[i] : 0.f;
-    float r0 = 0.f, r1 = 0.f; bool bad = false;
+    float r0 = 0.f, r1 = 0.f; ExChk bad;
     switch (op) {
         case 0: mbx_sincospi(a, &r0, &r1); break;
         case 1: r0 = mbx_atan2(a, b); break;
         case 2: r0 = mbx_acos(a); break;
         case 3: r0 = mbx_asin01(a); break;
         case 4: r0 = mbx_rsqrt(a); r1 = __frsqrt_rn(a); break;
-        case 5: r0 = xdiv_pos(a, b, bad); r1 = __fdiv_rn(a, b); if (bad) r0 = r1; break;
-        case 6: r0 = xsqrt_pos(a, bad); r1 = __fsqrt_rn(a); if (bad) r0 = r1; break;
+        case 5: r0 = xdiv_pos(a, b, bad); r1 = __fdiv_rn(a, b); if (bad.bad()) r0 = r1; break;
+        case 6: r0 = xsqrt_pos(a, bad); r1 = __fsqrt_rn(a); if (bad.bad()) r0 = r1; break;
         default: break;
     }
     o0[i] = r0; if (o1) o1[i] = r1;
