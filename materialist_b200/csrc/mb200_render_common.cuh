@@ -149,6 +149,7 @@ inline size_t plan_env_staging(RenderParams& P, const mb200_hier_desc* d, size_t
         if (bytes > budget) break;
         P.hier.smem_from = l; P.hier.smem_off0 = d->lvl_off[l]; P.hier.smem_floats = d->total_floats - d->lvl_off[l];
     }
+    for (int l = 0; l < d->n_levels; ++l) P.hier.lvl_sm[l] = make_int2(4 * (d->lvl_off[l] - P.hier.smem_off0), 4 * d->lvl_w[l]);
     size_t used = sizeof(float) * (size_t)((P.hier.smem_floats + 3) & ~3);
     const size_t tex = sizeof(float4) * (size_t)d->res_x * d->res_y;
     if (P.hier.smem_from == 0 && used + tex <= budget) { P.env_smem_texels = d->res_x * d->res_y; used += tex; }
