@@ -284,16 +284,24 @@ __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_BWD) shade_bwd_kernel(
             float3 dl = gbox;
             if (FILTER == MB200_FILTER_GAUSSIAN) {
                 float wx[5], wy[5]; film_taps(jx, wx); film_taps(jy, wy);
+                // One of the two outer taps of an axis is EXACTLY zero (film_taps: w[0] = 0 for j > 0.5, w[4] = 0 otherwise), and an
+                // fmaf with a zero weight leaves its accumulator unchanged: the 4 x 4 taps that can be non-zero give the same sum, term
+                // for term in the same order, with 16 cotangent loads and 60 FMAs instead of 25 and 90.
+                const int ox = jx > 0.5f ? 1 : 0, oy = jy > 0.5f ? 1 : 0;
+                float vx[4], vy[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { vx[k] = ox ? wx[k + 1] : wx[k]; vy[k] = oy ? wy[k + 1] : wy[k]; }
+                const float4* g0 = gt + (oy * 5 + ox);
                 dl = f3(0, 0, 0);
 #pragma unroll
-                for (int j = 0; j < 5; ++j) {
+                for (int j = 0; j < 4; ++j) {
                     float3 row = f3(0, 0, 0);
 #pragma unroll
-                    for (int i = 0; i < 5; ++i) {
-                        const float4 g = gt[j * 5 + i];
-                        row.x = fmaf(wx[i], g.x, row.x); row.y = fmaf(wx[i], g.y, row.y); row.z = fmaf(wx[i], g.z, row.z);
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 g = g0[j * 5 + i];
+                        row.x = fmaf(vx[i], g.x, row.x); row.y = fmaf(vx[i], g.y, row.y); row.z = fmaf(vx[i], g.z, row.z);
                     }
-                    dl.x = fmaf(wy[j], row.x, dl.x); dl.y = fmaf(wy[j], row.y, dl.y); dl.z = fmaf(wy[j], row.z, dl.z);
+                    dl.x = fmaf(vy[j], row.x, dl.x); dl.y = fmaf(vy[j], row.y, dl.y); dl.z = fmaf(vy[j], row.z, dl.z);
                 }
             }
             if (!c.valid) {
