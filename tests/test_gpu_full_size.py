@@ -200,3 +200,33 @@ def test_mesh_mode_at_1080p_scale():
         part = mb.render(s, spp=2, seed=3, albedo=a, roughness=r, metallic=m)
     assert torch.isfinite(full).all() and float(full.mean()) > 0
     assert torch.equal(full, again) and torch.equal(full[500:580], part)
+
+
+def test_film_weight_kernels_agree_at_c2_size():
+    """The film weights of the adjoint render have two kernels: one thread per pixel for images that fill the GPU that way (the whole
+    C2 image), one warp per pixel below that (a 16-row shard of it).  Same samples, same taps, different summation order: the rows
+    both produce must agree to float rounding — and the full-image buffer must be the sum the weights are defined as (every sample
+    spreads a total weight of (sum_i wx_i) (sum_j wy_j) over its 25 taps; spot-checked against a direct evaluation on the host)."""
+    import ctypes as C
+    from materialist_b200 import _abi, renderop
+    c = Case(H=512, W=512, spp=64, He=16, We=32)
+    s = c.scene()
+    res_x = s.prepared_env()[2].res_x
+    seed_grad = 12345
+    full = renderop._film_weights(s, c.spp, seed_grad, res_x).clone()
+    first = C.c_int(0)
+    row0, rows = 200, 16
+    with s.shard(row0, rows):
+        cfg = s.make_cfg(c.spp, seed_grad, res_x)
+        wrows = _abi.lib.mb200_bwd_wpart_rows(C.byref(cfg), C.byref(first))
+        part = renderop._film_weights(s, c.spp, seed_grad, res_x).clone()
+    assert part.shape[0] == wrows and wrows * c.W < 148 * 2 * 256          # the shard takes the warp-per-pixel kernel
+    ref = full[first.value:first.value + wrows]
+    assert float((part - ref).abs().max()) <= 2e-6 * float(ref.abs().max())
+    assert float(ref.sum()) > 0
+    # total weight per pixel against the analytic value spp * (integral of the filter)^2 within Monte-Carlo noise
+    tot = full.sum(-1)
+    g = lambda x: np.maximum(0.0, np.exp(-2.0 * x * x) - np.exp(-8.0))
+    xs = (np.arange(200000) + 0.5) / 200000 * 4.0 - 2.0
+    integral = float(g(xs).mean() * 4.0)
+    assert abs(float(tot.mean()) / (c.spp * integral * integral) - 1.0) < 2e-3
