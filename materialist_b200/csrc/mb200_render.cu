@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_BWD) shade_bwd_kernel(
             if (b2.pdf > 0.f) w_bs = b2.f * (1.f / b2.pdf);
             else {
                 const BsdfVal bv = eval_brdf(wi_bs, c.view, c.mt);
-                w_bs = bv.pdf > 1e-6f ? bv.f * (1.f / (bv.pdf + 1e-6f)) : f3(0.f, 0.f, 0.f);
+                w_bs = bv.pdf > 1e-6f ? bv.f * frcp(bv.pdf + 1e-6f) : f3(0.f, 0.f, 0.f);
             }
             if (fmax3(w_bs.x, w_bs.y, w_bs.z) != 0.f && bs_pdf > 0.f) {
                 float u, v; dir_to_uv(d_bs, u, v);
