@@ -272,6 +272,7 @@ __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_BWD) shade_bwd_kernel(
             gbox = f3(g.x, g.y, g.z);
         }
         float3 ga = f3(0, 0, 0), gn = f3(0, 0, 0); float gr = 0.f, gm = 0.f;
+        const BrdfPix bp = brdf_pixel_terms(c.view, c.mt);      // view / material terms of the BSDF: once per pixel, not per evaluation
         for (int s0 = 0; s0 < P.spp; s0 += LPP) {         // uniform trip count: the aggregated envmap scatter below is warp-collective
             const int s = s0 + sl;
             Bilerp bA, bB; float3 cA = f3(0, 0, 0), cB = f3(0, 0, 0); bool aA = false, aB = false;   // this lane's envmap-gradient updates
@@ -321,11 +322,11 @@ __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_BWD) shade_bwd_kernel(
             const EmSample em = env_sample_direction(P.hier, P.env, uex, uey, S.hier);
             if (em.pdf != 0.f) {
                 BrdfGradCtx gc;
-                const BsdfVal fv = WANT_MAT ? eval_brdf_ctx<WANT_N>(em.d, c.view, c.mt, gc) : eval_brdf(em.d, c.view, c.mt);
+                const BsdfVal fv = WANT_MAT ? eval_brdf_ctx<WANT_N>(em.d, c.view, c.mt, bp, gc) : eval_brdf(em.d, c.view, c.mt);
                 const float k = mis_weight(em.pdf, fv.pdf) / em.pdf;
                 if (WANT_MAT) {
                     const float3 le = env_value(P.env, em.b, S.tex);
-                    const BsdfGrad bg = brdf_grad_apply<WANT_N>(gc, em.d, c.view, c.mt, dl * le * k);
+                    const BsdfGrad bg = brdf_grad_apply<WANT_N>(gc, em.d, c.view, c.mt, bp, dl * le * k);
                     ga = ga + bg.ga; gr += bg.gr; gm += bg.gm; if (WANT_N) gn = gn + bg.gn;
                 }
                 if (WANT_ENV) { bA = em.b; cA = dl * fv.f * k; aA = true; if (!ENVAGG) env_scatter(genv, P.env.Wi, bA, cA); }
@@ -334,11 +335,11 @@ __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_BWD) shade_bwd_kernel(
             // are needed (the primal weight f/(pdf+eps) only where the re-evaluated pdf is 0: a rare fallback, evaluated lazily)
             int lobe;
             const float3 wi_bs = sample_lobe_direction(s1, s2x, s2y, c.view, c.mt.r, c.fshade, lobe);
-            const float pdf_s = eval_brdf_pdf(wi_bs, c.view, c.mt);
+            const float pdf_s = eval_brdf_pdf(wi_bs, c.view, c.mt, bp);
             const float bs_pdf = pdf_s > 0.f ? pdf_s : 0.f;
             const float3 d_bs = (P.flags & MB200_FLAG_WO_WORLD_QUIRK) ? to_world(c.fgeo, wi_bs) : wi_bs;
             BrdfGradCtx gc2;
-            const BsdfVal b2 = WANT_MAT ? eval_brdf_ctx<WANT_N>(d_bs, c.view, c.mt, gc2) : eval_brdf(d_bs, c.view, c.mt);
+            const BsdfVal b2 = WANT_MAT ? eval_brdf_ctx<WANT_N>(d_bs, c.view, c.mt, bp, gc2) : eval_brdf(d_bs, c.view, c.mt);
             float3 w_bs;
             if (b2.pdf > 0.f) w_bs = b2.f * (1.f / b2.pdf);
             else {
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_BWD) shade_bwd_kernel(
                 const Bilerp bb = env_lookup(P.env, u, v);
                 if (WANT_MAT && b2.pdf > 0.f) {
                     const float3 le = env_value(P.env, bb, S.tex);
-                    const BsdfGrad bg = brdf_grad_apply<WANT_N>(gc2, d_bs, c.view, c.mt, dl * le * (mis / b2.pdf));
+                    const BsdfGrad bg = brdf_grad_apply<WANT_N>(gc2, d_bs, c.view, c.mt, bp, dl * le * (mis / b2.pdf));
                     ga = ga + bg.ga; gr += bg.gr; gm += bg.gm; if (WANT_N) gn = gn + bg.gn;
                 }
                 if (WANT_ENV) { bB = bb; cB = dl * w_bs * mis; aB = true; if (!ENVAGG) env_scatter(genv, P.env.Wi, bB, cB); }
