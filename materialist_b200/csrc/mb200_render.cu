@@ -34,12 +34,18 @@ constexpr size_t kStageBudgetFwd = 27 * 1024, kStageBudgetBwd = 44 * 1024;
 template <int FILTER, bool AD_W, bool TRANS = false, int LPP = 32, bool NMAP = true>
 __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_FWD) shade_fwd_kernel(const __grid_constant__ RenderParams P) {
     constexpr int PPW = 32 / LPP;
-    __shared__ __align__(16) float s_rec[FILTER == MB200_FILTER_GAUSSIAN ? kWarpsPerBlock * 32 * kRecStride : 4];
+    // Staged tap records of the warp's 32 in-flight samples, STRUCTURE OF ARRAYS: rows 0..4 = wx[i][record], rows 5..9 = wy[j][record]
+    // (row stride 36 floats: the five rows a 128-bit load touches start 4 banks apart), then one float4 (L, 1) per record.  A tap
+    // lane fetches the weights of FOUR records with two 128-bit loads (26 instructions per four records instead of 32 with one
+    // 16-float record per sample and two scalar loads per record and tap).
+    constexpr int kTapRow = 36, kTapWarp = 10 * kTapRow + 32 * 4;
+    __shared__ __align__(16) float s_rec[FILTER == MB200_FILTER_GAUSSIAN ? kWarpsPerBlock * kTapWarp : 4];
     extern __shared__ float4 s_dyn[];
     const StagedEnv S = stage_env(P, s_dyn);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane / LPP, sl = lane % LPP;
-    float* rec = s_rec + (FILTER == MB200_FILTER_GAUSSIAN ? warp * 32 * kRecStride : 0);
+    float* rec = s_rec + (FILTER == MB200_FILTER_GAUSSIAN ? warp * kTapWarp : 0);
+    float4* recL = reinterpret_cast<float4*>(rec + 10 * kTapRow);
     const int npix = P.prows * P.W;
     const int ti = lane % 5, tj = lane / 5;              // tap owned by this lane (lanes 0..24)
     for (int pix0 = (blockIdx.x * kWarpsPerBlock + warp) * PPW; pix0 < npix; pix0 += gridDim.x * kWarpsPerBlock * PPW) {
@@ -59,23 +65,27 @@ __global__ void __launch_bounds__(kThreads, MB_MIN_BLOCKS_FWD) shade_fwd_kernel(
             if (FILTER == MB200_FILTER_GAUSSIAN) {
                 float wx[5], wy[5]; film_taps(jx, wx); film_taps(jy, wy);
                 if (!act) { wx[0] = wx[1] = wx[2] = wx[3] = wx[4] = 0.f; }
-                float4* r4 = reinterpret_cast<float4*>(rec + lane * kRecStride);
-                r4[0] = make_float4(wx[0], wx[1], wx[2], wx[3]);
-                r4[1] = make_float4(wx[4], wy[0], wy[1], wy[2]);
-                r4[2] = make_float4(wy[3], wy[4], 0.f, 0.f);
-                r4[3] = make_float4(L.x, L.y, L.z, 1.f);
+#pragma unroll
+                for (int i = 0; i < 5; ++i) { rec[i * kTapRow + lane] = wx[i]; rec[(5 + i) * kTapRow + lane] = wy[i]; }
+                recL[lane] = make_float4(L.x, L.y, L.z, 1.f);
                 __syncwarp();
                 if (lane < MB200_FILM_TAPS) {
-                    // inactive lanes staged wx = 0 -> w = 0: always 32 records (LPP per pixel group), fully unrollable
-                    const float* rt = rec + ti; const float* ru = rec + 5 + tj;
+                    // inactive lanes staged wx = 0 -> w = 0: always 32 records (LPP per pixel group), fully unrollable; records are
+                    // added in their order, as before
+                    const float* rt = rec + ti * kTapRow; const float* ru = rec + (5 + tj) * kTapRow;
 #pragma unroll
                     for (int g = 0; g < PPW; ++g) {
-#pragma unroll 8
-                        for (int kk = 0; kk < LPP; ++kk) {
+#pragma unroll 2
+                        for (int kk = 0; kk < LPP; kk += 4) {
                             const int k = g * LPP + kk;
-                            const float w = rt[k * kRecStride] * ru[k * kRecStride];
-                            const float4 l4 = *reinterpret_cast<const float4*>(rec + k * kRecStride + 12);
-                            acc[g].x = fmaf(w, l4.x, acc[g].x); acc[g].y = fmaf(w, l4.y, acc[g].y); acc[g].z = fmaf(w, l4.z, acc[g].z); acc[g].w += w;
+                            const float4 a4 = *reinterpret_cast<const float4*>(rt + k), b4 = *reinterpret_cast<const float4*>(ru + k);
+                            const float w4[4] = {a4.x * b4.x, a4.y * b4.y, a4.z * b4.z, a4.w * b4.w};
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float4 l4 = recL[k + q];
+                                acc[g].x = fmaf(w4[q], l4.x, acc[g].x); acc[g].y = fmaf(w4[q], l4.y, acc[g].y); acc[g].z = fmaf(w4[q], l4.z, acc[g].z);
+                                acc[g].w += w4[q];
+                            }
                         }
                     }
                 }
